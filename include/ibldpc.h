@@ -1,0 +1,160 @@
+/*
+ * ibldpc.h -- C ABI of the B200-native LDPC decoding engine (libibldpc.so).
+ *
+ * This is the drop-in boundary for the reference's data-parallel hot path.  Each entry
+ * point names the reference interface it replaces (paths relative to the reference
+ * repository root).  Plain pointers and sizes only; no torch / CUDA runtime types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative IBLDPC_E_* code otherwise;
+ *     ibldpc_last_error() gives the message of the calling thread's last failure;
+ *   - buffers are row-major (rows, B) with the frame index fastest, exactly the
+ *     (N_var, msg_at_time) C-order arrays of the reference
+ *     (Discrete_LDPC_decoding/kernels_template.cl:27 indexes row*msg_at_time+gid2);
+ *   - "_dev" pointers are device pointers on the handle's GPU, "_host" pointers host memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); device-buffer calls
+ *     are asynchronous on it unless they return a scalar to the host;
+ *   - cluster indices travel as uint8 (the reference uses int32; values are < |T| <= 256).
+ */
+#ifndef IBLDPC_H
+#define IBLDPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IBLDPC_OK 0
+#define IBLDPC_E_INVALID (-1)  /* bad argument / inconsistent tables */
+#define IBLDPC_E_CUDA (-2)     /* CUDA runtime error                 */
+#define IBLDPC_E_STATE (-3)    /* call order (e.g. decode before set_luts) */
+#define IBLDPC_E_NOMEM (-4)
+
+#define IBLDPC_ALGO_MINSUM 0
+#define IBLDPC_ALGO_BP 1
+#define IBLDPC_F32 32
+#define IBLDPC_F64 64
+
+typedef struct ibldpc_decoder *ibldpc_handle;
+
+/* The six int32 tables the reference uploads in init_OpenCL_decoding
+ * (Discrete_LDPC_decoding/discrete_LDPC_decoder_irreg.py:191-205), host pointers. */
+typedef struct ibldpc_code_desc {
+    int32_t n_var, n_chk, n_edge;
+    const int32_t *inbox_start_chk;  /* [n_chk] inbox_memory_start_checknodes  */
+    const int32_t *degree_chk;       /* [n_chk] degree_checknode_nr            */
+    const int32_t *target_cells_chk; /* [n_edge] target_memory_cells_checknodes */
+    const int32_t *inbox_start_var;  /* [n_var] inbox_memory_start_varnodes    */
+    const int32_t *degree_var;       /* [n_var] degree_varnode_nr              */
+    const int32_t *target_cells_var; /* [n_edge] target_memory_cells_varnodes  */
+} ibldpc_code_desc;
+
+/* Look-up tables of the IB decoder in the reference layout:
+ * Trellis_checknode_vector_a / Trellis_varnode_vector_a / matching_vector_* as int32,
+ * exactly the arrays init_OpenCL_decoding uploads (discrete_LDPC_decoder_irreg.py:207-213).
+ * cn_degree / vn_degree are the CN_DEGREE / VN_DEGREE macros (d_c_max / d_v_max,
+ * discrete_LDPC_decoder_irreg.py:184).  cn_match == NULL means MATCH false. */
+typedef struct ibldpc_lut_desc {
+    int32_t card_channel;  /* cardinality_T_channel      */
+    int32_t card_decoder;  /* cardinality_T_decoder_ops  */
+    int32_t imax;          /* iterations the tables were designed for */
+    int32_t cn_degree, vn_degree;
+    const int32_t *cn_lut;
+    int64_t cn_lut_len;
+    const int32_t *vn_lut;
+    int64_t vn_lut_len;
+    const int32_t *cn_match;
+    int64_t cn_match_len;
+    const int32_t *vn_match;
+    int64_t vn_match_len;
+} ibldpc_lut_desc;
+
+/* Replaces the table upload half of init_OpenCL_decoding (discrete_LDPC_decoder.py:132-200,
+ * discrete_LDPC_decoder_irreg.py:172-243, min_sum_decoder_irreg.py:167-218,
+ * bp_decoder_irreg.py:167-219).  Validates and copies the tables to `device`. */
+int ibldpc_create(const ibldpc_code_desc *code, int device, ibldpc_handle *out);
+
+/* Replaces the LUT upload of init_OpenCL_decoding and update_trellis_vectors
+ * (discrete_LDPC_decoder.py:53-55).  May be called again to swap tables. */
+int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc *luts);
+
+/* Replaces decode_OpenCL with buffer_in=True, return_buffer=True
+ * (discrete_LDPC_decoder.py:202-295, discrete_LDPC_decoder_irreg.py:245-341):
+ * send + checknode_update_iter0 + (imax-1) x {varnode_update, checknode_update, calc_syndrome}
+ * + calc_varnode_output.  ch_dev / out_dev: uint8 (n_var, B).
+ * early_term = 1 reproduces the reference's batch-granular stop (all B frames of the call
+ * have zero syndrome); 0 always runs imax-1 passes.  If i_num_host != NULL the call
+ * synchronises the stream and stores the reference's i_num (number of passes + 1). */
+int ibldpc_decode_ib(ibldpc_handle h, const uint8_t *ch_dev, int64_t B, int imax, int early_term,
+                     uint8_t *out_dev, int32_t *i_num_host, void *stream);
+
+/* Replaces decode_OpenCL with buffer_in=False, return_buffer=False (numpy in, numpy out;
+ * H2D at discrete_LDPC_decoder_irreg.py:250, D2H at :340) and decode_on_host.
+ * Host buffers uint8 (n_var, B); copies are issued inside the call (pinned memory overlaps
+ * them with compute when early_term == 0: frames are processed in independent chunks). */
+int ibldpc_decode_ib_host(ibldpc_handle h, const uint8_t *ch_host, int64_t B, int imax, int early_term,
+                          uint8_t *out_host, int32_t *i_num_host);
+
+/* Replaces decode_OpenCL_min_sum (min_sum_decoder_irreg.py:221-287) and
+ * decode_OpenCL_belief_propagation (bp_decoder_irreg.py:221-286).  ch_dev / out_dev are
+ * (n_var, B) LLR arrays of `dtype` (IBLDPC_F32: fp32 messages, the fast path;
+ * IBLDPC_F64: float64 like the reference). */
+int ibldpc_decode_llr(ibldpc_handle h, int algo, int dtype, const void *ch_dev, int64_t B, int imax,
+                      int early_term, void *out_dev, int32_t *i_num_host, void *stream);
+
+/* Replaces return_errors_all_zero (discrete_LDPC_decoder.py:297-300,
+ * discrete_LDPC_decoder_irreg.py:343-349) and the host-side comparison of the _enc drivers
+ * (Irregular_LDPC_Decoding/WLAN/BER_simulation_OpenCL_enc.py:134): over the first `rows`
+ * rows of out_dev (rows_total x B), decoded bit = (out < threshold); counters_host[0] = bit
+ * errors, [1] = frames with at least one bit error.  ref_bits_dev == NULL means the all-zero
+ * codeword, else uint8 (rows, B) transmitted bits.  Synchronises the stream. */
+int ibldpc_count_errors_u8(int device, const uint8_t *out_dev, int64_t rows, int64_t B, int threshold,
+                           const uint8_t *ref_bits_dev, int64_t *counters_host, void *stream);
+
+/* LLR twin (min_sum_decoder_irreg.py:290-295, bp_decoder_irreg.py:288-293): bit = (LLR < 0). */
+int ibldpc_count_errors_llr(int device, const void *out_dev, int dtype, int64_t rows, int64_t B,
+                            const uint8_t *ref_bits_dev, int64_t *counters_host, void *stream);
+
+/* Replaces the `quantize` kernel (AWGN_Channel_Transmission/kernels_quanti_template.cl:2-27)
+ * as launched by quantize_OpenCL (AWGN_Quantizer_BPSK.py:183-199):
+ * cluster = #{w in [1,card) : x - limits[w] > 0}, float64 compare.  limits_host: card doubles. */
+int ibldpc_quantize(int device, const double *x_dev, int64_t n, const double *limits_host, int card,
+                    uint8_t *out_dev, void *stream);
+
+/* Replaces `quantize_LLR` (kernels_quanti_template.cl:29-52): out = llr_host[cluster]. */
+int ibldpc_quantize_llr(int device, const double *x_dev, int64_t n, const double *limits_host, int card,
+                        const double *llr_host, int dtype, void *out_dev, void *stream);
+
+/* Replaces quantize_direct_OpenCL / quantize_direct_OpenCL_LLR (AWGN_Quantizer_BPSK.py:201-248):
+ * u ~ U[0,1) drawn ON THE DEVICE (Philox4x32-10, element i uses counter offset+i of key `seed`)
+ * instead of np.random.rand + H2D, then the same inversion-method compare against
+ * cdf_host (card = |T|+1 entries).  ibldpc_uniform exposes the very same u for checking. */
+int ibldpc_sample_direct(int device, const double *cdf_host, int card, uint64_t seed, uint64_t offset,
+                         int64_t n, uint8_t *out_dev, void *stream);
+int ibldpc_sample_direct_llr(int device, const double *cdf_host, int card, const double *llr_host,
+                             uint64_t seed, uint64_t offset, int64_t n, int dtype, void *out_dev,
+                             void *stream);
+int ibldpc_uniform(int device, uint64_t seed, uint64_t offset, int64_t n, double *out_dev, void *stream);
+
+/* Introspection for tests / benchmarks: which[0] = 1 if the shared-memory fast path is
+ * active for the loaded tables (0 = generic path), which[1] = kernels launched by the
+ * last decode call, which[2] = persistent grid size, which[3] = dynamic smem bytes. */
+int ibldpc_info(ibldpc_handle h, int32_t *which4);
+
+/* Average device time (ms) of the kernels of the last ibldpc_decode_ib call split by phase:
+ * ms3[0] = CN kernels, ms3[1] = VN kernels, ms3[2] = iter-0 + output.  Needs
+ * ibldpc_set_profiling(h, 1) before the decode call; synchronises. */
+int ibldpc_set_profiling(ibldpc_handle h, int on);
+int ibldpc_phase_times(ibldpc_handle h, float *ms3, int32_t *launches3);
+
+/* Frames per chunk of the pinned-host pipeline of ibldpc_decode_ib_host (default 4096). */
+int ibldpc_set_host_chunk(ibldpc_handle h, int frames);
+
+const char *ibldpc_last_error(void);
+int ibldpc_destroy(ibldpc_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IBLDPC_H */

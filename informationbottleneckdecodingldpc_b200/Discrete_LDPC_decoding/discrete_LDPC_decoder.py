@@ -1,0 +1,204 @@
+"""Information-bottleneck (look-up table) decoder for regular LDPC codes -- B200 back-end.
+
+Drop-in for ``Discrete_LDPC_decoding/discrete_LDPC_decoder.py`` of the reference: same
+constructor, ``init_OpenCL_decoding`` / ``decode_OpenCL`` / ``return_errors_all_zero`` /
+``decode_on_host`` / ``update_trellis_vectors`` and the attributes the BER drivers read.
+The OpenCL context, Mako rendering and every CPU path are gone: all decoding runs in
+libibldpc.so (hand-written sm_100a kernels) and raises if that library or a GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..device_array import DeviceArray
+from ..engine import GraphDecoderBase, count_errors, current_device, stream_ptr
+from ..luts import as_int32
+
+
+class Discrete_LDPC_Decoder_class(GraphDecoderBase):
+    """Reference signature: discrete_LDPC_decoder.py:30-31."""
+
+    _irregular = False
+
+    def __init__(self, filename, imax_, cardinality_T_channel_, cardinality_T_decoder_ops_,
+                 Trellis_checknode_vector_a_, Trellis_varnode_vector_a_, msg_at_time_):
+        self._load_graph(filename)
+        if np.unique(self.degree_checknode_nr).size != 1 or np.unique(self.degree_varnode_nr).size != 1:
+            raise ValueError("Discrete_LDPC_Decoder_class needs a regular code; use "
+                             "Discrete_LDPC_Decoder_class_irregular for irregular parity-check matrices")
+        self.imax = imax_
+        self.cardinality_T_channel = cardinality_T_channel_
+        self.cardinality_T_decoder_ops = cardinality_T_decoder_ops_
+        self.matching_vector_checknode = None
+        self.matching_vector_varnode = None
+        self.match = 'false'
+        self.update_trellis_vectors(Trellis_checknode_vector_a_, Trellis_varnode_vector_a_)
+        self.msg_at_time = msg_at_time_
+        self._post_init()
+
+    def _post_init(self):
+        # The reference always stops as soon as the whole batch has zero syndrome
+        # (discrete_LDPC_decoder.py:233-276).  Set False for fixed-imax (throughput) runs.
+        self.early_termination = True
+        self.host_output_dtype = np.int32   # dtype decode_OpenCL(..., return_buffer=False) returns
+        self.last_i_num = None
+        self._luts_uploaded = False
+        self._host_out = None
+
+    # ---- tables ------------------------------------------------------------------------
+    def update_trellis_vectors(self, Trellis_checknode_vector_a_, Trellis_varnode_vector_a_):
+        """discrete_LDPC_decoder.py:53-55"""
+        T = int(self.cardinality_T_decoder_ops)
+        self.Trellis_checknode_vector_a = as_int32(Trellis_checknode_vector_a_, "Trellis_checknode_vector_a", T).astype(int)
+        self.Trellis_varnode_vector_a = as_int32(Trellis_varnode_vector_a_, "Trellis_varnode_vector_a", T).astype(int)
+        self._luts_uploaded = False
+
+    def _upload_luts(self):
+        h = self._ensure_handle()
+        if self._luts_uploaded:
+            return h
+        T = int(self.cardinality_T_decoder_ops)
+        cn = np.ascontiguousarray(self.Trellis_checknode_vector_a, dtype=np.int32)
+        vn = np.ascontiguousarray(self.Trellis_varnode_vector_a, dtype=np.int32)
+        use_match = self._irregular and str(self.match).lower() == 'true'
+        mc = mv = None
+        if use_match:
+            if self.matching_vector_checknode is None or self.matching_vector_varnode is None:
+                raise ValueError("match='true' needs matching_vector_checknode and matching_vector_varnode")
+            mc = as_int32(self.matching_vector_checknode, "matching_vector_checknode", T)
+            mv = as_int32(self.matching_vector_varnode, "matching_vector_varnode", T)
+        d = _lib.LutDesc()
+        d.card_channel = int(self.cardinality_T_channel)
+        d.card_decoder = T
+        d.imax = int(self.imax)
+        d.cn_degree, d.vn_degree = int(self.d_c_max), int(self.d_v_max)
+        d.cn_lut, d.cn_lut_len = cn.ctypes.data, cn.size
+        d.vn_lut, d.vn_lut_len = vn.ctypes.data, vn.size
+        if use_match:
+            d.cn_match, d.cn_match_len = mc.ctypes.data, mc.size
+            d.vn_match, d.vn_match_len = mv.ctypes.data, mv.size
+        _lib.check(_lib.lib().ibldpc_set_luts(h, C.byref(d)))
+        self._luts_uploaded = True
+        return h
+
+    # ---- reference entry points ------------------------------------------------------------
+    def init_OpenCL_decoding(self, msg_at_time_, context_=False):
+        """Upload graph tables and LUTs to the current GPU (discrete_LDPC_decoder.py:132-200).
+        ``context_`` is accepted and ignored (there is no OpenCL context)."""
+        self.msg_at_time = msg_at_time_
+        self.context = context_
+        self._upload_luts()
+
+    init_decoding = init_OpenCL_decoding
+
+    def decode_OpenCL(self, received_blocks, buffer_in=False, return_buffer=False, early_termination=None):
+        """discrete_LDPC_decoder.py:202-295 / discrete_LDPC_decoder_irreg.py:245-341.
+
+        buffer_in=True: ``received_blocks`` is a device buffer (DeviceArray / CUDA tensor) of
+        cluster indices (N_v, B); otherwise a numpy array, copied inside the call.
+        return_buffer=True returns a DeviceArray (uint8), else a numpy array of
+        ``host_output_dtype``.  ``self.last_i_num`` holds the reference's ``i_num`` afterwards
+        (device-buffer calls: only when early termination is on, to stay asynchronous otherwise)."""
+        h = self._upload_luts()
+        early = self.early_termination if early_termination is None else early_termination
+        L = _lib.lib()
+        inum = C.c_int32(0)
+        if buffer_in:
+            ch = self._device_input(received_blocks, torch.uint8)
+            B = ch.shape[1]
+            out = torch.empty_like(ch)
+            want_inum = bool(early) or not return_buffer
+            _lib.check(L.ibldpc_decode_ib(h, C.c_void_p(ch.data_ptr()), B, int(self.imax), int(bool(early)),
+                                          C.c_void_p(out.data_ptr()), C.byref(inum) if want_inum else None,
+                                          C.c_void_p(stream_ptr())))
+            self.last_i_num = int(inum.value) if want_inum else int(self.imax)
+            if return_buffer:
+                return DeviceArray(out)
+            return out.cpu().numpy().astype(self.host_output_dtype, copy=False)
+        # host buffers
+        rb = np.asarray(received_blocks)
+        if rb.ndim == 1:
+            rb = rb[:, None]
+        if rb.shape[0] != self.N_v:
+            raise ValueError(f"expected {self.N_v} rows (variable nodes), got {rb.shape[0]}")
+        if rb.dtype != np.uint8:
+            if rb.size and (rb.min() < 0 or rb.max() >= int(self.cardinality_T_channel)):
+                raise ValueError("channel cluster indices must lie in [0, cardinality_T_channel)")
+            rb = rb.astype(np.uint8)
+        rb = np.ascontiguousarray(rb)
+        B = rb.shape[1]
+        if self._host_out is None or self._host_out.shape != rb.shape:
+            from ..device_array import pinned_empty
+            self._host_out = pinned_empty(rb.shape, np.uint8)
+        out = self._host_out
+        current_device()
+        _lib.check(L.ibldpc_decode_ib_host(h, C.c_void_p(rb.ctypes.data), B, int(self.imax), int(bool(early)),
+                                           C.c_void_p(out.ctypes.data), C.byref(inum)))
+        self.last_i_num = int(inum.value)
+        if return_buffer:
+            return DeviceArray(torch.from_numpy(out).cuda())
+        if np.dtype(self.host_output_dtype) == np.uint8:
+            return out          # pinned buffer owned by the decoder, overwritten by the next call
+        return out.astype(self.host_output_dtype)
+
+    decode = decode_OpenCL
+
+    def return_errors_all_zero(self, varnode_output_buffer):
+        """Number of decoded 1-bits, all-zero codeword assumed, over ALL rows
+        (discrete_LDPC_decoder.py:297-300)."""
+        return self._errors(varnode_output_buffer, self.N_v)
+
+    def _errors(self, buf, rows):
+        thr = int(self.cardinality_T_decoder_ops / 2)
+        if isinstance(buf, np.ndarray):
+            buf = DeviceArray(torch.from_numpy(np.ascontiguousarray(buf.astype(np.uint8))).cuda())
+        bit, _frame = count_errors(buf, rows, thr)
+        return bit
+
+    def count_errors(self, varnode_output_buffer, ref_bits=None, rows=None):
+        """(bit_errors, frame_errors); ``ref_bits`` (rows, B) device buffer of transmitted bits or
+        None for the all-zero codeword (host comparison of WLAN/BER_simulation_OpenCL_enc.py:134)."""
+        rows = (self.N_v if not self._irregular else int(self.data_len)) if rows is None else rows
+        return count_errors(varnode_output_buffer, rows, int(self.cardinality_T_decoder_ops / 2), ref_bits)
+
+    def decode_on_host(self, channel_values_):
+        """Single frame, host vector in / host vector out (discrete_LDPC_decoder.py:357-400, which
+        raises ValueError as shipped).  Runs imax-1 passes without early termination like the
+        reference's loop (:374) -- on the GPU: this package has no CPU decoding path."""
+        ch = np.asarray(channel_values_).reshape(-1)
+        out = self.decode_OpenCL(ch[:, None], buffer_in=False, return_buffer=False, early_termination=False)
+        return np.array(out[:, 0], dtype=np.float64)
+
+    # ---- table-inspection helpers kept from the reference API -----------------------------------
+    def discrete_cn_operation(self, vec_y_c, iter_):
+        """One check-node look-up chain per row of ``vec_y_c`` (discrete_LDPC_decoder.py:302-335).
+        Host-side numpy helper for inspecting tables; no decode path uses it."""
+        Tc, T = int(self.cardinality_T_channel), int(self.cardinality_T_decoder_ops)
+        C_ = self.Trellis_checknode_vector_a
+        y = np.asarray(vec_y_c).astype(int)
+        n_in = y.shape[1]
+        if iter_ == 0:
+            t = C_[y[:, 0] * Tc + y[:, 1]]
+            for l in range(n_in - 2):
+                t = C_[t * T + y[:, l + 2] + Tc ** 2 + l * T * Tc]
+        else:
+            off = (self.d_c_max - 3) * Tc * T + Tc ** 2 + (iter_ - 1) * (self.d_c_max - 2) * T ** 2
+            t = y[:, 0]
+            for l in range(n_in - 1):
+                t = C_[off + l * T ** 2 + t * T + y[:, l + 1]]
+        return t
+
+    def discrete_vn_operation(self, vec_y_v, iter_):
+        """One variable-node chain per row (column 0 = channel value) (discrete_LDPC_decoder.py:337-355)."""
+        Tc, T = int(self.cardinality_T_channel), int(self.cardinality_T_decoder_ops)
+        V_ = self.Trellis_varnode_vector_a
+        y = np.asarray(vec_y_v).astype(int)
+        off = (Tc * T + (self.d_v_max - 1) * T ** 2) * iter_
+        t = V_[off + y[:, 0] * T + y[:, 1]]
+        for l in range(y.shape[1] - 2):
+            t = V_[off + Tc * T + l * T ** 2 + t * T + y[:, l + 2]]
+        return t

@@ -1,0 +1,99 @@
+"""ctypes binding of libibldpc.so (include/ibldpc.h).
+
+The CUDA library is the only execution path of this package: if it is missing or cannot be
+loaded every decoder / quantizer call raises.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libibldpc.so")
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("ibldpc.cu", "ib_kernels.cuh", "llr_kernels.cuh")]
+HEADER = os.path.join(os.path.dirname(HERE), "include", "ibldpc.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+ALGO_MINSUM, ALGO_BP = 0, 1
+F32, F64 = 32, 64
+
+
+class CodeDesc(C.Structure):
+    _fields_ = [("n_var", C.c_int32), ("n_chk", C.c_int32), ("n_edge", C.c_int32),
+                ("inbox_start_chk", C.c_void_p), ("degree_chk", C.c_void_p), ("target_cells_chk", C.c_void_p),
+                ("inbox_start_var", C.c_void_p), ("degree_var", C.c_void_p), ("target_cells_var", C.c_void_p)]
+
+
+class LutDesc(C.Structure):
+    _fields_ = [("card_channel", C.c_int32), ("card_decoder", C.c_int32), ("imax", C.c_int32),
+                ("cn_degree", C.c_int32), ("vn_degree", C.c_int32),
+                ("cn_lut", C.c_void_p), ("cn_lut_len", C.c_int64),
+                ("vn_lut", C.c_void_p), ("vn_lut_len", C.c_int64),
+                ("cn_match", C.c_void_p), ("cn_match_len", C.c_int64),
+                ("vn_match", C.c_void_p), ("vn_match_len", C.c_int64)]
+
+
+# every symbol include/ibldpc.h declares: name -> (restype, argtypes)
+_vp, _i, _i64, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+SIGNATURES = {
+    "ibldpc_create": (_i, [C.POINTER(CodeDesc), _i, C.POINTER(_vp)]),
+    "ibldpc_set_luts": (_i, [_vp, C.POINTER(LutDesc)]),
+    "ibldpc_decode_ib": (_i, [_vp, _vp, _i64, _i, _i, _vp, C.POINTER(C.c_int32), _vp]),
+    "ibldpc_decode_ib_host": (_i, [_vp, _vp, _i64, _i, _i, _vp, C.POINTER(C.c_int32)]),
+    "ibldpc_decode_llr": (_i, [_vp, _i, _i, _vp, _i64, _i, _i, _vp, C.POINTER(C.c_int32), _vp]),
+    "ibldpc_count_errors_u8": (_i, [_i, _vp, _i64, _i64, _i, _vp, C.POINTER(C.c_int64), _vp]),
+    "ibldpc_count_errors_llr": (_i, [_i, _vp, _i, _i64, _i64, _vp, C.POINTER(C.c_int64), _vp]),
+    "ibldpc_quantize": (_i, [_i, _vp, _i64, _vp, _i, _vp, _vp]),
+    "ibldpc_quantize_llr": (_i, [_i, _vp, _i64, _vp, _i, _vp, _i, _vp, _vp]),
+    "ibldpc_sample_direct": (_i, [_i, _vp, _i, _u64, _u64, _i64, _vp, _vp]),
+    "ibldpc_sample_direct_llr": (_i, [_i, _vp, _i, _vp, _u64, _u64, _i64, _i, _vp, _vp]),
+    "ibldpc_uniform": (_i, [_i, _u64, _u64, _i64, _vp, _vp]),
+    "ibldpc_info": (_i, [_vp, C.POINTER(C.c_int32)]),
+    "ibldpc_set_profiling": (_i, [_vp, _i]),
+    "ibldpc_phase_times": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "ibldpc_set_host_chunk": (_i, [_vp, _i]),
+    "ibldpc_last_error": (C.c_char_p, []),
+    "ibldpc_destroy": (_i, [_vp]),
+}
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/ibldpc.cu for sm_100a into the in-tree libibldpc.so (nvcc cross-compiles
+    without a GPU).  Rebuilds only when a source is newer than the library."""
+    deps = SOURCES + [HEADER]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in deps):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + [SOURCES[0], "-o", LIB_PATH]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libibldpc.so; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). This package has no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)     # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().ibldpc_last_error()
+        raise RuntimeError(f"libibldpc error {rc}: {msg.decode() if msg else '?'}")

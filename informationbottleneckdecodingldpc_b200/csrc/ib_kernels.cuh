@@ -1,0 +1,493 @@
+// ib_kernels.cuh -- sm_100a kernels of the information-bottleneck (LUT) decoders.
+//
+// Replaces the six OpenCL kernels of Discrete_LDPC_decoding/kernels_template.cl and
+// kernels_template_irreg.cl (reference file:line cited at each kernel).
+//
+// Data layout in HBM (all uint8, frame index fastest, `pitch` = B rounded up to 16):
+//   ch  [n_var ][pitch]  channel cluster indices
+//   msg [n_edge][pitch]  ONE in-place, check-node-major message array: row sc[c]+k holds the
+//                        VN->CN message of the k-th neighbour of check c before a CN phase and
+//                        the CN->VN message after it (the reference keeps two int32 inboxes,
+//                        discrete_LDPC_decoder.py:171-173).  A variable node reaches its rows
+//                        through tv[] (target_memory_cells_varnodes).
+//   out [n_var ][pitch]  decided cluster indices
+//
+// Thread mapping: one warp = one (node, 512-frame tile); every lane moves 16 frames per
+// message with one 128-bit load/store, so a warp touches 512 contiguous bytes per row.
+//
+// Look-ups (fast path, |T| <= 16): the iteration's stage tables are expanded in shared
+// memory to one 128*W-byte row per (message m, running value t) pair, row = m*T + t, each
+// lane owning one 32-bit bank column; byte (col & 3) of word (col >> 2) of that column
+// holds stage `col`.  A look-up is `IMAD addr = t*RS + (m*T*RS + lane*4)` + `LDS.U8`,
+// bank-conflict free for arbitrary data.  Leave-one-out chains share their common prefix
+// (the sequential order of the reference is preserved, so results are bit-identical).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ibldpc {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kMaxFastDc = 10;   // check-node degrees instantiated in the fast path
+constexpr int kMaxFastDv = 12;   // variable-node degrees instantiated in the fast path
+constexpr int kMaxGenericDeg = 64;
+
+struct IbArgs {
+    // graph
+    const int* __restrict__ sc;
+    const int* __restrict__ deg_c;
+    const int* __restrict__ sv;
+    const int* __restrict__ deg_v;
+    const int* __restrict__ tv;     // VN-major slot -> CN-major row
+    const int* __restrict__ vidx;   // CN-major row -> variable index
+    int n_var, n_chk;
+    // buffers
+    const uint8_t* __restrict__ ch;
+    uint8_t* msg;
+    uint8_t* out;
+    long long pitch;   // bytes per row (multiple of 16)
+    int B;             // valid frames
+    int tiles;         // ceil(pitch / 512)
+    // tables of this launch
+    const uint8_t* __restrict__ lut;    // [nst][T*T] stage tables of this iteration (compact, reference order t*T+m)
+    const uint8_t* __restrict__ match;  // [dmax][T] matching rows of this iteration or nullptr
+    int T, Tc, nst, dmax_match, W, nrows, tshift;
+    // iteration control
+    int* flags;        // flags[it] != 0  <=> some frame had a non-zero syndrome in pass `it`
+    int* inum;         // device copy of the reference's i_num
+    int it;            // pass index (-1 for the iteration-0 check-node kernel)
+    int early;
+    int imax;
+    int iter0;         // CN kernel only: read the channel values through vidx (send + iter0 fused)
+    // generic path only
+    const uint8_t* __restrict__ lut_all;   // whole table, reference layout
+    const uint8_t* __restrict__ match_all;
+    int DC, DV;
+    long long vn_it_stride;  // fast path, output kernel: bytes between two iterations' VN tables
+};
+
+// ------------------------------------------------------------------------------------------
+// shared-memory table staging
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_tables(uint32_t* s_tab, const IbArgs& a, const uint8_t* lut)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int TT = a.T * a.T;
+    const int total = a.nrows * a.W;
+    for (int rw = warp; rw < total; rw += kWarpsPerCta) {
+        const int r = rw / a.W, w = rw - r * a.W;
+        const int m = r / a.T, t = r - m * a.T;
+        uint32_t v = 0;
+        if (lane < 4) {
+            const int col = 4 * w + lane;
+            if (col < a.nst) {
+                if (r < TT) v = lut[col * TT + t * a.T + m];
+            } else if (col == a.nst && a.match != nullptr) {
+                if (m < a.dmax_match) v = a.match[m * a.T + t];
+            }
+            v <<= 8 * lane;
+        }
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        s_tab[rw * 32 + lane] = v;
+    }
+}
+
+#define IB_SO(l) ((uint32_t)((((l) >> 2) << 7) + ((l) & 3)))   // byte offset of stage column l
+
+__device__ __forceinline__ uint32_t lut_ld(const uint8_t* tab, uint32_t addr) { return tab[addr]; }
+
+// ------------------------------------------------------------------------------------------
+// check node: D inputs, D leave-one-out outputs, 4 frames (one 32-bit word per message).
+// Chain of kernels_template_irreg.cl:205-245 (iterations >= 1) and :60-96 (iteration 0; same
+// address arithmetic when Tc == T): t = m[0]; for l: t = C[off + l*T^2 + t*T + m[l+1]].
+// ------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void cn_word(const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab,
+                                        uint32_t RS, uint32_t TRS, uint32_t lane4, bool match, uint32_t match_off)
+{
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        uint32_t b[D], ms[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            b[k] = (w[k] >> (8 * f)) & 0xffu;
+            ms[k] = b[k] * TRS + lane4;
+        }
+        uint32_t P[D > 1 ? D : 2];
+        P[1] = b[0];
+#pragma unroll
+        for (int j = 1; j <= D - 2; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(j - 1));
+#pragma unroll
+        for (int wo = 0; wo < D; ++wo) {
+            uint32_t t = (wo == 0) ? b[1] : P[wo];
+#pragma unroll
+            for (int k = (wo == 0 ? 2 : wo + 1); k < D; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
+            if (match) t = lut_ld(tab, t * RS + match_off);
+            o[wo] |= t << (8 * f);
+        }
+    }
+}
+
+template <int D>
+__device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab, int s, long long col,
+                                            uint32_t lane4, uint32_t RS, uint32_t TRS, uint32_t valid_frames)
+{
+    uint4 m[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const uint8_t* p = a.iter0 ? a.ch + (long long)a.vidx[s + k] * a.pitch
+                                   : a.msg + (long long)(s + k) * a.pitch;
+        m[k] = *reinterpret_cast<const uint4*>(p + col);
+    }
+    const bool match = a.match != nullptr;
+    const uint32_t match_off = (uint32_t)(D - 1) * TRS + lane4 + IB_SO(a.nst);
+    uint32_t syn = 0;
+    uint4 r[D];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t w[D], o[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) w[k] = j == 0 ? m[k].x : j == 1 ? m[k].y : j == 2 ? m[k].z : m[k].w;
+        if (a.early && !a.iter0) {
+            // calc_syndrome (kernels_template_irreg.cl:304-325) on the VN->CN messages just read:
+            // parity of (msg < T/2) over the D inputs, per frame byte.
+            uint32_t par = 0;
+            if (a.tshift >= 0) {   // T power of two: (m < T/2) == !bit(log2(T)-1)
+                uint32_t x = 0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) x ^= w[k];
+                par = ((x >> a.tshift) & 0x01010101u) ^ ((D & 1) ? 0x01010101u : 0u);
+            } else {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    uint32_t p1 = 0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) p1 ^= (((w[k] >> (8 * f)) & 0xffu) < (uint32_t)(a.T / 2)) ? 1u : 0u;
+                    par |= p1 << (8 * f);
+                }
+            }
+            // ignore padding frames
+            const int nv = (int)valid_frames - 4 * j;
+            const uint32_t vmask = nv >= 4 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u);
+            syn |= par & vmask;
+        }
+        cn_word<D>(w, o, tab, RS, TRS, lane4, match, match_off);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            if (j == 0) r[k].x = o[k]; else if (j == 1) r[k].y = o[k]; else if (j == 2) r[k].z = o[k]; else r[k].w = o[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+        *reinterpret_cast<uint4*>(a.msg + (long long)(s + k) * a.pitch + col) = r[k];
+    return syn;
+}
+
+// send_channel_values_to_checknode_inbox + checknode_update_iter0 (kernels_template_irreg.cl:13-99)
+// when a.iter0, checknode_update + calc_syndrome (:181-246, :304-325) otherwise.
+// One instantiation per check-node degree; `nodes` lists the checks of that degree, so every
+// launch has exactly the register budget its degree needs.
+template <int D>
+__global__ void __launch_bounds__(kThreads) ib_cn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
+{
+    extern __shared__ __align__(16) uint32_t s_tab[];
+    if (a.early && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
+    stage_tables(s_tab, a, a.lut);
+    __syncthreads();
+    const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_tab);
+    const int lane = threadIdx.x & 31;
+    const uint32_t lane4 = lane * 4, RS = 128u * a.W, TRS = RS * a.T;
+    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+    const long long items = (long long)n_nodes * a.tiles;
+    uint32_t syn = 0;
+    for (long long item = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); item < items; item += nwarps) {
+        const int i = (int)(item / a.tiles);
+        const int tile = (int)(item - (long long)i * a.tiles);
+        const long long col = ((long long)tile * 32 + lane) * 16;
+        if (col >= a.pitch) continue;
+        const long long vf = (long long)a.B - col;
+        const uint32_t valid = vf >= 16 ? 16u : vf <= 0 ? 0u : (uint32_t)vf;
+        const int c = nodes[i];
+        syn |= cn_node<D>(a, tab, a.sc[c], col, lane4, RS, TRS, valid);
+    }
+    if (a.early && !a.iter0) {
+        // warp-ballot syndrome check: one flag write per warp that saw an unsatisfied check
+        const unsigned any = __ballot_sync(0xffffffffu, syn != 0);
+        if (any != 0 && lane == 0) atomicOr(&a.flags[a.it], 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// variable node: channel value + D inbox messages.
+// Update chain kernels_template_irreg.cl:125-177, decision chain :277-300:
+//   t = V[off + m0*T + m1]; for l>=1: t = V[off + Tc*T + (l-1)*T^2 + t*T + m[l+1]].
+// ------------------------------------------------------------------------------------------
+template <int D, bool DECIDE>
+__device__ __forceinline__ void vn_word(uint32_t chw, const uint32_t (&w)[D], uint32_t (&o)[D], uint32_t& dec,
+                                        const uint8_t* tab, uint32_t RS, uint32_t TRS, uint32_t lane4, bool match,
+                                        uint32_t match_off)
+{
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = 0;
+    dec = 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        uint32_t ms[D + 1];   // ms[k] for y_k, k = 1..D
+#pragma unroll
+        for (int k = 1; k <= D; ++k) ms[k] = ((w[k - 1] >> (8 * f)) & 0xffu) * TRS + lane4;
+        uint32_t P[D + 2];
+        P[1] = (chw >> (8 * f)) & 0xffu;
+#pragma unroll
+        for (int j = 1; j <= D - 1; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(j - 1));
+        if (DECIDE) {
+            dec |= lut_ld(tab, P[D] * RS + ms[D] + IB_SO(D - 1)) << (8 * f);
+        } else {
+#pragma unroll
+            for (int wo = 1; wo <= D; ++wo) {
+                uint32_t t = P[wo];
+#pragma unroll
+                for (int k = wo + 1; k <= D; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
+                if (match) t = lut_ld(tab, t * RS + match_off);
+                o[wo - 1] |= t << (8 * f);
+            }
+        }
+    }
+}
+
+template <int D, bool DECIDE>
+__device__ __forceinline__ void vn_node(const IbArgs& a, const uint8_t* tab, int v, int s, long long col,
+                                        uint32_t lane4, uint32_t RS, uint32_t TRS)
+{
+    const uint4 c4 = *reinterpret_cast<const uint4*>(a.ch + (long long)v * a.pitch + col);
+    int rows[D];
+    uint4 m[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) rows[k] = a.tv[s + k];
+#pragma unroll
+    for (int k = 0; k < D; ++k) m[k] = *reinterpret_cast<const uint4*>(a.msg + (long long)rows[k] * a.pitch + col);
+    if (!DECIDE && D == 1) {   // degree-1 variable node forwards the raw channel value (:132-136)
+        *reinterpret_cast<uint4*>(a.msg + (long long)rows[0] * a.pitch + col) = c4;
+        return;
+    }
+    const bool match = a.match != nullptr;
+    const uint32_t match_off = (uint32_t)(D - 1) * TRS + lane4 + IB_SO(a.nst);
+    uint4 r[D];
+    uint4 dec4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t w[D], o[D], dec;
+        const uint32_t chw = j == 0 ? c4.x : j == 1 ? c4.y : j == 2 ? c4.z : c4.w;
+#pragma unroll
+        for (int k = 0; k < D; ++k) w[k] = j == 0 ? m[k].x : j == 1 ? m[k].y : j == 2 ? m[k].z : m[k].w;
+        vn_word<D, DECIDE>(chw, w, o, dec, tab, RS, TRS, lane4, match, match_off);
+        if (DECIDE) {
+            if (j == 0) dec4.x = dec; else if (j == 1) dec4.y = dec; else if (j == 2) dec4.z = dec; else dec4.w = dec;
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                if (j == 0) r[k].x = o[k]; else if (j == 1) r[k].y = o[k]; else if (j == 2) r[k].z = o[k]; else r[k].w = o[k];
+            }
+        }
+    }
+    if (DECIDE) {
+        *reinterpret_cast<uint4*>(a.out + (long long)v * a.pitch + col) = dec4;
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k) *reinterpret_cast<uint4*>(a.msg + (long long)rows[k] * a.pitch + col) = r[k];
+    }
+}
+
+template <int D, bool DECIDE>
+__device__ __forceinline__ void vn_loop(const IbArgs& a, const uint8_t* tab, const int* __restrict__ nodes, int n_nodes)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t lane4 = lane * 4, RS = 128u * a.W, TRS = RS * a.T;
+    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+    const long long items = (long long)n_nodes * a.tiles;
+    for (long long item = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); item < items; item += nwarps) {
+        const int i = (int)(item / a.tiles);
+        const int tile = (int)(item - (long long)i * a.tiles);
+        const long long col = ((long long)tile * 32 + lane) * 16;
+        if (col >= a.pitch) continue;
+        const int v = nodes[i];
+        vn_node<D, DECIDE>(a, tab, v, a.sv[v], col, lane4, RS, TRS);
+    }
+}
+
+// Number of executed passes under the reference's stop rule (discrete_LDPC_decoder.py:233-276):
+// pass `it` runs iff it == 0 or pass it-1 left a non-zero syndrome somewhere in the batch.
+__device__ __forceinline__ int executed_passes(const IbArgs& a)
+{
+    int passes = a.imax - 1;
+    if (a.early)
+        for (int it = 0; it < a.imax - 1; ++it)
+            if (a.flags[it] == 0) { passes = it + 1; break; }
+    return passes;
+}
+
+// varnode_update (kernels_template_irreg.cl:103-179); one instantiation per variable-node degree.
+template <int D>
+__global__ void __launch_bounds__(kThreads) ib_vn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
+{
+    extern __shared__ __align__(16) uint32_t s_tab[];
+    if (a.early && a.it >= 1 && a.flags[a.it - 1] == 0) return;
+    if (D > 1) {   // degree-1 nodes forward the channel value, no tables needed
+        stage_tables(s_tab, a, a.lut);
+        __syncthreads();
+    }
+    vn_loop<D, false>(a, reinterpret_cast<const uint8_t*>(s_tab), nodes, n_nodes);
+}
+
+// calc_varnode_output (kernels_template_irreg.cl:249-302) with the VN table of iteration i_num-1
+template <int D>
+__global__ void __launch_bounds__(kThreads) ib_out_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
+{
+    extern __shared__ __align__(16) uint32_t s_tab[];
+    __shared__ int s_passes;
+    if (threadIdx.x == 0) {
+        s_passes = executed_passes(a);
+        if (blockIdx.x == 0) *a.inum = s_passes + 1;
+    }
+    __syncthreads();
+    stage_tables(s_tab, a, a.lut + (long long)s_passes * a.vn_it_stride);
+    __syncthreads();
+    vn_loop<D, true>(a, reinterpret_cast<const uint8_t*>(s_tab), nodes, n_nodes);
+}
+
+// ------------------------------------------------------------------------------------------
+// generic path: any |T| <= 256, Tc != T, degrees <= 64.  One thread per (node, frame), tables
+// read from global memory with the reference's index arithmetic.  Same in-place layout.
+// ------------------------------------------------------------------------------------------
+__global__ void ib_cn_generic_kernel(IbArgs a)
+{
+    if (a.early && a.it >= 1 && a.flags[a.it - 1] == 0) return;
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int T = a.T, Tc = a.Tc;
+    const uint8_t* C = a.lut_all;
+    bool bad = false;
+    if (f < a.pitch) {
+        for (int c = blockIdx.y; c < a.n_chk; c += gridDim.y) {
+            const int d = a.deg_c[c], s = a.sc[c];
+            uint8_t in[kMaxGenericDeg];
+            int par = 0;
+            for (int k = 0; k < d; ++k) {
+                in[k] = a.iter0 ? a.ch[(long long)a.vidx[s + k] * a.pitch + f] : a.msg[(long long)(s + k) * a.pitch + f];
+                par ^= (in[k] < T / 2);
+            }
+            if (par && f < a.B) bad = true;
+            for (int w = 0; w < d; ++w) {
+                int t;
+                if (a.iter0) {   // kernels_template_irreg.cl:60-96
+                    int i0 = (w == 0) ? 1 : 0, i1 = (w <= 1) ? 2 : 1;
+                    t = (d >= 3) ? C[in[i0] * Tc + in[i1]] : in[i0];
+                    int l = 1;
+                    for (int k = i1 + 1; k < d; ++k) {
+                        if (k == w) continue;
+                        t = C[t * T + in[k] + Tc * Tc + (l - 1) * Tc * T];
+                        ++l;
+                    }
+                    if (a.match_all) t = a.match_all[(d - 1) * T + t];
+                } else {         // :205-245
+                    const int off = Tc * Tc + (a.DC - 3) * Tc * T + a.it * ((a.DC - 2) * T * T);
+                    int first = (w == 0) ? 1 : 0;
+                    t = in[first];
+                    int l = 0;
+                    for (int k = first + 1; k < d; ++k) {
+                        if (k == w) continue;
+                        t = C[off + t * T + in[k] + l * T * T];
+                        ++l;
+                    }
+                    if (a.match_all) t = a.match_all[(a.it + 1) * T * a.DC + (d - 1) * T + t];
+                }
+                a.msg[(long long)(s + w) * a.pitch + f] = (uint8_t)t;
+            }
+        }
+    }
+    if (a.early && !a.iter0) {
+        const unsigned any = __ballot_sync(0xffffffffu, bad);
+        if (any != 0 && (threadIdx.x & 31) == 0) atomicOr(&a.flags[a.it], 1);
+    }
+}
+
+template <bool DECIDE>
+__global__ void ib_vn_generic_kernel(IbArgs a)
+{
+    __shared__ int s_passes;
+    int it = a.it;
+    if (DECIDE) {
+        if (threadIdx.x == 0) {
+            s_passes = executed_passes(a);
+            if (blockIdx.x == 0 && blockIdx.y == 0) *a.inum = s_passes + 1;
+        }
+        __syncthreads();
+        it = s_passes;
+    } else if (a.early && a.it >= 1 && a.flags[a.it - 1] == 0) {
+        return;
+    }
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.pitch) return;
+    const int T = a.T, Tc = a.Tc;
+    const uint8_t* V = a.lut_all;
+    const int off = it * (Tc * T + (a.DV - 1) * T * T);
+    for (int v = blockIdx.y; v < a.n_var; v += gridDim.y) {
+        const int d = a.deg_v[v], s = a.sv[v];
+        const int m0 = a.ch[(long long)v * a.pitch + f];
+        uint8_t in[kMaxGenericDeg];
+        int rows[kMaxGenericDeg];
+        for (int k = 0; k < d; ++k) {
+            rows[k] = a.tv[s + k];
+            in[k] = a.msg[(long long)rows[k] * a.pitch + f];
+        }
+        if (DECIDE) {            // :277-300
+            int t = V[off + m0 * T + in[0]];
+            for (int l = 1; l < d; ++l) t = V[off + t * T + in[l] + Tc * T + (l - 1) * T * T];
+            a.out[(long long)v * a.pitch + f] = (uint8_t)t;
+        } else if (d == 1) {     // :132-136
+            a.msg[(long long)rows[0] * a.pitch + f] = (uint8_t)m0;
+        } else {                 // :137-177
+            for (int w = 0; w < d; ++w) {
+                int first = (w == 0) ? 1 : 0;
+                int t = V[off + m0 * T + in[first]];
+                int l = 1;
+                for (int k = first + 1; k < d; ++k) {
+                    if (k == w) continue;
+                    t = V[off + t * T + in[k] + Tc * T + (l - 1) * T * T];
+                    ++l;
+                }
+                if (a.match_all) t = a.match_all[it * T * a.DV + (d - 1) * T + t];
+                a.msg[(long long)rows[w] * a.pitch + f] = (uint8_t)t;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pitch helpers: (rows, B) contiguous <-> (rows, pitch) padded
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pad_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, long long rows, long long B,
+                                long long pitch, T fill)
+{
+    const long long n = rows * pitch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / pitch, c = i - r * pitch;
+        dst[i] = c < B ? src[r * B + c] : fill;
+    }
+}
+template <typename T>
+__global__ void unpad_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, long long rows, long long B,
+                                  long long pitch)
+{
+    const long long n = rows * B;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / B, c = i - r * B;
+        dst[i] = src[r * pitch + c];
+    }
+}
+
+}  // namespace ibldpc

@@ -1,0 +1,921 @@
+// ibldpc.cu -- host side of libibldpc.so: C ABI (include/ibldpc.h), table upload, launch
+// sequencing of the flooding schedule, pinned-host pipeline.  Kernels live in ib_kernels.cuh
+// and llr_kernels.cuh.  Compiled for sm_100a only; there is no CPU fallback anywhere.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/ibldpc.h"
+#include "ib_kernels.cuh"
+#include "llr_kernels.cuh"
+
+using namespace ibldpc;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(IBLDPC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+struct NodeClass {
+    int degree = 0;
+    int count = 0;
+    int* d_nodes = nullptr;
+};
+
+struct Workspace {
+    uint8_t* msg = nullptr;     // IB in-place message array
+    size_t msg_bytes = 0;
+    void* cin = nullptr;        // LLR inboxes
+    void* vin = nullptr;
+    size_t llr_bytes = 0;
+    uint8_t* padbuf_in = nullptr;   // padded copies of caller buffers when B is not vector-aligned
+    uint8_t* padbuf_out = nullptr;
+    size_t pad_bytes = 0;
+    uint8_t* stage_in = nullptr;    // device staging of the host-buffer path
+    uint8_t* stage_out = nullptr;
+    size_t stage_bytes = 0;
+    int* flags = nullptr;           // [kMaxIter]
+    int* inum = nullptr;
+    cudaStream_t stream = nullptr;  // host-path stream
+};
+
+constexpr int kMaxIter = 4096;
+
+using NodeKernel = void (*)(IbArgs, const int*, int);
+using LlrNodeKernel = void (*)(LlrArgs, const int*, int);
+
+struct PhaseEvent { cudaEvent_t a, b; int phase; };
+
+}  // namespace
+
+struct ibldpc_decoder {
+    int device = 0;
+    int sm_count = 148;
+    int N = 0, M = 0, E = 0;
+    int dc_max = 0, dv_max = 0, dc_min = 0, dv_min = 0;
+    int *d_sc = nullptr, *d_dc = nullptr, *d_tc = nullptr, *d_sv = nullptr, *d_dv = nullptr, *d_tv = nullptr,
+        *d_vidx = nullptr;
+    std::vector<NodeClass> cn_classes, vn_classes;
+    // LUTs
+    bool have_luts = false;
+    int T = 0, Tc = 0, lut_imax = 0, DC = 0, DV = 0;
+    bool match = false;
+    uint8_t *d_cn8 = nullptr, *d_vn8 = nullptr, *d_mc8 = nullptr, *d_mv8 = nullptr;
+    bool fast = false;
+    int Wc = 1, Wv = 1, Wo = 1, nrows_c = 0, nrows_v = 0, nrows_o = 0, tshift = -1;
+    Workspace ws[2];
+    int host_chunk = 4096;
+    // introspection
+    int last_launches = 0, last_grid = 0, last_smem = 0;
+    bool profiling = false;
+    std::vector<PhaseEvent> events;
+    std::map<std::pair<const void*, int>, int> occ_cache;
+};
+
+namespace {
+
+template <typename T>
+int upload(T** dst, const T* src, size_t n)
+{
+    CK(cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) CK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return IBLDPC_OK;
+}
+
+int build_classes(const std::vector<int>& deg, std::vector<NodeClass>& out)
+{
+    std::map<int, std::vector<int>> by;
+    for (int i = 0; i < (int)deg.size(); ++i) by[deg[i]].push_back(i);
+    for (auto& kv : by) {
+        NodeClass c;
+        c.degree = kv.first;
+        c.count = (int)kv.second.size();
+        int rc = upload(&c.d_nodes, kv.second.data(), kv.second.size());
+        if (rc) return rc;
+        out.push_back(c);
+    }
+    return IBLDPC_OK;
+}
+
+int ensure(void** p, size_t* have, size_t need, bool zero = false)
+{
+    if (*have >= need && *p) return IBLDPC_OK;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) return fail(IBLDPC_E_NOMEM, std::string("cudaMalloc of ") + std::to_string(need) + " bytes: " + cudaGetErrorString(e));
+    if (zero) CK(cudaMemset(*p, 0, need));
+    *have = need;
+    return IBLDPC_OK;
+}
+
+int ensure_ws_common(ibldpc_decoder* h, Workspace& w)
+{
+    if (!w.flags) {
+        CK(cudaMalloc((void**)&w.flags, sizeof(int) * kMaxIter));
+        CK(cudaMalloc((void**)&w.inum, sizeof(int)));
+    }
+    (void)h;
+    return IBLDPC_OK;
+}
+
+NodeKernel cn_fast_kernel_for(int d)
+{
+    switch (d) {
+    case 2: return ib_cn_fast_kernel<2>;
+    case 3: return ib_cn_fast_kernel<3>;
+    case 4: return ib_cn_fast_kernel<4>;
+    case 5: return ib_cn_fast_kernel<5>;
+    case 6: return ib_cn_fast_kernel<6>;
+    case 7: return ib_cn_fast_kernel<7>;
+    case 8: return ib_cn_fast_kernel<8>;
+    case 9: return ib_cn_fast_kernel<9>;
+    case 10: return ib_cn_fast_kernel<10>;
+    default: return nullptr;
+    }
+}
+NodeKernel vn_fast_kernel_for(int d, bool decide)
+{
+#define VNK(D) case D: return decide ? (NodeKernel)ib_out_fast_kernel<D> : (NodeKernel)ib_vn_fast_kernel<D>;
+    switch (d) {
+        VNK(1) VNK(2) VNK(3) VNK(4) VNK(5) VNK(6) VNK(7) VNK(8) VNK(9) VNK(10) VNK(11) VNK(12)
+    default: return nullptr;
+    }
+#undef VNK
+}
+
+template <typename F, int ALGO>
+LlrNodeKernel llr_cn_kernel_for(int d)
+{
+    if (sizeof(F) == 8) return llr_cn_kernel<F, ALGO, 0>;
+    switch (d) {
+    case 2: return llr_cn_kernel<float, ALGO, 2>;
+    case 3: return llr_cn_kernel<float, ALGO, 3>;
+    case 4: return llr_cn_kernel<float, ALGO, 4>;
+    case 5: return llr_cn_kernel<float, ALGO, 5>;
+    case 6: return llr_cn_kernel<float, ALGO, 6>;
+    case 7: return llr_cn_kernel<float, ALGO, 7>;
+    case 8: return llr_cn_kernel<float, ALGO, 8>;
+    case 9: return llr_cn_kernel<float, ALGO, 9>;
+    case 10: return llr_cn_kernel<float, ALGO, 10>;
+    default: return llr_cn_kernel<float, ALGO, 0>;
+    }
+}
+template <typename F, int MODE>
+LlrNodeKernel llr_vn_kernel_for(int d)
+{
+    if (sizeof(F) == 8) return llr_vn_kernel<F, MODE, 0>;
+    switch (d) {
+    case 1: return llr_vn_kernel<float, MODE, 1>;
+    case 2: return llr_vn_kernel<float, MODE, 2>;
+    case 3: return llr_vn_kernel<float, MODE, 3>;
+    case 4: return llr_vn_kernel<float, MODE, 4>;
+    case 5: return llr_vn_kernel<float, MODE, 5>;
+    case 6: return llr_vn_kernel<float, MODE, 6>;
+    case 7: return llr_vn_kernel<float, MODE, 7>;
+    case 8: return llr_vn_kernel<float, MODE, 8>;
+    case 9: return llr_vn_kernel<float, MODE, 9>;
+    case 10: return llr_vn_kernel<float, MODE, 10>;
+    case 11: return llr_vn_kernel<float, MODE, 11>;
+    case 12: return llr_vn_kernel<float, MODE, 12>;
+    default: return llr_vn_kernel<float, MODE, 0>;
+    }
+}
+
+// persistent grid: resident CTAs per SM x SM count, capped by the work available
+int grid_for(ibldpc_decoder* h, const void* fn, int smem, long long items, int* out)
+{
+    auto key = std::make_pair(fn, smem);
+    auto it = h->occ_cache.find(key);
+    int occ;
+    if (it == h->occ_cache.end()) {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, smem));
+        if (occ < 1) return fail(IBLDPC_E_CUDA, "kernel does not fit on an SM");
+        h->occ_cache[key] = occ;
+    } else {
+        occ = it->second;
+    }
+    long long want = (items + kWarpsPerCta - 1) / kWarpsPerCta;
+    long long cap = (long long)occ * h->sm_count;
+    *out = (int)std::max<long long>(1, std::min(want, cap));
+    return IBLDPC_OK;
+}
+
+struct Prof {
+    ibldpc_decoder* h;
+    cudaStream_t st;
+    int idx = -1;
+    int begin(int phase)
+    {
+        if (!h->profiling) return IBLDPC_OK;
+        PhaseEvent ev;
+        ev.phase = phase;
+        CK(cudaEventCreate(&ev.a));
+        CK(cudaEventCreate(&ev.b));
+        CK(cudaEventRecord(ev.a, st));
+        h->events.push_back(ev);
+        idx = (int)h->events.size() - 1;
+        return IBLDPC_OK;
+    }
+    int end()
+    {
+        if (!h->profiling || idx < 0) return IBLDPC_OK;
+        CK(cudaEventRecord(h->events[idx].b, st));
+        return IBLDPC_OK;
+    }
+};
+
+void clear_events(ibldpc_decoder* h)
+{
+    for (auto& e : h->events) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    h->events.clear();
+}
+
+// ------------------------------------------------------------------------------------------
+// IB decode on padded device buffers (pitch multiple of 16, pointers 16-byte aligned)
+// ------------------------------------------------------------------------------------------
+int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long pitch, long long B, int imax,
+                     int early, uint8_t* out, cudaStream_t st)
+{
+    int rc = ensure_ws_common(h, w);
+    if (rc) return rc;
+    size_t need = (size_t)h->E * (size_t)pitch;
+    {
+        void* p = w.msg;
+        rc = ensure(&p, &w.msg_bytes, need);
+        w.msg = (uint8_t*)p;
+        if (rc) return rc;
+    }
+    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)std::max(imax, 1), st));
+    IbArgs a{};
+    a.sc = h->d_sc; a.deg_c = h->d_dc; a.sv = h->d_sv; a.deg_v = h->d_dv; a.tv = h->d_tv; a.vidx = h->d_vidx;
+    a.n_var = h->N; a.n_chk = h->M;
+    a.ch = ch; a.msg = w.msg; a.out = out;
+    a.pitch = pitch; a.B = (int)B; a.tiles = (int)((pitch + 511) / 512);
+    a.T = h->T; a.Tc = h->Tc; a.tshift = h->tshift;
+    a.flags = w.flags; a.inum = w.inum; a.early = early; a.imax = imax;
+    a.DC = h->DC; a.DV = h->DV;
+    const int T = h->T, Tc = h->Tc, TT = T * T;
+    h->last_launches = 0;
+    Prof prof{h, st};
+
+    if (h->fast) {
+        auto launch_cn = [&](int it) -> int {
+            IbArgs b = a;
+            b.it = it; b.iter0 = (it < 0);
+            const int blk = it + 1;   // table block: 0 = iteration-0 tables
+            b.lut = h->d_cn8 + (size_t)blk * (h->DC - 2) * TT;
+            b.match = h->match ? h->d_mc8 + (size_t)blk * h->DC * T : nullptr;
+            b.nst = h->DC - 2; b.dmax_match = h->DC; b.W = h->Wc; b.nrows = h->nrows_c;
+            const int smem = h->nrows_c * h->Wc * 128;
+            int r = prof.begin(it < 0 ? 2 : 0);
+            if (r) return r;
+            for (auto& c : h->cn_classes) {
+                NodeKernel k = cn_fast_kernel_for(c.degree);
+                int grid;
+                r = grid_for(h, (const void*)k, smem, (long long)c.count * b.tiles, &grid);
+                if (r) return r;
+                k<<<grid, kThreads, smem, st>>>(b, c.d_nodes, c.count);
+                h->last_launches++; h->last_grid = grid; h->last_smem = smem;
+            }
+            return prof.end();
+        };
+        auto launch_vn = [&](int it, bool decide) -> int {
+            IbArgs b = a;
+            b.it = it; b.iter0 = 0;
+            if (decide) {
+                b.lut = h->d_vn8; b.vn_it_stride = (long long)h->DV * TT; b.match = nullptr;
+                b.nst = h->DV; b.W = h->Wo; b.nrows = h->nrows_o; b.dmax_match = 0;
+            } else {
+                b.lut = h->d_vn8 + (size_t)it * h->DV * TT;
+                b.match = h->match ? h->d_mv8 + (size_t)it * h->DV * T : nullptr;
+                b.nst = h->DV - 1; b.dmax_match = h->DV; b.W = h->Wv; b.nrows = h->nrows_v;
+            }
+            const int smem = b.nrows * b.W * 128;
+            int r = prof.begin(decide ? 2 : 1);
+            if (r) return r;
+            for (auto& c : h->vn_classes) {
+                NodeKernel k = vn_fast_kernel_for(c.degree, decide);
+                int grid;
+                r = grid_for(h, (const void*)k, smem, (long long)c.count * b.tiles, &grid);
+                if (r) return r;
+                k<<<grid, kThreads, smem, st>>>(b, c.d_nodes, c.count);
+                h->last_launches++;
+            }
+            return prof.end();
+        };
+        if ((rc = launch_cn(-1))) return rc;
+        for (int it = 0; it < imax - 1; ++it) {
+            if ((rc = launch_vn(it, false))) return rc;
+            if ((rc = launch_cn(it))) return rc;
+        }
+        if ((rc = launch_vn(0, true))) return rc;
+    } else {
+        a.lut_all = h->d_cn8;
+        const dim3 blk(128);
+        auto grid2 = [&](int nodes) { return dim3((unsigned)((pitch + 127) / 128), (unsigned)std::min(nodes, 4096)); };
+        auto launch_cn = [&](int it) -> int {
+            IbArgs b = a;
+            b.it = it < 0 ? 0 : it; b.iter0 = (it < 0);
+            b.lut_all = h->d_cn8; b.match_all = h->match ? h->d_mc8 : nullptr;
+            int r = prof.begin(it < 0 ? 2 : 0);
+            if (r) return r;
+            ib_cn_generic_kernel<<<grid2(h->M), blk, 0, st>>>(b);
+            h->last_launches++;
+            return prof.end();
+        };
+        auto launch_vn = [&](int it, bool decide) -> int {
+            IbArgs b = a;
+            b.it = it; b.lut_all = h->d_vn8; b.match_all = h->match ? h->d_mv8 : nullptr;
+            int r = prof.begin(decide ? 2 : 1);
+            if (r) return r;
+            if (decide) ib_vn_generic_kernel<true><<<grid2(h->N), blk, 0, st>>>(b);
+            else ib_vn_generic_kernel<false><<<grid2(h->N), blk, 0, st>>>(b);
+            h->last_launches++;
+            return prof.end();
+        };
+        (void)Tc;
+        if ((rc = launch_cn(-1))) return rc;
+        for (int it = 0; it < imax - 1; ++it) {
+            if ((rc = launch_vn(it, false))) return rc;
+            if ((rc = launch_cn(it))) return rc;
+        }
+        if ((rc = launch_vn(0, true))) return rc;
+    }
+    CK(cudaGetLastError());
+    return IBLDPC_OK;
+}
+
+int check_decode_args(ibldpc_decoder* h, int64_t B, int imax)
+{
+    if (!h) return fail(IBLDPC_E_INVALID, "null handle");
+    if (!h->have_luts) return fail(IBLDPC_E_STATE, "ibldpc_set_luts must be called before decoding");
+    if (B <= 0) return fail(IBLDPC_E_INVALID, "B must be positive");
+    if (B > 0x7fffffffLL - 1024) return fail(IBLDPC_E_INVALID, "B too large");
+    if (imax < 1 || imax > h->lut_imax)
+        return fail(IBLDPC_E_INVALID, "imax must be in [1, " + std::to_string(h->lut_imax) + "] (the tables hold that many iterations)");
+    if (imax >= kMaxIter) return fail(IBLDPC_E_INVALID, "imax too large");
+    return IBLDPC_OK;
+}
+
+template <typename T>
+int launch_pad(const T* src, T* dst, long long rows, long long B, long long pitch, T fill, cudaStream_t st)
+{
+    const long long n = rows * pitch;
+    int grid = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    pad_rows_kernel<T><<<grid, 256, 0, st>>>(src, dst, rows, B, pitch, fill);
+    CK(cudaGetLastError());
+    return IBLDPC_OK;
+}
+template <typename T>
+int launch_unpad(const T* src, T* dst, long long rows, long long B, long long pitch, cudaStream_t st)
+{
+    const long long n = rows * B;
+    int grid = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    unpad_rows_kernel<T><<<grid, 256, 0, st>>>(src, dst, rows, B, pitch);
+    CK(cudaGetLastError());
+    return IBLDPC_OK;
+}
+
+int ensure_pad(Workspace& w, size_t bytes)
+{
+    if (w.pad_bytes >= bytes && w.padbuf_in) return IBLDPC_OK;
+    if (w.padbuf_in) CK(cudaFree(w.padbuf_in));
+    if (w.padbuf_out) CK(cudaFree(w.padbuf_out));
+    w.padbuf_in = w.padbuf_out = nullptr;
+    w.pad_bytes = 0;
+    if (cudaMalloc((void**)&w.padbuf_in, bytes) != cudaSuccess || cudaMalloc((void**)&w.padbuf_out, bytes) != cudaSuccess)
+        return fail(IBLDPC_E_NOMEM, "cudaMalloc of padding buffers failed");
+    w.pad_bytes = bytes;
+    return IBLDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// LLR decoders
+// ------------------------------------------------------------------------------------------
+template <typename F, int ALGO>
+int decode_llr_padded(ibldpc_decoder* h, Workspace& w, const F* ch, long long pitch, long long B, int imax, int early,
+                      F* out, cudaStream_t st)
+{
+    constexpr int V = VecOf<F>::N;
+    int rc = ensure_ws_common(h, w);
+    if (rc) return rc;
+    const size_t need = (size_t)h->E * (size_t)pitch * sizeof(F);
+    if (w.llr_bytes < need || !w.cin) {
+        if (w.cin) CK(cudaFree(w.cin));
+        if (w.vin) CK(cudaFree(w.vin));
+        w.cin = w.vin = nullptr;
+        w.llr_bytes = 0;
+        if (cudaMalloc(&w.cin, need) != cudaSuccess || cudaMalloc(&w.vin, need) != cudaSuccess)
+            return fail(IBLDPC_E_NOMEM, "cudaMalloc of LLR message arrays failed");
+        w.llr_bytes = need;
+    }
+    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)std::max(imax, 1), st));
+    LlrArgs a{};
+    a.sc = h->d_sc; a.deg_c = h->d_dc; a.tc = h->d_tc; a.sv = h->d_sv; a.deg_v = h->d_dv; a.tv = h->d_tv;
+    a.n_var = h->N; a.n_chk = h->M;
+    a.ch = ch; a.cin = w.cin; a.vin = w.vin; a.out = out;
+    a.pitch = pitch; a.B = (int)B; a.tiles = (int)((pitch + 32 * V - 1) / (32 * V));
+    a.flags = w.flags; a.inum = w.inum; a.early = early; a.imax = imax;
+    h->last_launches = 0;
+    auto run_vn = [&](int mode, int it) -> int {
+        LlrArgs b = a;
+        b.it = it;
+        for (auto& c : h->vn_classes) {
+            LlrNodeKernel k = mode == 0 ? llr_vn_kernel_for<F, 0>(c.degree)
+                            : mode == 1 ? llr_vn_kernel_for<F, 1>(c.degree) : llr_vn_kernel_for<F, 2>(c.degree);
+            int grid;
+            int r = grid_for(h, (const void*)k, 0, (long long)c.count * b.tiles, &grid);
+            if (r) return r;
+            k<<<grid, kThreads, 0, st>>>(b, c.d_nodes, c.count);
+            h->last_launches++;
+        }
+        return IBLDPC_OK;
+    };
+    auto run_cn = [&](int it) -> int {
+        LlrArgs b = a;
+        b.it = it;
+        for (auto& c : h->cn_classes) {
+            LlrNodeKernel k = llr_cn_kernel_for<F, ALGO>(c.degree);
+            int grid;
+            int r = grid_for(h, (const void*)k, 0, (long long)c.count * b.tiles, &grid);
+            if (r) return r;
+            k<<<grid, kThreads, 0, st>>>(b, c.d_nodes, c.count);
+            h->last_launches++;
+        }
+        return IBLDPC_OK;
+    };
+    if ((rc = run_vn(2, 0))) return rc;
+    for (int it = 0; it < imax - 1; ++it) {
+        if ((rc = run_cn(it))) return rc;
+        if ((rc = run_vn(0, it))) return rc;
+        if (early) {
+            LlrArgs b = a;
+            b.it = it;
+            int grid;
+            if ((rc = grid_for(h, (const void*)llr_syndrome_kernel<F>, 0, (long long)h->M * b.tiles, &grid))) return rc;
+            llr_syndrome_kernel<F><<<grid, kThreads, 0, st>>>(b);
+            h->last_launches++;
+        }
+    }
+    if ((rc = run_vn(1, 0))) return rc;
+    CK(cudaGetLastError());
+    return IBLDPC_OK;
+}
+
+template <typename F>
+int decode_llr_typed(ibldpc_decoder* h, int algo, const F* ch, int64_t B, int imax, int early, F* out,
+                     int32_t* i_num_host, cudaStream_t st)
+{
+    constexpr int V = VecOf<F>::N;
+    Workspace& w = h->ws[0];
+    const long long pitch = (B + V - 1) / V * V;
+    const bool aligned = (B % V == 0) && ((uintptr_t)ch % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    const F* chp = ch;
+    F* outp = out;
+    int rc;
+    if (!aligned) {
+        if ((rc = ensure_pad(w, (size_t)h->N * pitch * sizeof(F)))) return rc;
+        if ((rc = launch_pad<F>(ch, (F*)w.padbuf_in, h->N, B, pitch, F(0), st))) return rc;
+        chp = (const F*)w.padbuf_in;
+        outp = (F*)w.padbuf_out;
+    }
+    rc = algo == IBLDPC_ALGO_MINSUM ? decode_llr_padded<F, 0>(h, w, chp, pitch, B, imax, early, outp, st)
+                                    : decode_llr_padded<F, 1>(h, w, chp, pitch, B, imax, early, outp, st);
+    if (rc) return rc;
+    if (!aligned && (rc = launch_unpad<F>(outp, out, h->N, B, pitch, st))) return rc;
+    if (i_num_host) {
+        CK(cudaMemcpyAsync(i_num_host, w.inum, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return IBLDPC_OK;
+}
+
+template <int SRC>
+int quantize_common(int device, const double* x_dev, int64_t n, const double* limits_host, int card,
+                    const double* llr_host, int out_kind, uint64_t seed, uint64_t offset, void* out_dev, void* stream)
+{
+    if (n < 0 || card < 1 || card > 4096) return fail(IBLDPC_E_INVALID, "bad n / card");
+    if (out_kind != 3 && !limits_host) return fail(IBLDPC_E_INVALID, "limits missing");
+    if ((out_kind == 1 || out_kind == 2) && !llr_host) return fail(IBLDPC_E_INVALID, "LLR vector missing");
+    if (n == 0) return IBLDPC_OK;
+    CK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double* d_tab = nullptr;
+    CK(cudaMallocAsync((void**)&d_tab, sizeof(double) * 2 * card, st));
+    if (limits_host) CK(cudaMemcpyAsync(d_tab, limits_host, sizeof(double) * card, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(d_tab, 0, sizeof(double) * card, st));
+    if (llr_host) CK(cudaMemcpyAsync(d_tab + card, llr_host, sizeof(double) * card, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(d_tab + card, 0, sizeof(double) * card, st));
+    // pageable host memory: the copies above complete (are staged) before the call returns
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    const size_t smem = sizeof(double) * 2 * card;
+    switch (out_kind) {
+    case 0: quantize_kernel<SRC, 0><<<grid, 256, smem, st>>>(x_dev, n, d_tab, card, d_tab + card, seed, offset, out_dev); break;
+    case 1: quantize_kernel<SRC, 1><<<grid, 256, smem, st>>>(x_dev, n, d_tab, card, d_tab + card, seed, offset, out_dev); break;
+    case 2: quantize_kernel<SRC, 2><<<grid, 256, smem, st>>>(x_dev, n, d_tab, card, d_tab + card, seed, offset, out_dev); break;
+    default: quantize_kernel<SRC, 3><<<grid, 256, smem, st>>>(x_dev, n, d_tab, card, d_tab + card, seed, offset, out_dev); break;
+    }
+    CK(cudaGetLastError());
+    CK(cudaFreeAsync(d_tab, st));
+    return IBLDPC_OK;
+}
+
+template <typename E>
+int count_errors_common(int device, const E* out_dev, int64_t rows, int64_t B, E threshold, const uint8_t* ref_bits,
+                        int64_t* counters_host, void* stream)
+{
+    if (!out_dev || !counters_host || rows < 0 || B <= 0) return fail(IBLDPC_E_INVALID, "bad arguments");
+    CK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* d_cnt = nullptr;
+    int* d_fe = nullptr;
+    CK(cudaMallocAsync((void**)&d_cnt, sizeof(unsigned long long) * 2, st));
+    CK(cudaMallocAsync((void**)&d_fe, sizeof(int) * B, st));
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 2, st));
+    CK(cudaMemsetAsync(d_fe, 0, sizeof(int) * B, st));
+    if (rows > 0) {
+        dim3 grid((unsigned)((B + 255) / 256), (unsigned)((rows + 63) / 64));
+        count_errors_kernel<E><<<grid, 256, 0, st>>>(out_dev, rows, B, threshold, ref_bits, d_cnt, d_fe);
+        count_frames_kernel<<<(unsigned)std::min<int64_t>((B + 255) / 256, 1024), 256, 0, st>>>(d_fe, B, d_cnt);
+    }
+    CK(cudaGetLastError());
+    unsigned long long hc[2];
+    CK(cudaMemcpyAsync(hc, d_cnt, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFreeAsync(d_cnt, st));
+    CK(cudaFreeAsync(d_fe, st));
+    counters_host[0] = (int64_t)hc[0];
+    counters_host[1] = (int64_t)hc[1];
+    return IBLDPC_OK;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+const char* ibldpc_last_error(void) { return g_err.c_str(); }
+
+int ibldpc_create(const ibldpc_code_desc* code, int device, ibldpc_handle* out)
+{
+    if (!code || !out) return fail(IBLDPC_E_INVALID, "null argument");
+    const int N = code->n_var, M = code->n_chk, E = code->n_edge;
+    if (N <= 0 || M <= 0 || E <= 0) return fail(IBLDPC_E_INVALID, "empty graph");
+    if (!code->inbox_start_chk || !code->degree_chk || !code->target_cells_chk || !code->inbox_start_var ||
+        !code->degree_var || !code->target_cells_var)
+        return fail(IBLDPC_E_INVALID, "null table pointer");
+    // ---- validation: prefix sums, inverse permutations
+    long long acc = 0;
+    for (int c = 0; c < M; ++c) {
+        if (code->inbox_start_chk[c] != acc) return fail(IBLDPC_E_INVALID, "inbox_start_chk is not the exclusive prefix sum of degree_chk");
+        if (code->degree_chk[c] < 2 || code->degree_chk[c] > kMaxGenericDeg)
+            return fail(IBLDPC_E_INVALID, "check-node degrees must lie in [2, 64]");
+        acc += code->degree_chk[c];
+    }
+    if (acc != E) return fail(IBLDPC_E_INVALID, "sum(degree_chk) != n_edge");
+    acc = 0;
+    for (int v = 0; v < N; ++v) {
+        if (code->inbox_start_var[v] != acc) return fail(IBLDPC_E_INVALID, "inbox_start_var is not the exclusive prefix sum of degree_var");
+        if (code->degree_var[v] < 1 || code->degree_var[v] > kMaxGenericDeg)
+            return fail(IBLDPC_E_INVALID, "variable-node degrees must lie in [1, 64]");
+        acc += code->degree_var[v];
+    }
+    if (acc != E) return fail(IBLDPC_E_INVALID, "sum(degree_var) != n_edge");
+    for (int e = 0; e < E; ++e) {
+        const int t = code->target_cells_chk[e];
+        if (t < 0 || t >= E || code->target_cells_var[t] != e)
+            return fail(IBLDPC_E_INVALID, "target_cells_chk / target_cells_var are not inverse permutations");
+    }
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(IBLDPC_E_INVALID, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    ibldpc_decoder* h = new ibldpc_decoder();
+    h->device = device;
+    h->N = N; h->M = M; h->E = E;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    std::vector<int> dc(code->degree_chk, code->degree_chk + M), dv(code->degree_var, code->degree_var + N);
+    h->dc_max = *std::max_element(dc.begin(), dc.end());
+    h->dc_min = *std::min_element(dc.begin(), dc.end());
+    h->dv_max = *std::max_element(dv.begin(), dv.end());
+    h->dv_min = *std::min_element(dv.begin(), dv.end());
+    // variable index of every CN-major row: row tv[sv[v]+k] belongs to variable v
+    std::vector<int> vidx(E);
+    for (int v = 0; v < N; ++v)
+        for (int k = 0; k < dv[v]; ++k) vidx[code->target_cells_var[code->inbox_start_var[v] + k]] = v;
+    int rc = 0;
+    rc |= upload(&h->d_sc, code->inbox_start_chk, M);
+    rc |= upload(&h->d_dc, code->degree_chk, M);
+    rc |= upload(&h->d_tc, code->target_cells_chk, E);
+    rc |= upload(&h->d_sv, code->inbox_start_var, N);
+    rc |= upload(&h->d_dv, code->degree_var, N);
+    rc |= upload(&h->d_tv, code->target_cells_var, E);
+    rc |= upload(&h->d_vidx, vidx.data(), E);
+    if (!rc) rc = build_classes(dc, h->cn_classes);
+    if (!rc) rc = build_classes(dv, h->vn_classes);
+    if (rc) { ibldpc_destroy(h); return rc; }
+    // the LLR decoders need no tables
+    h->have_luts = false;
+    *out = h;
+    return IBLDPC_OK;
+}
+
+int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
+{
+    if (!h || !L) return fail(IBLDPC_E_INVALID, "null argument");
+    const int T = L->card_decoder, Tc = L->card_channel, imax = L->imax, DC = L->cn_degree, DV = L->vn_degree;
+    if (T < 2 || T > 256 || Tc < 2 || Tc > 256) return fail(IBLDPC_E_INVALID, "cardinalities must lie in [2, 256]");
+    if (imax < 1 || imax >= kMaxIter) return fail(IBLDPC_E_INVALID, "imax out of range");
+    if (DC < h->dc_max || DV < h->dv_max)
+        return fail(IBLDPC_E_INVALID, "cn_degree / vn_degree must be at least the maximum node degrees of the code");
+    if (!L->cn_lut || !L->vn_lut) return fail(IBLDPC_E_INVALID, "null LUT pointer");
+    const long long need_cn = (long long)Tc * Tc + (long long)(DC - 3) * Tc * T + (long long)(imax - 1) * (DC - 2) * T * T;
+    const long long need_vn = (long long)imax * ((long long)Tc * T + (long long)(DV - 1) * T * T);
+    if (L->cn_lut_len < need_cn)
+        return fail(IBLDPC_E_INVALID, "Trellis_checknode_vector_a too short: need " + std::to_string(need_cn) + ", got " + std::to_string(L->cn_lut_len));
+    if (L->vn_lut_len < need_vn)
+        return fail(IBLDPC_E_INVALID, "Trellis_varnode_vector_a too short: need " + std::to_string(need_vn) + ", got " + std::to_string(L->vn_lut_len));
+    const bool match = L->cn_match != nullptr || L->vn_match != nullptr;
+    if (match) {
+        if (!L->cn_match || !L->vn_match) return fail(IBLDPC_E_INVALID, "both matching vectors are required");
+        if (L->cn_match_len < (long long)imax * DC * T || L->vn_match_len < (long long)imax * DV * T)
+            return fail(IBLDPC_E_INVALID, "matching vectors too short (need imax*degree*T entries)");
+    }
+    auto to_u8 = [&](const int32_t* src, long long n, std::vector<uint8_t>& dst, const char* name) -> int {
+        dst.resize((size_t)std::max<long long>(n, 1));
+        for (long long i = 0; i < n; ++i) {
+            if (src[i] < 0 || src[i] >= T) return fail(IBLDPC_E_INVALID, std::string(name) + ": entry out of range [0,T)");
+            dst[(size_t)i] = (uint8_t)src[i];
+        }
+        return IBLDPC_OK;
+    };
+    std::vector<uint8_t> cn, vn, mc, mv;
+    int rc;
+    if ((rc = to_u8(L->cn_lut, std::max<long long>(need_cn, 0), cn, "Trellis_checknode_vector_a"))) return rc;
+    if ((rc = to_u8(L->vn_lut, need_vn, vn, "Trellis_varnode_vector_a"))) return rc;
+    if (match) {
+        if ((rc = to_u8(L->cn_match, (long long)imax * DC * T, mc, "matching_vector_checknode"))) return rc;
+        if ((rc = to_u8(L->vn_match, (long long)imax * DV * T, mv, "matching_vector_varnode"))) return rc;
+    }
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    for (uint8_t** p : {&h->d_cn8, &h->d_vn8, &h->d_mc8, &h->d_mv8}) {
+        if (*p) CK(cudaFree(*p));
+        *p = nullptr;
+    }
+    if ((rc = upload(&h->d_cn8, cn.data(), cn.size()))) return rc;
+    if ((rc = upload(&h->d_vn8, vn.data(), vn.size()))) return rc;
+    if (match) {
+        if ((rc = upload(&h->d_mc8, mc.data(), mc.size()))) return rc;
+        if ((rc = upload(&h->d_mv8, mv.data(), mv.size()))) return rc;
+    }
+    h->T = T; h->Tc = Tc; h->lut_imax = imax; h->DC = DC; h->DV = DV; h->match = match;
+    h->tshift = -1;
+    for (int s = 1; s <= 8; ++s)
+        if ((1 << s) == T) h->tshift = s - 1;
+    // ---- fast path: lane-striped shared-memory tables
+    auto words = [](int cols) { return std::max(1, (cols + 3) / 4); };
+    h->Wc = words((DC - 2) + (match ? 1 : 0));
+    h->Wv = words((DV - 1) + (match ? 1 : 0));
+    h->Wo = words(DV);
+    h->nrows_c = std::max(T * T, match ? DC * T : 0);
+    h->nrows_v = std::max(T * T, match ? DV * T : 0);
+    h->nrows_o = T * T;
+    const size_t smem_max = 227 * 1024;
+    h->fast = (T <= 16) && (Tc == T) && h->dc_max <= kMaxFastDc && h->dv_max <= kMaxFastDv &&
+              (size_t)h->nrows_c * h->Wc * 128 <= smem_max && (size_t)h->nrows_v * h->Wv * 128 <= smem_max &&
+              (size_t)h->nrows_o * h->Wo * 128 <= smem_max;
+    if (getenv("IBLDPC_FORCE_GENERIC")) h->fast = false;
+    h->occ_cache.clear();
+    h->have_luts = true;
+    return IBLDPC_OK;
+}
+
+int ibldpc_decode_ib(ibldpc_handle h, const uint8_t* ch_dev, int64_t B, int imax, int early_term, uint8_t* out_dev,
+                     int32_t* i_num_host, void* stream)
+{
+    int rc = check_decode_args(h, B, imax);
+    if (rc) return rc;
+    if (!ch_dev || !out_dev) return fail(IBLDPC_E_INVALID, "null buffer");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace& w = h->ws[0];
+    if (h->profiling) clear_events(h);
+    const long long pitch = (B + 15) / 16 * 16;
+    const bool aligned = (B % 16 == 0) && ((uintptr_t)ch_dev % 16 == 0) && ((uintptr_t)out_dev % 16 == 0);
+    if (aligned) {
+        rc = decode_ib_padded(h, w, ch_dev, pitch, B, imax, early_term, out_dev, st);
+        if (rc) return rc;
+    } else {
+        if ((rc = ensure_pad(w, (size_t)h->N * pitch))) return rc;
+        if ((rc = launch_pad<uint8_t>(ch_dev, w.padbuf_in, h->N, B, pitch, 0, st))) return rc;
+        if ((rc = decode_ib_padded(h, w, w.padbuf_in, pitch, B, imax, early_term, w.padbuf_out, st))) return rc;
+        if ((rc = launch_unpad<uint8_t>(w.padbuf_out, out_dev, h->N, B, pitch, st))) return rc;
+    }
+    if (i_num_host) {
+        CK(cudaMemcpyAsync(i_num_host, w.inum, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return IBLDPC_OK;
+}
+
+int ibldpc_decode_ib_host(ibldpc_handle h, const uint8_t* ch_host, int64_t B, int imax, int early_term,
+                          uint8_t* out_host, int32_t* i_num_host)
+{
+    int rc = check_decode_args(h, B, imax);
+    if (rc) return rc;
+    if (!ch_host || !out_host) return fail(IBLDPC_E_INVALID, "null buffer");
+    CK(cudaSetDevice(h->device));
+    // Early termination is a property of the whole call (all B frames), so it cannot be chunked.
+    const int64_t chunk = early_term ? B : std::min<int64_t>(B, std::max(16, h->host_chunk / 16 * 16));
+    const long long cpitch = (chunk + 15) / 16 * 16;
+    const int nslots = (chunk < B) ? 2 : 1;
+    for (int s = 0; s < nslots; ++s) {
+        Workspace& w = h->ws[s];
+        if (!w.stream) CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+        const size_t need = (size_t)h->N * cpitch;
+        if (w.stage_bytes < need) {
+            if (w.stage_in) CK(cudaFree(w.stage_in));
+            if (w.stage_out) CK(cudaFree(w.stage_out));
+            w.stage_in = w.stage_out = nullptr;
+            w.stage_bytes = 0;
+            if (cudaMalloc((void**)&w.stage_in, need) != cudaSuccess || cudaMalloc((void**)&w.stage_out, need) != cudaSuccess)
+                return fail(IBLDPC_E_NOMEM, "cudaMalloc of staging buffers failed");
+            CK(cudaMemset(w.stage_in, 0, need));
+            w.stage_bytes = need;
+        }
+    }
+    if (h->profiling) clear_events(h);
+    int slot = 0;
+    for (int64_t off = 0; off < B; off += chunk, slot ^= (nslots - 1)) {
+        Workspace& w = h->ws[slot];
+        const int64_t wd = std::min<int64_t>(chunk, B - off);
+        const long long pitch = (wd + 15) / 16 * 16;   // the tail chunk may be narrower
+        CK(cudaMemcpy2DAsync(w.stage_in, (size_t)pitch, ch_host + off, (size_t)B, (size_t)wd, (size_t)h->N,
+                             cudaMemcpyHostToDevice, w.stream));
+        if ((rc = decode_ib_padded(h, w, w.stage_in, pitch, wd, imax, early_term, w.stage_out, w.stream))) return rc;
+        CK(cudaMemcpy2DAsync(out_host + off, (size_t)B, w.stage_out, (size_t)pitch, (size_t)wd, (size_t)h->N,
+                             cudaMemcpyDeviceToHost, w.stream));
+    }
+    for (int s = 0; s < nslots; ++s) CK(cudaStreamSynchronize(h->ws[s].stream));
+    if (i_num_host) CK(cudaMemcpy(i_num_host, h->ws[0].inum, sizeof(int), cudaMemcpyDeviceToHost));
+    return IBLDPC_OK;
+}
+
+int ibldpc_decode_llr(ibldpc_handle h, int algo, int dtype, const void* ch_dev, int64_t B, int imax, int early_term,
+                      void* out_dev, int32_t* i_num_host, void* stream)
+{
+    if (!h) return fail(IBLDPC_E_INVALID, "null handle");
+    if (!ch_dev || !out_dev) return fail(IBLDPC_E_INVALID, "null buffer");
+    if (B <= 0 || B > 0x7fffffffLL - 1024) return fail(IBLDPC_E_INVALID, "bad B");
+    if (imax < 1 || imax >= kMaxIter) return fail(IBLDPC_E_INVALID, "imax out of range");
+    if (algo != IBLDPC_ALGO_MINSUM && algo != IBLDPC_ALGO_BP) return fail(IBLDPC_E_INVALID, "unknown algorithm");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == IBLDPC_F32)
+        return decode_llr_typed<float>(h, algo, (const float*)ch_dev, B, imax, early_term, (float*)out_dev, i_num_host, st);
+    if (dtype == IBLDPC_F64)
+        return decode_llr_typed<double>(h, algo, (const double*)ch_dev, B, imax, early_term, (double*)out_dev, i_num_host, st);
+    return fail(IBLDPC_E_INVALID, "dtype must be IBLDPC_F32 or IBLDPC_F64");
+}
+
+int ibldpc_count_errors_u8(int device, const uint8_t* out_dev, int64_t rows, int64_t B, int threshold,
+                           const uint8_t* ref_bits_dev, int64_t* counters_host, void* stream)
+{
+    if (threshold < 0 || threshold > 255) return fail(IBLDPC_E_INVALID, "threshold out of range");
+    return count_errors_common<uint8_t>(device, out_dev, rows, B, (uint8_t)threshold, ref_bits_dev, counters_host, stream);
+}
+
+int ibldpc_count_errors_llr(int device, const void* out_dev, int dtype, int64_t rows, int64_t B,
+                            const uint8_t* ref_bits_dev, int64_t* counters_host, void* stream)
+{
+    if (dtype == IBLDPC_F32)
+        return count_errors_common<float>(device, (const float*)out_dev, rows, B, 0.f, ref_bits_dev, counters_host, stream);
+    if (dtype == IBLDPC_F64)
+        return count_errors_common<double>(device, (const double*)out_dev, rows, B, 0.0, ref_bits_dev, counters_host, stream);
+    return fail(IBLDPC_E_INVALID, "dtype must be IBLDPC_F32 or IBLDPC_F64");
+}
+
+int ibldpc_quantize(int device, const double* x_dev, int64_t n, const double* limits_host, int card, uint8_t* out_dev,
+                    void* stream)
+{
+    if (card > 256) return fail(IBLDPC_E_INVALID, "card must be <= 256 for uint8 clusters");
+    return quantize_common<0>(device, x_dev, n, limits_host, card, nullptr, 0, 0, 0, out_dev, stream);
+}
+
+int ibldpc_quantize_llr(int device, const double* x_dev, int64_t n, const double* limits_host, int card,
+                        const double* llr_host, int dtype, void* out_dev, void* stream)
+{
+    if (dtype != IBLDPC_F32 && dtype != IBLDPC_F64) return fail(IBLDPC_E_INVALID, "bad dtype");
+    return quantize_common<0>(device, x_dev, n, limits_host, card, llr_host, dtype == IBLDPC_F32 ? 1 : 2, 0, 0, out_dev, stream);
+}
+
+int ibldpc_sample_direct(int device, const double* cdf_host, int card, uint64_t seed, uint64_t offset, int64_t n,
+                         uint8_t* out_dev, void* stream)
+{
+    if (card > 257) return fail(IBLDPC_E_INVALID, "card must be <= 257");
+    return quantize_common<1>(device, nullptr, n, cdf_host, card, nullptr, 0, seed, offset, out_dev, stream);
+}
+
+int ibldpc_sample_direct_llr(int device, const double* cdf_host, int card, const double* llr_host, uint64_t seed,
+                             uint64_t offset, int64_t n, int dtype, void* out_dev, void* stream)
+{
+    if (dtype != IBLDPC_F32 && dtype != IBLDPC_F64) return fail(IBLDPC_E_INVALID, "bad dtype");
+    return quantize_common<1>(device, nullptr, n, cdf_host, card, llr_host, dtype == IBLDPC_F32 ? 1 : 2, seed, offset, out_dev, stream);
+}
+
+int ibldpc_uniform(int device, uint64_t seed, uint64_t offset, int64_t n, double* out_dev, void* stream)
+{
+    return quantize_common<1>(device, nullptr, n, nullptr, 1, nullptr, 3, seed, offset, out_dev, stream);
+}
+
+int ibldpc_info(ibldpc_handle h, int32_t* which4)
+{
+    if (!h || !which4) return fail(IBLDPC_E_INVALID, "null argument");
+    which4[0] = h->fast ? 1 : 0;
+    which4[1] = h->last_launches;
+    which4[2] = h->last_grid;
+    which4[3] = h->last_smem;
+    return IBLDPC_OK;
+}
+
+int ibldpc_set_profiling(ibldpc_handle h, int on)
+{
+    if (!h) return fail(IBLDPC_E_INVALID, "null handle");
+    h->profiling = on != 0;
+    if (!on) clear_events(h);
+    return IBLDPC_OK;
+}
+
+int ibldpc_set_host_chunk(ibldpc_handle h, int frames)
+{
+    if (!h || frames < 16) return fail(IBLDPC_E_INVALID, "bad chunk");
+    h->host_chunk = frames;
+    return IBLDPC_OK;
+}
+
+int ibldpc_phase_times(ibldpc_handle h, float* ms3, int32_t* launches3)
+{
+    if (!h || !ms3 || !launches3) return fail(IBLDPC_E_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < 3; ++i) { ms3[i] = 0.f; launches3[i] = 0; }
+    for (auto& e : h->events) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e.a, e.b));
+        ms3[e.phase] += ms;
+        launches3[e.phase] += 1;
+    }
+    return IBLDPC_OK;
+}
+
+int ibldpc_destroy(ibldpc_handle h)
+{
+    if (!h) return IBLDPC_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    clear_events(h);
+    for (int* p : {h->d_sc, h->d_dc, h->d_tc, h->d_sv, h->d_dv, h->d_tv, h->d_vidx})
+        if (p) cudaFree(p);
+    for (uint8_t* p : {h->d_cn8, h->d_vn8, h->d_mc8, h->d_mv8})
+        if (p) cudaFree(p);
+    for (auto& c : h->cn_classes) if (c.d_nodes) cudaFree(c.d_nodes);
+    for (auto& c : h->vn_classes) if (c.d_nodes) cudaFree(c.d_nodes);
+    for (auto& w : h->ws) {
+        for (void* p : {(void*)w.msg, w.cin, w.vin, (void*)w.padbuf_in, (void*)w.padbuf_out, (void*)w.stage_in,
+                        (void*)w.stage_out, (void*)w.flags, (void*)w.inum})
+            if (p) cudaFree(p);
+        if (w.stream) cudaStreamDestroy(w.stream);
+    }
+    delete h;
+    return IBLDPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,357 @@
+"""GPU suite (-m gpu): the CUDA path (through the class API, i.e. the ctypes C ABI) against the
+golden vectors frozen from the reference and against the CPU oracle on seeded inputs; full-size
+runs are checked through size-independent properties."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import IB_CASES, LLR_CASES, load_golden
+from informationbottleneckdecodingldpc_b200 import codes, graph, luts
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk_ib(g_or_H, T, imax, cn, vn, mc=None, mv=None, irregular=True, B=1):
+    import informationbottleneckdecodingldpc_b200 as pkg
+    if irregular:
+        return pkg.Discrete_LDPC_Decoder_class_irregular(g_or_H, imax, T, T, cn, vn, mc, mv, B,
+                                                         match='true' if mc is not None else 'false')
+    return pkg.Discrete_LDPC_Decoder_class(g_or_H, imax, T, T, cn, vn, B)
+
+
+def _dev(a):
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    return pkg.DeviceArray(torch.from_numpy(np.ascontiguousarray(a)).cuda())
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+@pytest.mark.parametrize("case", IB_CASES)
+def test_ib_golden_device_buffers(gpu, case, force_generic, monkeypatch):
+    g = load_golden(case)
+    if force_generic:
+        monkeypatch.setenv("IBLDPC_FORCE_GENERIC", "1")
+    T, imax = int(g["T"]), int(g["imax"])
+    match = bool(int(g["match"]))
+    irregular = bool(int(g["irregular"])) or match
+    dec = _mk_ib(g["H"], T, imax, g["cn_lut"], g["vn_lut"], g["cn_match"] if match else None,
+                 g["vn_match"] if match else None, irregular, g["ch"].shape[1])
+    dec.init_OpenCL_decoding(g["ch"].shape[1])
+    dec.early_termination = bool(int(g["early"]))
+    out = dec.decode_OpenCL(_dev(g["ch"]), buffer_in=True, return_buffer=True)
+    fast = dec.info()[0]
+    assert fast == (0 if (force_generic or T > 16) else 1)
+    assert np.array_equal(out.get(), g["out"]), case
+    if dec.early_termination:
+        assert dec.last_i_num == int(g["i_num"])
+    # error counter: all-zero codeword, rows = N (regular) or data_len (irregular)
+    rows = dec.N_v if not irregular else int(dec.data_len)
+    assert dec.return_errors_all_zero(out) == int((g["out"][:rows] < T // 2).sum())
+
+
+@pytest.mark.parametrize("case", ["ib_toy_3_6_n24", "ib_wlan_T16_match", "ib_c1_minsumlut_imax50_et", "ib_irreg_deg1vn"])
+def test_ib_golden_host_buffers(gpu, case):
+    """numpy in -> numpy int32 out (decode_OpenCL(buffer_in=False, return_buffer=False))."""
+    g = load_golden(case)
+    T, imax = int(g["T"]), int(g["imax"])
+    match = bool(int(g["match"]))
+    irregular = bool(int(g["irregular"])) or match
+    dec = _mk_ib(g["H"], T, imax, g["cn_lut"], g["vn_lut"], g["cn_match"] if match else None,
+                 g["vn_match"] if match else None, irregular)
+    dec.init_OpenCL_decoding(g["ch"].shape[1])
+    dec.early_termination = bool(int(g["early"]))
+    out = dec.decode_OpenCL(g["ch"].astype(np.int32), buffer_in=False, return_buffer=False)
+    assert out.dtype == np.int32 and np.array_equal(out, g["out"])
+    assert dec.last_i_num == int(g["i_num"])
+    # decode_on_host: one frame, no early termination
+    if not int(g["early"]):
+        v = dec.decode_on_host(g["ch"][:, 0])
+        assert np.array_equal(v.astype(np.uint8), g["out"][:, 0])
+
+
+def _oracle_ib(t, ch, T, imax, tb, early):
+    from oracle import oracle
+    return oracle.ib_decode(t, ch, T=T, imax=imax, cn_lut=tb.Trellis_checknodevector_a,
+                            vn_lut=tb.Trellis_varnodevector_a, cn_match=tb.matching_vector_checknode,
+                            vn_match=tb.matching_vector_varnode, early=early)
+
+
+@pytest.mark.parametrize("B", [1, 15, 16, 100, 513, 1040])
+def test_ib_c1_vs_oracle_ragged_batches(gpu, B):
+    """(3,6) n=8000, random tables: every batch-size class (sub-vector, unaligned, multi-tile)."""
+    H = codes.regular_random(8000, 3, 6)
+    t = graph.edge_tables(H)
+    T, imax = 16, 6
+    tb = luts.random_tables(T, 6, 3, imax, seed=B)
+    ch = np.random.Generator(np.random.PCG64(B)).integers(0, T, size=(8000, B)).astype(np.uint8)
+    dec = _mk_ib(H, T, imax, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a, irregular=False)
+    dec.early_termination = False
+    got = dec.decode_OpenCL(_dev(ch), buffer_in=True, return_buffer=True).get()
+    ref, _ = _oracle_ib(t, ch, T, imax, tb, False)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("name,H,T", [
+    ("wlan1296", lambda: codes.wlan_80211n(54), 16),
+    ("wlan1944", lambda: codes.wlan_80211n(81), 16),
+    ("wlan1296_T8", lambda: codes.wlan_80211n(54), 8),
+    ("dvb6480", lambda: codes.dvbs2_like_half_rate(6480, q_groups=36), 16),
+    ("deg2checks", lambda: codes.random_from_degrees([1, 1] + [2] * 30 + [3] * 20 + [5] * 4,
+                                                     [2] * 10 + [3] * 10 + [4] * 11 + [6] * 3 + [10], seed=9), 16),
+    ("wlan1296_T12", lambda: codes.wlan_80211n(54), 12),
+])
+@pytest.mark.parametrize("match", [True, False])
+def test_ib_irregular_vs_oracle(gpu, name, H, T, match):
+    H = H()
+    t = graph.edge_tables(H)
+    imax, B = 7, 77
+    tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=11, matching=match)
+    ch = np.random.Generator(np.random.PCG64(12)).integers(0, T, size=(t.n_var, B)).astype(np.uint8)
+    dec = _mk_ib(H, T, imax, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                 tb.matching_vector_checknode, tb.matching_vector_varnode)
+    got = dec.decode_OpenCL(_dev(ch), buffer_in=True, return_buffer=True).get()
+    ref, i_num = _oracle_ib(t, ch, T, imax, tb, True)
+    assert dec.info()[0] == 1
+    assert np.array_equal(got, ref) and dec.last_i_num == i_num
+
+
+def test_ib_dvbs2_full_size_vs_oracle(gpu):
+    """DVB-S2-like n=64800 (degree-1 VN, d_v 8, d_c 6/7, matching), a few frames, 4 iterations."""
+    H = codes.dvbs2_like_half_rate()
+    t = graph.edge_tables(H)
+    T, imax, B = 16, 4, 20
+    tb = luts.random_tables(T, 7, 8, imax, seed=21, matching=True)
+    ch = np.random.Generator(np.random.PCG64(22)).integers(0, T, size=(t.n_var, B)).astype(np.uint8)
+    dec = _mk_ib(H, T, imax, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                 tb.matching_vector_checknode, tb.matching_vector_varnode)
+    assert int(dec.data_len) == 32399          # the reference's float arithmetic gives int(0.4999..*64800)
+    got = dec.decode_OpenCL(_dev(ch), buffer_in=True, return_buffer=True).get()
+    ref, _ = _oracle_ib(t, ch, T, imax, tb, True)
+    assert np.array_equal(got, ref)
+
+
+def test_ib_generic_path_T32_and_Tc_ne_T(gpu):
+    from oracle import oracle
+    H = codes.wlan_80211n(54)
+    t = graph.edge_tables(H)
+    imax, B = 4, 9
+    for T, Tc in ((32, 32), (16, 8), (20, 20)):
+        tb = luts.random_tables(T, 8, 11, imax, seed=5, Tc=Tc, matching=True)
+        ch = np.random.Generator(np.random.PCG64(6)).integers(0, Tc, size=(t.n_var, B)).astype(np.uint8)
+        import informationbottleneckdecodingldpc_b200 as pkg
+        dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, imax, Tc, T, tb.Trellis_checknodevector_a,
+                                                        tb.Trellis_varnodevector_a, tb.matching_vector_checknode,
+                                                        tb.matching_vector_varnode, B)
+        got = dec.decode_OpenCL(_dev(ch), buffer_in=True, return_buffer=True).get()
+        ref, i_num = oracle.ib_decode(t, ch, T=T, Tc=Tc, imax=imax, cn_lut=tb.Trellis_checknodevector_a,
+                                      vn_lut=tb.Trellis_varnodevector_a, cn_match=tb.matching_vector_checknode,
+                                      vn_match=tb.matching_vector_varnode, early=True)
+        assert dec.info()[0] == 0
+        assert np.array_equal(got, ref) and dec.last_i_num == i_num
+
+
+def test_ib_full_size_properties(gpu):
+    """BASELINE size (3,6) n=8000, i_max=50, B=16384 (too large for the oracle): determinism,
+    frame independence (sub-batches and a column permutation give the same per-frame answer), the
+    host-buffer pipeline equals the device path, and the all-zero codeword is decoded error-free
+    from a converging input."""
+    import torch
+    H = codes.regular_random(8000, 3, 6)
+    T, imax, B = 16, 50, 16384
+    tb = luts.minsum_like_tables(T, 6, 3, imax)
+    rng = np.random.Generator(np.random.PCG64(77))
+    ch = np.clip(np.round(rng.normal(T * 0.70, T * 0.15, size=(8000, B))), 0, T - 1).astype(np.uint8)
+    dec = _mk_ib(H, T, imax, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a, irregular=False)
+    dec.early_termination = False
+    d_ch = torch.from_numpy(ch).cuda()
+    out1 = dec.decode_OpenCL(d_ch, buffer_in=True, return_buffer=True).tensor
+    out2 = dec.decode_OpenCL(d_ch, buffer_in=True, return_buffer=True).tensor
+    assert torch.equal(out1, out2)
+    assert dec.return_errors_all_zero(out1) == 0
+    bit, frame = dec.count_errors(out1)
+    assert (bit, frame) == (0, 0)
+    perm = torch.randperm(B, device="cuda")
+    outp = dec.decode_OpenCL(d_ch[:, perm].contiguous(), buffer_in=True, return_buffer=True).tensor
+    assert torch.equal(outp, out1[:, perm])
+    sub = dec.decode_OpenCL(d_ch[:, 1000:1777].contiguous(), buffer_in=True, return_buffer=True).tensor
+    assert torch.equal(sub, out1[:, 1000:1777])
+    # random tables: outputs are "random" but must still be frame-independent and equal to the host pipeline
+    tbr = luts.random_tables(T, 6, 3, imax, seed=3)
+    decr = _mk_ib(H, T, imax, tbr.Trellis_checknodevector_a, tbr.Trellis_varnodevector_a, irregular=False)
+    decr.early_termination = False
+    decr.host_output_dtype = np.uint8
+    chr_ = rng.integers(0, T, size=(8000, B)).astype(np.uint8)
+    full = decr.decode_OpenCL(torch.from_numpy(chr_).cuda(), buffer_in=True, return_buffer=True).get()
+    host = decr.decode_OpenCL(chr_, buffer_in=False, return_buffer=False)
+    assert np.array_equal(full, host)
+    from oracle import oracle
+    t = graph.edge_tables(H)
+    ref, _ = oracle.ib_decode(t, chr_[:, 5000:5016], T=T, imax=imax, cn_lut=tbr.Trellis_checknodevector_a,
+                              vn_lut=tbr.Trellis_varnodevector_a, early=False)
+    assert np.array_equal(full[:, 5000:5016], ref)
+
+
+def test_early_termination_is_batch_granular(gpu):
+    """One noisy frame keeps the whole batch iterating (reference stop rule, decoder.py:273)."""
+    g = load_golden("ib_c1_minsumlut_imax50_et")
+    T, imax = int(g["T"]), int(g["imax"])
+    dec = _mk_ib(g["H"], T, imax, g["cn_lut"], g["vn_lut"], irregular=False)
+    dec.decode_OpenCL(_dev(g["ch"]), buffer_in=True, return_buffer=True)
+    assert dec.last_i_num == int(g["i_num"]) < imax
+    ch = g["ch"].copy()
+    ch[:, 3] = np.random.Generator(np.random.PCG64(1)).integers(0, T, size=ch.shape[0])
+    from oracle import oracle
+    t = graph.edge_tables(g["H"])
+    ref, i_ref = oracle.ib_decode(t, ch, T=T, imax=imax, cn_lut=g["cn_lut"], vn_lut=g["vn_lut"], early=True)
+    got = dec.decode_OpenCL(_dev(ch), buffer_in=True, return_buffer=True).get()
+    assert dec.last_i_num == i_ref == imax
+    assert np.array_equal(got, ref)
+
+
+# ---------------------------------------------------------------------------------- min-sum / BP
+@pytest.mark.parametrize("case", LLR_CASES)
+def test_llr_golden_float64_exact(gpu, case):
+    """float64 messages: min-sum bit-identical to the reference, BP to 1e-9 (exp/log rounding)."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    g = load_golden(case)
+    imax = int(g["imax"])
+    for cls, algo, meth in ((pkg.Min_Sum_Decoder_class_irregular, "minsum", "decode_OpenCL_min_sum"),
+                            (pkg.BeliefPropagationDecoderClassIrregular, "bp", "decode_OpenCL_belief_propagation")):
+        dec = cls(g["H"], imax, 16, g["ch"].shape[1])
+        dec.init_OpenCL_decoding(g["ch"].shape[1])
+        dec.early_termination = bool(int(g["early"]))
+        out = getattr(dec, meth)(_dev(g["ch"]), buffer_in=True, return_buffer=True)
+        assert out.tensor.dtype == torch.float64
+        assert dec.last_i_num == int(g[f"i_num_{algo}"])
+        if algo == "minsum":
+            assert np.array_equal(out.get(), g["out_minsum"])
+        else:
+            assert np.allclose(out.get(), g["out_bp"], rtol=1e-9, atol=1e-9)
+        assert dec.return_errors_all_zero(out) == int((g[f"out_{algo}"][:int(dec.data_len)] < 0).sum())
+
+
+@pytest.mark.parametrize("case", LLR_CASES)
+def test_llr_golden_float32_tolerance(gpu, case):
+    """fp32 messages (the fast path).  Stated tolerance: identical hard
+    decisions on >= 99.99 % of frames ... here every golden case has < 100 frames, so: identical
+    decisions wherever the reference LLR is not within 1e-3 of zero, and |LLR error| <= 1e-3*(1+|LLR|)."""
+    import informationbottleneckdecodingldpc_b200 as pkg
+    g = load_golden(case)
+    imax = int(g["imax"])
+    for cls, algo, meth in ((pkg.Min_Sum_Decoder_class_irregular, "minsum", "decode_OpenCL_min_sum"),
+                            (pkg.BeliefPropagationDecoderClassIrregular, "bp", "decode_OpenCL_belief_propagation")):
+        dec = cls(g["H"], imax, 16, g["ch"].shape[1])
+        dec.early_termination = False if not int(g["early"]) else True
+        out = getattr(dec, meth)(g["ch"], buffer_in=False, return_buffer=False)   # numpy in, f32 on device
+        ref = g[f"out_{algo}"]
+        if dec.last_i_num != int(g[f"i_num_{algo}"]):
+            pytest.skip("fp32 rounding moved the batch-wide stop by one pass")
+        assert np.all(np.abs(out - ref) <= 1e-3 * (1 + np.abs(ref)))
+        safe = np.abs(ref) > 1e-3
+        assert np.array_equal((out < 0)[safe], (ref < 0)[safe])
+
+
+def test_llr_float32_frame_agreement_large_batch(gpu):
+    """>= 99.99 % of frames with identical hard decisions, fp32 GPU vs float64 oracle, 20000 frames
+    of the WLAN code at an operating point where most frames converge."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    from oracle import oracle
+    H = codes.wlan_80211n(54)
+    t = graph.edge_tables(H)
+    q = pkg.AWGN_Channel_Quantizer(10 ** (-2.0 / 10) / (2 * 0.5), 3, 16, 2000)
+    rng = np.random.Generator(np.random.PCG64(5))
+    B, imax = 20000, 20
+    u = rng.random(size=(t.n_var, B))
+    cl = ((u[:, :, None] - q.cdf_t_given_x_equals_zero) > 0).sum(2) - 1
+    ch = q.output_LLRs[cl]
+    for cls, algo, meth in ((pkg.Min_Sum_Decoder_class_irregular, "minsum", "decode_OpenCL_min_sum"),
+                            (pkg.BeliefPropagationDecoderClassIrregular, "bp", "decode_OpenCL_belief_propagation")):
+        dec = cls(H, imax, 16, B)
+        dec.early_termination = False
+        got = getattr(dec, meth)(torch.from_numpy(ch.astype(np.float32)).cuda(), buffer_in=True, return_buffer=True).get()
+        ref, _ = oracle.llr_decode(t, ch, algo=algo, imax=imax, early=False)
+        frames_equal = np.all((got < 0) == (ref < 0), axis=0)
+        assert frames_equal.mean() >= 0.9999, (algo, frames_equal.mean())
+        ber_ref = (ref[:648] < 0).mean()
+        ber_got = (got[:648] < 0).mean()
+        ci = 1.96 * np.sqrt(max(ber_ref, 1e-9) * (1 - ber_ref) / (648 * B)) + 1e-7
+        assert abs(ber_got - ber_ref) <= ci, (algo, ber_got, ber_ref)
+
+
+# ---------------------------------------------------------------------------------- quantizer
+def test_quantizer_golden(gpu):
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    g = load_golden("quantizer")
+    q = pkg.AWGN_Channel_Quantizer(0.5, 3, int(g["T"]), 2000, dont_calc=True)
+    q.limits = g["limits"]
+    q.cdf_t_given_x_equals_zero = g["cdf"]
+    q.output_LLRs = g["llr_values"][:-1]
+    q.init_OpenCL_quanti(40, 7)
+    assert np.array_equal(q.quantize_OpenCL(g["x"]), g["clusters"])
+    q.return_buffer_only = True
+    assert np.array_equal(q.quantize_OpenCL(torch.from_numpy(g["x"]).cuda()).get(), g["clusters"])
+
+
+def test_direct_sampling_matches_inversion_of_its_own_uniforms(gpu):
+    """quantize_direct_OpenCL draws u on the device; ibldpc_uniform exposes the same u, and the
+    oracle's quantize kernel applied to it must give the same clusters / LLRs."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    from informationbottleneckdecodingldpc_b200 import _lib
+    from oracle import oracle
+    q = pkg.AWGN_Channel_Quantizer(10 ** (-1.2 / 10) / (2 * 0.5), 3, 16, 2000)
+    N, B = 300, 40
+    q.init_OpenCL_quanti(N, B, return_buffer_only=True)
+    q.llr_dtype = np.float64
+    cl = q.quantize_direct_OpenCL(N, B).get()
+    llr = q.quantize_direct_OpenCL_LLR(N, B).get()
+    u = torch.empty(2 * N * B, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().ibldpc_uniform(0, q.seed, 0, 2 * N * B, C.c_void_p(u.data_ptr()), None))
+    torch.cuda.synchronize()
+    u = u.cpu().numpy()
+    assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
+    assert np.array_equal(cl, oracle.quantize(u[:N * B].reshape(N, B), q.cdf_t_given_x_equals_zero, 17))
+    ref_llr = oracle.quantize_llr(u[N * B:].reshape(N, B), q.cdf_t_given_x_equals_zero, 17,
+                                  np.append(q.output_LLRs, q.output_LLRs[-1]))
+    assert np.array_equal(llr, ref_llr)
+    # empirical distribution ~ p(t | x=0)
+    big = q.quantize_direct_OpenCL(2000, 500).get()
+    emp = np.bincount(big.ravel(), minlength=16) / big.size
+    assert np.allclose(emp, np.diff(q.cdf_t_given_x_equals_zero), atol=3e-3)
+
+
+def test_error_counters(gpu):
+    import torch
+    from informationbottleneckdecodingldpc_b200.engine import count_errors
+    rng = np.random.Generator(np.random.PCG64(8))
+    out = rng.integers(0, 16, size=(333, 77)).astype(np.uint8)
+    out[:, 5] = 15
+    bits = rng.integers(0, 2, size=(333, 77)).astype(np.uint8)
+    for rows in (333, 100, 1):
+        b, f = count_errors(torch.from_numpy(out).cuda(), rows, 8)
+        assert b == int((out[:rows] < 8).sum()) and f == int(((out[:rows] < 8).sum(0) > 0).sum())
+        b, f = count_errors(torch.from_numpy(out).cuda(), rows, 8, torch.from_numpy(bits).cuda())
+        e = (out[:rows] < 8) != (bits[:rows] != 0)
+        assert b == int(e.sum()) and f == int((e.sum(0) > 0).sum())
+    llr = rng.normal(size=(50, 9))
+    b, f = count_errors(torch.from_numpy(llr).cuda(), 20, None)
+    assert b == int((llr[:20] < 0).sum())
+
+
+def test_cabi_argument_errors(gpu):
+    import informationbottleneckdecodingldpc_b200 as pkg
+    H = codes.regular_random(24, 3, 6, seed=1)
+    tb = luts.random_tables(16, 6, 3, 4, seed=1)
+    dec = pkg.Discrete_LDPC_Decoder_class(H, 4, 16, 16, tb.Trellis_checknodevector_a[:100], tb.Trellis_varnodevector_a, 2)
+    with pytest.raises(RuntimeError, match="too short"):
+        dec.init_OpenCL_decoding(2)
+    dec = pkg.Discrete_LDPC_Decoder_class(H, 4, 16, 16, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a, 2)
+    with pytest.raises(ValueError):
+        dec.decode_OpenCL(np.full((24, 2), 16, dtype=np.int32))
+    with pytest.raises(ValueError):
+        dec.decode_OpenCL(np.zeros((23, 2), dtype=np.int32))

@@ -1,0 +1,172 @@
+"""CPU suite: host-side logic (graph tables, generators, table layout, config files, quantizer design)
+and the C-ABI library surface.  No GPU compute here."""
+import ctypes
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from informationbottleneckdecodingldpc_b200 import codes, graph, luts
+
+
+def test_edge_tables_match_reference_classes():
+    """Tables frozen from the reference's map_node_connections (dense and sparse variants)."""
+    g = load_golden("reference_host_tables")
+    import scipy.sparse as sp
+    Hr = sp.csr_matrix((np.ones(g["reg_H_indices"].size), g["reg_H_indices"], g["reg_H_indptr"]), shape=tuple(g["reg_shape"]))
+    t = graph.edge_tables(Hr)
+    assert np.array_equal(t.inbox_start_chk, g["reg_sc"]) and np.array_equal(t.inbox_start_var, g["reg_sv"])
+    assert np.array_equal(t.target_cells_chk, g["reg_tc"]) and np.array_equal(t.target_cells_var, g["reg_tv"])
+    tw = graph.edge_tables(codes.wlan_80211n(54))
+    assert np.array_equal(tw.inbox_start_chk, g["wlan_sc"]) and np.array_equal(tw.inbox_start_var, g["wlan_sv"])
+    assert np.array_equal(tw.target_cells_chk, g["wlan_tc"]) and np.array_equal(tw.target_cells_var, g["wlan_tv"])
+    assert (tw.d_c_max, tw.d_v_max) == (int(g["wlan_d_c_max"]), int(g["wlan_d_v_max"]))
+
+
+def test_rate_and_data_len_match_reference():
+    g = load_golden("reference_host_tables")
+    Hw = codes.wlan_80211n(54)
+    r = graph.code_rate_from_degrees(Hw)
+    assert r == float(g["wlan_R_c"]) and int(r * 1296) == int(g["wlan_data_len"]) == 648
+    Hd = codes.dvbs2_like_half_rate(6480, q_groups=36)
+    rd = graph.code_rate_from_degrees(Hd)
+    assert rd == float(g["dvb_small_R_c"]) and int(rd * 6480) == int(g["dvb_small_data_len"])
+
+
+def test_tables_are_inverse_permutations():
+    for H in (codes.regular_random(96, 3, 6, seed=5), codes.wlan_80211n(54)):
+        t = graph.edge_tables(H)
+        assert np.array_equal(t.target_cells_var[t.target_cells_chk], np.arange(t.n_edge))
+        # slot k of check c holds its k-th neighbour in ascending variable order
+        for c in (0, t.n_chk - 1):
+            s, d = t.inbox_start_chk[c], t.degree_chk[c]
+            assert np.all(np.diff(t.var_of_chk_slot[s:s + d]) > 0)
+
+
+def test_alist_docstring_example_and_roundtrip(tmp_path):
+    # the one executable example of the reference (discrete_LDPC_decoder.py:64-67)
+    H = graph.alist_to_csr([[3, 2], [2, 2], [1, 1, 2], [2, 2], [1], [2], [1, 2], [1, 2, 3, 4]]).toarray()
+    assert np.array_equal(H, [[1, 0, 1], [0, 1, 1]])
+    Hr = codes.regular_random(60, 3, 6, seed=2)
+    f = str(tmp_path / "c.alist")
+    graph.write_alist(Hr, f)
+    assert (graph.load_check_matrix(f) != Hr).nnz == 0
+    f2 = str(tmp_path / "c.npz")
+    codes.save_csr_npz(Hr, f2)
+    assert (graph.load_check_matrix(f2) != Hr).nnz == 0
+    f3 = str(tmp_path / "c.npy")
+    np.save(f3, Hr.toarray().astype(float))
+    assert (graph.load_check_matrix(f3) != Hr).nnz == 0
+
+
+def test_code_generators_have_the_reference_degree_profiles():
+    t = graph.edge_tables(codes.regular_random(8000, 3, 6))
+    assert (t.n_var, t.n_chk, t.n_edge) == (8000, 4000, 24000)
+    assert set(t.degree_chk) == {6} and set(t.degree_var) == {3}
+    tw = graph.edge_tables(codes.wlan_80211n(54))
+    assert (tw.n_var, tw.n_chk, tw.n_edge) == (1296, 648, 4644)
+    assert dict(zip(*np.unique(tw.degree_var, return_counts=True))) == {2: 594, 3: 486, 4: 54, 11: 162}
+    assert dict(zip(*np.unique(tw.degree_chk, return_counts=True))) == {7: 540, 8: 108}
+    tw2 = graph.edge_tables(codes.wlan_80211n(81))
+    assert tw2.n_var == 1944 and set(tw2.degree_chk) == {7, 8}
+    td = graph.edge_tables(codes.dvbs2_like_half_rate())
+    assert (td.n_var, td.n_chk, td.n_edge) == (64800, 32400, 226799)
+    assert dict(zip(*np.unique(td.degree_var, return_counts=True))) == {1: 1, 2: 32399, 3: 19440, 8: 12960}
+    assert dict(zip(*np.unique(td.degree_chk, return_counts=True))) == {6: 1, 7: 32399}
+
+
+def test_lut_lengths_match_appendix_b():
+    assert luts.cn_lut_len(16, 16, 6, 50) == 51200 and luts.vn_lut_len(16, 16, 3, 50) == 38400
+    assert luts.cn_lut_len(16, 16, 8, 50) == 76800 and luts.vn_lut_len(16, 16, 11, 50) == 140800
+    assert luts.match_len(16, 8, 50) == 6400 and luts.match_len(16, 11, 50) == 8800
+    assert luts.cn_lut_len(32, 32, 8, 50) == 307200 and luts.vn_lut_len(32, 32, 11, 50) == 563200
+
+
+def test_config_file_roundtrip(tmp_path):
+    tb = luts.random_tables(16, 8, 11, 5, seed=1, matching=True)
+    for ext in (".pkl", ".npz"):
+        f = str(tmp_path / ("decoder_config_EbN0_gen_0.9_16" + ext))
+        luts.save_config(tb, f, sigma_n2=0.5)
+        d = luts.load_config(f)
+        assert int(d["cardinality_T_decoder_ops"]) == 16 and int(d["imax"]) == 5
+        for k in ("Trellis_checknodevector_a", "Trellis_varnodevector_a", "matching_vector_checknode",
+                  "matching_vector_varnode"):
+            assert np.array_equal(d[k], getattr(tb, k))
+    # a pickle written the way the reference does (a plain dict of the generator's attributes)
+    f = str(tmp_path / "ref_style.pkl")
+    with open(f, "wb") as fh:
+        pickle.dump(dict(tb.as_dict(), EbN0=0.9, nror=5), fh)
+    assert int(luts.load_config(f)["imax"]) == 5
+
+
+def test_node_op_helpers_match_reference():
+    g = load_golden("reference_host_tables")
+    import scipy.sparse as sp
+    from informationbottleneckdecodingldpc_b200 import Discrete_LDPC_Decoder_class
+    Hr = sp.csr_matrix((np.ones(g["reg_H_indices"].size), g["reg_H_indices"], g["reg_H_indptr"]), shape=tuple(g["reg_shape"]))
+    dec = Discrete_LDPC_Decoder_class(Hr, 4, 16, 16, g["reg_cn_lut"], g["reg_vn_lut"], 2)
+    assert np.array_equal(dec.discrete_cn_operation(g["yc"], 0), g["cn_op_iter0"])
+    assert np.array_equal(dec.discrete_cn_operation(g["yc"], 2), g["cn_op_iter2"])
+    assert np.array_equal(dec.discrete_vn_operation(g["yv"], 1), g["vn_op_iter1"])
+
+
+def test_constructor_validation():
+    from informationbottleneckdecodingldpc_b200 import Discrete_LDPC_Decoder_class
+    H = codes.regular_random(24, 3, 6, seed=1)
+    tb = luts.random_tables(16, 6, 3, 4, seed=1)
+    bad = tb.Trellis_checknodevector_a.copy()
+    bad[3] = 16
+    with pytest.raises(ValueError):
+        Discrete_LDPC_Decoder_class(H, 4, 16, 16, bad, tb.Trellis_varnodevector_a, 2)
+    with pytest.raises(ValueError):   # irregular H in the regular class
+        Discrete_LDPC_Decoder_class(codes.wlan_80211n(54), 4, 16, 16, tb.Trellis_checknodevector_a,
+                                    tb.Trellis_varnodevector_a, 2)
+
+
+def test_quantizer_design_properties():
+    from informationbottleneckdecodingldpc_b200 import AWGN_Channel_Quantizer
+    q = AWGN_Channel_Quantizer(10 ** (-1.2 / 10) / (2 * 0.5), 3, 16, 2000)
+    assert np.all(np.diff(q.limits) > 0) and q.limits[8] == 0
+    assert np.allclose(q.output_LLRs, -q.output_LLRs[::-1]) and np.all(np.diff(q.output_LLRs) > 0)
+    assert q.cdf_t_given_x_equals_zero[0] == 0 and abs(q.cdf_t_given_x_equals_zero[-1] - 1) < 1e-12
+    assert np.array_equal(q.p_t_given_y.sum(1), np.ones(2000))
+    x = np.array([[-5.0, -1e-9, 0.0, 1e-9, 5.0]])
+    assert np.array_equal(q.quantize_on_host(x)[0], [0, 7, 7, 8, 15])
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from informationbottleneckdecodingldpc_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "ibldpc.h")).read()
+    declared = set(re.findall(r"\b(ibldpc_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build_library()
+    dll = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(dll, name), name
+    _lib.lib()
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from informationbottleneckdecodingldpc_b200 import Discrete_LDPC_Decoder_class
+    H = codes.regular_random(24, 3, 6, seed=1)
+    tb = luts.random_tables(16, 6, 3, 4, seed=1)
+    dec = Discrete_LDPC_Decoder_class(H, 4, 16, 16, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a, 2)
+    with pytest.raises(RuntimeError):
+        dec.decode_OpenCL(np.zeros((24, 2), dtype=np.int32))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "informationbottleneckdecodingldpc_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert "ldpc_oracle" not in txt and "libref_kernels" not in txt, f
