@@ -1,0 +1,368 @@
+#!/usr/bin/env python3
+"""Headline benchmark: decoded info Gbit/s of the IB decoder at fixed i_max (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own kernels on the host cores
+
+Workload (BASELINE.json configs[0], the configuration the metric is quoted on): regular (3,6)
+LDPC code n=8000, R=1/2, BPSK/AWGN, IB decoder |T|=16, i_max=50, early termination off,
+B=16384 frames per GPU and step, channel cluster indices drawn by the inversion method from the
+|T|=16 quantizer at Eb/N0 = 1.2 dB (all-zero codeword), exactly like quantize_direct_OpenCL.
+A "step" = decode one batch + count bit/frame errors (+ all-reduce of the 4 counters for N>1).
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decoded info Gbit/s @ fixed i_max"
+N_VAR, D_V, D_C, T, IMAX = 8000, 3, 6, 16, 50
+EBN0_DB = 1.2
+SEED = 20181001
+
+
+def workload(name):
+    from informationbottleneckdecodingldpc_b200 import codes
+    if name == "c1":
+        return dict(name="(3,6) n=8000 R=0.5 IB |T|=16 i_max=50 ET off", H=codes.regular_random(8000, 3, 6, seed=SEED),
+                    irregular=False, B=16384, ebn0=1.2)
+    if name == "wlan":
+        return dict(name="802.11n n=1296 R=0.5 IB |T|=16 i_max=50 ET off, message alignment", H=codes.wlan_80211n(54),
+                    irregular=True, B=100096, ebn0=1.5)
+    if name == "wlan1944":
+        return dict(name="802.11n n=1944 R=0.5 IB |T|=16 i_max=50 ET off, message alignment", H=codes.wlan_80211n(81),
+                    irregular=True, B=65536, ebn0=1.5)
+    if name == "dvbs2":
+        return dict(name="DVB-S2-like n=64800 R=0.5 IB |T|=16 i_max=50 ET off, message alignment",
+                    H=codes.dvbs2_like_half_rate(), irregular=True, B=2048, ebn0=1.0)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def algorithmic_bytes_per_frame(N, E, imax):
+    """uint8 messages, two-phase flooding, syndrome fused:
+    (imax-1)(4E+N) + 2E + 3N bytes per frame."""
+    return (imax - 1) * (4 * E + N) + 2 * E + 3 * N
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = str(gpu_index)
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", self.gpu], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+                for nm, val in zip(names, r[4:8]):
+                    if val.lower() == "active":
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_tables(wl):
+    from informationbottleneckdecodingldpc_b200 import graph, luts
+    t = graph.edge_tables(wl["H"])
+    tb = luts.minsum_like_tables(T, t.d_c_max, t.d_v_max, IMAX)
+    if not wl["irregular"]:
+        tb.matching_vector_checknode = tb.matching_vector_varnode = None
+    return t, tb
+
+
+def cpu_reference_run(wl, frames, seed=SEED):
+    """The reference's own kernels (oracle/_ref) -- or the C port when that library is absent -- on
+    `frames` frames of the workload, all host threads.  Returns (seconds, kind, cores)."""
+    from oracle import oracle
+    from informationbottleneckdecodingldpc_b200 import AWGN_Channel_Quantizer
+    t, tb = make_tables(wl)
+    R = 1 - t.n_chk / t.n_var
+    q = AWGN_Channel_Quantizer(10 ** (-wl["ebn0"] / 10) / (2 * R), 3, T, 2000)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u = rng.random(size=(t.n_var, frames))
+    ch = ((u[:, :, None] - q.cdf_t_given_x_equals_zero) > 0).sum(2) - 1
+    kind = "reference" if oracle.ref_available() else "port"
+    cores = os.cpu_count() or 1
+    if kind == "reference":
+        try:
+            cores = int(oracle.ref_lib().ref_num_threads())
+        except Exception:
+            pass
+    kw = dict(T=T, imax=IMAX, cn_lut=tb.Trellis_checknodevector_a, vn_lut=tb.Trellis_varnodevector_a,
+              cn_match=tb.matching_vector_checknode, vn_match=tb.matching_vector_varnode, early=False)
+    t0 = time.perf_counter()
+    try:
+        oracle.ib_decode(t, ch, backend=kind, irregular=wl["irregular"], **kw)
+    except KeyError:
+        kind = "port"
+        t0 = time.perf_counter()
+        oracle.ib_decode(t, ch, backend="port", **kw)
+    return time.perf_counter() - t0, kind, cores, t
+
+
+def size_cpu_sample(wl, target_s):
+    """Calibrate on a small batch, then pick a frame count worth about `target_s` seconds."""
+    cores = os.cpu_count() or 1
+    cal = max(2, min(2 * cores, 64))
+    dt, _, _, _ = cpu_reference_run(wl, cal)
+    return int(max(cal, min(16384, cal * target_s / max(dt, 1e-3)))) // 1 or cal
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = workload(args.workload)
+    frames = size_cpu_sample(wl, 8.0)
+    times = []
+    kind = cores = t = None
+    for i in range(args.warmup + args.steps):
+        dt, kind, cores, t = cpu_reference_run(wl, frames, seed=SEED + i)
+        if i >= args.warmup:
+            times.append(dt)
+    K = t.n_var - t.n_chk
+    total = sum(times)
+    value = K * frames * len(times) / total / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": wl["name"], "frames_per_step": frames, "i_max": IMAX, "early_termination": False,
+                   "note": "reference OpenCL kernels compiled for the host CPU (oracle/_ref), OpenMP over all host threads"
+                   if kind == "reference" else "C port of the reference kernels (oracle/ldpc_oracle.c), OpenMP"},
+        "cpu_baseline": {"value": value, "unit": "Gbit/s", "cores": cores, "kind": kind,
+                         "sample": f"{frames} frames x {len(times)} steps of the workload, i_max={IMAX}, ET off"},
+        "e2e": {"value": value, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c1", choices=["c1", "wlan", "wlan1944", "dvbs2"])
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU and step (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import informationbottleneckdecodingldpc_b200 as pkg
+    from informationbottleneckdecodingldpc_b200 import _lib
+    from informationbottleneckdecodingldpc_b200.parallel import allreduce_counters, init_distributed
+
+    rank, world, local = init_distributed(args.gpus)
+    torch.cuda.set_device(local)
+    wl = workload(args.workload)
+    B = args.frames or wl["B"]
+    t, tb = make_tables(wl)
+    N, M, E = t.n_var, t.n_chk, t.n_edge
+    K_info = N - M
+    R = K_info / N
+    # --- objects the BER drivers build (Regular_LDPC_Decoding/BPSK/BER_simulation_OpenCL.py:76-91)
+    quanti = pkg.AWGN_Channel_Quantizer(10 ** (-wl["ebn0"] / 10) / (2 * R), 3, T, 2000)
+    quanti.seed = SEED
+    quanti._offset = rank * (1 << 40)            # disjoint Philox sub-streams per rank
+    quanti.init_OpenCL_quanti(N, B, return_buffer_only=True)
+    if wl["irregular"]:
+        decodi = pkg.Discrete_LDPC_Decoder_class_irregular(wl["H"], IMAX, T, T, tb.Trellis_checknodevector_a,
+                                                           tb.Trellis_varnodevector_a, tb.matching_vector_checknode,
+                                                           tb.matching_vector_varnode, B)
+    else:
+        decodi = pkg.Discrete_LDPC_Decoder_class(wl["H"], IMAX, T, T, tb.Trellis_checknodevector_a,
+                                                 tb.Trellis_varnodevector_a, B)
+    decodi.init_OpenCL_decoding(B, quanti.context)
+    decodi.early_termination = False
+    ch = quanti.quantize_direct_OpenCL(N, B)      # resident in HBM before the timed region
+    torch.cuda.synchronize()
+
+    counters = torch.zeros(4, dtype=torch.int64)
+
+    def step():
+        out = decodi.decode_OpenCL(ch, buffer_in=True, return_buffer=True)
+        bit, frame = decodi.count_errors(out)
+        c = allreduce_counters([bit, frame, B, IMAX * B], world)
+        counters.add_(torch.tensor(c, dtype=torch.int64))
+        return out
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    launches_per_step = decodi.info()[1] + 2      # decode kernels + the two error-count kernels
+    counters.zero_()
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    frames_total = B * world * args.steps
+    value = K_info * frames_total / (ms * 1e-3) / 1e9
+
+    # --- roofline of the dominant kernel: per-launch CUDA-event times on the launch stream
+    h = decodi._ensure_handle()
+    L = _lib.lib()
+    import ctypes as C
+    _lib.check(L.ibldpc_set_profiling(h, 1))
+    decodi.decode_OpenCL(ch, buffer_in=True, return_buffer=True)
+    ms3 = (C.c_float * 3)()
+    n3 = (C.c_int32 * 3)()
+    _lib.check(L.ibldpc_phase_times(h, ms3, n3))
+    _lib.check(L.ibldpc_set_profiling(h, 0))
+    cn_ms, vn_ms = ms3[0] / max(n3[0], 1), ms3[1] / max(n3[1], 1)
+    peak, peak_src = measured_peak_gbs()
+    cn_bytes, vn_bytes = 2 * E * B, (2 * E + N) * B
+    if ms3[0] >= ms3[1]:
+        dom, dom_ms, dom_bytes = "ib_cn_fast_kernel (check-node update + syndrome)", cn_ms, cn_bytes
+    else:
+        dom, dom_ms, dom_bytes = "ib_vn_fast_kernel (variable-node update)", vn_ms, vn_bytes
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tfile):
+        try:
+            traffic = json.load(open(tfile)).get(args.workload)
+        except Exception:
+            traffic = None
+    bytes_frame = algorithmic_bytes_per_frame(N, E, IMAX)
+    decode_ms = ms3[0] + ms3[1] + ms3[2]
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+        "avg_launch_ms": dom_ms, "cn_avg_ms": cn_ms, "vn_avg_ms": vn_ms,
+        "cn_share_of_decode": ms3[0] / decode_ms, "vn_share_of_decode": ms3[1] / decode_ms,
+        "whole_decode": {"bytes_per_frame": bytes_frame, "achieved_gbs": bytes_frame * B / (decode_ms * 1e-3) / 1e9,
+                         "frac": bytes_frame * B / (decode_ms * 1e-3) / 1e9 / peak},
+    }
+
+    # --- end to end through the class API with HOST buffers (H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        host_in = pkg.pinned_empty((N, B), np.uint8)
+        host_in[:] = ch.get()
+        decodi.host_output_dtype = np.uint8
+        for _ in range(2):
+            decodi.decode_OpenCL(host_in, buffer_in=False, return_buffer=False)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = decodi.decode_OpenCL(host_in, buffer_in=False, return_buffer=False)
+            _bit = int((res[:8] < T // 2).sum())      # touch the result on the host
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tm = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dt = float(tm.item())
+        e2e = {"value": K_info * B * world * args.steps / dt / 1e9, "unit": "Gbit/s",
+               "h2d_bytes_per_step": int(N) * int(B), "d2h_bytes_per_step": int(N) * int(B),
+               "api": "Discrete_LDPC_Decoder_class.decode_OpenCL(numpy uint8 pinned, buffer_in=False, return_buffer=False)"
+                      " -> ibldpc_decode_ib_host"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        frames = size_cpu_sample(wl, 12.0)
+        dtc, kind, cores, _ = cpu_reference_run(wl, frames)
+        cpu = {"value": K_info * frames / dtc / 1e9, "unit": "Gbit/s", "cores": cores, "kind": kind,
+               "sample": f"{frames} frames of the workload (same tables, i_max={IMAX}, ET off) in {dtc:.1f} s"}
+
+    if rank == 0:
+        tot = counters.tolist()
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": wl["name"], "frames_per_gpu_per_step": B, "n_var": N, "n_chk": M, "n_edge": E,
+                       "info_bits": K_info, "i_max": IMAX, "EbN0_dB": wl["ebn0"], "tables": "min-sum-like LUTs (deterministic)",
+                       "l2": "inputs_larger_than_L2 (message array %.0f MB)" % (E * B / 1e6), "parallelism": f"frames sharded x{world}",
+                       "fast_path": bool(decodi.info()[0])},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu,
+            "errors": {"bit": tot[0], "frame": tot[1], "frames": tot[2]},
+            "frames_per_s": frames_total / (ms * 1e-3),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,50 @@
+"""Multi-GPU plumbing: one process per GPU, frames sharded across ranks, NCCL (over
+NVLink/NVSwitch) used only to all-reduce the error counters so that every rank takes the same
+``while errors < min_errors`` decision as the single-device reference loop
+(Regular_LDPC_Decoding/BPSK/BER_simulation_OpenCL.py:98).  Codewords are independent: there is
+no collective inside a decode.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(n_gpus: int = 1, backend: str | None = None):
+    """Join the torchrun rendezvous if there is one.  Returns (rank, world_size, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_frames(total_frames: int, rank: int, world: int):
+    """Contiguous frame range [lo, hi) of this rank (remainder spread over the first ranks)."""
+    base, rem = divmod(int(total_frames), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_counters(counters, world: int | None = None):
+    """Sum a short list of integer counters {bit_errors, frame_errors, frames, iterations} over all
+    ranks (int64 payload of a few bytes: latency-bound, issue it once per batch, never per iteration).
+    Returns a list of Python ints.  No-op without a process group."""
+    vals = [int(c) for c in counters]
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return vals
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor(vals, dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [int(x) for x in t.tolist()]

@@ -99,7 +99,7 @@ def test_ib_c1_vs_oracle_ragged_batches(gpu, B):
     ("wlan1296_T8", lambda: codes.wlan_80211n(54), 8),
     ("dvb6480", lambda: codes.dvbs2_like_half_rate(6480, q_groups=36), 16),
     ("deg2checks", lambda: codes.random_from_degrees([1, 1] + [2] * 30 + [3] * 20 + [5] * 4,
-                                                     [2] * 10 + [3] * 10 + [4] * 11 + [6] * 3 + [10], seed=9), 16),
+                                                     [2] * 10 + [3] * 10 + [4] * 11 + [5] * 4 + [6] * 3 + [10], seed=9), 16),
     ("wlan1296_T12", lambda: codes.wlan_80211n(54), 12),
 ])
 @pytest.mark.parametrize("match", [True, False])
