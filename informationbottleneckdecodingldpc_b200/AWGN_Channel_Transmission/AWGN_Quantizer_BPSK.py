@@ -37,7 +37,7 @@ class AWGN_Channel_Quantizer:
         self.delta = self.y_vec[1] - self.y_vec[0]
         self.seed = 20181001          # Philox key of the direct-sampling methods
         self._offset = 0              # Philox counter: advances by N_var*msg_at_time per call
-        self.llr_dtype = np.float32   # dtype of quantize_direct_OpenCL_LLR buffers (np.float64 = reference)
+        self.llr_dtype = np.float64   # dtype of quantize_direct_OpenCL_LLR buffers (np.float32 = fast path)
         self.return_buffer_only = False
         self.context = None
         if not dont_calc:

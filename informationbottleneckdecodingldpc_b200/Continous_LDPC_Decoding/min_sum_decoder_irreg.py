@@ -2,8 +2,11 @@
 
 Drop-in for ``Continous_LDPC_Decoding/min_sum_decoder_irreg.py`` of the reference
 (constructor :23, ``decode_OpenCL_min_sum`` :221-287, ``return_errors_all_zero`` :290-295).
-Messages are fp32 by default (the fast path); pass float64 buffers (or set
-``self.precision = 'f64'`` for host inputs) to reproduce the reference's float64 arithmetic.
+Messages follow the dtype of the input buffer: float64 (the reference's dtype and the default of
+the quantizer / of numpy inputs) reproduces the reference arithmetic -- min-sum bit for bit --
+while float32 buffers (``quanti.llr_dtype = np.float32`` or ``self.precision = 'f32'`` for host
+inputs) select the faster fp32 kernels, whose hard decisions differ from float64 only where an
+a-posteriori LLR is a rounding-level tie (see tests/test_gpu_parity.py for the measured agreement).
 """
 from __future__ import annotations
 
@@ -27,7 +30,7 @@ class _LlrDecoderBase(GraphDecoderBase):
         self._set_rate()
         self.msg_at_time = msg_at_time_
         self.early_termination = True     # the reference always checks the syndrome (:262-270)
-        self.precision = 'f32'            # dtype used for host (numpy) inputs
+        self.precision = 'f64'            # dtype used for host (numpy) inputs ('f32' = fast path)
         self.last_i_num = None
 
     def init_OpenCL_decoding(self, msg_at_time_, context_=False):
@@ -43,7 +46,7 @@ class _LlrDecoderBase(GraphDecoderBase):
         early = self.early_termination if early_termination is None else early_termination
         if buffer_in:
             t = received_blocks.tensor if isinstance(received_blocks, DeviceArray) else received_blocks
-            tdt = t.dtype if t.dtype in (torch.float32, torch.float64) else torch.float32
+            tdt = t.dtype if t.dtype in (torch.float32, torch.float64) else torch.float64
             ch = self._device_input(received_blocks, tdt)
         else:
             rb = np.asarray(received_blocks, dtype=np.float64)

@@ -46,9 +46,11 @@ struct IbArgs {
     const uint8_t* __restrict__ ch;
     uint8_t* msg;
     uint8_t* out;
-    long long pitch;   // bytes per row (multiple of 16)
+    uint32_t pitch;    // bytes per row (multiple of 16)
     int B;             // valid frames
-    int tiles;         // ceil(pitch / 512)
+    int tiles;         // ceil(pitch / 512): 512-frame tiles per row
+    int tpc_log2;      // log2(tiles handled by one CTA) in 0..3; a CTA's 8 warps cover 2^tpc_log2
+                       // consecutive tiles of 8 >> tpc_log2 nodes; blockIdx.y selects the tile group
     // tables of this launch
     const uint8_t* __restrict__ lut;    // [nst][T*T] stage tables of this iteration (compact, reference order t*T+m)
     const uint8_t* __restrict__ match;  // [dmax][T] matching rows of this iteration or nullptr
@@ -115,7 +117,7 @@ __device__ __forceinline__ void cn_word(const uint32_t (&w)[D], uint32_t (&o)[D]
         uint32_t b[D], ms[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            b[k] = (w[k] >> (8 * f)) & 0xffu;
+            b[k] = __byte_perm(w[k], 0u, 0x4440u + f);   // byte f, zero-extended (one PRMT)
             ms[k] = b[k] * TRS + lane4;
         }
         uint32_t P[D > 1 ? D : 2];
@@ -134,14 +136,14 @@ __device__ __forceinline__ void cn_word(const uint32_t (&w)[D], uint32_t (&o)[D]
 }
 
 template <int D>
-__device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab, int s, long long col,
+__device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab, int s, uint32_t col,
                                             uint32_t lane4, uint32_t RS, uint32_t TRS, uint32_t valid_frames)
 {
     uint4 m[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        const uint8_t* p = a.iter0 ? a.ch + (long long)a.vidx[s + k] * a.pitch
-                                   : a.msg + (long long)(s + k) * a.pitch;
+        const uint8_t* p = a.iter0 ? a.ch + (uint64_t)(uint32_t)a.vidx[s + k] * a.pitch
+                                   : a.msg + (uint64_t)(uint32_t)(s + k) * a.pitch;
         m[k] = *reinterpret_cast<const uint4*>(p + col);
     }
     const bool match = a.match != nullptr;
@@ -184,7 +186,7 @@ __device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab,
     }
 #pragma unroll
     for (int k = 0; k < D; ++k)
-        *reinterpret_cast<uint4*>(a.msg + (long long)(s + k) * a.pitch + col) = r[k];
+        *reinterpret_cast<uint4*>(a.msg + (uint64_t)(uint32_t)(s + k) * a.pitch + col) = r[k];
     return syn;
 }
 
@@ -193,27 +195,27 @@ __device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab,
 // One instantiation per check-node degree; `nodes` lists the checks of that degree, so every
 // launch has exactly the register budget its degree needs.
 template <int D>
-__global__ void __launch_bounds__(kThreads) ib_cn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
+__global__ void __launch_bounds__(kThreads, (D <= 6 ? 4 : (D <= 8 ? 3 : 2))) ib_cn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 {
     extern __shared__ __align__(16) uint32_t s_tab[];
     if (a.early && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
     stage_tables(s_tab, a, a.lut);
     __syncthreads();
     const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_tab);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lane4 = lane * 4, RS = 128u * a.W, TRS = RS * a.T;
-    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
-    const long long items = (long long)n_nodes * a.tiles;
+    // CTA -> (tile group, node subset): no divisions, 32-bit offsets
+    const int tile = (blockIdx.y << a.tpc_log2) + (warp & ((1 << a.tpc_log2) - 1));
+    const int nps = kWarpsPerCta >> a.tpc_log2;          // nodes per CTA step
+    const uint32_t col = ((uint32_t)tile * 32u + lane) * 16u;
     uint32_t syn = 0;
-    for (long long item = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); item < items; item += nwarps) {
-        const int i = (int)(item / a.tiles);
-        const int tile = (int)(item - (long long)i * a.tiles);
-        const long long col = ((long long)tile * 32 + lane) * 16;
-        if (col >= a.pitch) continue;
-        const long long vf = (long long)a.B - col;
+    if (tile < a.tiles && col < a.pitch) {
+        const int vf = a.B - (int)col;
         const uint32_t valid = vf >= 16 ? 16u : vf <= 0 ? 0u : (uint32_t)vf;
-        const int c = nodes[i];
-        syn |= cn_node<D>(a, tab, a.sc[c], col, lane4, RS, TRS, valid);
+        for (int i = blockIdx.x * nps + (warp >> a.tpc_log2); i < n_nodes; i += gridDim.x * nps) {
+            const int c = nodes[i];
+            syn |= cn_node<D>(a, tab, a.sc[c], col, lane4, RS, TRS, valid);
+        }
     }
     if (a.early && !a.iter0) {
         // warp-ballot syndrome check: one flag write per warp that saw an unsatisfied check
@@ -239,9 +241,9 @@ __device__ __forceinline__ void vn_word(uint32_t chw, const uint32_t (&w)[D], ui
     for (int f = 0; f < 4; ++f) {
         uint32_t ms[D + 1];   // ms[k] for y_k, k = 1..D
 #pragma unroll
-        for (int k = 1; k <= D; ++k) ms[k] = ((w[k - 1] >> (8 * f)) & 0xffu) * TRS + lane4;
+        for (int k = 1; k <= D; ++k) ms[k] = __byte_perm(w[k - 1], 0u, 0x4440u + f) * TRS + lane4;
         uint32_t P[D + 2];
-        P[1] = (chw >> (8 * f)) & 0xffu;
+        P[1] = __byte_perm(chw, 0u, 0x4440u + f);
 #pragma unroll
         for (int j = 1; j <= D - 1; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(j - 1));
         if (DECIDE) {
@@ -260,18 +262,18 @@ __device__ __forceinline__ void vn_word(uint32_t chw, const uint32_t (&w)[D], ui
 }
 
 template <int D, bool DECIDE>
-__device__ __forceinline__ void vn_node(const IbArgs& a, const uint8_t* tab, int v, int s, long long col,
+__device__ __forceinline__ void vn_node(const IbArgs& a, const uint8_t* tab, int v, int s, uint32_t col,
                                         uint32_t lane4, uint32_t RS, uint32_t TRS)
 {
-    const uint4 c4 = *reinterpret_cast<const uint4*>(a.ch + (long long)v * a.pitch + col);
+    const uint4 c4 = *reinterpret_cast<const uint4*>(a.ch + (uint64_t)(uint32_t)v * a.pitch + col);
     int rows[D];
     uint4 m[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) rows[k] = a.tv[s + k];
 #pragma unroll
-    for (int k = 0; k < D; ++k) m[k] = *reinterpret_cast<const uint4*>(a.msg + (long long)rows[k] * a.pitch + col);
+    for (int k = 0; k < D; ++k) m[k] = *reinterpret_cast<const uint4*>(a.msg + (uint64_t)(uint32_t)rows[k] * a.pitch + col);
     if (!DECIDE && D == 1) {   // degree-1 variable node forwards the raw channel value (:132-136)
-        *reinterpret_cast<uint4*>(a.msg + (long long)rows[0] * a.pitch + col) = c4;
+        *reinterpret_cast<uint4*>(a.msg + (uint64_t)(uint32_t)rows[0] * a.pitch + col) = c4;
         return;
     }
     const bool match = a.match != nullptr;
@@ -295,25 +297,23 @@ __device__ __forceinline__ void vn_node(const IbArgs& a, const uint8_t* tab, int
         }
     }
     if (DECIDE) {
-        *reinterpret_cast<uint4*>(a.out + (long long)v * a.pitch + col) = dec4;
+        *reinterpret_cast<uint4*>(a.out + (uint64_t)(uint32_t)v * a.pitch + col) = dec4;
     } else {
 #pragma unroll
-        for (int k = 0; k < D; ++k) *reinterpret_cast<uint4*>(a.msg + (long long)rows[k] * a.pitch + col) = r[k];
+        for (int k = 0; k < D; ++k) *reinterpret_cast<uint4*>(a.msg + (uint64_t)(uint32_t)rows[k] * a.pitch + col) = r[k];
     }
 }
 
 template <int D, bool DECIDE>
 __device__ __forceinline__ void vn_loop(const IbArgs& a, const uint8_t* tab, const int* __restrict__ nodes, int n_nodes)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lane4 = lane * 4, RS = 128u * a.W, TRS = RS * a.T;
-    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
-    const long long items = (long long)n_nodes * a.tiles;
-    for (long long item = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); item < items; item += nwarps) {
-        const int i = (int)(item / a.tiles);
-        const int tile = (int)(item - (long long)i * a.tiles);
-        const long long col = ((long long)tile * 32 + lane) * 16;
-        if (col >= a.pitch) continue;
+    const int tile = (blockIdx.y << a.tpc_log2) + (warp & ((1 << a.tpc_log2) - 1));
+    const int nps = kWarpsPerCta >> a.tpc_log2;
+    const uint32_t col = ((uint32_t)tile * 32u + lane) * 16u;
+    if (tile >= a.tiles || col >= a.pitch) return;
+    for (int i = blockIdx.x * nps + (warp >> a.tpc_log2); i < n_nodes; i += gridDim.x * nps) {
         const int v = nodes[i];
         vn_node<D, DECIDE>(a, tab, v, a.sv[v], col, lane4, RS, TRS);
     }

@@ -165,39 +165,66 @@ NodeKernel vn_fast_kernel_for(int d, bool decide)
 template <typename F, int ALGO>
 LlrNodeKernel llr_cn_kernel_for(int d)
 {
-    if (sizeof(F) == 8) return llr_cn_kernel<F, ALGO, 0>;
     switch (d) {
-    case 2: return llr_cn_kernel<float, ALGO, 2>;
-    case 3: return llr_cn_kernel<float, ALGO, 3>;
-    case 4: return llr_cn_kernel<float, ALGO, 4>;
-    case 5: return llr_cn_kernel<float, ALGO, 5>;
-    case 6: return llr_cn_kernel<float, ALGO, 6>;
-    case 7: return llr_cn_kernel<float, ALGO, 7>;
-    case 8: return llr_cn_kernel<float, ALGO, 8>;
-    case 9: return llr_cn_kernel<float, ALGO, 9>;
-    case 10: return llr_cn_kernel<float, ALGO, 10>;
-    default: return llr_cn_kernel<float, ALGO, 0>;
+    case 2: return llr_cn_kernel<F, ALGO, 2>;
+    case 3: return llr_cn_kernel<F, ALGO, 3>;
+    case 4: return llr_cn_kernel<F, ALGO, 4>;
+    case 5: return llr_cn_kernel<F, ALGO, 5>;
+    case 6: return llr_cn_kernel<F, ALGO, 6>;
+    case 7: return llr_cn_kernel<F, ALGO, 7>;
+    case 8: return llr_cn_kernel<F, ALGO, 8>;
+    case 9: return llr_cn_kernel<F, ALGO, 9>;
+    case 10: return llr_cn_kernel<F, ALGO, 10>;
+    default: return llr_cn_kernel<F, ALGO, 0>;
     }
 }
 template <typename F, int MODE>
 LlrNodeKernel llr_vn_kernel_for(int d)
 {
-    if (sizeof(F) == 8) return llr_vn_kernel<F, MODE, 0>;
     switch (d) {
-    case 1: return llr_vn_kernel<float, MODE, 1>;
-    case 2: return llr_vn_kernel<float, MODE, 2>;
-    case 3: return llr_vn_kernel<float, MODE, 3>;
-    case 4: return llr_vn_kernel<float, MODE, 4>;
-    case 5: return llr_vn_kernel<float, MODE, 5>;
-    case 6: return llr_vn_kernel<float, MODE, 6>;
-    case 7: return llr_vn_kernel<float, MODE, 7>;
-    case 8: return llr_vn_kernel<float, MODE, 8>;
-    case 9: return llr_vn_kernel<float, MODE, 9>;
-    case 10: return llr_vn_kernel<float, MODE, 10>;
-    case 11: return llr_vn_kernel<float, MODE, 11>;
-    case 12: return llr_vn_kernel<float, MODE, 12>;
-    default: return llr_vn_kernel<float, MODE, 0>;
+    case 1: return llr_vn_kernel<F, MODE, 1>;
+    case 2: return llr_vn_kernel<F, MODE, 2>;
+    case 3: return llr_vn_kernel<F, MODE, 3>;
+    case 4: return llr_vn_kernel<F, MODE, 4>;
+    case 5: return llr_vn_kernel<F, MODE, 5>;
+    case 6: return llr_vn_kernel<F, MODE, 6>;
+    case 7: return llr_vn_kernel<F, MODE, 7>;
+    case 8: return llr_vn_kernel<F, MODE, 8>;
+    case 9: return llr_vn_kernel<F, MODE, 9>;
+    case 10: return llr_vn_kernel<F, MODE, 10>;
+    case 11: return llr_vn_kernel<F, MODE, 11>;
+    case 12: return llr_vn_kernel<F, MODE, 12>;
+    default: return llr_vn_kernel<F, MODE, 0>;
     }
+}
+
+int occupancy_of(ibldpc_decoder* h, const void* fn, int smem, int* occ_out)
+{
+    auto key = std::make_pair(fn, smem);
+    auto it = h->occ_cache.find(key);
+    if (it == h->occ_cache.end()) {
+        int occ;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, smem));
+        if (occ < 1) return fail(IBLDPC_E_CUDA, "kernel does not fit on an SM");
+        h->occ_cache[key] = occ;
+        *occ_out = occ;
+    } else {
+        *occ_out = it->second;
+    }
+    return IBLDPC_OK;
+}
+
+// IB fast path: grid.x CTAs per tile group so that grid.x * tile_groups fills the resident slots
+int grid_for(ibldpc_decoder* h, const void* fn, int smem, int tile_groups, int nodes_per_step, int n_nodes, int* out)
+{
+    int occ;
+    int rc = occupancy_of(h, fn, smem, &occ);
+    if (rc) return rc;
+    const long long cap = std::max<long long>(1, (long long)occ * h->sm_count / tile_groups);
+    const long long want = ((long long)n_nodes + nodes_per_step - 1) / nodes_per_step;
+    *out = (int)std::max<long long>(1, std::min(want, cap));
+    return IBLDPC_OK;
 }
 
 // persistent grid: resident CTAs per SM x SM count, capped by the work available
@@ -273,7 +300,10 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
     a.sc = h->d_sc; a.deg_c = h->d_dc; a.sv = h->d_sv; a.deg_v = h->d_dv; a.tv = h->d_tv; a.vidx = h->d_vidx;
     a.n_var = h->N; a.n_chk = h->M;
     a.ch = ch; a.msg = w.msg; a.out = out;
-    a.pitch = pitch; a.B = (int)B; a.tiles = (int)((pitch + 511) / 512);
+    a.pitch = (uint32_t)pitch; a.B = (int)B; a.tiles = (int)((pitch + 511) / 512);
+    a.tpc_log2 = a.tiles >= 8 ? 3 : a.tiles > 2 ? 2 : a.tiles == 2 ? 1 : 0;
+    const int tile_groups = (a.tiles + (1 << a.tpc_log2) - 1) >> a.tpc_log2;
+    const int nps = kWarpsPerCta >> a.tpc_log2;
     a.T = h->T; a.Tc = h->Tc; a.tshift = h->tshift;
     a.flags = w.flags; a.inum = w.inum; a.early = early; a.imax = imax;
     a.DC = h->DC; a.DV = h->DV;
@@ -295,10 +325,10 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
             for (auto& c : h->cn_classes) {
                 NodeKernel k = cn_fast_kernel_for(c.degree);
                 int grid;
-                r = grid_for(h, (const void*)k, smem, (long long)c.count * b.tiles, &grid);
+                r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid);
                 if (r) return r;
-                k<<<grid, kThreads, smem, st>>>(b, c.d_nodes, c.count);
-                h->last_launches++; h->last_grid = grid; h->last_smem = smem;
+                k<<<dim3(grid, tile_groups), kThreads, smem, st>>>(b, c.d_nodes, c.count);
+                h->last_launches++; h->last_grid = grid * tile_groups; h->last_smem = smem;
             }
             return prof.end();
         };
@@ -319,9 +349,9 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
             for (auto& c : h->vn_classes) {
                 NodeKernel k = vn_fast_kernel_for(c.degree, decide);
                 int grid;
-                r = grid_for(h, (const void*)k, smem, (long long)c.count * b.tiles, &grid);
+                r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid);
                 if (r) return r;
-                k<<<grid, kThreads, smem, st>>>(b, c.d_nodes, c.count);
+                k<<<dim3(grid, tile_groups), kThreads, smem, st>>>(b, c.d_nodes, c.count);
                 h->last_launches++;
             }
             return prof.end();
