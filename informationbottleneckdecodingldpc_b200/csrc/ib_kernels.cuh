@@ -101,14 +101,22 @@ __device__ __forceinline__ void stage_tables(uint32_t* s_tab, const IbArgs& a, c
 
 __device__ __forceinline__ uint32_t lut_ld(const uint8_t* tab, uint32_t addr) { return tab[addr]; }
 
+// byte f of `o` replaced by the low byte of `t` (one PRMT; f is a compile-time constant)
+__device__ __forceinline__ uint32_t put_byte(uint32_t o, uint32_t t, int f)
+{
+    return f == 0 ? t : f == 1 ? __byte_perm(o, t, 0x3240u) : f == 2 ? __byte_perm(o, t, 0x3410u)
+                                                                     : __byte_perm(o, t, 0x4210u);
+}
+
 // ------------------------------------------------------------------------------------------
 // check node: D inputs, D leave-one-out outputs, 4 frames (one 32-bit word per message).
 // Chain of kernels_template_irreg.cl:205-245 (iterations >= 1) and :60-96 (iteration 0; same
 // address arithmetic when Tc == T): t = m[0]; for l: t = C[off + l*T^2 + t*T + m[l+1]].
+// MATCH is a template parameter so that the 16-frame body is one basic block.
 // ------------------------------------------------------------------------------------------
-template <int D>
+template <int D, bool MATCH>
 __device__ __forceinline__ void cn_word(const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab,
-                                        uint32_t RS, uint32_t TRS, uint32_t lane4, bool match, uint32_t match_off)
+                                        uint32_t RS, uint32_t TRS, uint32_t lane4, uint32_t match_off)
 {
 #pragma unroll
     for (int k = 0; k < D; ++k) o[k] = 0;
@@ -129,24 +137,26 @@ __device__ __forceinline__ void cn_word(const uint32_t (&w)[D], uint32_t (&o)[D]
             uint32_t t = (wo == 0) ? b[1] : P[wo];
 #pragma unroll
             for (int k = (wo == 0 ? 2 : wo + 1); k < D; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
-            if (match) t = lut_ld(tab, t * RS + match_off);
-            o[wo] |= t << (8 * f);
+            if (MATCH) t = lut_ld(tab, t * RS + match_off);
+            o[wo] = put_byte(o[wo], t, f);
         }
     }
 }
 
-template <int D>
+template <int D, bool MATCH, bool EARLY>
 __device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab, int s, uint32_t col,
                                             uint32_t lane4, uint32_t RS, uint32_t TRS, uint32_t valid_frames)
 {
     uint4 m[D];
+    if (a.iter0) {
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        const uint8_t* p = a.iter0 ? a.ch + (uint64_t)(uint32_t)a.vidx[s + k] * a.pitch
-                                   : a.msg + (uint64_t)(uint32_t)(s + k) * a.pitch;
-        m[k] = *reinterpret_cast<const uint4*>(p + col);
+        for (int k = 0; k < D; ++k)
+            m[k] = *reinterpret_cast<const uint4*>(a.ch + (uint64_t)(uint32_t)a.vidx[s + k] * a.pitch + col);
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            m[k] = *reinterpret_cast<const uint4*>(a.msg + (uint64_t)(uint32_t)(s + k) * a.pitch + col);
     }
-    const bool match = a.match != nullptr;
     const uint32_t match_off = (uint32_t)(D - 1) * TRS + lane4 + IB_SO(a.nst);
     uint32_t syn = 0;
     uint4 r[D];
@@ -155,7 +165,7 @@ __device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab,
         uint32_t w[D], o[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) w[k] = j == 0 ? m[k].x : j == 1 ? m[k].y : j == 2 ? m[k].z : m[k].w;
-        if (a.early && !a.iter0) {
+        if (EARLY && !a.iter0) {
             // calc_syndrome (kernels_template_irreg.cl:304-325) on the VN->CN messages just read:
             // parity of (msg < T/2) over the D inputs, per frame byte.
             uint32_t par = 0;
@@ -178,7 +188,7 @@ __device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab,
             const uint32_t vmask = nv >= 4 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u);
             syn |= par & vmask;
         }
-        cn_word<D>(w, o, tab, RS, TRS, lane4, match, match_off);
+        cn_word<D, MATCH>(w, o, tab, RS, TRS, lane4, match_off);
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             if (j == 0) r[k].x = o[k]; else if (j == 1) r[k].y = o[k]; else if (j == 2) r[k].z = o[k]; else r[k].w = o[k];
@@ -194,11 +204,12 @@ __device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab,
 // when a.iter0, checknode_update + calc_syndrome (:181-246, :304-325) otherwise.
 // One instantiation per check-node degree; `nodes` lists the checks of that degree, so every
 // launch has exactly the register budget its degree needs.
-template <int D>
-__global__ void __launch_bounds__(kThreads, (D <= 6 ? 4 : (D <= 8 ? 3 : 2))) ib_cn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
+template <int D, bool MATCH, bool EARLY>
+__global__ void __launch_bounds__(kThreads, (D <= 6 ? 4 : (D <= 8 ? 3 : 2)))
+ib_cn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 {
     extern __shared__ __align__(16) uint32_t s_tab[];
-    if (a.early && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
+    if (EARLY && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
     stage_tables(s_tab, a, a.lut);
     __syncthreads();
     const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_tab);
@@ -207,17 +218,24 @@ __global__ void __launch_bounds__(kThreads, (D <= 6 ? 4 : (D <= 8 ? 3 : 2))) ib_
     // CTA -> (tile group, node subset): no divisions, 32-bit offsets
     const int tile = (blockIdx.y << a.tpc_log2) + (warp & ((1 << a.tpc_log2) - 1));
     const int nps = kWarpsPerCta >> a.tpc_log2;          // nodes per CTA step
+    const int stride = gridDim.x * nps;
     const uint32_t col = ((uint32_t)tile * 32u + lane) * 16u;
     uint32_t syn = 0;
     if (tile < a.tiles && col < a.pitch) {
         const int vf = a.B - (int)col;
         const uint32_t valid = vf >= 16 ? 16u : vf <= 0 ? 0u : (uint32_t)vf;
-        for (int i = blockIdx.x * nps + (warp >> a.tpc_log2); i < n_nodes; i += gridDim.x * nps) {
-            const int c = nodes[i];
-            syn |= cn_node<D>(a, tab, a.sc[c], col, lane4, RS, TRS, valid);
+        int i = blockIdx.x * nps + (warp >> a.tpc_log2);
+        int s = i < n_nodes ? a.sc[nodes[i]] : 0;
+        while (i < n_nodes) {
+            // the next node's slot index is fetched while this node is being computed
+            const int i2 = i + stride;
+            const int s2 = i2 < n_nodes ? a.sc[nodes[i2]] : 0;
+            syn |= cn_node<D, MATCH, EARLY>(a, tab, s, col, lane4, RS, TRS, valid);
+            i = i2;
+            s = s2;
         }
     }
-    if (a.early && !a.iter0) {
+    if (EARLY && !a.iter0) {
         // warp-ballot syndrome check: one flag write per warp that saw an unsatisfied check
         const unsigned any = __ballot_sync(0xffffffffu, syn != 0);
         if (any != 0 && lane == 0) atomicOr(&a.flags[a.it], 1);
@@ -229,9 +247,9 @@ __global__ void __launch_bounds__(kThreads, (D <= 6 ? 4 : (D <= 8 ? 3 : 2))) ib_
 // Update chain kernels_template_irreg.cl:125-177, decision chain :277-300:
 //   t = V[off + m0*T + m1]; for l>=1: t = V[off + Tc*T + (l-1)*T^2 + t*T + m[l+1]].
 // ------------------------------------------------------------------------------------------
-template <int D, bool DECIDE>
+template <int D, bool MATCH, bool DECIDE>
 __device__ __forceinline__ void vn_word(uint32_t chw, const uint32_t (&w)[D], uint32_t (&o)[D], uint32_t& dec,
-                                        const uint8_t* tab, uint32_t RS, uint32_t TRS, uint32_t lane4, bool match,
+                                        const uint8_t* tab, uint32_t RS, uint32_t TRS, uint32_t lane4,
                                         uint32_t match_off)
 {
 #pragma unroll
@@ -247,36 +265,32 @@ __device__ __forceinline__ void vn_word(uint32_t chw, const uint32_t (&w)[D], ui
 #pragma unroll
         for (int j = 1; j <= D - 1; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(j - 1));
         if (DECIDE) {
-            dec |= lut_ld(tab, P[D] * RS + ms[D] + IB_SO(D - 1)) << (8 * f);
+            dec = put_byte(dec, lut_ld(tab, P[D] * RS + ms[D] + IB_SO(D - 1)), f);
         } else {
 #pragma unroll
             for (int wo = 1; wo <= D; ++wo) {
                 uint32_t t = P[wo];
 #pragma unroll
                 for (int k = wo + 1; k <= D; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
-                if (match) t = lut_ld(tab, t * RS + match_off);
-                o[wo - 1] |= t << (8 * f);
+                if (MATCH) t = lut_ld(tab, t * RS + match_off);
+                o[wo - 1] = put_byte(o[wo - 1], t, f);
             }
         }
     }
 }
 
-template <int D, bool DECIDE>
-__device__ __forceinline__ void vn_node(const IbArgs& a, const uint8_t* tab, int v, int s, uint32_t col,
-                                        uint32_t lane4, uint32_t RS, uint32_t TRS)
+template <int D, bool MATCH, bool DECIDE>
+__device__ __forceinline__ void vn_node(const IbArgs& a, const uint8_t* tab, int v, const int (&rows)[D],
+                                        uint32_t col, uint32_t lane4, uint32_t RS, uint32_t TRS)
 {
     const uint4 c4 = *reinterpret_cast<const uint4*>(a.ch + (uint64_t)(uint32_t)v * a.pitch + col);
-    int rows[D];
     uint4 m[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) rows[k] = a.tv[s + k];
 #pragma unroll
     for (int k = 0; k < D; ++k) m[k] = *reinterpret_cast<const uint4*>(a.msg + (uint64_t)(uint32_t)rows[k] * a.pitch + col);
     if (!DECIDE && D == 1) {   // degree-1 variable node forwards the raw channel value (:132-136)
         *reinterpret_cast<uint4*>(a.msg + (uint64_t)(uint32_t)rows[0] * a.pitch + col) = c4;
         return;
     }
-    const bool match = a.match != nullptr;
     const uint32_t match_off = (uint32_t)(D - 1) * TRS + lane4 + IB_SO(a.nst);
     uint4 r[D];
     uint4 dec4;
@@ -286,7 +300,7 @@ __device__ __forceinline__ void vn_node(const IbArgs& a, const uint8_t* tab, int
         const uint32_t chw = j == 0 ? c4.x : j == 1 ? c4.y : j == 2 ? c4.z : c4.w;
 #pragma unroll
         for (int k = 0; k < D; ++k) w[k] = j == 0 ? m[k].x : j == 1 ? m[k].y : j == 2 ? m[k].z : m[k].w;
-        vn_word<D, DECIDE>(chw, w, o, dec, tab, RS, TRS, lane4, match, match_off);
+        vn_word<D, MATCH, DECIDE>(chw, w, o, dec, tab, RS, TRS, lane4, match_off);
         if (DECIDE) {
             if (j == 0) dec4.x = dec; else if (j == 1) dec4.y = dec; else if (j == 2) dec4.z = dec; else dec4.w = dec;
         } else {
@@ -304,18 +318,44 @@ __device__ __forceinline__ void vn_node(const IbArgs& a, const uint8_t* tab, int
     }
 }
 
-template <int D, bool DECIDE>
+template <int D, bool MATCH, bool DECIDE>
 __device__ __forceinline__ void vn_loop(const IbArgs& a, const uint8_t* tab, const int* __restrict__ nodes, int n_nodes)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lane4 = lane * 4, RS = 128u * a.W, TRS = RS * a.T;
     const int tile = (blockIdx.y << a.tpc_log2) + (warp & ((1 << a.tpc_log2) - 1));
     const int nps = kWarpsPerCta >> a.tpc_log2;
+    const int stride = gridDim.x * nps;
     const uint32_t col = ((uint32_t)tile * 32u + lane) * 16u;
     if (tile >= a.tiles || col >= a.pitch) return;
-    for (int i = blockIdx.x * nps + (warp >> a.tpc_log2); i < n_nodes; i += gridDim.x * nps) {
-        const int v = nodes[i];
-        vn_node<D, DECIDE>(a, tab, v, a.sv[v], col, lane4, RS, TRS);
+    int i = blockIdx.x * nps + (warp >> a.tpc_log2);
+    int v = 0, rows[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) rows[k] = 0;
+    if (i < n_nodes) {
+        v = nodes[i];
+        const int s = a.sv[v];
+#pragma unroll
+        for (int k = 0; k < D; ++k) rows[k] = a.tv[s + k];
+    }
+    while (i < n_nodes) {
+        // the next node's (variable, slot, row) indices -- a chain of three dependent loads -- are
+        // fetched while this node is being computed
+        const int i2 = i + stride;
+        int v2 = 0, rows2[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) rows2[k] = 0;
+        if (i2 < n_nodes) {
+            v2 = nodes[i2];
+            const int s2 = a.sv[v2];
+#pragma unroll
+            for (int k = 0; k < D; ++k) rows2[k] = a.tv[s2 + k];
+        }
+        vn_node<D, MATCH, DECIDE>(a, tab, v, rows, col, lane4, RS, TRS);
+        i = i2;
+        v = v2;
+#pragma unroll
+        for (int k = 0; k < D; ++k) rows[k] = rows2[k];
     }
 }
 
@@ -331,7 +371,7 @@ __device__ __forceinline__ int executed_passes(const IbArgs& a)
 }
 
 // varnode_update (kernels_template_irreg.cl:103-179); one instantiation per variable-node degree.
-template <int D>
+template <int D, bool MATCH>
 __global__ void __launch_bounds__(kThreads) ib_vn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 {
     extern __shared__ __align__(16) uint32_t s_tab[];
@@ -340,7 +380,7 @@ __global__ void __launch_bounds__(kThreads) ib_vn_fast_kernel(IbArgs a, const in
         stage_tables(s_tab, a, a.lut);
         __syncthreads();
     }
-    vn_loop<D, false>(a, reinterpret_cast<const uint8_t*>(s_tab), nodes, n_nodes);
+    vn_loop<D, MATCH, false>(a, reinterpret_cast<const uint8_t*>(s_tab), nodes, n_nodes);
 }
 
 // calc_varnode_output (kernels_template_irreg.cl:249-302) with the VN table of iteration i_num-1
@@ -351,12 +391,12 @@ __global__ void __launch_bounds__(kThreads) ib_out_fast_kernel(IbArgs a, const i
     __shared__ int s_passes;
     if (threadIdx.x == 0) {
         s_passes = executed_passes(a);
-        if (blockIdx.x == 0) *a.inum = s_passes + 1;
+        if (blockIdx.x == 0 && blockIdx.y == 0) *a.inum = s_passes + 1;
     }
     __syncthreads();
     stage_tables(s_tab, a, a.lut + (long long)s_passes * a.vn_it_stride);
     __syncthreads();
-    vn_loop<D, true>(a, reinterpret_cast<const uint8_t*>(s_tab), nodes, n_nodes);
+    vn_loop<D, false, true>(a, reinterpret_cast<const uint8_t*>(s_tab), nodes, n_nodes);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -137,24 +137,41 @@ int ensure_ws_common(ibldpc_decoder* h, Workspace& w)
     return IBLDPC_OK;
 }
 
-NodeKernel cn_fast_kernel_for(int d)
+template <bool MATCH, bool EARLY>
+NodeKernel cn_fast_kernel_sel(int d)
 {
     switch (d) {
-    case 2: return ib_cn_fast_kernel<2>;
-    case 3: return ib_cn_fast_kernel<3>;
-    case 4: return ib_cn_fast_kernel<4>;
-    case 5: return ib_cn_fast_kernel<5>;
-    case 6: return ib_cn_fast_kernel<6>;
-    case 7: return ib_cn_fast_kernel<7>;
-    case 8: return ib_cn_fast_kernel<8>;
-    case 9: return ib_cn_fast_kernel<9>;
-    case 10: return ib_cn_fast_kernel<10>;
+    case 2: return ib_cn_fast_kernel<2, MATCH, EARLY>;
+    case 3: return ib_cn_fast_kernel<3, MATCH, EARLY>;
+    case 4: return ib_cn_fast_kernel<4, MATCH, EARLY>;
+    case 5: return ib_cn_fast_kernel<5, MATCH, EARLY>;
+    case 6: return ib_cn_fast_kernel<6, MATCH, EARLY>;
+    case 7: return ib_cn_fast_kernel<7, MATCH, EARLY>;
+    case 8: return ib_cn_fast_kernel<8, MATCH, EARLY>;
+    case 9: return ib_cn_fast_kernel<9, MATCH, EARLY>;
+    case 10: return ib_cn_fast_kernel<10, MATCH, EARLY>;
     default: return nullptr;
     }
 }
-NodeKernel vn_fast_kernel_for(int d, bool decide)
+NodeKernel cn_fast_kernel_for(int d, bool match, bool early)
 {
-#define VNK(D) case D: return decide ? (NodeKernel)ib_out_fast_kernel<D> : (NodeKernel)ib_vn_fast_kernel<D>;
+    return match ? (early ? cn_fast_kernel_sel<true, true>(d) : cn_fast_kernel_sel<true, false>(d))
+                 : (early ? cn_fast_kernel_sel<false, true>(d) : cn_fast_kernel_sel<false, false>(d));
+}
+template <bool MATCH>
+NodeKernel vn_fast_kernel_sel(int d)
+{
+#define VNK(D) case D: return ib_vn_fast_kernel<D, MATCH>;
+    switch (d) {
+        VNK(1) VNK(2) VNK(3) VNK(4) VNK(5) VNK(6) VNK(7) VNK(8) VNK(9) VNK(10) VNK(11) VNK(12)
+    default: return nullptr;
+    }
+#undef VNK
+}
+NodeKernel vn_fast_kernel_for(int d, bool decide, bool match)
+{
+    if (!decide) return match ? vn_fast_kernel_sel<true>(d) : vn_fast_kernel_sel<false>(d);
+#define VNK(D) case D: return ib_out_fast_kernel<D>;
     switch (d) {
         VNK(1) VNK(2) VNK(3) VNK(4) VNK(5) VNK(6) VNK(7) VNK(8) VNK(9) VNK(10) VNK(11) VNK(12)
     default: return nullptr;
@@ -323,7 +340,7 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
             int r = prof.begin(it < 0 ? 2 : 0);
             if (r) return r;
             for (auto& c : h->cn_classes) {
-                NodeKernel k = cn_fast_kernel_for(c.degree);
+                NodeKernel k = cn_fast_kernel_for(c.degree, h->match, early != 0);
                 int grid;
                 r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid);
                 if (r) return r;
@@ -347,7 +364,7 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
             int r = prof.begin(decide ? 2 : 1);
             if (r) return r;
             for (auto& c : h->vn_classes) {
-                NodeKernel k = vn_fast_kernel_for(c.degree, decide);
+                NodeKernel k = vn_fast_kernel_for(c.degree, decide, h->match);
                 int grid;
                 r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid);
                 if (r) return r;
