@@ -11,11 +11,12 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libibldpc.so")
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("ibldpc.cu", "ib_kernels.cuh", "llr_kernels.cuh")]
+UNITS = ["ibldpc.cu", "ib_fast_cn.cu", "ib_fast_vn.cu", "llr_f32.cu", "llr_f64.cu"]   # compiled in parallel
+SOURCES = [os.path.join(HERE, "csrc", f) for f in UNITS + ["ib_kernels.cuh", "llr_kernels.cuh", "kernel_tables.h"]]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "ibldpc.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC"]
 
 ALGO_MINSUM, ALGO_BP = 0, 1
 F32, F64 = 32, 64
@@ -66,9 +67,27 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     deps = SOURCES + [HEADER]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in deps):
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + [SOURCES[0], "-o", LIB_PATH]
+    from concurrent.futures import ThreadPoolExecutor
+    build_dir = os.path.join(HERE, "csrc", "build")
+    os.makedirs(build_dir, exist_ok=True)
+
+    def compile_unit(unit):
+        obj = os.path.join(build_dir, unit.replace(".cu", ".o"))
+        src = os.path.join(HERE, "csrc", unit)
+        hdrs = [s for s in deps if not s.endswith(".cu")]
+        if not force and os.path.exists(obj) and all(os.path.getmtime(obj) >= os.path.getmtime(s) for s in [src] + hdrs):
+            return obj
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
+        objs = list(pool.map(compile_unit, UNITS))
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs
     if verbose:
-        print(" ".join(cmd))
+        print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
     return LIB_PATH
 

@@ -72,27 +72,48 @@ struct IbArgs {
 // ------------------------------------------------------------------------------------------
 // shared-memory table staging
 // ------------------------------------------------------------------------------------------
+// Two steps: (1) the compact tables of this iteration (nst x T^2 bytes + matching rows, a few KB)
+// are copied global -> shared with coalesced loads into a scratch area behind the expanded
+// table; (2) every warp expands rows from that scratch copy (broadcast LDS) into the
+// lane-striped layout.  Host side: dynamic smem = nrows*W*128 + stage_scratch_bytes().
+__host__ __device__ __forceinline__ int stage_scratch_bytes(int nst, int T, int dmax_match)
+{
+    return ((nst * T * T + dmax_match * T + 15) / 16) * 16;
+}
+
 __device__ __forceinline__ void stage_tables(uint32_t* s_tab, const IbArgs& a, const uint8_t* lut)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int TT = a.T * a.T;
     const int total = a.nrows * a.W;
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(s_tab) + (size_t)total * 128;
+    const int n_lut = a.nst * TT;
+    if (((n_lut | (int)(reinterpret_cast<uintptr_t>(lut) & 3)) & 3) == 0) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(lut);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(scratch);
+        for (int i = threadIdx.x; i < n_lut / 4; i += kThreads) dst[i] = src[i];
+    } else {
+        for (int i = threadIdx.x; i < n_lut; i += kThreads) scratch[i] = lut[i];
+    }
+    uint8_t* smatch = scratch + n_lut;
+    if (a.match != nullptr)
+        for (int i = threadIdx.x; i < a.dmax_match * a.T; i += kThreads) smatch[i] = a.match[i];
+    __syncthreads();
     for (int rw = warp; rw < total; rw += kWarpsPerCta) {
         const int r = rw / a.W, w = rw - r * a.W;
         const int m = r / a.T, t = r - m * a.T;
         uint32_t v = 0;
-        if (lane < 4) {
-            const int col = 4 * w + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int col = 4 * w + q;
+            uint32_t e = 0;
             if (col < a.nst) {
-                if (r < TT) v = lut[col * TT + t * a.T + m];
+                if (r < TT) e = scratch[col * TT + t * a.T + m];
             } else if (col == a.nst && a.match != nullptr) {
-                if (m < a.dmax_match) v = a.match[m * a.T + t];
+                if (m < a.dmax_match) e = smatch[m * a.T + t];
             }
-            v <<= 8 * lane;
+            v |= e << (8 * q);
         }
-        v |= __shfl_xor_sync(0xffffffffu, v, 1);
-        v |= __shfl_xor_sync(0xffffffffu, v, 2);
-        v = __shfl_sync(0xffffffffu, v, 0);
         s_tab[rw * 32 + lane] = v;
     }
 }
@@ -403,7 +424,7 @@ __global__ void __launch_bounds__(kThreads) ib_out_fast_kernel(IbArgs a, const i
 // generic path: any |T| <= 256, Tc != T, degrees <= 64.  One thread per (node, frame), tables
 // read from global memory with the reference's index arithmetic.  Same in-place layout.
 // ------------------------------------------------------------------------------------------
-__global__ void ib_cn_generic_kernel(IbArgs a)
+static __global__ void ib_cn_generic_kernel(IbArgs a)
 {
     if (a.early && a.it >= 1 && a.flags[a.it - 1] == 0) return;
     const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -13,6 +13,7 @@
 #include "../../include/ibldpc.h"
 #include "ib_kernels.cuh"
 #include "llr_kernels.cuh"
+#include "kernel_tables.h"
 
 using namespace ibldpc;
 
@@ -58,8 +59,6 @@ struct Workspace {
 
 constexpr int kMaxIter = 4096;
 
-using NodeKernel = void (*)(IbArgs, const int*, int);
-using LlrNodeKernel = void (*)(LlrArgs, const int*, int);
 
 struct PhaseEvent { cudaEvent_t a, b; int phase; };
 
@@ -81,7 +80,7 @@ struct ibldpc_decoder {
     bool fast = false;
     int Wc = 1, Wv = 1, Wo = 1, nrows_c = 0, nrows_v = 0, nrows_o = 0, tshift = -1;
     Workspace ws[2];
-    int host_chunk = 4096;
+    int host_chunk = 8192;
     // introspection
     int last_launches = 0, last_grid = 0, last_smem = 0;
     bool profiling = false;
@@ -135,84 +134,6 @@ int ensure_ws_common(ibldpc_decoder* h, Workspace& w)
     }
     (void)h;
     return IBLDPC_OK;
-}
-
-template <bool MATCH, bool EARLY>
-NodeKernel cn_fast_kernel_sel(int d)
-{
-    switch (d) {
-    case 2: return ib_cn_fast_kernel<2, MATCH, EARLY>;
-    case 3: return ib_cn_fast_kernel<3, MATCH, EARLY>;
-    case 4: return ib_cn_fast_kernel<4, MATCH, EARLY>;
-    case 5: return ib_cn_fast_kernel<5, MATCH, EARLY>;
-    case 6: return ib_cn_fast_kernel<6, MATCH, EARLY>;
-    case 7: return ib_cn_fast_kernel<7, MATCH, EARLY>;
-    case 8: return ib_cn_fast_kernel<8, MATCH, EARLY>;
-    case 9: return ib_cn_fast_kernel<9, MATCH, EARLY>;
-    case 10: return ib_cn_fast_kernel<10, MATCH, EARLY>;
-    default: return nullptr;
-    }
-}
-NodeKernel cn_fast_kernel_for(int d, bool match, bool early)
-{
-    return match ? (early ? cn_fast_kernel_sel<true, true>(d) : cn_fast_kernel_sel<true, false>(d))
-                 : (early ? cn_fast_kernel_sel<false, true>(d) : cn_fast_kernel_sel<false, false>(d));
-}
-template <bool MATCH>
-NodeKernel vn_fast_kernel_sel(int d)
-{
-#define VNK(D) case D: return ib_vn_fast_kernel<D, MATCH>;
-    switch (d) {
-        VNK(1) VNK(2) VNK(3) VNK(4) VNK(5) VNK(6) VNK(7) VNK(8) VNK(9) VNK(10) VNK(11) VNK(12)
-    default: return nullptr;
-    }
-#undef VNK
-}
-NodeKernel vn_fast_kernel_for(int d, bool decide, bool match)
-{
-    if (!decide) return match ? vn_fast_kernel_sel<true>(d) : vn_fast_kernel_sel<false>(d);
-#define VNK(D) case D: return ib_out_fast_kernel<D>;
-    switch (d) {
-        VNK(1) VNK(2) VNK(3) VNK(4) VNK(5) VNK(6) VNK(7) VNK(8) VNK(9) VNK(10) VNK(11) VNK(12)
-    default: return nullptr;
-    }
-#undef VNK
-}
-
-template <typename F, int ALGO>
-LlrNodeKernel llr_cn_kernel_for(int d)
-{
-    switch (d) {
-    case 2: return llr_cn_kernel<F, ALGO, 2>;
-    case 3: return llr_cn_kernel<F, ALGO, 3>;
-    case 4: return llr_cn_kernel<F, ALGO, 4>;
-    case 5: return llr_cn_kernel<F, ALGO, 5>;
-    case 6: return llr_cn_kernel<F, ALGO, 6>;
-    case 7: return llr_cn_kernel<F, ALGO, 7>;
-    case 8: return llr_cn_kernel<F, ALGO, 8>;
-    case 9: return llr_cn_kernel<F, ALGO, 9>;
-    case 10: return llr_cn_kernel<F, ALGO, 10>;
-    default: return llr_cn_kernel<F, ALGO, 0>;
-    }
-}
-template <typename F, int MODE>
-LlrNodeKernel llr_vn_kernel_for(int d)
-{
-    switch (d) {
-    case 1: return llr_vn_kernel<F, MODE, 1>;
-    case 2: return llr_vn_kernel<F, MODE, 2>;
-    case 3: return llr_vn_kernel<F, MODE, 3>;
-    case 4: return llr_vn_kernel<F, MODE, 4>;
-    case 5: return llr_vn_kernel<F, MODE, 5>;
-    case 6: return llr_vn_kernel<F, MODE, 6>;
-    case 7: return llr_vn_kernel<F, MODE, 7>;
-    case 8: return llr_vn_kernel<F, MODE, 8>;
-    case 9: return llr_vn_kernel<F, MODE, 9>;
-    case 10: return llr_vn_kernel<F, MODE, 10>;
-    case 11: return llr_vn_kernel<F, MODE, 11>;
-    case 12: return llr_vn_kernel<F, MODE, 12>;
-    default: return llr_vn_kernel<F, MODE, 0>;
-    }
 }
 
 int occupancy_of(ibldpc_decoder* h, const void* fn, int smem, int* occ_out)
@@ -336,7 +257,7 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
             b.lut = h->d_cn8 + (size_t)blk * (h->DC - 2) * TT;
             b.match = h->match ? h->d_mc8 + (size_t)blk * h->DC * T : nullptr;
             b.nst = h->DC - 2; b.dmax_match = h->DC; b.W = h->Wc; b.nrows = h->nrows_c;
-            const int smem = h->nrows_c * h->Wc * 128;
+            const int smem = h->nrows_c * h->Wc * 128 + stage_scratch_bytes(b.nst, T, h->match ? b.dmax_match : 0);
             int r = prof.begin(it < 0 ? 2 : 0);
             if (r) return r;
             for (auto& c : h->cn_classes) {
@@ -360,7 +281,7 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
                 b.match = h->match ? h->d_mv8 + (size_t)it * h->DV * T : nullptr;
                 b.nst = h->DV - 1; b.dmax_match = h->DV; b.W = h->Wv; b.nrows = h->nrows_v;
             }
-            const int smem = b.nrows * b.W * 128;
+            const int smem = b.nrows * b.W * 128 + stage_scratch_bytes(b.nst, T, b.match ? b.dmax_match : 0);
             int r = prof.begin(decide ? 2 : 1);
             if (r) return r;
             for (auto& c : h->vn_classes) {
@@ -491,8 +412,7 @@ int decode_llr_padded(ibldpc_decoder* h, Workspace& w, const F* ch, long long pi
         LlrArgs b = a;
         b.it = it;
         for (auto& c : h->vn_classes) {
-            LlrNodeKernel k = mode == 0 ? llr_vn_kernel_for<F, 0>(c.degree)
-                            : mode == 1 ? llr_vn_kernel_for<F, 1>(c.degree) : llr_vn_kernel_for<F, 2>(c.degree);
+            LlrNodeKernel k = llr_vn_kernel_for(sizeof(F) == 8, mode, c.degree);
             int grid;
             int r = grid_for(h, (const void*)k, 0, (long long)c.count * b.tiles, &grid);
             if (r) return r;
@@ -505,7 +425,7 @@ int decode_llr_padded(ibldpc_decoder* h, Workspace& w, const F* ch, long long pi
         LlrArgs b = a;
         b.it = it;
         for (auto& c : h->cn_classes) {
-            LlrNodeKernel k = llr_cn_kernel_for<F, ALGO>(c.degree);
+            LlrNodeKernel k = llr_cn_kernel_for(sizeof(F) == 8, ALGO, c.degree);
             int grid;
             int r = grid_for(h, (const void*)k, 0, (long long)c.count * b.tiles, &grid);
             if (r) return r;
@@ -522,8 +442,9 @@ int decode_llr_padded(ibldpc_decoder* h, Workspace& w, const F* ch, long long pi
             LlrArgs b = a;
             b.it = it;
             int grid;
-            if ((rc = grid_for(h, (const void*)llr_syndrome_kernel<F>, 0, (long long)h->M * b.tiles, &grid))) return rc;
-            llr_syndrome_kernel<F><<<grid, kThreads, 0, st>>>(b);
+            LlrSynKernel ks = llr_syndrome_kernel_for(sizeof(F) == 8);
+            if ((rc = grid_for(h, (const void*)ks, 0, (long long)h->M * b.tiles, &grid))) return rc;
+            ks<<<grid, kThreads, 0, st>>>(b);
             h->last_launches++;
         }
     }
@@ -755,7 +676,7 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
     h->nrows_c = std::max(T * T, match ? DC * T : 0);
     h->nrows_v = std::max(T * T, match ? DV * T : 0);
     h->nrows_o = T * T;
-    const size_t smem_max = 227 * 1024;
+    const size_t smem_max = 227 * 1024 - 4096;   // leaves room for the staging scratch
     h->fast = (T <= 16) && (Tc == T) && h->dc_max <= kMaxFastDc && h->dv_max <= kMaxFastDv &&
               (size_t)h->nrows_c * h->Wc * 128 <= smem_max && (size_t)h->nrows_v * h->Wv * 128 <= smem_max &&
               (size_t)h->nrows_o * h->Wo * 128 <= smem_max;

@@ -1,0 +1,24 @@
+// kernel_tables.h -- per-degree kernel instantiations live in their own translation units
+// (ib_fast_cn.cu, ib_fast_vn.cu, llr_f32.cu, llr_f64.cu) so that they compile in parallel;
+// the host code picks them through these selectors.
+#pragma once
+#include "ib_kernels.cuh"
+#include "llr_kernels.cuh"
+
+namespace ibldpc {
+using NodeKernel = void (*)(IbArgs, const int*, int);
+using LlrNodeKernel = void (*)(LlrArgs, const int*, int);
+using LlrSynKernel = void (*)(LlrArgs);
+
+NodeKernel cn_fast_kernel_for(int d, bool match, bool early);
+NodeKernel vn_fast_kernel_for(int d, bool decide, bool match);
+LlrNodeKernel llr_cn_kernel_for(bool f64, int algo, int d);
+LlrNodeKernel llr_vn_kernel_for(bool f64, int mode, int d);
+LlrSynKernel llr_syndrome_kernel_for(bool f64);
+LlrNodeKernel llr_cn_kernel_f32(int algo, int d);
+LlrNodeKernel llr_vn_kernel_f32(int mode, int d);
+LlrNodeKernel llr_cn_kernel_f64(int algo, int d);
+LlrNodeKernel llr_vn_kernel_f64(int mode, int d);
+LlrSynKernel llr_syndrome_kernel_f32();
+LlrSynKernel llr_syndrome_kernel_f64();
+}  // namespace ibldpc

@@ -330,7 +330,7 @@ __global__ void count_errors_kernel(const E* __restrict__ out, long long rows, l
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if ((threadIdx.x & 31) == 0 && e) atomicAdd(&counters[0], (unsigned long long)e);
 }
-__global__ void count_frames_kernel(const int* __restrict__ frame_err, long long B, unsigned long long* counters)
+static __global__ void count_frames_kernel(const int* __restrict__ frame_err, long long B, unsigned long long* counters)
 {
     unsigned int e = 0;
     for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < B; f += (long long)gridDim.x * blockDim.x)
