@@ -393,7 +393,8 @@ __device__ __forceinline__ int executed_passes(const IbArgs& a)
 
 // varnode_update (kernels_template_irreg.cl:103-179); one instantiation per variable-node degree.
 template <int D, bool MATCH>
-__global__ void __launch_bounds__(kThreads) ib_vn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
+__global__ void __launch_bounds__(kThreads, (D <= 4 ? 4 : (D <= 8 ? 3 : 2)))
+ib_vn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 {
     extern __shared__ __align__(16) uint32_t s_tab[];
     if (a.early && a.it >= 1 && a.flags[a.it - 1] == 0) return;

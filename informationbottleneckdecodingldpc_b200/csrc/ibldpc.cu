@@ -80,7 +80,7 @@ struct ibldpc_decoder {
     bool fast = false;
     int Wc = 1, Wv = 1, Wo = 1, nrows_c = 0, nrows_v = 0, nrows_o = 0, tshift = -1;
     Workspace ws[2];
-    int host_chunk = 8192;
+    int host_chunk = 0;   // 0 = auto: about 64 MiB of channel values per chunk
     // introspection
     int last_launches = 0, last_grid = 0, last_smem = 0;
     bool profiling = false;
@@ -250,17 +250,25 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
     Prof prof{h, st};
 
     if (h->fast) {
+        // Each degree class only stages the tables its chains reach (stages 0..d-3 for a check of
+        // degree d, 0..d-2 / 0..d-1 for a variable node), so low-degree classes of an irregular code
+        // get small shared-memory footprints and high occupancy.
+        auto words = [](int cols) { return std::max(1, (cols + 3) / 4); };
         auto launch_cn = [&](int it) -> int {
             IbArgs b = a;
             b.it = it; b.iter0 = (it < 0);
             const int blk = it + 1;   // table block: 0 = iteration-0 tables
             b.lut = h->d_cn8 + (size_t)blk * (h->DC - 2) * TT;
             b.match = h->match ? h->d_mc8 + (size_t)blk * h->DC * T : nullptr;
-            b.nst = h->DC - 2; b.dmax_match = h->DC; b.W = h->Wc; b.nrows = h->nrows_c;
-            const int smem = h->nrows_c * h->Wc * 128 + stage_scratch_bytes(b.nst, T, h->match ? b.dmax_match : 0);
+            b.dmax_match = h->DC;
             int r = prof.begin(it < 0 ? 2 : 0);
             if (r) return r;
             for (auto& c : h->cn_classes) {
+                b.nst = c.degree - 2;
+                b.W = words(b.nst + (h->match ? 1 : 0));
+                b.nrows = std::max(TT, h->match ? c.degree * T : 0);
+                if (h->match) b.dmax_match = c.degree;
+                const int smem = b.nrows * b.W * 128 + stage_scratch_bytes(b.nst, T, h->match ? b.dmax_match : 0);
                 NodeKernel k = cn_fast_kernel_for(c.degree, h->match, early != 0);
                 int grid;
                 r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid);
@@ -275,16 +283,19 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
             b.it = it; b.iter0 = 0;
             if (decide) {
                 b.lut = h->d_vn8; b.vn_it_stride = (long long)h->DV * TT; b.match = nullptr;
-                b.nst = h->DV; b.W = h->Wo; b.nrows = h->nrows_o; b.dmax_match = 0;
             } else {
                 b.lut = h->d_vn8 + (size_t)it * h->DV * TT;
                 b.match = h->match ? h->d_mv8 + (size_t)it * h->DV * T : nullptr;
-                b.nst = h->DV - 1; b.dmax_match = h->DV; b.W = h->Wv; b.nrows = h->nrows_v;
             }
-            const int smem = b.nrows * b.W * 128 + stage_scratch_bytes(b.nst, T, b.match ? b.dmax_match : 0);
             int r = prof.begin(decide ? 2 : 1);
             if (r) return r;
             for (auto& c : h->vn_classes) {
+                const bool m = b.match != nullptr;
+                b.nst = decide ? c.degree : c.degree - 1;
+                b.W = words(b.nst + (m ? 1 : 0));
+                b.nrows = std::max(TT, m ? c.degree * T : 0);
+                b.dmax_match = m ? c.degree : 0;
+                const int smem = b.nrows * b.W * 128 + stage_scratch_bytes(b.nst, T, b.dmax_match);
                 NodeKernel k = vn_fast_kernel_for(c.degree, decide, h->match);
                 int grid;
                 r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid);
@@ -722,7 +733,8 @@ int ibldpc_decode_ib_host(ibldpc_handle h, const uint8_t* ch_host, int64_t B, in
     if (!ch_host || !out_host) return fail(IBLDPC_E_INVALID, "null buffer");
     CK(cudaSetDevice(h->device));
     // Early termination is a property of the whole call (all B frames), so it cannot be chunked.
-    const int64_t chunk = early_term ? B : std::min<int64_t>(B, std::max(16, h->host_chunk / 16 * 16));
+    int64_t want = h->host_chunk > 0 ? h->host_chunk : std::max<int64_t>(512, ((64LL << 20) / h->N) / 512 * 512);
+    const int64_t chunk = early_term ? B : std::min<int64_t>(B, std::max<int64_t>(16, want / 16 * 16));
     const long long cpitch = (chunk + 15) / 16 * 16;
     const int nslots = (chunk < B) ? 2 : 1;
     for (int s = 0; s < nslots; ++s) {
@@ -844,7 +856,7 @@ int ibldpc_set_profiling(ibldpc_handle h, int on)
 
 int ibldpc_set_host_chunk(ibldpc_handle h, int frames)
 {
-    if (!h || frames < 16) return fail(IBLDPC_E_INVALID, "bad chunk");
+    if (!h || (frames != 0 && frames < 16)) return fail(IBLDPC_E_INVALID, "bad chunk");
     h->host_chunk = frames;
     return IBLDPC_OK;
 }
