@@ -112,6 +112,12 @@ int ibldpc_decode_llr(ibldpc_handle h, int algo, int dtype, const void *ch_dev, 
 int ibldpc_count_errors_u8(int device, const uint8_t *out_dev, int64_t rows, int64_t B, int threshold,
                            const uint8_t *ref_bits_dev, int64_t *counters_host, void *stream);
 
+/* Same counters, asynchronous: counters_dev[0] += bit errors, counters_dev[1] += frame errors
+ * (int64 device memory), no host synchronisation -- for pipelined BER loops where the per-batch
+ * counters are all-reduced on the device and read back one batch late. */
+int ibldpc_count_errors_u8_async(int device, const uint8_t *out_dev, int64_t rows, int64_t B, int threshold,
+                                 const uint8_t *ref_bits_dev, int64_t *counters_dev, void *stream);
+
 /* LLR twin (min_sum_decoder_irreg.py:290-295, bp_decoder_irreg.py:288-293): bit = (LLR < 0). */
 int ibldpc_count_errors_llr(int device, const void *out_dev, int dtype, int64_t rows, int64_t B,
                             const uint8_t *ref_bits_dev, int64_t *counters_host, void *stream);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "ibldpc_decode_ib_host": (_i, [_vp, _vp, _i64, _i, _i, _vp, C.POINTER(C.c_int32)]),
     "ibldpc_decode_llr": (_i, [_vp, _i, _i, _vp, _i64, _i, _i, _vp, C.POINTER(C.c_int32), _vp]),
     "ibldpc_count_errors_u8": (_i, [_i, _vp, _i64, _i64, _i, _vp, C.POINTER(C.c_int64), _vp]),
+    "ibldpc_count_errors_u8_async": (_i, [_i, _vp, _i64, _i64, _i, _vp, _vp, _vp]),
     "ibldpc_count_errors_llr": (_i, [_i, _vp, _i, _i64, _i64, _vp, C.POINTER(C.c_int64), _vp]),
     "ibldpc_quantize": (_i, [_i, _vp, _i64, _vp, _i, _vp, _vp]),
     "ibldpc_quantize_llr": (_i, [_i, _vp, _i64, _vp, _i, _vp, _i, _vp, _vp]),

@@ -524,16 +524,18 @@ int quantize_common(int device, const double* x_dev, int64_t n, const double* li
 
 template <typename E>
 int count_errors_common(int device, const E* out_dev, int64_t rows, int64_t B, E threshold, const uint8_t* ref_bits,
-                        int64_t* counters_host, void* stream)
+                        int64_t* counters_host, int64_t* counters_dev, void* stream)
 {
-    if (!out_dev || !counters_host || rows < 0 || B <= 0) return fail(IBLDPC_E_INVALID, "bad arguments");
+    if (!out_dev || (!counters_host && !counters_dev) || rows < 0 || B <= 0) return fail(IBLDPC_E_INVALID, "bad arguments");
     CK(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long* d_cnt = nullptr;
+    unsigned long long* d_cnt = (unsigned long long*)counters_dev;   // async variant: accumulate in place
     int* d_fe = nullptr;
-    CK(cudaMallocAsync((void**)&d_cnt, sizeof(unsigned long long) * 2, st));
+    if (!counters_dev) {
+        CK(cudaMallocAsync((void**)&d_cnt, sizeof(unsigned long long) * 2, st));
+        CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 2, st));
+    }
     CK(cudaMallocAsync((void**)&d_fe, sizeof(int) * B, st));
-    CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 2, st));
     CK(cudaMemsetAsync(d_fe, 0, sizeof(int) * B, st));
     if (rows > 0) {
         dim3 grid((unsigned)((B + 255) / 256), (unsigned)((rows + 63) / 64));
@@ -541,13 +543,15 @@ int count_errors_common(int device, const E* out_dev, int64_t rows, int64_t B, E
         count_frames_kernel<<<(unsigned)std::min<int64_t>((B + 255) / 256, 1024), 256, 0, st>>>(d_fe, B, d_cnt);
     }
     CK(cudaGetLastError());
-    unsigned long long hc[2];
-    CK(cudaMemcpyAsync(hc, d_cnt, sizeof(hc), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaFreeAsync(d_cnt, st));
     CK(cudaFreeAsync(d_fe, st));
-    counters_host[0] = (int64_t)hc[0];
-    counters_host[1] = (int64_t)hc[1];
+    if (!counters_dev) {
+        unsigned long long hc[2];
+        CK(cudaMemcpyAsync(hc, d_cnt, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaFreeAsync(d_cnt, st));
+        counters_host[0] = (int64_t)hc[0];
+        counters_host[1] = (int64_t)hc[1];
+    }
     return IBLDPC_OK;
 }
 
@@ -790,16 +794,24 @@ int ibldpc_count_errors_u8(int device, const uint8_t* out_dev, int64_t rows, int
                            const uint8_t* ref_bits_dev, int64_t* counters_host, void* stream)
 {
     if (threshold < 0 || threshold > 255) return fail(IBLDPC_E_INVALID, "threshold out of range");
-    return count_errors_common<uint8_t>(device, out_dev, rows, B, (uint8_t)threshold, ref_bits_dev, counters_host, stream);
+    return count_errors_common<uint8_t>(device, out_dev, rows, B, (uint8_t)threshold, ref_bits_dev, counters_host, nullptr, stream);
+}
+
+int ibldpc_count_errors_u8_async(int device, const uint8_t* out_dev, int64_t rows, int64_t B, int threshold,
+                                 const uint8_t* ref_bits_dev, int64_t* counters_dev, void* stream)
+{
+    if (threshold < 0 || threshold > 255) return fail(IBLDPC_E_INVALID, "threshold out of range");
+    if (!counters_dev) return fail(IBLDPC_E_INVALID, "null device counters");
+    return count_errors_common<uint8_t>(device, out_dev, rows, B, (uint8_t)threshold, ref_bits_dev, nullptr, counters_dev, stream);
 }
 
 int ibldpc_count_errors_llr(int device, const void* out_dev, int dtype, int64_t rows, int64_t B,
                             const uint8_t* ref_bits_dev, int64_t* counters_host, void* stream)
 {
     if (dtype == IBLDPC_F32)
-        return count_errors_common<float>(device, (const float*)out_dev, rows, B, 0.f, ref_bits_dev, counters_host, stream);
+        return count_errors_common<float>(device, (const float*)out_dev, rows, B, 0.f, ref_bits_dev, counters_host, nullptr, stream);
     if (dtype == IBLDPC_F64)
-        return count_errors_common<double>(device, (const double*)out_dev, rows, B, 0.0, ref_bits_dev, counters_host, stream);
+        return count_errors_common<double>(device, (const double*)out_dev, rows, B, 0.0, ref_bits_dev, counters_host, nullptr, stream);
     return fail(IBLDPC_E_INVALID, "dtype must be IBLDPC_F32 or IBLDPC_F64");
 }
 

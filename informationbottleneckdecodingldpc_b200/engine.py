@@ -143,3 +143,22 @@ def count_errors(buf, rows: int, threshold=None, ref_bits=None):
     else:
         raise TypeError(f"unsupported buffer dtype {t.dtype}")
     return int(cnt[0]), int(cnt[1])
+
+
+def count_errors_async(buf, rows: int, threshold: int, counters: torch.Tensor, ref_bits=None) -> None:
+    """Asynchronous twin for cluster buffers: ``counters`` is an int64 CUDA tensor whose elements 0/1
+    are incremented by the bit / frame errors on the current stream; nothing is read back."""
+    t = as_tensor(buf)
+    if t.dim() == 1:
+        t = t[:, None]
+    t = t.contiguous()
+    if t.dtype != torch.uint8 or counters.dtype != torch.int64 or not counters.is_cuda or counters.numel() < 2:
+        raise TypeError("count_errors_async needs a uint8 buffer and an int64 CUDA counter tensor")
+    ref_ptr = None
+    if ref_bits is not None:
+        r = as_tensor(ref_bits).to(torch.uint8).contiguous()
+        ref_ptr = C.c_void_p(r.data_ptr())
+    dev = t.device.index if t.device.index is not None else current_device()
+    _lib.check(_lib.lib().ibldpc_count_errors_u8_async(dev, C.c_void_p(t.data_ptr()), int(min(rows, t.shape[0])), t.shape[1],
+                                                       int(threshold), ref_ptr, C.c_void_p(counters.data_ptr()),
+                                                       C.c_void_p(stream_ptr())))
