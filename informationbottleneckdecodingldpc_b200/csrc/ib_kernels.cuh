@@ -300,16 +300,41 @@ __device__ __forceinline__ void vn_word(uint32_t chw, const uint32_t (&w)[D], ui
     }
 }
 
-template <int D, bool MATCH, bool DECIDE>
-__device__ __forceinline__ void vn_node(const IbArgs& a, const uint8_t* tab, int v, const int (&rows)[D],
-                                        uint32_t col, uint32_t lane4, uint32_t RS, uint32_t TRS)
+template <int D> struct VnIn { uint4 c4; uint4 m[D]; };
+template <int D> struct VnIdx { int v; int rows[D]; bool ok; };
+
+template <int D>
+__device__ __forceinline__ void vn_load_idx(const IbArgs& a, const int* __restrict__ nodes, int n_nodes, int i, VnIdx<D>& x)
 {
-    const uint4 c4 = *reinterpret_cast<const uint4*>(a.ch + (uint64_t)(uint32_t)v * a.pitch + col);
-    uint4 m[D];
+    x.ok = i < n_nodes;
+    x.v = 0;
 #pragma unroll
-    for (int k = 0; k < D; ++k) m[k] = *reinterpret_cast<const uint4*>(a.msg + (uint64_t)(uint32_t)rows[k] * a.pitch + col);
+    for (int k = 0; k < D; ++k) x.rows[k] = 0;
+    if (x.ok) {
+        x.v = nodes[i];
+        const int s = a.sv[x.v];
+#pragma unroll
+        for (int k = 0; k < D; ++k) x.rows[k] = a.tv[s + k];
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void vn_load_msgs(const IbArgs& a, const VnIdx<D>& x, uint32_t col, VnIn<D>& in)
+{
+    if (x.ok) {
+        in.c4 = *reinterpret_cast<const uint4*>(a.ch + (uint64_t)(uint32_t)x.v * a.pitch + col);
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            in.m[k] = *reinterpret_cast<const uint4*>(a.msg + (uint64_t)(uint32_t)x.rows[k] * a.pitch + col);
+    }
+}
+
+template <int D, bool MATCH, bool DECIDE>
+__device__ __forceinline__ void vn_compute_store(const IbArgs& a, const uint8_t* tab, const VnIdx<D>& x, const VnIn<D>& in,
+                                                 uint32_t col, uint32_t lane4, uint32_t RS, uint32_t TRS)
+{
     if (!DECIDE && D == 1) {   // degree-1 variable node forwards the raw channel value (:132-136)
-        *reinterpret_cast<uint4*>(a.msg + (uint64_t)(uint32_t)rows[0] * a.pitch + col) = c4;
+        *reinterpret_cast<uint4*>(a.msg + (uint64_t)(uint32_t)x.rows[0] * a.pitch + col) = in.c4;
         return;
     }
     const uint32_t match_off = (uint32_t)(D - 1) * TRS + lane4 + IB_SO(a.nst);
@@ -318,9 +343,9 @@ __device__ __forceinline__ void vn_node(const IbArgs& a, const uint8_t* tab, int
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         uint32_t w[D], o[D], dec;
-        const uint32_t chw = j == 0 ? c4.x : j == 1 ? c4.y : j == 2 ? c4.z : c4.w;
+        const uint32_t chw = j == 0 ? in.c4.x : j == 1 ? in.c4.y : j == 2 ? in.c4.z : in.c4.w;
 #pragma unroll
-        for (int k = 0; k < D; ++k) w[k] = j == 0 ? m[k].x : j == 1 ? m[k].y : j == 2 ? m[k].z : m[k].w;
+        for (int k = 0; k < D; ++k) w[k] = j == 0 ? in.m[k].x : j == 1 ? in.m[k].y : j == 2 ? in.m[k].z : in.m[k].w;
         vn_word<D, MATCH, DECIDE>(chw, w, o, dec, tab, RS, TRS, lane4, match_off);
         if (DECIDE) {
             if (j == 0) dec4.x = dec; else if (j == 1) dec4.y = dec; else if (j == 2) dec4.z = dec; else dec4.w = dec;
@@ -332,16 +357,26 @@ __device__ __forceinline__ void vn_node(const IbArgs& a, const uint8_t* tab, int
         }
     }
     if (DECIDE) {
-        *reinterpret_cast<uint4*>(a.out + (uint64_t)(uint32_t)v * a.pitch + col) = dec4;
+        *reinterpret_cast<uint4*>(a.out + (uint64_t)(uint32_t)x.v * a.pitch + col) = dec4;
     } else {
 #pragma unroll
-        for (int k = 0; k < D; ++k) *reinterpret_cast<uint4*>(a.msg + (uint64_t)(uint32_t)rows[k] * a.pitch + col) = r[k];
+        for (int k = 0; k < D; ++k) *reinterpret_cast<uint4*>(a.msg + (uint64_t)(uint32_t)x.rows[k] * a.pitch + col) = r[k];
     }
 }
 
+// Software pipeline over the node list of one degree class.  The variable-node phase is a
+// gather (row indices through sv[] and tv[]: three dependent loads before the first message
+// byte arrives), so both the indices (two nodes ahead) and -- for small degrees -- the messages
+// (one node ahead, ping-pong register buffers) are fetched while the current node is computed.
+// Every message row belongs to exactly one variable node, so prefetching the next node's rows
+// before the current node's results are stored cannot alias.
 template <int D, bool MATCH, bool DECIDE>
 __device__ __forceinline__ void vn_loop(const IbArgs& a, const uint8_t* tab, const int* __restrict__ nodes, int n_nodes)
 {
+    // Measured on B200, (3,6) n=8000, B=16384: message double-buffering costs 16 registers per
+    // thread (80 instead of 64 -> 3 instead of 4 CTAs per SM) and is slower (0.183 ms vs 0.172 ms per
+    // launch) than index prefetch alone, so it is compiled out.
+    constexpr bool kPrefetchMsgs = false;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lane4 = lane * 4, RS = 128u * a.W, TRS = RS * a.T;
     const int tile = (blockIdx.y << a.tpc_log2) + (warp & ((1 << a.tpc_log2) - 1));
@@ -350,33 +385,38 @@ __device__ __forceinline__ void vn_loop(const IbArgs& a, const uint8_t* tab, con
     const uint32_t col = ((uint32_t)tile * 32u + lane) * 16u;
     if (tile >= a.tiles || col >= a.pitch) return;
     int i = blockIdx.x * nps + (warp >> a.tpc_log2);
-    int v = 0, rows[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) rows[k] = 0;
-    if (i < n_nodes) {
-        v = nodes[i];
-        const int s = a.sv[v];
-#pragma unroll
-        for (int k = 0; k < D; ++k) rows[k] = a.tv[s + k];
-    }
-    while (i < n_nodes) {
-        // the next node's (variable, slot, row) indices -- a chain of three dependent loads -- are
-        // fetched while this node is being computed
-        const int i2 = i + stride;
-        int v2 = 0, rows2[D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) rows2[k] = 0;
-        if (i2 < n_nodes) {
-            v2 = nodes[i2];
-            const int s2 = a.sv[v2];
-#pragma unroll
-            for (int k = 0; k < D; ++k) rows2[k] = a.tv[s2 + k];
+    VnIdx<D> cur, nxt, nn;
+    vn_load_idx<D>(a, nodes, n_nodes, i, cur);
+    vn_load_idx<D>(a, nodes, n_nodes, i + stride, nxt);
+    int inn = i + 2 * stride;
+    if (kPrefetchMsgs) {
+        VnIn<D> bufA, bufB;
+        vn_load_msgs<D>(a, cur, col, bufA);
+        while (cur.ok) {
+            vn_load_msgs<D>(a, nxt, col, bufB);
+            vn_load_idx<D>(a, nodes, n_nodes, inn, nn);
+            inn += stride;
+            vn_compute_store<D, MATCH, DECIDE>(a, tab, cur, bufA, col, lane4, RS, TRS);
+            cur = nxt;
+            nxt = nn;
+            if (!cur.ok) break;
+            vn_load_msgs<D>(a, nxt, col, bufA);
+            vn_load_idx<D>(a, nodes, n_nodes, inn, nn);
+            inn += stride;
+            vn_compute_store<D, MATCH, DECIDE>(a, tab, cur, bufB, col, lane4, RS, TRS);
+            cur = nxt;
+            nxt = nn;
         }
-        vn_node<D, MATCH, DECIDE>(a, tab, v, rows, col, lane4, RS, TRS);
-        i = i2;
-        v = v2;
-#pragma unroll
-        for (int k = 0; k < D; ++k) rows[k] = rows2[k];
+    } else {
+        while (cur.ok) {
+            VnIn<D> buf;
+            vn_load_msgs<D>(a, cur, col, buf);
+            vn_load_idx<D>(a, nodes, n_nodes, inn, nn);
+            inn += stride;
+            vn_compute_store<D, MATCH, DECIDE>(a, tab, cur, buf, col, lane4, RS, TRS);
+            cur = nxt;
+            nxt = nn;
+        }
     }
 }
 
@@ -393,7 +433,7 @@ __device__ __forceinline__ int executed_passes(const IbArgs& a)
 
 // varnode_update (kernels_template_irreg.cl:103-179); one instantiation per variable-node degree.
 template <int D, bool MATCH>
-__global__ void __launch_bounds__(kThreads, (D <= 4 ? 4 : (D <= 8 ? 3 : 2)))
+__global__ void __launch_bounds__(kThreads, (D <= 4 ? 4 : (D <= 8 ? 3 : 2)))   // 5 CTAs/SM (<= 51 regs) spills and is 1.5x slower
 ib_vn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 {
     extern __shared__ __align__(16) uint32_t s_tab[];
