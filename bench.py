@@ -7,7 +7,8 @@
 Workload (BASELINE.json configs[0], the configuration the metric is quoted on): regular (3,6)
 LDPC code n=8000, R=1/2, BPSK/AWGN, IB decoder |T|=16, i_max=50, early termination off,
 B=16384 frames per GPU and step, channel cluster indices drawn by the inversion method from the
-|T|=16 quantizer at Eb/N0 = 1.2 dB (all-zero codeword), exactly like quantize_direct_OpenCL.
+|T|=16 quantizer at Eb/N0 = 1.6 dB (all-zero codeword), exactly like quantize_direct_OpenCL;
+IB tables designed at 1.2 dB by the in-repo discrete density evolution.
 A "step" = decode one batch + count bit/frame errors (+ all-reduce of the 4 counters for N>1).
 One JSON line is printed by rank 0.
 """
@@ -37,7 +38,7 @@ def workload(name):
     from informationbottleneckdecodingldpc_b200 import codes
     if name == "c1":
         return dict(name="(3,6) n=8000 R=0.5 IB |T|=16 i_max=50 ET off", H=codes.regular_random(8000, 3, 6, seed=SEED),
-                    irregular=False, B=16384, ebn0=1.2)
+                    irregular=False, B=16384, ebn0=1.6, design_ebn0=1.2)
     if name == "wlan":
         return dict(name="802.11n n=1296 R=0.5 IB |T|=16 i_max=50 ET off, message alignment", H=codes.wlan_80211n(54),
                     irregular=True, B=100096, ebn0=1.5)
@@ -114,11 +115,19 @@ class ClockSampler:
 
 
 def make_tables(wl):
+    """Regular code: IB tables designed by discrete density evolution (decoder_config_generation.py,
+    the in-repo stand-in for the reference's design chain).  Irregular codes: deterministic
+    min-sum-like tables + identity matching (no irregular design tool yet); the kernels' work does not
+    depend on the table contents."""
     from informationbottleneckdecodingldpc_b200 import graph, luts
     t = graph.edge_tables(wl["H"])
-    tb = luts.minsum_like_tables(T, t.d_c_max, t.d_v_max, IMAX)
     if not wl["irregular"]:
-        tb.matching_vector_checknode = tb.matching_vector_varnode = None
+        from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_regular_config
+        tb, _ = generate_regular_config(wl["design_ebn0"], t.d_v_max, t.d_c_max, T, IMAX)
+        wl["tables"] = "IB tables, discrete density evolution at Eb/N0 = %.1f dB (in-repo design)" % wl["design_ebn0"]
+    else:
+        tb = luts.minsum_like_tables(T, t.d_c_max, t.d_v_max, IMAX)
+        wl["tables"] = "min-sum-like LUTs + identity matching (deterministic)"
     return t, tb
 
 
@@ -370,7 +379,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl["name"], "frames_per_gpu_per_step": B, "n_var": N, "n_chk": M, "n_edge": E,
-                       "info_bits": K_info, "i_max": IMAX, "EbN0_dB": wl["ebn0"], "tables": "min-sum-like LUTs (deterministic)",
+                       "info_bits": K_info, "i_max": IMAX, "EbN0_dB": wl["ebn0"], "tables": wl.get("tables"),
                        "l2": "inputs_larger_than_L2 (message array %.0f MB)" % (E * B / 1e6), "parallelism": f"frames sharded x{world}",
                        "fast_path": bool(decodi.info()[0])},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,

@@ -25,6 +25,32 @@ def _pair_gain(a, b):
     return 2.0 * (ga + gb)
 
 
+def _dp_bounds(a_mass: np.ndarray, b_mass: np.ndarray, K: int):
+    """Optimal split of `n` LLR-sorted symbols (joint masses a = p(x=0,y), b = p(x=1,y)) into K
+    contiguous clusters maximising the sum of `_pair_gain`.  Returns the K+1 boundaries
+    0 = b_0 < ... < b_K = n.  Vectorised over (i, j): O(K n^2) numpy work."""
+    n = a_mass.shape[0]
+    ca = np.concatenate(([0.0], np.cumsum(a_mass)))
+    cb = np.concatenate(([0.0], np.cumsum(b_mass)))
+    ii, jj = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    gain = np.where(ii < jj, _pair_gain(np.maximum(ca[None, :] - ca[:, None], 0.0),
+                                        np.maximum(cb[None, :] - cb[:, None], 0.0)), -np.inf)
+    best = np.full(n + 1, -np.inf)
+    best[0] = 0.0
+    args = []
+    for _k in range(K):
+        cand = best[:, None] + gain                 # cand[i, j]: last cluster = symbols [i, j)
+        arg = np.argmax(cand, axis=0)
+        best = cand[arg, np.arange(n + 1)]
+        args.append(arg)
+    bounds = [n]
+    j = n
+    for k in range(K - 1, -1, -1):
+        j = int(args[k][j])
+        bounds.append(j)
+    return bounds[::-1]
+
+
 def symmetric_mi_quantizer(p_xy: np.ndarray, cardinality_T: int):
     """p_xy: (Y, 2) joint pmf of the fine channel output y (increasing LLR order, mirror
     symmetric: p(y_i, x=0) = p(y_{Y-1-i}, x=1)) and the bit x.  Returns
@@ -35,26 +61,7 @@ def symmetric_mi_quantizer(p_xy: np.ndarray, cardinality_T: int):
         raise ValueError("cardinality_Y and cardinality_T must be even")
     half, K = Y // 2, T // 2
     pos = p_xy[half:, :]                          # y > 0 side, bins 0..half-1
-    ca = np.concatenate(([0.0], np.cumsum(pos[:, 0])))
-    cb = np.concatenate(([0.0], np.cumsum(pos[:, 1])))
-    # best[k][j]: best gain of splitting bins [0, j) into k clusters
-    best = np.full((K + 1, half + 1), -np.inf)
-    arg = np.zeros((K + 1, half + 1), dtype=np.int64)
-    best[0, 0] = 0.0
-    j_idx = np.arange(half + 1)
-    for k in range(1, K + 1):
-        for j in range(k, half + 1):
-            i = j_idx[k - 1:j]                     # last cluster = bins [i, j)
-            g = best[k - 1, i] + _pair_gain(ca[j] - ca[i], cb[j] - cb[i])
-            m = int(np.argmax(g))
-            best[k, j] = g[m]
-            arg[k, j] = i[m]
-    bounds = [half]
-    j = half
-    for k in range(K, 0, -1):
-        j = int(arg[k, j])
-        bounds.append(j)
-    bounds = bounds[::-1]                          # 0 = b_0 < b_1 < ... < b_K = half
+    bounds = _dp_bounds(pos[:, 0], pos[:, 1], K)   # 0 = b_0 < b_1 < ... < b_K = half
     cluster = np.empty(Y, dtype=np.int64)
     for k in range(K):
         cluster[half + bounds[k]: half + bounds[k + 1]] = K + k
@@ -65,3 +72,104 @@ def symmetric_mi_quantizer(p_xy: np.ndarray, cardinality_T: int):
     p_t = p_xt.sum(1)
     p_x_given_t = p_xt / p_t[:, None]
     return p_t_given_y, p_x_given_t, p_t
+
+
+# ---------------------------------------------------------------------------------------------
+# Discrete density evolution for regular codes: designs the look-up tables of the IB decoder.
+#
+# Replaces the design chain of the reference (Discrete_LDPC_decoding/Discrete_Density_Evolution.py
+# + ib_base's lin_sym_sIB, driven by Regular_LDPC_Decoding/BPSK/decoder_config_generation.py) with
+# the deterministic max-MI quantizer above.  The table LAYOUT is the reference's
+# (Discrete_Density_Evolution.py:299-344); the table CONTENTS differ from
+# the authors' sequential-IB tables (random restarts, no artefact to pin against): parity unpinned.
+# ---------------------------------------------------------------------------------------------
+_P_MIN = 1e-15
+
+
+def _guard(p):
+    """numerical guard of the reference (Discrete_Density_Evolution.py:434-440)."""
+    p = np.clip(p, _P_MIN, 0.5 - _P_MIN)
+    return p / p.sum()
+
+
+def quantize_joint(p_xy: np.ndarray, T: int):
+    """Mutual-information-maximising, mirror-symmetric quantizer of an arbitrary-order joint pmf
+    p_xy (n, 2) [columns x=0, x=1].  Returns (labels (n,), p_xt (T, 2)): cluster index per row,
+    clusters contiguous in LLR, numbered by increasing LLR log p(x=0|t)/p(x=1|t)."""
+    n = p_xy.shape[0]
+    if n % 2 or T % 2:
+        raise ValueError("even sizes expected")
+    llr = np.log(p_xy[:, 0]) - np.log(p_xy[:, 1])
+    order = np.argsort(llr, kind="stable")
+    half, K = n // 2, T // 2
+    pos = p_xy[order[half:], :]                       # upper half in increasing LLR
+    if half <= K:                                     # fewer symbols than clusters: one each
+        bounds = list(range(half + 1)) + [half] * (K - half)
+    else:
+        bounds = _dp_bounds(pos[:, 0], pos[:, 1], K)
+    lab_sorted = np.empty(n, dtype=np.int64)
+    for k in range(K):
+        lab_sorted[half + bounds[k]: half + bounds[k + 1]] = K + k
+    lab_sorted[:half] = T - 1 - lab_sorted[half:][::-1]
+    labels = np.empty(n, dtype=np.int64)
+    labels[order] = lab_sorted
+    p_xt = np.zeros((T, 2))
+    np.add.at(p_xt, labels, p_xy)
+    return labels, p_xt
+
+
+def _cn_joint(p_t, p_y):
+    """p(x, [t, y]) of a partial check-node operation, x = b_t xor b_y; row index t*|Y| + y
+    (Discrete_Density_Evolution.py:346-386)."""
+    same = p_t[:, None, 0] * p_y[None, :, 0] + p_t[:, None, 1] * p_y[None, :, 1]
+    diff = p_t[:, None, 0] * p_y[None, :, 1] + p_t[:, None, 1] * p_y[None, :, 0]
+    return np.stack([same.reshape(-1), diff.reshape(-1)], axis=1)
+
+
+def _vn_joint(p_t, p_y):
+    """p(x, [t, y]) of a partial variable-node operation (both observe the same bit); row index
+    t*|Y| + y (Discrete_Density_Evolution.py:390-430)."""
+    j = 2.0 * p_t[:, None, :] * p_y[None, :, :]
+    return j.reshape(-1, 2)
+
+
+def _mi(p_xt):
+    p = p_xt / p_xt.sum()
+    px, pt = p.sum(0), p.sum(1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return float(np.nansum(p * np.log2(p / (pt[:, None] * px[None, :]))))
+
+
+def design_regular_ib_decoder(p_x_and_t_channel: np.ndarray, d_v: int, d_c: int, T: int, imax: int):
+    """Discrete density evolution for a (d_v, d_c)-regular code.
+
+    p_x_and_t_channel: (Tc, 2) joint pmf of the channel cluster and the bit, e.g.
+    ``AWGN_Channel_Quantizer.p_x_and_t`` (Tc must equal T, as in every script of the reference).
+    Returns (Trellis_checknodevector_a, Trellis_varnodevector_a, mi_vn_out[imax]) in the reference
+    layout: CN ``[Tc^2 | (d_c-3) x Tc*T | (imax-1) x (d_c-2) x T^2]``, VN ``imax x [Tc*T | (d_v-1) x T^2]``."""
+    p_ch = np.asarray(p_x_and_t_channel, dtype=np.float64)
+    p_ch = p_ch / p_ch.sum()
+    Tc = p_ch.shape[0]
+    if Tc != T:
+        raise ValueError("cardinality_T_channel must equal cardinality_T_decoder_ops")
+    cn_vec, vn_vec, mi_hist = [], [], []
+    vn_msg = p_ch
+    for _it in range(imax):
+        p_t = vn_msg
+        for _l in range(d_c - 2):
+            lab, p_t = quantize_joint(_guard(_cn_joint(p_t, vn_msg)), T)
+            cn_vec.append(lab)
+        cn_out = p_t / p_t.sum()
+        p_t = p_ch
+        nxt = None
+        for l in range(d_v):
+            lab, p_t = quantize_joint(_guard(_vn_joint(p_t, cn_out)), T)
+            p_t = p_t / p_t.sum()
+            vn_vec.append(lab)
+            if l == d_v - 2:
+                nxt = p_t                          # extrinsic message: channel + d_v-1 check messages
+        vn_msg = nxt if nxt is not None else p_t
+        mi_hist.append(_mi(vn_msg))
+    cn = np.concatenate(cn_vec).astype(np.float64) if cn_vec else np.zeros(0)
+    vn = np.concatenate(vn_vec).astype(np.float64)
+    return cn, vn, np.array(mi_hist)

@@ -193,6 +193,28 @@ def test_ib_full_size_properties(gpu):
     assert np.array_equal(full[:, 5000:5016], ref)
 
 
+def test_ib_designed_tables_decode_the_all_zero_codeword(gpu):
+    """End-to-end sanity with tables from the in-repo design tool: quantizer -> direct sampling on the
+    device -> IB decoder; at Eb/N0 = 1.7 dB the (3,6) n=8000 code must decode every frame, stop early,
+    and agree bit for bit (and in i_num) with the oracle on the same device-drawn inputs."""
+    import informationbottleneckdecodingldpc_b200 as pkg
+    from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_regular_config
+    from oracle import oracle
+    H = codes.regular_random(8000, 3, 6)
+    tb, _ = generate_regular_config(1.2, 3, 6, 16, 50)
+    q = pkg.AWGN_Channel_Quantizer(10 ** (-1.7 / 10) / (2 * 0.5), 3, 16, 2000)
+    q.init_OpenCL_quanti(8000, 48, return_buffer_only=True)
+    dec = pkg.Discrete_LDPC_Decoder_class(H, 50, 16, 16, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a, 48)
+    dec.init_OpenCL_decoding(48, q.context)
+    rec = q.quantize_direct_OpenCL(8000, 48)
+    out = dec.decode_OpenCL(rec, buffer_in=True, return_buffer=True)
+    assert dec.return_errors_all_zero(out) == 0
+    assert 5 < dec.last_i_num < 50
+    ref, i_num = oracle.ib_decode(graph.edge_tables(H), rec.get(), T=16, imax=50, cn_lut=tb.Trellis_checknodevector_a,
+                                  vn_lut=tb.Trellis_varnodevector_a, early=True)
+    assert np.array_equal(out.get(), ref) and dec.last_i_num == i_num
+
+
 def test_early_termination_is_batch_granular(gpu):
     """One noisy frame keeps the whole batch iterating (reference stop rule, decoder.py:273)."""
     g = load_golden("ib_c1_minsumlut_imax50_et")

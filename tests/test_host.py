@@ -170,3 +170,34 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
                 assert "ldpc_oracle" not in txt and "libref_kernels" not in txt, f
+
+
+def test_ib_design_tool_layout_and_convergence():
+    """In-repo replacement of the reference's design chain (decoder_config_generation.py): table
+    lengths of SURVEY Appendix B, entries in [0,T), mutual information non-decreasing over the
+    iterations and reaching ~1 bit above the decoder's threshold; a mirror-symmetric design
+    (t -> T-1-t under x -> 1-x), which every hard decision of the code base relies on."""
+    from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_regular_config
+    tb, ex = generate_regular_config(1.4, 3, 6, 16, 30)
+    cn, vn = tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a
+    assert cn.size == luts.cn_lut_len(16, 16, 6, 30) and vn.size == luts.vn_lut_len(16, 16, 3, 30)
+    assert cn.min() >= 0 and cn.max() < 16 and vn.min() >= 0 and vn.max() < 16
+    mi = ex["ext_mi_varnode_in_iter"]
+    assert np.all(np.diff(mi) > -1e-9) and mi[-1] > 0.999
+    T = 16
+    st = vn[:T * T].reshape(T, T).astype(int)                  # VN stage 0 of iteration 0: [ch][m]
+    assert np.array_equal(st, T - 1 - st[::-1, ::-1])
+    c0 = cn[:T * T].reshape(T, T).astype(int)                  # CN stage 0: flipping one input flips the output
+    assert np.array_equal(c0, T - 1 - c0[::-1, :])
+    # below threshold the evolution stalls (no free lunch)
+    _, ex2 = generate_regular_config(0.6, 3, 6, 16, 30)
+    assert ex2["ext_mi_varnode_in_iter"][-1] < 0.9
+
+
+def test_decoder_config_cli_writes_reference_named_pickle(tmp_path, monkeypatch):
+    from informationbottleneckdecodingldpc_b200 import decoder_config_generation as g
+    monkeypatch.chdir(tmp_path)
+    g.main(["--ebn0", "1.2", "--imax", "3"])
+    d = luts.load_config(str(tmp_path / "decoder_config_EbN0_gen_1.2_16.pkl"))
+    assert int(d["imax"]) == 3 and int(d["cardinality_T_decoder_ops"]) == 16
+    assert d["Trellis_checknodevector_a"].size == luts.cn_lut_len(16, 16, 6, 3)
