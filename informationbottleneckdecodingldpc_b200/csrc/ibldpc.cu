@@ -432,9 +432,23 @@ int decode_llr_padded(ibldpc_decoder* h, Workspace& w, const F* ch, long long pi
         }
         return IBLDPC_OK;
     };
+    // low-batch min-sum: lanes = edges (warp-shuffle min/argmin), see llr_cn_minsum_shfl_kernel
+    const bool low_batch = (ALGO == 0) && (B <= 8) && (h->dc_max <= 32) && !getenv("IBLDPC_NO_SHFL");
+    int seg_log2 = 1;
+    while ((1 << seg_log2) < h->dc_max) ++seg_log2;
     auto run_cn = [&](int it) -> int {
         LlrArgs b = a;
         b.it = it;
+        if (low_batch) {
+            LlrShflKernel k = llr_cn_minsum_shfl_kernel_for(sizeof(F) == 8);
+            const long long per_warp = 32 >> seg_log2;
+            int grid;
+            int r = grid_for(h, (const void*)k, 0, ((long long)h->M + per_warp - 1) / per_warp, &grid);
+            if (r) return r;
+            k<<<grid, kThreads, 0, st>>>(b, seg_log2);
+            h->last_launches++;
+            return IBLDPC_OK;
+        }
         for (auto& c : h->cn_classes) {
             LlrNodeKernel k = llr_cn_kernel_for(sizeof(F) == 8, ALGO, c.degree);
             int grid;

@@ -9,6 +9,7 @@ namespace ibldpc {
 using NodeKernel = void (*)(IbArgs, const int*, int);
 using LlrNodeKernel = void (*)(LlrArgs, const int*, int);
 using LlrSynKernel = void (*)(LlrArgs);
+using LlrShflKernel = void (*)(LlrArgs, int);
 
 NodeKernel cn_fast_kernel_for(int d, bool match, bool early);
 NodeKernel vn_fast_kernel_for(int d, bool decide, bool match);
@@ -21,4 +22,7 @@ LlrNodeKernel llr_cn_kernel_f64(int algo, int d);
 LlrNodeKernel llr_vn_kernel_f64(int mode, int d);
 LlrSynKernel llr_syndrome_kernel_f32();
 LlrSynKernel llr_syndrome_kernel_f64();
+LlrShflKernel llr_cn_minsum_shfl_kernel_for(bool f64);
+LlrShflKernel llr_cn_minsum_shfl_kernel_f32();
+LlrShflKernel llr_cn_minsum_shfl_kernel_f64();
 }  // namespace ibldpc

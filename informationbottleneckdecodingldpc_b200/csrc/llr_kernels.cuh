@@ -63,7 +63,8 @@ __device__ __forceinline__ float boxplus(float a, float b)
 {
     const float s = fminf(fabsf(a), fabsf(b));
     const float sg = ((a < 0.f) != (b < 0.f)) ? -s : s;
-    const float bp = sg + log1pf(__expf(-fabsf(a + b))) - log1pf(__expf(-fabsf(a - b)));
+    // MUFU-based: e^-x in (0,1], so 1 + e^-x in (1,2] where __logf is accurate to ~1e-7 absolute
+    const float bp = sg + __logf(1.0f + __expf(-fabsf(a + b))) - __logf(1.0f + __expf(-fabsf(a - b)));
     return clip150((a == 0.f || b == 0.f) ? 0.f : bp);
 }
 
@@ -104,6 +105,24 @@ __device__ __forceinline__ void llr_cn_compute(const Vec<F>* m, Vec<F>* o, int d
                 o[k].v[e] = r;
             }
         }
+    } else if (sizeof(F) == 4 && dd >= 4) {
+        // fp32 fast path: forward/backward box-plus, 3(d-2) operations instead of
+        // 2(d-2) + (d-1)(d-2)/2.  Box-plus is associative in exact arithmetic; the result differs
+        // from the reference's sequential order only by fp32 rounding (covered by the fp32 tolerance).
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            F fw[D > 0 ? D : kMaxGenericDeg], bw[D > 0 ? D : kMaxGenericDeg];
+            fw[0] = m[0].v[e];
+#pragma unroll
+            for (int k = 1; k <= dd - 2; ++k) fw[k] = boxplus(m[k].v[e], fw[k - 1]);
+            bw[dd - 1] = m[dd - 1].v[e];
+#pragma unroll
+            for (int k = dd - 2; k >= 1; --k) bw[k] = boxplus(m[k].v[e], bw[k + 1]);
+            o[0].v[e] = clip150(bw[1]);
+            o[dd - 1].v[e] = clip150(fw[dd - 2]);
+#pragma unroll
+            for (int k = 1; k <= dd - 2; ++k) o[k].v[e] = clip150(boxplus(fw[k - 1], bw[k + 1]));
+        }
     } else {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
@@ -117,6 +136,64 @@ __device__ __forceinline__ void llr_cn_compute(const Vec<F>* m, Vec<F>* o, int d
 #pragma unroll
                 for (int k = (wo == 0 ? 2 : wo + 1); k < dd; ++k) t = boxplus(m[k].v[e], t);
                 o[wo].v[e] = clip150(t);
+            }
+        }
+    }
+}
+
+// Low-batch min-sum check-node kernel (the reference runs DVB-S2 / WLAN min-sum with msg_at_time = 2,
+// Irregular_LDPC_Decoding/DVB-S2/BER_simulation_OpenCL_min_sum.py): with only a handful of frames the
+// frame-per-lane mapping leaves most lanes idle, so here the lanes of a warp are the EDGES of
+// 32/seg check nodes (seg = power of two >= d_c_max): min / argmin / second min by warp-shuffle
+// butterflies inside each seg-lane segment, the sign parity by a warp ballot.  Same results as
+// checknode_update_minsum (kernels_min_and_BP.cl:126-167): the first minimum (lowest slot) wins ties.
+template <typename F>
+__global__ void __launch_bounds__(kThreads) llr_cn_minsum_shfl_kernel(LlrArgs a, int seg_log2)
+{
+    if (a.early && a.it >= 1 && a.flags[a.it - 1] == 0) return;
+    const int seg = 1 << seg_log2;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane >> seg_log2, e = lane & (seg - 1);
+    const int per_warp = 32 >> seg_log2;
+    const long long gwarp = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+    const F* cin = static_cast<const F*>(a.cin);
+    F* vin = static_cast<F*>(a.vin);
+    const F inf = sizeof(F) == 4 ? F(3.0e38f) : F(1e300);
+    const unsigned segmask = (seg == 32 ? 0xffffffffu : ((1u << seg) - 1u)) << (sub * seg);
+    for (long long base = gwarp * per_warp; base < a.n_chk; base += nwarps * per_warp) {
+        const int c = (int)base + sub;
+        const int d = c < a.n_chk ? a.deg_c[c] : 0;
+        const bool valid = e < d;
+        const int slot = valid ? a.sc[c] + e : 0;
+        const int dst = valid ? a.tc[slot] : 0;
+        for (int f = 0; f < a.B; ++f) {
+            const F x = valid ? cin[(long long)slot * a.pitch + f] : inf;
+            const F ax = x < F(0) ? -x : x;
+            const unsigned negb = __ballot_sync(0xffffffffu, valid && x < F(0)) & segmask;
+            F m1 = ax;
+            int idx = e;
+            for (int off = seg >> 1; off > 0; off >>= 1) {
+                const F om = __shfl_xor_sync(0xffffffffu, m1, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+                if (om < m1 || (om == m1 && oi < idx)) { m1 = om; idx = oi; }
+            }
+            F m2 = (e == idx) ? inf : ax;
+            for (int off = seg >> 1; off > 0; off >>= 1) {
+                const F om = __shfl_xor_sync(0xffffffffu, m2, off);
+                m2 = om < m2 ? om : m2;
+            }
+            const F other = __shfl_xor_sync(0xffffffffu, x, 1);   // degree-2 checks forward the other input as is
+            if (valid) {
+                F r;
+                if (d == 2) {
+                    r = other;
+                } else {
+                    const F mag = (e == idx) ? m2 : m1;
+                    const int sneg = (__popc(negb) & 1) ^ (x < F(0) ? 1 : 0);
+                    r = mag == F(0) ? F(0) : (sneg ? -mag : mag);
+                }
+                vin[(long long)dst * a.pitch + f] = r;
             }
         }
     }

@@ -337,6 +337,31 @@ def test_llr_float32_fast_path_statistics(gpu):
         print(algo, "fp32 vs f64 frame agreement", frames_equal.mean(), "BER", ber_got, ber_ref)
 
 
+@pytest.mark.parametrize("B", [1, 2, 5, 8])
+def test_minsum_low_batch_warp_shuffle_path(gpu, B, monkeypatch):
+    """msg_at_time = 2 (the reference's DVB-S2 / WLAN min-sum drivers): the edge-per-lane warp-shuffle
+    check-node kernel must give the same float64 LLRs, bit for bit, as the oracle and as the
+    frame-per-lane kernel."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    from oracle import oracle
+    for H in (codes.wlan_80211n(54), codes.dvbs2_like_half_rate(6480, q_groups=36), codes.regular_random(96, 2, 4, seed=3)):
+        t = graph.edge_tables(H)
+        rng = np.random.Generator(np.random.PCG64(B))
+        vals = np.concatenate([-np.sort(np.abs(rng.normal(0, 3, 8)))[::-1], np.sort(np.abs(rng.normal(0, 3, 8)))])
+        ch = vals[rng.integers(0, 16, size=(t.n_var, B))]
+        ch[3, 0] = 0.0
+        ref, i_ref = oracle.llr_decode(t, ch, algo="minsum", imax=9, early=True)
+        for no_shfl in (False, True):
+            if no_shfl:
+                monkeypatch.setenv("IBLDPC_NO_SHFL", "1")
+            else:
+                monkeypatch.delenv("IBLDPC_NO_SHFL", raising=False)
+            dec = pkg.Min_Sum_Decoder_class_irregular(H, 9, 16, B)
+            got = dec.decode_OpenCL_min_sum(torch.from_numpy(ch).cuda(), buffer_in=True, return_buffer=True).get()
+            assert np.array_equal(got, ref) and dec.last_i_num == i_ref
+
+
 # ---------------------------------------------------------------------------------- quantizer
 def test_quantizer_golden(gpu):
     import torch
