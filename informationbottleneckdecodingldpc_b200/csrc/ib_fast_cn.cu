@@ -17,9 +17,14 @@ NodeKernel cn_fast_kernel_sel(int d)
     default: return nullptr;
     }
 }
+// `match` = explicit matching look-up, needed by degree-2 checks only (all other degrees get the
+// matching folded into their last-stage table at staging time, see stage_tables).
 NodeKernel cn_fast_kernel_for(int d, bool match, bool early)
 {
-    return match ? (early ? cn_fast_kernel_sel<true, true>(d) : cn_fast_kernel_sel<true, false>(d))
-                 : (early ? cn_fast_kernel_sel<false, true>(d) : cn_fast_kernel_sel<false, false>(d));
+    if (match) {
+        if (d != 2) return nullptr;
+        return early ? (NodeKernel)ib_cn_fast_kernel<2, true, true> : (NodeKernel)ib_cn_fast_kernel<2, true, false>;
+    }
+    return early ? cn_fast_kernel_sel<false, true>(d) : cn_fast_kernel_sel<false, false>(d);
 }
 }  // namespace ibldpc

@@ -13,7 +13,8 @@ NodeKernel vn_fast_kernel_sel(int d)
 }
 NodeKernel vn_fast_kernel_for(int d, bool decide, bool match)
 {
-    if (!decide) return match ? vn_fast_kernel_sel<true>(d) : vn_fast_kernel_sel<false>(d);
+    (void)match;   // message alignment is folded into the staged tables: one instantiation serves both
+    if (!decide) return vn_fast_kernel_sel<false>(d);
 #define VNK(D) case D: return ib_out_fast_kernel<D>;
     switch (d) {
         VNK(1) VNK(2) VNK(3) VNK(4) VNK(5) VNK(6) VNK(7) VNK(8) VNK(9) VNK(10) VNK(11) VNK(12)

@@ -99,6 +99,12 @@ __device__ __forceinline__ void stage_tables(uint32_t* s_tab, const IbArgs& a, c
     if (a.match != nullptr)
         for (int i = threadIdx.x; i < a.dmax_match * a.T; i += kThreads) smatch[i] = a.match[i];
     __syncthreads();
+    // Message alignment (MATCH, kernels_template_irreg.cl:84-96,162-173,233-241) is folded into the
+    // tables: within the kernel of degree class d the last stage (d-3 for a check, d-2 for a variable
+    // node) only ever produces final edge outputs, so its entries are passed through the matching row
+    // of degree d here and the kernels need no separate matching look-up.  Only degree-2 checks have
+    // no stage at all and keep an explicit matching column (col == nst == 0).
+    const bool fold = a.match != nullptr && a.nst >= 1;
     for (int rw = warp; rw < total; rw += kWarpsPerCta) {
         const int r = rw / a.W, w = rw - r * a.W;
         const int m = r / a.T, t = r - m * a.T;
@@ -108,8 +114,11 @@ __device__ __forceinline__ void stage_tables(uint32_t* s_tab, const IbArgs& a, c
             const int col = 4 * w + q;
             uint32_t e = 0;
             if (col < a.nst) {
-                if (r < TT) e = scratch[col * TT + t * a.T + m];
-            } else if (col == a.nst && a.match != nullptr) {
+                if (r < TT) {
+                    e = scratch[col * TT + t * a.T + m];
+                    if (fold && col == a.nst - 1) e = smatch[(a.dmax_match - 1) * a.T + e];
+                }
+            } else if (col == a.nst && a.match != nullptr && !fold) {
                 if (m < a.dmax_match) e = smatch[m * a.T + t];
             }
             v |= e << (8 * q);

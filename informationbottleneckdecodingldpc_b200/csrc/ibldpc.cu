@@ -265,11 +265,12 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
             if (r) return r;
             for (auto& c : h->cn_classes) {
                 b.nst = c.degree - 2;
-                b.W = words(b.nst + (h->match ? 1 : 0));
-                b.nrows = std::max(TT, h->match ? c.degree * T : 0);
+                const bool explicit_match = h->match && b.nst == 0;   // matching is folded into the last stage otherwise
+                b.W = words(b.nst + (explicit_match ? 1 : 0));
+                b.nrows = std::max(TT, explicit_match ? c.degree * T : 0);
                 if (h->match) b.dmax_match = c.degree;
                 const int smem = b.nrows * b.W * 128 + stage_scratch_bytes(b.nst, T, h->match ? b.dmax_match : 0);
-                NodeKernel k = cn_fast_kernel_for(c.degree, h->match, early != 0);
+                NodeKernel k = cn_fast_kernel_for(c.degree, explicit_match, early != 0);
                 int grid;
                 r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid);
                 if (r) return r;
@@ -292,11 +293,11 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
             for (auto& c : h->vn_classes) {
                 const bool m = b.match != nullptr;
                 b.nst = decide ? c.degree : c.degree - 1;
-                b.W = words(b.nst + (m ? 1 : 0));
-                b.nrows = std::max(TT, m ? c.degree * T : 0);
+                b.W = words(b.nst);                   // matching is folded into the last stage (stage_tables)
+                b.nrows = TT;
                 b.dmax_match = m ? c.degree : 0;
                 const int smem = b.nrows * b.W * 128 + stage_scratch_bytes(b.nst, T, b.dmax_match);
-                NodeKernel k = vn_fast_kernel_for(c.degree, decide, h->match);
+                NodeKernel k = vn_fast_kernel_for(c.degree, decide, false);
                 int grid;
                 r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid);
                 if (r) return r;
