@@ -67,6 +67,10 @@ struct IbArgs {
     const uint8_t* __restrict__ match_all;
     int DC, DV;
     long long vn_it_stride;  // fast path, output kernel: bytes between two iterations' VN tables
+    // check-node "tail pair" table (see cn_word_pair): compact [T*T rows (a*T+b)][8 bytes] of this
+    // launch, and the byte offset of its expanded copy inside the dynamic shared memory
+    const uint8_t* __restrict__ pair;
+    uint32_t pair_off;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -173,7 +177,54 @@ __device__ __forceinline__ void cn_word(const uint32_t (&w)[D], uint32_t (&o)[D]
     }
 }
 
-template <int D, bool MATCH, bool EARLY>
+// Tail-pair variant (D >= 4).  All outputs w <= D-3 end with the same two look-ups
+//   out_w = L_{D-3}( L_{D-4}(x_w, m_{D-2}), m_{D-1} ),
+// which for one frame is a fixed function G of x_w alone (16 values -> 16 nibbles = 64 bits).
+// The host composes G for every (m_{D-2}, m_{D-1}) pair (ibldpc_set_luts); the kernel fetches
+// the 64-bit row once per frame with one LDS.64 and evaluates the D-2 applications with ALU
+// nibble selects.  Shared-memory wavefronts per check and frame drop from
+// 2(D-2) + (D-1)(D-2)/2 to (D-3) + 2 + (D-4) + (D-4)(D-3)/2 + 2   (D=6: 18 -> 12),
+// the exact sequential look-up order of the reference is untouched (G is its composition).
+__device__ __forceinline__ uint32_t pair_apply(uint2 g, uint32_t x)
+{
+    const uint32_t word = (x & 8u) ? g.y : g.x;
+    return (word >> ((x & 7u) * 4u)) & 15u;
+}
+
+template <int D>
+__device__ __forceinline__ void cn_word_pair(const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab,
+                                             uint32_t RS, uint32_t TRS, uint32_t lane4, uint32_t pair_base, uint32_t T128)
+{
+    static_assert(D >= 4, "tail-pair variant needs at least two look-up stages");
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        uint32_t b[D], ms[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            b[k] = __byte_perm(w[k], 0u, 0x4440u + f);
+            ms[k] = b[k] * TRS + lane4;
+        }
+        const uint2 g = *reinterpret_cast<const uint2*>(tab + (b[D - 2] * T128 + b[D - 1] * 128u + pair_base));
+        uint32_t P[D];
+        P[1] = b[0];
+#pragma unroll
+        for (int j = 1; j <= D - 3; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(j - 1));
+        // the two outputs that do not pass through both tail stages
+        o[D - 1] = put_byte(o[D - 1], lut_ld(tab, P[D - 2] * RS + ms[D - 2] + IB_SO(D - 3)), f);
+        o[D - 2] = put_byte(o[D - 2], lut_ld(tab, P[D - 2] * RS + ms[D - 1] + IB_SO(D - 3)), f);
+#pragma unroll
+        for (int wo = 0; wo <= D - 3; ++wo) {
+            uint32_t t = (wo == 0) ? b[1] : P[wo];
+#pragma unroll
+            for (int k = (wo == 0 ? 2 : wo + 1); k <= D - 3; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
+            o[wo] = put_byte(o[wo], pair_apply(g, t), f);
+        }
+    }
+}
+
+template <int D, bool MATCH, bool EARLY, bool PAIR>
 __device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab, int s, uint32_t col,
                                             uint32_t lane4, uint32_t RS, uint32_t TRS, uint32_t valid_frames)
 {
@@ -218,7 +269,8 @@ __device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab,
             const uint32_t vmask = nv >= 4 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u);
             syn |= par & vmask;
         }
-        cn_word<D, MATCH>(w, o, tab, RS, TRS, lane4, match_off);
+        if constexpr (PAIR) cn_word_pair<D>(w, o, tab, RS, TRS, lane4, a.pair_off + (lane4 & 60u) * 2u, 128u * a.T);
+        else cn_word<D, MATCH>(w, o, tab, RS, TRS, lane4, match_off);
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             if (j == 0) r[k].x = o[k]; else if (j == 1) r[k].y = o[k]; else if (j == 2) r[k].z = o[k]; else r[k].w = o[k];
@@ -234,13 +286,21 @@ __device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab,
 // when a.iter0, checknode_update + calc_syndrome (:181-246, :304-325) otherwise.
 // One instantiation per check-node degree; `nodes` lists the checks of that degree, so every
 // launch has exactly the register budget its degree needs.
-template <int D, bool MATCH, bool EARLY>
-__global__ void __launch_bounds__(kThreads, (D <= 6 ? 4 : (D <= 8 ? 3 : 2)))
+template <int D, bool MATCH, bool EARLY, bool PAIR>
+__global__ void __launch_bounds__(kThreads, (D <= 6 ? (PAIR ? 3 : 4) : (D <= 8 ? 3 : 2)))
 ib_cn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 {
     extern __shared__ __align__(16) uint32_t s_tab[];
     if (EARLY && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
     stage_tables(s_tab, a, a.lut);
+    if (PAIR) {
+        // expand the composed tail-pair rows: 16 lane slots x 8 bytes per (a,b) row, so that the two
+        // half-warp phases of an LDS.64 are bank-conflict free for arbitrary data
+        const uint2* src = reinterpret_cast<const uint2*>(a.pair);
+        uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(s_tab) + a.pair_off);
+        const int n = a.T * a.T * 16;
+        for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = src[i >> 4];
+    }
     __syncthreads();
     const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_tab);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -260,7 +320,7 @@ ib_cn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
             // the next node's slot index is fetched while this node is being computed
             const int i2 = i + stride;
             const int s2 = i2 < n_nodes ? a.sc[nodes[i2]] : 0;
-            syn |= cn_node<D, MATCH, EARLY>(a, tab, s, col, lane4, RS, TRS, valid);
+            syn |= cn_node<D, MATCH, EARLY, PAIR>(a, tab, s, col, lane4, RS, TRS, valid);
             i = i2;
             s = s2;
         }

@@ -77,6 +77,9 @@ struct ibldpc_decoder {
     int T = 0, Tc = 0, lut_imax = 0, DC = 0, DV = 0;
     bool match = false;
     uint8_t *d_cn8 = nullptr, *d_vn8 = nullptr, *d_mc8 = nullptr, *d_mv8 = nullptr;
+    uint8_t* d_cn_pair = nullptr;   // [imax blocks][cn classes][T*T rows][8 bytes] composed tail-pair tables
+    bool use_pair = true;
+    int pair_min_degree = 7;
     bool fast = false;
     int Wc = 1, Wv = 1, Wo = 1, nrows_c = 0, nrows_v = 0, nrows_o = 0, tshift = -1;
     Workspace ws[2];
@@ -269,8 +272,20 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
                 b.W = words(b.nst + (explicit_match ? 1 : 0));
                 b.nrows = std::max(TT, explicit_match ? c.degree * T : 0);
                 if (h->match) b.dmax_match = c.degree;
-                const int smem = b.nrows * b.W * 128 + stage_scratch_bytes(b.nst, T, h->match ? b.dmax_match : 0);
-                NodeKernel k = cn_fast_kernel_for(c.degree, explicit_match, early != 0);
+                // Measured on B200: the tail-pair variant needs 64 KB of shared memory and 80 registers (3 CTAs/SM);
+                // it wins for d_c >= 7 (WLAN, DVB-S2: -3 % CN time) and loses for d_c = 6 (+5 %), so it is used
+                // from degree 7 on (IBLDPC_PAIR_MIN_DEGREE overrides, IBLDPC_NO_PAIR disables).
+                const bool pair = h->use_pair && c.degree >= h->pair_min_degree && h->d_cn_pair != nullptr;
+                int smem_main = b.nrows * b.W * 128;
+                smem_main += stage_scratch_bytes(b.nst, T, h->match ? b.dmax_match : 0);   // [tables][scratch][pair rows]
+                if (pair) {
+                    const size_t ci = (size_t)(&c - &h->cn_classes[0]);
+                    b.pair = h->d_cn_pair + ((size_t)blk * h->cn_classes.size() + ci) * (size_t)TT * 8;
+                    b.pair_off = (uint32_t)smem_main;
+                    smem_main += TT * 128;
+                }
+                NodeKernel k = cn_fast_kernel_for(c.degree, explicit_match, early != 0, pair);
+                const int smem = smem_main;
                 int grid;
                 r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid);
                 if (r) return r;
@@ -711,6 +726,34 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
               (size_t)h->nrows_c * h->Wc * 128 <= smem_max && (size_t)h->nrows_v * h->Wv * 128 <= smem_max &&
               (size_t)h->nrows_o * h->Wo * 128 <= smem_max;
     if (getenv("IBLDPC_FORCE_GENERIC")) h->fast = false;
+    h->use_pair = getenv("IBLDPC_NO_PAIR") == nullptr;
+    if (const char* pm = getenv("IBLDPC_PAIR_MIN_DEGREE")) h->pair_min_degree = std::max(4, atoi(pm));
+    if (h->d_cn_pair) { CK(cudaFree(h->d_cn_pair)); h->d_cn_pair = nullptr; }
+    if (h->fast && h->use_pair) {
+        // Composed tail-pair tables of the check-node kernel (cn_word_pair): for every iteration block and
+        // every check degree d >= 4, G(a,b)[x] = S_b'( S_a(x, a), b ) with S_a = stage d-4, S_b = stage d-3
+        // (matching folded into S_b), 16 nibbles per (a,b) row.
+        const int TT = T * T;
+        const size_t ncls = h->cn_classes.size();
+        std::vector<uint8_t> pair((size_t)imax * ncls * TT * 8, 0);
+        for (int blk = 0; blk < imax; ++blk)
+            for (size_t ci = 0; ci < ncls; ++ci) {
+                const int d = h->cn_classes[ci].degree;
+                if (d < 4) continue;
+                const uint8_t* Sa = cn.data() + ((size_t)blk * (DC - 2) + (d - 4)) * TT;
+                const uint8_t* Sb = cn.data() + ((size_t)blk * (DC - 2) + (d - 3)) * TT;
+                const uint8_t* mrow = match ? mc.data() + ((size_t)blk * DC + (d - 1)) * T : nullptr;
+                uint8_t* dst = pair.data() + ((size_t)blk * ncls + ci) * TT * 8;
+                for (int a = 0; a < T; ++a)
+                    for (int b = 0; b < T; ++b)
+                        for (int x = 0; x < T; ++x) {
+                            int v = Sb[Sa[x * T + a] * T + b];
+                            if (mrow) v = mrow[v];
+                            dst[(a * T + b) * 8 + (x >> 1)] |= (uint8_t)(v << ((x & 1) * 4));
+                        }
+            }
+        if ((rc = upload(&h->d_cn_pair, pair.data(), pair.size()))) return rc;
+    }
     h->occ_cache.clear();
     h->have_luts = true;
     return IBLDPC_OK;
@@ -911,7 +954,7 @@ int ibldpc_destroy(ibldpc_handle h)
     clear_events(h);
     for (int* p : {h->d_sc, h->d_dc, h->d_tc, h->d_sv, h->d_dv, h->d_tv, h->d_vidx})
         if (p) cudaFree(p);
-    for (uint8_t* p : {h->d_cn8, h->d_vn8, h->d_mc8, h->d_mv8})
+    for (uint8_t* p : {h->d_cn8, h->d_vn8, h->d_mc8, h->d_mv8, h->d_cn_pair})
         if (p) cudaFree(p);
     for (auto& c : h->cn_classes) if (c.d_nodes) cudaFree(c.d_nodes);
     for (auto& c : h->vn_classes) if (c.d_nodes) cudaFree(c.d_nodes);

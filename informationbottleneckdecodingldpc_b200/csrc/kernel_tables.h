@@ -11,7 +11,7 @@ using LlrNodeKernel = void (*)(LlrArgs, const int*, int);
 using LlrSynKernel = void (*)(LlrArgs);
 using LlrShflKernel = void (*)(LlrArgs, int);
 
-NodeKernel cn_fast_kernel_for(int d, bool match, bool early);
+NodeKernel cn_fast_kernel_for(int d, bool match, bool early, bool pair);
 NodeKernel vn_fast_kernel_for(int d, bool decide, bool match);
 LlrNodeKernel llr_cn_kernel_for(bool f64, int algo, int d);
 LlrNodeKernel llr_vn_kernel_for(bool f64, int mode, int d);

@@ -117,6 +117,25 @@ def test_ib_irregular_vs_oracle(gpu, name, H, T, match):
     assert np.array_equal(got, ref) and dec.last_i_num == i_num
 
 
+def test_ib_tail_pair_variant_all_degrees(gpu, monkeypatch):
+    """The composed tail-pair check-node kernels (cn_word_pair) for every degree 4..10, forced on with
+    IBLDPC_PAIR_MIN_DEGREE=4, with and without message alignment, against the oracle."""
+    monkeypatch.setenv("IBLDPC_PAIR_MIN_DEGREE", "4")
+    H = codes.random_from_degrees([2] * 40 + [3] * 40 + [4] * 16, [4] * 8 + [5] * 8 + [6] * 8 + [7] * 6 + [8] * 4 + [9] * 2 + [10] * 2, seed=4)
+    t = graph.edge_tables(H)
+    assert sorted(set(t.degree_chk)) == [4, 5, 6, 7, 8, 9, 10]
+    for T in (16, 8):
+        for match in (True, False):
+            imax, B = 6, 50
+            tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=31, matching=match)
+            ch = np.random.Generator(np.random.PCG64(32)).integers(0, T, size=(t.n_var, B)).astype(np.uint8)
+            dec = _mk_ib(H, T, imax, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                         tb.matching_vector_checknode, tb.matching_vector_varnode)
+            got = dec.decode_OpenCL(_dev(ch), buffer_in=True, return_buffer=True).get()
+            ref, i_num = _oracle_ib(t, ch, T, imax, tb, True)
+            assert np.array_equal(got, ref) and dec.last_i_num == i_num
+
+
 def test_ib_dvbs2_full_size_vs_oracle(gpu):
     """DVB-S2-like n=64800 (degree-1 VN, d_v 8, d_c 6/7, matching), a few frames, 4 iterations."""
     H = codes.dvbs2_like_half_rate()
