@@ -121,7 +121,7 @@ def test_ib_tail_pair_variant_all_degrees(gpu, monkeypatch):
     """The composed tail-pair check-node kernels (cn_word_pair) for every degree 4..10, forced on with
     IBLDPC_PAIR_MIN_DEGREE=4, with and without message alignment, against the oracle."""
     monkeypatch.setenv("IBLDPC_PAIR_MIN_DEGREE", "4")
-    H = codes.random_from_degrees([2] * 40 + [3] * 40 + [4] * 16, [4] * 8 + [5] * 8 + [6] * 8 + [7] * 6 + [8] * 4 + [9] * 2 + [10] * 2, seed=4)
+    H = codes.random_from_degrees([2] * 40 + [3] * 40 + [4] * 16, [4] * 16 + [5] * 8 + [6] * 8 + [7] * 6 + [8] * 4 + [9] * 2 + [10] * 2, seed=4)
     t = graph.edge_tables(H)
     assert sorted(set(t.degree_chk)) == [4, 5, 6, 7, 8, 9, 10]
     for T in (16, 8):
