@@ -55,6 +55,9 @@ struct Workspace {
     int* flags = nullptr;           // [kMaxIter]
     int* inum = nullptr;
     cudaStream_t stream = nullptr;  // host-path stream
+    // degree classes of one phase run concurrently on these (fork/join around every phase)
+    cudaStream_t aux[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 constexpr int kMaxIter = 4096;
@@ -157,12 +160,14 @@ int occupancy_of(ibldpc_decoder* h, const void* fn, int smem, int* occ_out)
 }
 
 // IB fast path: grid.x CTAs per tile group so that grid.x * tile_groups fills the resident slots
-int grid_for(ibldpc_decoder* h, const void* fn, int smem, int tile_groups, int nodes_per_step, int n_nodes, int* out)
+int grid_for(ibldpc_decoder* h, const void* fn, int smem, int tile_groups, int nodes_per_step, int n_nodes, int* out,
+             double share = 1.0)
 {
     int occ;
     int rc = occupancy_of(h, fn, smem, &occ);
     if (rc) return rc;
-    const long long cap = std::max<long long>(1, (long long)occ * h->sm_count / tile_groups);
+    // floor: one CTA more than the resident slots would run as a second wave
+    const long long cap = std::max<long long>(1, (long long)(share * ((long long)occ * h->sm_count / tile_groups)));
     const long long want = ((long long)n_nodes + nodes_per_step - 1) / nodes_per_step;
     *out = (int)std::max<long long>(1, std::min(want, cap));
     return IBLDPC_OK;
@@ -252,6 +257,37 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
     h->last_launches = 0;
     Prof prof{h, st};
 
+    // Irregular codes: the degree classes of one phase are independent, so their kernels CAN run
+    // concurrently -- class 0 on the caller's stream, the others on auxiliary streams forked from and
+    // joined back to it by events -- each with a share of the resident CTA slots proportional to its
+    // estimated work.  Measured on B200 (round 1) this is SLOWER than launching the classes one after
+    // the other (WLAN n=1296: 1.52 vs 1.78 Gbit/s, DVB-S2-like: 1.72 vs 2.05): the static split leaves the
+    // phase waiting for its slowest class.  Kept behind IBLDPC_CONCURRENT_CLASSES=1 for further tuning.
+    const bool concurrent = std::max(h->cn_classes.size(), h->vn_classes.size()) > 1 && getenv("IBLDPC_CONCURRENT_CLASSES");
+    if (concurrent && !w.fork_ev) {
+        CK(cudaEventCreateWithFlags(&w.fork_ev, cudaEventDisableTiming));
+        for (int i = 0; i < 7; ++i) {
+            CK(cudaStreamCreateWithFlags(&w.aux[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&w.join_ev[i], cudaEventDisableTiming));
+        }
+    }
+    auto cn_cost = [](int d) { return 2.0 * (d - 2) + 0.5 * (d - 1) * (d - 2) + 0.5 * d + 1.0; };
+    auto vn_cost = [](int d) { return (d - 1) + 0.5 * d * (d - 1) + 0.25 * (2 * d + 1) + 1.0; };
+    auto class_stream = [&](size_t i) -> cudaStream_t { return (concurrent && i > 0) ? w.aux[(i - 1) % 7] : st; };
+    auto fork_phase = [&](size_t nclasses) -> int {
+        if (concurrent && nclasses > 1) {
+            CK(cudaEventRecord(w.fork_ev, st));
+            for (size_t i = 1; i < nclasses; ++i) CK(cudaStreamWaitEvent(class_stream(i), w.fork_ev, 0));
+        }
+        return IBLDPC_OK;
+    };
+    auto join_class = [&](size_t i) -> int {
+        if (concurrent && i > 0) {
+            CK(cudaEventRecord(w.join_ev[(i - 1) % 7], class_stream(i)));
+            CK(cudaStreamWaitEvent(st, w.join_ev[(i - 1) % 7], 0));
+        }
+        return IBLDPC_OK;
+    };
     if (h->fast) {
         // Each degree class only stages the tables its chains reach (stages 0..d-3 for a check of
         // degree d, 0..d-2 / 0..d-1 for a variable node), so low-degree classes of an irregular code
@@ -266,7 +302,13 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
             b.dmax_match = h->DC;
             int r = prof.begin(it < 0 ? 2 : 0);
             if (r) return r;
+            if ((r = fork_phase(h->cn_classes.size()))) return r;
+            double total_work = 0;
+            for (auto& c : h->cn_classes) total_work += c.count * cn_cost(c.degree);
+            size_t ci_run = 0;
             for (auto& c : h->cn_classes) {
+                cudaStream_t cs = class_stream(ci_run);
+                const double share = concurrent ? c.count * cn_cost(c.degree) / total_work : 1.0;
                 b.nst = c.degree - 2;
                 const bool explicit_match = h->match && b.nst == 0;   // matching is folded into the last stage otherwise
                 b.W = words(b.nst + (explicit_match ? 1 : 0));
@@ -287,10 +329,11 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
                 NodeKernel k = cn_fast_kernel_for(c.degree, explicit_match, early != 0, pair);
                 const int smem = smem_main;
                 int grid;
-                r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid);
+                r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid, share);
                 if (r) return r;
-                k<<<dim3(grid, tile_groups), kThreads, smem, st>>>(b, c.d_nodes, c.count);
+                k<<<dim3(grid, tile_groups), kThreads, smem, cs>>>(b, c.d_nodes, c.count);
                 h->last_launches++; h->last_grid = grid * tile_groups; h->last_smem = smem;
+                if ((r = join_class(ci_run++))) return r;
             }
             return prof.end();
         };
@@ -305,7 +348,13 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
             }
             int r = prof.begin(decide ? 2 : 1);
             if (r) return r;
+            if ((r = fork_phase(h->vn_classes.size()))) return r;
+            double total_work = 0;
+            for (auto& c : h->vn_classes) total_work += c.count * vn_cost(c.degree);
+            size_t ci_run = 0;
             for (auto& c : h->vn_classes) {
+                cudaStream_t cs = class_stream(ci_run);
+                const double share = concurrent ? c.count * vn_cost(c.degree) / total_work : 1.0;
                 const bool m = b.match != nullptr;
                 b.nst = decide ? c.degree : c.degree - 1;
                 b.W = words(b.nst);                   // matching is folded into the last stage (stage_tables)
@@ -314,10 +363,11 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
                 const int smem = b.nrows * b.W * 128 + stage_scratch_bytes(b.nst, T, b.dmax_match);
                 NodeKernel k = vn_fast_kernel_for(c.degree, decide, false);
                 int grid;
-                r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid);
+                r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid, share);
                 if (r) return r;
-                k<<<dim3(grid, tile_groups), kThreads, smem, st>>>(b, c.d_nodes, c.count);
+                k<<<dim3(grid, tile_groups), kThreads, smem, cs>>>(b, c.d_nodes, c.count);
                 h->last_launches++;
+                if ((r = join_class(ci_run++))) return r;
             }
             return prof.end();
         };
@@ -963,6 +1013,11 @@ int ibldpc_destroy(ibldpc_handle h)
                         (void*)w.stage_out, (void*)w.flags, (void*)w.inum})
             if (p) cudaFree(p);
         if (w.stream) cudaStreamDestroy(w.stream);
+        if (w.fork_ev) cudaEventDestroy(w.fork_ev);
+        for (int i = 0; i < 7; ++i) {
+            if (w.aux[i]) cudaStreamDestroy(w.aux[i]);
+            if (w.join_ev[i]) cudaEventDestroy(w.join_ev[i]);
+        }
     }
     delete h;
     return IBLDPC_OK;
