@@ -41,13 +41,13 @@ def workload(name):
                     irregular=False, B=32768, ebn0=1.6, design_ebn0=1.2)
     if name == "wlan":
         return dict(name="802.11n n=1296 R=0.5 IB |T|=16 i_max=50 ET off, message alignment", H=codes.wlan_80211n(54),
-                    irregular=True, B=100096, ebn0=1.5)
+                    irregular=True, B=100096, ebn0=2.0, design_ebn0=1.0)
     if name == "wlan1944":
         return dict(name="802.11n n=1944 R=0.5 IB |T|=16 i_max=50 ET off, message alignment", H=codes.wlan_80211n(81),
-                    irregular=True, B=65536, ebn0=1.5)
+                    irregular=True, B=65536, ebn0=2.0, design_ebn0=1.0)
     if name == "dvbs2":
         return dict(name="DVB-S2-like n=64800 R=0.5 IB |T|=16 i_max=50 ET off, message alignment",
-                    H=codes.dvbs2_like_half_rate(), irregular=True, B=2048, ebn0=1.0)
+                    H=codes.dvbs2_like_half_rate(), irregular=True, B=2048, ebn0=1.6, design_ebn0=1.0)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -115,10 +115,8 @@ class ClockSampler:
 
 
 def make_tables(wl):
-    """Regular code: IB tables designed by discrete density evolution (decoder_config_generation.py,
-    the in-repo stand-in for the reference's design chain).  Irregular codes: deterministic
-    min-sum-like tables + identity matching (no irregular design tool yet); the kernels' work does not
-    depend on the table contents."""
+    """IB tables designed by discrete density evolution (decoder_config_generation.py, the in-repo
+    stand-in for the reference's design chain); irregular codes with message alignment."""
     from informationbottleneckdecodingldpc_b200 import graph, luts
     t = graph.edge_tables(wl["H"])
     if not wl["irregular"]:
@@ -126,8 +124,10 @@ def make_tables(wl):
         tb, _ = generate_regular_config(wl["design_ebn0"], t.d_v_max, t.d_c_max, T, IMAX)
         wl["tables"] = "IB tables, discrete density evolution at Eb/N0 = %.1f dB (in-repo design)" % wl["design_ebn0"]
     else:
-        tb = luts.minsum_like_tables(T, t.d_c_max, t.d_v_max, IMAX)
-        wl["tables"] = "min-sum-like LUTs + identity matching (deterministic)"
+        from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_irregular_config
+        tb, _ = generate_irregular_config(wl["design_ebn0"], wl["H"], T, IMAX)
+        wl["tables"] = ("IB tables + message alignment, degree-mixed density evolution at Eb/N0 = %.1f dB "
+                        "(in-repo design)" % wl["design_ebn0"])
     return t, tb
 
 

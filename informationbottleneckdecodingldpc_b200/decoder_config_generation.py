@@ -13,7 +13,7 @@ import argparse
 import numpy as np
 
 from .AWGN_Channel_Transmission.AWGN_Quantizer_BPSK import AWGN_Channel_Quantizer
-from .design import design_regular_ib_decoder
+from .design import design_irregular_ib_decoder, design_regular_ib_decoder, edge_degree_distribution
 from .luts import DecoderTables, save_config
 
 
@@ -29,6 +29,26 @@ def generate_regular_config(EbN0_dB: float, d_v: int = 3, d_c: int = 6, cardinal
     extras = dict(sigma_n2=sigma_n2, EbN0=EbN0_dB, d_v=d_v, d_c=d_c, AD_max_abs=AD_max_abs,
                   cardinality_Y_channel=cardinality_Y_channel, cardinality_T_channel=cardinality_T,
                   p_x_and_t_input=quanti.p_x_and_t, ext_mi_varnode_in_iter=np.asarray(mi))
+    return tables, extras
+
+
+def generate_irregular_config(EbN0_dB: float, H, cardinality_T: int = 16, imax: int = 50, AD_max_abs: float = 3.0,
+                              cardinality_Y_channel: int = 2000):
+    """Irregular codes (stand-in for Irregular_LDPC_Decoding/{WLAN,DVB-S2}/decoder_config_generation.py):
+    degree distributions are read off the parity-check matrix H, tables and matching vectors come from
+    design.design_irregular_ib_decoder.  Returns (DecoderTables incl. matching vectors, extras)."""
+    from .graph import code_rate_from_degrees, edge_tables
+    t = edge_tables(H)
+    R_c = float(code_rate_from_degrees(H))
+    sigma_n2 = 10 ** (-EbN0_dB / 10) / (2 * R_c)
+    quanti = AWGN_Channel_Quantizer(sigma_n2, AD_max_abs, cardinality_T, cardinality_Y_channel)
+    lam = edge_degree_distribution(t.degree_var)
+    rho = edge_degree_distribution(t.degree_chk)
+    cn, vn, mc, mv, mi = design_irregular_ib_decoder(quanti.p_x_and_t, lam, rho, cardinality_T, imax)
+    tables = DecoderTables(cn, vn, cardinality_T, imax, mc, mv)
+    extras = dict(sigma_n2=sigma_n2, EbN0=EbN0_dB, lambda_vec=lam, rho_vec=rho, R_c=R_c, match='true',
+                  cardinality_T_channel=cardinality_T, p_x_and_t_input=quanti.p_x_and_t,
+                  ext_mi_varnode_in_iter=np.asarray(mi))
     return tables, extras
 
 

@@ -173,3 +173,108 @@ def design_regular_ib_decoder(p_x_and_t_channel: np.ndarray, d_v: int, d_c: int,
     cn = np.concatenate(cn_vec).astype(np.float64) if cn_vec else np.zeros(0)
     vn = np.concatenate(vn_vec).astype(np.float64)
     return cn, vn, np.array(mi_hist)
+
+
+# ---------------------------------------------------------------------------------------------
+# Irregular codes: degree-mixed density evolution with message alignment.
+#
+# Follows the structure of the reference's irregular design chain
+# (Discrete_LDPC_decoding/Discrete_Density_Evolution_irreg.py:95-135,225-300 and
+# Information_Matching.py:34-78): one chain of partial node operations is designed for the
+# maximum degree, a node of degree d taps the chain after its own last stage, every tapped
+# message is aligned to a reference meaning by z*(t) = argmin_z KL(p(x|t) || p_ref(x|z)), and the
+# aligned densities are mixed with the edge-perspective degree distributions.  Deterministic;
+# contents not pinned to the authors' tables (no artefact, ib_base absent).
+# ---------------------------------------------------------------------------------------------
+def edge_degree_distribution(node_degrees: np.ndarray) -> np.ndarray:
+    """Edge-perspective distribution: entry d-1 = fraction of edges attached to degree-d nodes
+    (Information_Matching.py:23-31)."""
+    node_degrees = np.asarray(node_degrees, dtype=np.int64)
+    hist = np.bincount(node_degrees, minlength=int(node_degrees.max()) + 1)[1:].astype(np.float64)
+    w = hist * (np.arange(hist.size) + 1)
+    return w / w.sum()
+
+
+def _kl_rows(p_row, q_rows):
+    p = np.clip(p_row, 1e-300, None)
+    q = np.clip(q_rows, 1e-300, None)
+    return np.sum(p[None, :] * (np.log(p[None, :]) - np.log(q)), axis=1)
+
+
+def align_messages(p_xt: np.ndarray, p_ref: np.ndarray):
+    """Message alignment (information matching): z*(t) = argmin_z KL(p(x|t) || p_ref(x|z)).
+    Returns (z_star (T,), aligned joint pmf (T, 2))."""
+    T = p_xt.shape[0]
+    cond = p_xt / np.clip(p_xt.sum(1, keepdims=True), 1e-300, None)
+    ref = p_ref / np.clip(p_ref.sum(1, keepdims=True), 1e-300, None)
+    z = np.array([int(np.argmin(_kl_rows(cond[t], ref))) for t in range(T)], dtype=np.int64)
+    out = np.zeros_like(p_xt)
+    np.add.at(out, z, p_xt)
+    return z, out
+
+
+def _mean_abs_llr(p_xt):
+    p = np.clip(p_xt, 1e-300, None)
+    return float(np.sum(p.sum(1) * np.abs(np.log(p[:, 0]) - np.log(p[:, 1]))))
+
+
+def design_irregular_ib_decoder(p_x_and_t_channel, lambda_edge, rho_edge, T: int, imax: int):
+    """Design tables for an irregular ensemble.  lambda_edge / rho_edge: edge-perspective degree
+    distributions (index d-1).  Returns (cn_vec, vn_vec, mc_vec, mv_vec, mi[imax]) in the reference
+    layout with DC = len(rho_edge), DV = len(lambda_edge)."""
+    p_ch = np.asarray(p_x_and_t_channel, dtype=np.float64)
+    p_ch = p_ch / p_ch.sum()
+    if p_ch.shape[0] != T:
+        raise ValueError("cardinality_T_channel must equal cardinality_T_decoder_ops")
+    lam = np.asarray(lambda_edge, dtype=np.float64)
+    rho = np.asarray(rho_edge, dtype=np.float64)
+    DV, DC = lam.size, rho.size
+    ident = np.arange(T)
+    cn_vec, vn_vec, mi_hist = [], [], []
+    MC = np.tile(ident, (imax, DC, 1))
+    MV = np.tile(ident, (imax, DV, 1))
+    p_in = p_ch
+    for g in range(imax):
+        # ---- check nodes: chain of DC-2 stages, degree d taps after stage d-3
+        taps = {2: p_in}
+        p_t = p_in
+        for l in range(DC - 2):
+            lab, p_t = quantize_joint(_guard(_cn_joint(p_t, p_in)), T)
+            p_t = p_t / p_t.sum()
+            cn_vec.append(lab)
+            taps[l + 3] = p_t
+        active = [d for d in range(2, DC + 1) if rho[d - 1] > 0]
+        ref_d = max(active, key=lambda d: _mean_abs_llr(taps[d]))       # most reliable = lowest degree
+        p_c = np.zeros((T, 2))
+        for d in active:
+            if d == ref_d:
+                q = taps[d]
+            else:
+                z, q = align_messages(taps[d], taps[ref_d])
+                MC[g, d - 1, :] = z
+            p_c += rho[d - 1] * q
+        p_c = p_c / p_c.sum()
+        # ---- variable nodes: chain of DV stages (last = decision stage), degree d taps after stage d-2
+        vtaps = {1: p_ch}
+        p_t = p_ch
+        for l in range(DV):
+            lab, p_t = quantize_joint(_guard(_vn_joint(p_t, p_c)), T)
+            p_t = p_t / p_t.sum()
+            vn_vec.append(lab)
+            vtaps[l + 2] = p_t
+        vactive = [d for d in range(1, DV + 1) if lam[d - 1] > 0]
+        cand = [d for d in vactive if d >= 2]
+        ref_d = max(cand, key=lambda d: _mean_abs_llr(vtaps[d])) if cand else 1
+        p_v = np.zeros((T, 2))
+        for d in vactive:
+            if d == 1 or d == ref_d:          # degree-1 nodes forward the raw channel value unaligned
+                q = vtaps[d]
+            else:
+                z, q = align_messages(vtaps[d], vtaps[ref_d])
+                MV[g, d - 1, :] = z
+            p_v += lam[d - 1] * q
+        p_in = p_v / p_v.sum()
+        mi_hist.append(_mi(p_in))
+    cn = np.concatenate(cn_vec).astype(np.float64) if cn_vec else np.zeros(0)
+    vn = np.concatenate(vn_vec).astype(np.float64)
+    return cn, vn, MC.reshape(-1).astype(np.float64), MV.reshape(-1).astype(np.float64), np.array(mi_hist)

@@ -234,6 +234,34 @@ def test_ib_designed_tables_decode_the_all_zero_codeword(gpu):
     assert np.array_equal(out.get(), ref) and dec.last_i_num == i_num
 
 
+def test_ib_designed_irregular_tables_with_alignment(gpu):
+    """802.11n code with tables + matching vectors from the in-repo irregular design: at 2.2 dB every
+    frame is decoded when message alignment is on, and the result equals the oracle's bit for bit;
+    with match='false' the same tables leave errors (alignment matters, as in the reference's papers)."""
+    import informationbottleneckdecodingldpc_b200 as pkg
+    from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_irregular_config
+    from oracle import oracle
+    H = codes.wlan_80211n(54)
+    tb, _ = generate_irregular_config(1.0, H, 16, 50)
+    q = pkg.AWGN_Channel_Quantizer(10 ** (-2.2 / 10) / (2 * 0.5), 3, 16, 2000)
+    q.init_OpenCL_quanti(1296, 400, return_buffer_only=True)
+    rec = q.quantize_direct_OpenCL(1296, 400)
+    errs = {}
+    for match in ('true', 'false'):
+        dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, 50, 16, 16, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                        tb.matching_vector_checknode, tb.matching_vector_varnode, 400, match=match)
+        dec.init_OpenCL_decoding(400, q.context)
+        dec.early_termination = False
+        out = dec.decode_OpenCL(rec, buffer_in=True, return_buffer=True)
+        errs[match] = dec.return_errors_all_zero(out)
+        ref, _ = oracle.ib_decode(graph.edge_tables(H), rec.get(), T=16, imax=50, cn_lut=tb.Trellis_checknodevector_a,
+                                  vn_lut=tb.Trellis_varnodevector_a,
+                                  cn_match=tb.matching_vector_checknode if match == 'true' else None,
+                                  vn_match=tb.matching_vector_varnode if match == 'true' else None, early=False)
+        assert np.array_equal(out.get(), ref)
+    assert errs['true'] == 0 and errs['false'] > 0
+
+
 def test_early_termination_is_batch_granular(gpu):
     """One noisy frame keeps the whole batch iterating (reference stop rule, decoder.py:273)."""
     g = load_golden("ib_c1_minsumlut_imax50_et")

@@ -201,3 +201,26 @@ def test_decoder_config_cli_writes_reference_named_pickle(tmp_path, monkeypatch)
     d = luts.load_config(str(tmp_path / "decoder_config_EbN0_gen_1.2_16.pkl"))
     assert int(d["imax"]) == 3 and int(d["cardinality_T_decoder_ops"]) == 16
     assert d["Trellis_checknodevector_a"].size == luts.cn_lut_len(16, 16, 6, 3)
+
+
+def test_irregular_design_tool_with_message_alignment():
+    """Irregular stand-in for the reference's WLAN / DVB-S2 decoder_config_generation: table and
+    matching-vector lengths of SURVEY Appendix B, identity rows for the reference degree and for unused
+    degrees, mirror-symmetric alignment maps, mutual information growing to ~1 bit."""
+    from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_irregular_config
+    H = codes.wlan_80211n(54)
+    tb, ex = generate_irregular_config(1.4, H, 16, 20)
+    assert tb.Trellis_checknodevector_a.size == luts.cn_lut_len(16, 16, 8, 20)
+    assert tb.Trellis_varnodevector_a.size == luts.vn_lut_len(16, 16, 11, 20)
+    mc = tb.matching_vector_checknode.reshape(20, 8, 16).astype(int)
+    mv = tb.matching_vector_varnode.reshape(20, 11, 16).astype(int)
+    assert mc.min() >= 0 and mc.max() < 16 and mv.min() >= 0 and mv.max() < 16
+    ident = np.arange(16)
+    for d in (1, 2, 3, 4, 5, 6):                       # no checks of these degrees in the 802.11n code
+        assert np.array_equal(mc[:, d - 1], np.tile(ident, (20, 1)))
+    assert np.array_equal(mc[:, 6], np.tile(ident, (20, 1)))     # degree 7 = most reliable = reference meaning
+    assert np.array_equal(mv, 15 - mv[:, :, ::-1])               # z*(T-1-t) = T-1-z*(t)
+    assert np.all(np.diff(mv, axis=2) >= 0)                      # alignment keeps the LLR order
+    mi = ex["ext_mi_varnode_in_iter"]
+    assert mi[-1] > 0.99 and np.all(np.diff(mi) > -1e-6)
+    assert abs(ex["lambda_vec"].sum() - 1) < 1e-12 and abs(ex["rho_vec"].sum() - 1) < 1e-12
