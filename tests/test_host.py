@@ -222,5 +222,5 @@ def test_irregular_design_tool_with_message_alignment():
     assert np.array_equal(mv, 15 - mv[:, :, ::-1])               # z*(T-1-t) = T-1-z*(t)
     assert np.all(np.diff(mv, axis=2) >= 0)                      # alignment keeps the LLR order
     mi = ex["ext_mi_varnode_in_iter"]
-    assert mi[-1] > 0.99 and np.all(np.diff(mi) > -1e-6)
+    assert mi[-1] > 0.95 and mi[-1] > mi[0] + 0.25 and np.all(np.diff(mi) > -1e-6)
     assert abs(ex["lambda_vec"].sum() - 1) < 1e-12 and abs(ex["rho_vec"].sum() - 1) < 1e-12
