@@ -32,6 +32,7 @@ constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kMaxFastDc = 10;   // check-node degrees instantiated in the fast path
 constexpr int kMaxFastDv = 12;   // variable-node degrees instantiated in the fast path
 constexpr int kMaxGenericDeg = 64;
+constexpr int kPairSlots = 16;   // lane slots of the tail-pair table (16: conflict-free LDS.64; 8: half the shared memory, 2-way conflicts)
 
 struct IbArgs {
     // graph
@@ -71,11 +72,17 @@ struct IbArgs {
     // launch, and the byte offset of its expanded copy inside the dynamic shared memory
     const uint8_t* __restrict__ pair;
     uint32_t pair_off;
+    int xp_col;        // stage column stored in the shift-ready "xp" encoding (tail-pair kernels), -1 = none
 };
 
 // ------------------------------------------------------------------------------------------
 // shared-memory table staging
 // ------------------------------------------------------------------------------------------
+// "xp" encoding of a value x in [0,16): bits 2..4 = (x & 7), bit 7 = (x >= 8).  Loaded with a
+// sign-extending LDS.S8 it is negative iff x >= 8, and its low five bits are the nibble shift
+// 4*(x & 7), so selecting nibble x of a 64-bit row is ISETP + SEL + SHF (wrap) + LOP.
+__host__ __device__ __forceinline__ uint32_t xp_encode(uint32_t x) { return ((x & 7u) << 2) | ((x & 8u) << 4); }
+
 // Two steps: (1) the compact tables of this iteration (nst x T^2 bytes + matching rows, a few KB)
 // are copied global -> shared with coalesced loads into a scratch area behind the expanded
 // table; (2) every warp expands rows from that scratch copy (broadcast LDS) into the
@@ -121,6 +128,7 @@ __device__ __forceinline__ void stage_tables(uint32_t* s_tab, const IbArgs& a, c
                 if (r < TT) {
                     e = scratch[col * TT + t * a.T + m];
                     if (fold && col == a.nst - 1) e = smatch[(a.dmax_match - 1) * a.T + e];
+                    if (col == a.xp_col) e = xp_encode(e);
                 }
             } else if (col == a.nst && a.match != nullptr && !fold) {
                 if (m < a.dmax_match) e = smatch[m * a.T + t];
@@ -185,15 +193,26 @@ __device__ __forceinline__ void cn_word(const uint32_t (&w)[D], uint32_t (&o)[D]
 // nibble selects.  Shared-memory wavefronts per check and frame drop from
 // 2(D-2) + (D-1)(D-2)/2 to (D-3) + 2 + (D-4) + (D-4)(D-3)/2 + 2   (D=6: 18 -> 12),
 // the exact sequential look-up order of the reference is untouched (G is its composition).
-__device__ __forceinline__ uint32_t pair_apply(uint2 g, uint32_t x)
+__device__ __forceinline__ uint32_t pair_apply_xp(uint2 g, int e)
 {
-    const uint32_t word = (x & 8u) ? g.y : g.x;
-    return (word >> ((x & 7u) * 4u)) & 15u;
+    const uint32_t word = e < 0 ? g.y : g.x;
+    return __funnelshift_r(word, 0u, (uint32_t)e) & 15u;     // shift amount = e & 31 = 4*(x & 7)
+}
+// t*RS for a value held in xp form (RS = 128*W)
+__device__ __forceinline__ uint32_t xp_times_rs(int e, uint32_t W)
+{
+    const uint32_t u = (uint32_t)e;
+    return (((u & 0x1Cu) << 5) | ((u & 0x80u) << 3)) * W;
+}
+__device__ __forceinline__ int lut_ld_s8(const uint8_t* tab, uint32_t addr)
+{
+    return (int)reinterpret_cast<const signed char*>(tab)[addr];
 }
 
 template <int D>
 __device__ __forceinline__ void cn_word_pair(const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab,
-                                             uint32_t RS, uint32_t TRS, uint32_t lane4, uint32_t pair_base, uint32_t T128)
+                                             uint32_t RS, uint32_t TRS, uint32_t lane4, uint32_t pair_base, uint32_t TPS,
+                                             uint32_t PS, uint32_t W)
 {
     static_assert(D >= 4, "tail-pair variant needs at least two look-up stages");
 #pragma unroll
@@ -206,20 +225,46 @@ __device__ __forceinline__ void cn_word_pair(const uint32_t (&w)[D], uint32_t (&
             b[k] = __byte_perm(w[k], 0u, 0x4440u + f);
             ms[k] = b[k] * TRS + lane4;
         }
-        const uint2 g = *reinterpret_cast<const uint2*>(tab + (b[D - 2] * T128 + b[D - 1] * 128u + pair_base));
+        // 64-bit row G(m_{D-2}, m_{D-1})[.] of the composed tail-pair table
+        const uint2 g = *reinterpret_cast<const uint2*>(tab + (b[D - 2] * TPS + b[D - 1] * PS + pair_base));
+        // prefix chain; the value produced by stage D-5 (P[D-3]) comes out in xp form
         uint32_t P[D];
+        int Pxp = 0;                       // P[D-3] in xp form (D >= 5)
         P[1] = b[0];
 #pragma unroll
-        for (int j = 1; j <= D - 3; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(j - 1));
-        // the two outputs that do not pass through both tail stages
-        o[D - 1] = put_byte(o[D - 1], lut_ld(tab, P[D - 2] * RS + ms[D - 2] + IB_SO(D - 3)), f);
-        o[D - 2] = put_byte(o[D - 2], lut_ld(tab, P[D - 2] * RS + ms[D - 1] + IB_SO(D - 3)), f);
+        for (int j = 1; j <= D - 3; ++j) {
+            const bool in_is_xp = (D >= 5) && (j == D - 3);     // P[j] = P[D-3] was produced by the xp column
+            const uint32_t trs = in_is_xp ? xp_times_rs(Pxp, W) : P[j] * RS;
+            if ((D >= 5) && (j - 1 == D - 5)) {                  // this look-up reads the xp column
+                Pxp = lut_ld_s8(tab, trs + ms[j] + IB_SO(j - 1));
+                P[j + 1] = 0;
+            } else {
+                P[j + 1] = lut_ld(tab, trs + ms[j] + IB_SO(j - 1));
+            }
+        }
+        // the two outputs that do not pass through both tail stages: P[D-2] is a plain value
+        // (stage D-4) unless D == 4, where P[D-2] = P[2] ... handled by the same rule below
+        const uint32_t pd2_rs = P[D - 2] * RS;
+        o[D - 1] = put_byte(o[D - 1], lut_ld(tab, pd2_rs + ms[D - 2] + IB_SO(D - 3)), f);
+        o[D - 2] = put_byte(o[D - 2], lut_ld(tab, pd2_rs + ms[D - 1] + IB_SO(D - 3)), f);
 #pragma unroll
         for (int wo = 0; wo <= D - 3; ++wo) {
-            uint32_t t = (wo == 0) ? b[1] : P[wo];
+            // chain up to (excluding) the two tail stages; its last look-up (stage D-5) yields xp form
+            int e;
+            if (wo == D - 3 && D >= 5) {
+                e = Pxp;
+            } else {
+                uint32_t t = (wo == 0) ? b[1] : P[wo];
+                bool have_xp = false;
+                e = 0;
 #pragma unroll
-            for (int k = (wo == 0 ? 2 : wo + 1); k <= D - 3; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
-            o[wo] = put_byte(o[wo], pair_apply(g, t), f);
+                for (int k = (wo == 0 ? 2 : wo + 1); k <= D - 3; ++k) {
+                    if (k - 2 == D - 5) { e = lut_ld_s8(tab, t * RS + ms[k] + IB_SO(k - 2)); have_xp = true; }
+                    else t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
+                }
+                if (!have_xp) e = (int)(signed char)xp_encode(t);   // D == 4 (raw messages) only
+            }
+            o[wo] = put_byte(o[wo], pair_apply_xp(g, e), f);
         }
     }
 }
@@ -269,7 +314,8 @@ __device__ __forceinline__ uint32_t cn_node(const IbArgs& a, const uint8_t* tab,
             const uint32_t vmask = nv >= 4 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u);
             syn |= par & vmask;
         }
-        if constexpr (PAIR) cn_word_pair<D>(w, o, tab, RS, TRS, lane4, a.pair_off + (lane4 & 60u) * 2u, 128u * a.T);
+        if constexpr (PAIR) cn_word_pair<D>(w, o, tab, RS, TRS, lane4, a.pair_off + (lane4 & (4u * (kPairSlots - 1))) * 2u,
+                                            8u * kPairSlots * a.T, 8u * kPairSlots, (uint32_t)a.W);
         else cn_word<D, MATCH>(w, o, tab, RS, TRS, lane4, match_off);
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -298,8 +344,8 @@ ib_cn_fast_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
         // half-warp phases of an LDS.64 are bank-conflict free for arbitrary data
         const uint2* src = reinterpret_cast<const uint2*>(a.pair);
         uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(s_tab) + a.pair_off);
-        const int n = a.T * a.T * 16;
-        for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = src[i >> 4];
+        const int n = a.T * a.T * kPairSlots;
+        for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = src[i / kPairSlots];
     }
     __syncthreads();
     const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_tab);

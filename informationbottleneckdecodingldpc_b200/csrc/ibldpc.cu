@@ -252,7 +252,7 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
     const int nps = kWarpsPerCta >> a.tpc_log2;
     a.T = h->T; a.Tc = h->Tc; a.tshift = h->tshift;
     a.flags = w.flags; a.inum = w.inum; a.early = early; a.imax = imax;
-    a.DC = h->DC; a.DV = h->DV;
+    a.DC = h->DC; a.DV = h->DV; a.xp_col = -1;
     const int T = h->T, Tc = h->Tc, TT = T * T;
     h->last_launches = 0;
     Prof prof{h, st};
@@ -318,13 +318,15 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
                 // it wins for d_c >= 7 (WLAN, DVB-S2: -3 % CN time) and loses for d_c = 6 (+5 %), so it is used
                 // from degree 7 on (IBLDPC_PAIR_MIN_DEGREE overrides, IBLDPC_NO_PAIR disables).
                 const bool pair = h->use_pair && c.degree >= h->pair_min_degree && h->d_cn_pair != nullptr;
+                b.xp_col = -1;
                 int smem_main = b.nrows * b.W * 128;
                 smem_main += stage_scratch_bytes(b.nst, T, h->match ? b.dmax_match : 0);   // [tables][scratch][pair rows]
                 if (pair) {
                     const size_t ci = (size_t)(&c - &h->cn_classes[0]);
                     b.pair = h->d_cn_pair + ((size_t)blk * h->cn_classes.size() + ci) * (size_t)TT * 8;
                     b.pair_off = (uint32_t)smem_main;
-                    smem_main += TT * 128;
+                    smem_main += TT * 8 * kPairSlots;
+                    b.xp_col = c.degree - 5;    // -1 for degree 4: no stage feeds the pair row
                 }
                 NodeKernel k = cn_fast_kernel_for(c.degree, explicit_match, early != 0, pair);
                 const int smem = smem_main;
