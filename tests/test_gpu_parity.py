@@ -470,6 +470,31 @@ def test_error_counters(gpu):
     assert b == int((llr[:20] < 0).sum())
 
 
+def test_decoder_object_reuse(gpu):
+    """One decoder object across what the BER drivers do to it: re-init per Eb/N0 point with another
+    batch size, update_trellis_vectors (discrete_LDPC_decoder.py:53), unpinned / int64 / uint8 host
+    inputs, alternating device- and host-buffer calls."""
+    from oracle import oracle
+    H = codes.regular_random(600, 3, 6, seed=8)
+    t = graph.edge_tables(H)
+    T, imax = 16, 6
+    tb1 = luts.random_tables(T, 6, 3, imax, seed=1)
+    tb2 = luts.random_tables(T, 6, 3, imax, seed=2)
+    dec = _mk_ib(H, T, imax, tb1.Trellis_checknodevector_a, tb1.Trellis_varnodevector_a, irregular=False)
+    rng = np.random.Generator(np.random.PCG64(4))
+    for B, tb in ((40, tb1), (7, tb1), (530, tb2), (40, tb2), (16, tb1)):
+        dec.update_trellis_vectors(tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a)
+        dec.init_OpenCL_decoding(B)
+        ch = rng.integers(0, T, size=(600, B))
+        ref, i_ref = oracle.ib_decode(t, ch, T=T, imax=imax, cn_lut=tb.Trellis_checknodevector_a,
+                                      vn_lut=tb.Trellis_varnodevector_a, early=True)
+        got_dev = dec.decode_OpenCL(_dev(ch.astype(np.uint8)), buffer_in=True, return_buffer=True).get()
+        got_i64 = dec.decode_OpenCL(ch.astype(np.int64), buffer_in=False, return_buffer=False)
+        got_f = dec.decode_OpenCL(np.asfortranarray(ch.astype(np.uint8)), buffer_in=False, return_buffer=True).get()
+        assert np.array_equal(got_dev, ref) and np.array_equal(got_i64, ref) and np.array_equal(got_f, ref)
+        assert dec.last_i_num == i_ref
+
+
 def test_cabi_argument_errors(gpu):
     import informationbottleneckdecodingldpc_b200 as pkg
     H = codes.regular_random(24, 3, 6, seed=1)
