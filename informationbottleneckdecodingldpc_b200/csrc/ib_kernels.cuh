@@ -48,6 +48,7 @@ struct IbArgs {
     uint8_t* msg;
     uint8_t* out;
     uint32_t pitch;    // bytes per row (multiple of 16)
+    uint32_t out_pitch; // packed-nibble path: bytes per row of `out` (uint8 per frame) while `pitch` is the packed pitch
     int B;             // valid frames
     int tiles;         // ceil(pitch / 512): 512-frame tiles per row
     int tpc_log2;      // log2(tiles handled by one CTA) in 0..3; a CTA's 8 warps cover 2^tpc_log2

@@ -1,0 +1,419 @@
+// ib_kernels_n4.cuh -- packed-nibble variant of the IB fast path (|T| <= 16, T even).
+//
+// Same flooding schedule, same in-place check-node-major message array and the same look-up
+// order as ib_kernels.cuh (so results stay bit-identical to the reference chains,
+// kernels_template_irreg.cl:33-99, :103-179, :181-246, :249-325), but every message and channel
+// value is stored in FOUR bits:
+//   ch4 [n_var ][pitch4]   channel cluster indices, two frames per byte
+//   msg [n_edge][pitch4]   messages, two frames per byte
+// frame F of a row sits in bits 4*(F&7).. of the 32-bit word F>>3, pitch4 = ceil(B/2) rounded up
+// to 16 bytes.  HBM traffic per iteration drops from 4E+N to 2E+N/2 bytes per frame (SURVEY 8d
+// names nibble packing as the lever above the uint8 roofline).
+//
+// Thread mapping: one warp = one (node, tile); a lane moves VEC 32-bit words (8*VEC frames) per
+// message with one 64- or 128-bit access, so a warp touches 128*VEC contiguous bytes per row.
+//
+// Tables: lane-striped shared-memory layout of ib_kernels.cuh with a fixed row stride of 16
+// values per message (row = m*16 + t), so every address term is a shift by a compile-time amount:
+//   addr = (t << log2(128 W)) + (m << log2(2048 W)) + lane*4 + column offset.
+#pragma once
+#include "ib_kernels.cuh"
+
+namespace ibldpc {
+
+constexpr int kTS = 16;   // row stride per message value of the n4 table layout
+
+__host__ __device__ constexpr int n4_words(int cols) { return cols <= 4 ? 1 : (cols + 3) / 4; }
+__host__ __device__ constexpr int n4_cn_words(int d, bool explicit_match) { return n4_words(d - 2 + (explicit_match ? 1 : 0)); }
+__host__ __device__ constexpr int n4_vn_words(int d, bool decide) { return n4_words(decide ? d : d - 1); }
+__host__ __device__ constexpr int n4_table_bytes(int W) { return kTS * kTS * W * 128; }
+
+// ------------------------------------------------------------------------------------------
+// word-vector loads / stores (VEC = 2: 64-bit, VEC = 4: 128-bit)
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__device__ __forceinline__ void ld_words(const uint8_t* p, uint32_t (&w)[VEC])
+{
+    if constexpr (VEC == 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else if constexpr (VEC == 2) {
+        const uint2 v = *reinterpret_cast<const uint2*>(p);
+        w[0] = v.x; w[1] = v.y;
+    } else {
+        w[0] = *reinterpret_cast<const uint32_t*>(p);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void st_words(uint8_t* p, const uint32_t (&w)[VEC])
+{
+    if constexpr (VEC == 4) *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    else if constexpr (VEC == 2) *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+    else *reinterpret_cast<uint32_t*>(p) = w[0];
+}
+
+// nibble f of w, multiplied by MUL (compile-time).  For a power-of-two MUL this is one shift and
+// one mask (the mask fuses with the following OR/ADD into a single LOP3 / IADD3).
+__host__ __device__ constexpr int n4_ilog2(uint32_t x) { return x <= 1 ? 0 : 1 + n4_ilog2(x >> 1); }
+
+template <uint32_t MUL>
+__device__ __forceinline__ uint32_t nib_times(uint32_t w, int f)
+{
+    if constexpr ((MUL & (MUL - 1)) == 0) {
+        constexpr int sh = n4_ilog2(MUL);
+        const int s = 4 * f - sh;
+        const uint32_t x = s >= 0 ? (w >> s) : (w << (-s));
+        return x & (15u << sh);
+    } else {
+        return ((w >> (4 * f)) & 15u) * MUL;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// table staging: compact tables of this launch -> scratch (coalesced) -> lane-striped rows
+// Host side: dynamic smem = n4_table_bytes(W) + stage_scratch_bytes(nst, T, dmax_match).
+// Message alignment is folded into the last stage exactly as in stage_tables().
+// ------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void stage_tables_n4(uint32_t* s_tab, const IbArgs& a, const uint8_t* lut)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int T = a.T, TT = T * T;
+    constexpr int total = kTS * kTS * W;
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(s_tab) + (size_t)total * 128;
+    const int n_lut = a.nst * TT;
+    if (((n_lut | (int)(reinterpret_cast<uintptr_t>(lut) & 3)) & 3) == 0) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(lut);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(scratch);
+        for (int i = threadIdx.x; i < n_lut / 4; i += kThreads) dst[i] = src[i];
+    } else {
+        for (int i = threadIdx.x; i < n_lut; i += kThreads) scratch[i] = lut[i];
+    }
+    uint8_t* smatch = scratch + n_lut;
+    if (a.match != nullptr)
+        for (int i = threadIdx.x; i < a.dmax_match * T; i += kThreads) smatch[i] = a.match[i];
+    __syncthreads();
+    const bool fold = a.match != nullptr && a.nst >= 1;
+    for (int rw = warp; rw < total; rw += kWarpsPerCta) {
+        const int r = rw / W, w = rw - r * W;
+        const int m = r / kTS, t = r - m * kTS;
+        uint32_t v = 0;
+        if (t < T) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int col = 4 * w + q;
+                uint32_t e = 0;
+                if (col < a.nst) {
+                    if (m < T) {
+                        e = scratch[col * TT + t * T + m];
+                        if (fold && col == a.nst - 1) e = smatch[(a.dmax_match - 1) * T + e];
+                    }
+                } else if (col == a.nst && a.match != nullptr && !fold) {
+                    if (m < a.dmax_match) e = smatch[m * T + t];
+                }
+                v |= e << (8 * q);
+            }
+        }
+        s_tab[rw * 32 + lane] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// check node, 8 frames (one 32-bit word per message)
+// ------------------------------------------------------------------------------------------
+template <int D, bool MATCH>
+__device__ __forceinline__ void cn_word_n4(const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab, uint32_t lane4)
+{
+    constexpr uint32_t W = n4_cn_words(D, MATCH), RS = 128u * W, TRS = RS * kTS;
+    const uint32_t match_off = (uint32_t)(D - 1) * TRS + IB_SO(D - 2) + lane4;
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = 0;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        uint32_t ms[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) ms[k] = nib_times<TRS>(w[k], f) | lane4;
+        uint32_t P[D > 1 ? D : 2];
+        P[1] = (w[0] >> (4 * f)) & 15u;
+#pragma unroll
+        for (int j = 1; j <= D - 2; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(j - 1));
+#pragma unroll
+        for (int wo = 0; wo < D; ++wo) {
+            uint32_t t = (wo == 0) ? ((w[1] >> (4 * f)) & 15u) : P[wo];
+#pragma unroll
+            for (int k = (wo == 0 ? 2 : wo + 1); k < D; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
+            if (MATCH) t = lut_ld(tab, t * RS + match_off);
+            o[wo] += t << (4 * f);
+        }
+    }
+}
+
+template <int D, bool MATCH, bool EARLY, int VEC>
+__device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* tab, int s, uint32_t col, uint32_t lane4,
+                                               int valid_frames)
+{
+    uint32_t m[D][VEC];
+    if (a.iter0) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) ld_words<VEC>(a.ch + (uint64_t)(uint32_t)a.vidx[s + k] * a.pitch + col, m[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k) ld_words<VEC>(a.msg + (uint64_t)(uint32_t)(s + k) * a.pitch + col, m[k]);
+    }
+    uint32_t syn = 0;
+    uint32_t r[D][VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        uint32_t w[D], o[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) w[k] = m[k][j];
+        if (EARLY && !a.iter0) {
+            // calc_syndrome (kernels_template_irreg.cl:304-325) on the VN->CN messages just read:
+            // parity of (msg < T/2) over the D inputs, one bit per frame nibble
+            uint32_t par = 0;
+            if (a.tshift >= 0) {   // T power of two: (m < T/2) == !bit(log2(T)-1)
+                uint32_t x = 0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) x ^= w[k];
+                par = ((x >> a.tshift) & 0x11111111u) ^ ((D & 1) ? 0x11111111u : 0u);
+            } else {
+#pragma unroll
+                for (int f = 0; f < 8; ++f) {
+                    uint32_t p1 = 0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) p1 ^= (((w[k] >> (4 * f)) & 15u) < (uint32_t)(a.T / 2)) ? 1u : 0u;
+                    par |= p1 << (4 * f);
+                }
+            }
+            const int nv = valid_frames - 8 * j;   // ignore padding frames
+            const uint32_t vmask = nv >= 8 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (4 * nv)) - 1u);
+            syn |= par & vmask;
+        }
+        cn_word_n4<D, MATCH>(w, o, tab, lane4);
+#pragma unroll
+        for (int k = 0; k < D; ++k) r[k][j] = o[k];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) st_words<VEC>(a.msg + (uint64_t)(uint32_t)(s + k) * a.pitch + col, r[k]);
+    return syn;
+}
+
+__host__ __device__ constexpr int cn_n4_min_blocks(int D, int VEC)
+{
+    return VEC == 2 ? (D <= 6 ? 5 : (D <= 8 ? 3 : 2)) : (D <= 6 ? 4 : (D <= 8 ? 3 : 2));
+}
+
+// send + checknode_update_iter0 (a.iter0) or checknode_update + calc_syndrome, packed nibbles.
+template <int D, bool MATCH, bool EARLY, int VEC>
+__global__ void __launch_bounds__(kThreads, cn_n4_min_blocks(D, VEC))
+ib_cn_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
+{
+    extern __shared__ __align__(16) uint32_t s_tab[];
+    if (EARLY && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
+    stage_tables_n4<n4_cn_words(D, MATCH)>(s_tab, a, a.lut);
+    __syncthreads();
+    const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_tab);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane4 = lane * 4;
+    const int tile = (blockIdx.y << a.tpc_log2) + (warp & ((1 << a.tpc_log2) - 1));
+    const int nps = kWarpsPerCta >> a.tpc_log2;
+    const int stride = gridDim.x * nps;
+    const uint32_t col = ((uint32_t)tile * 32u + lane) * (4u * VEC);
+    uint32_t syn = 0;
+    if (tile < a.tiles && col < a.pitch) {
+        const int valid = a.B - 2 * (int)col;
+        int i = blockIdx.x * nps + (warp >> a.tpc_log2);
+        int s = i < n_nodes ? a.sc[nodes[i]] : 0;
+        while (i < n_nodes) {
+            const int i2 = i + stride;
+            const int s2 = i2 < n_nodes ? a.sc[nodes[i2]] : 0;
+            syn |= cn_node_n4<D, MATCH, EARLY, VEC>(a, tab, s, col, lane4, valid);
+            i = i2;
+            s = s2;
+        }
+    }
+    if (EARLY && !a.iter0) {
+        const unsigned any = __ballot_sync(0xffffffffu, syn != 0);
+        if (any != 0 && lane == 0) atomicOr(&a.flags[a.it], 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// variable node: channel value + D inbox messages, 8 frames
+// ------------------------------------------------------------------------------------------
+template <int D, bool DECIDE>
+__device__ __forceinline__ void vn_word_n4(uint32_t chw, const uint32_t (&w)[D], uint32_t (&o)[D], uint32_t& dec_lo,
+                                           uint32_t& dec_hi, const uint8_t* tab, uint32_t lane4)
+{
+    constexpr uint32_t W = n4_vn_words(D, DECIDE), RS = 128u * W, TRS = RS * kTS;
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = 0;
+    dec_lo = dec_hi = 0;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        uint32_t ms[D + 1];   // ms[k] for y_k, k = 1..D
+#pragma unroll
+        for (int k = 1; k <= D; ++k) ms[k] = nib_times<TRS>(w[k - 1], f) | lane4;
+        uint32_t P[D + 2];
+        P[1] = (chw >> (4 * f)) & 15u;
+#pragma unroll
+        for (int j = 1; j <= D - 1; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(j - 1));
+        if (DECIDE) {
+            const uint32_t t = lut_ld(tab, P[D] * RS + ms[D] + IB_SO(D - 1));
+            if (f < 4) dec_lo = put_byte(dec_lo, t, f & 3);
+            else dec_hi = put_byte(dec_hi, t, f & 3);
+        } else {
+#pragma unroll
+            for (int wo = 1; wo <= D; ++wo) {
+                uint32_t t = P[wo];
+#pragma unroll
+                for (int k = wo + 1; k <= D; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
+                o[wo - 1] += t << (4 * f);
+            }
+        }
+    }
+}
+
+template <int D, int VEC> struct VnIn4 { uint32_t c[VEC]; uint32_t m[D][VEC]; };
+
+template <int D, int VEC>
+__device__ __forceinline__ void vn_load_msgs_n4(const IbArgs& a, const VnIdx<D>& x, uint32_t col, VnIn4<D, VEC>& in)
+{
+    if (x.ok) {
+        ld_words<VEC>(a.ch + (uint64_t)(uint32_t)x.v * a.pitch + col, in.c);
+#pragma unroll
+        for (int k = 0; k < D; ++k) ld_words<VEC>(a.msg + (uint64_t)(uint32_t)x.rows[k] * a.pitch + col, in.m[k]);
+    }
+}
+
+template <int D, bool DECIDE, int VEC>
+__device__ __forceinline__ void vn_compute_store_n4(const IbArgs& a, const uint8_t* tab, const VnIdx<D>& x,
+                                                    const VnIn4<D, VEC>& in, uint32_t col, uint32_t lane4)
+{
+    if (!DECIDE && D == 1) {   // degree-1 variable node forwards the raw channel value (:132-136)
+        st_words<VEC>(a.msg + (uint64_t)(uint32_t)x.rows[0] * a.pitch + col, in.c);
+        return;
+    }
+    uint32_t r[D][VEC];
+    uint32_t dec[2 * VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        uint32_t w[D], o[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) w[k] = in.m[k][j];
+        vn_word_n4<D, DECIDE>(in.c[j], w, o, dec[2 * j], dec[2 * j + 1], tab, lane4);
+        if (!DECIDE) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) r[k][j] = o[k];
+        }
+    }
+    if (DECIDE) {
+        // decided cluster indices leave as uint8 (one byte per frame): 8*VEC bytes per lane
+        const uint32_t ocol = 2u * col;
+        uint8_t* dst = a.out + (uint64_t)(uint32_t)x.v * a.out_pitch + ocol;
+#pragma unroll
+        for (int q = 0; q < VEC / 2; ++q)
+            if (ocol + 16u * q < a.out_pitch)
+                *reinterpret_cast<uint4*>(dst + 16 * q) = make_uint4(dec[4 * q], dec[4 * q + 1], dec[4 * q + 2], dec[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k) st_words<VEC>(a.msg + (uint64_t)(uint32_t)x.rows[k] * a.pitch + col, r[k]);
+    }
+}
+
+// Software pipeline over the node list of one degree class (row indices fetched two nodes ahead,
+// see vn_loop in ib_kernels.cuh).
+template <int D, bool DECIDE, int VEC>
+__device__ __forceinline__ void vn_loop_n4(const IbArgs& a, const uint8_t* tab, const int* __restrict__ nodes, int n_nodes)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane4 = lane * 4;
+    const int tile = (blockIdx.y << a.tpc_log2) + (warp & ((1 << a.tpc_log2) - 1));
+    const int nps = kWarpsPerCta >> a.tpc_log2;
+    const int stride = gridDim.x * nps;
+    const uint32_t col = ((uint32_t)tile * 32u + lane) * (4u * VEC);
+    if (tile >= a.tiles || col >= a.pitch) return;
+    int i = blockIdx.x * nps + (warp >> a.tpc_log2);
+    VnIdx<D> cur, nxt, nn;
+    vn_load_idx<D>(a, nodes, n_nodes, i, cur);
+    vn_load_idx<D>(a, nodes, n_nodes, i + stride, nxt);
+    int inn = i + 2 * stride;
+    while (cur.ok) {
+        VnIn4<D, VEC> buf;
+        vn_load_msgs_n4<D, VEC>(a, cur, col, buf);
+        vn_load_idx<D>(a, nodes, n_nodes, inn, nn);
+        inn += stride;
+        vn_compute_store_n4<D, DECIDE, VEC>(a, tab, cur, buf, col, lane4);
+        cur = nxt;
+        nxt = nn;
+    }
+}
+
+__host__ __device__ constexpr int vn_n4_min_blocks(int D, int VEC)
+{
+    return VEC == 2 ? (D <= 4 ? 5 : (D <= 8 ? 3 : 2)) : (D <= 4 ? 4 : (D <= 8 ? 3 : 2));
+}
+
+// varnode_update (kernels_template_irreg.cl:103-179), packed nibbles
+template <int D, int VEC>
+__global__ void __launch_bounds__(kThreads, vn_n4_min_blocks(D, VEC))
+ib_vn_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
+{
+    extern __shared__ __align__(16) uint32_t s_tab[];
+    if (a.early && a.it >= 1 && a.flags[a.it - 1] == 0) return;
+    if (D > 1) {
+        stage_tables_n4<n4_vn_words(D, false)>(s_tab, a, a.lut);
+        __syncthreads();
+    }
+    vn_loop_n4<D, false, VEC>(a, reinterpret_cast<const uint8_t*>(s_tab), nodes, n_nodes);
+}
+
+// calc_varnode_output (kernels_template_irreg.cl:249-302) with the VN table of iteration i_num-1;
+// reads packed nibbles, writes uint8 cluster indices
+template <int D, int VEC>
+__global__ void __launch_bounds__(kThreads) ib_out_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
+{
+    extern __shared__ __align__(16) uint32_t s_tab[];
+    __shared__ int s_passes;
+    if (threadIdx.x == 0) {
+        s_passes = executed_passes(a);
+        if (blockIdx.x == 0 && blockIdx.y == 0) *a.inum = s_passes + 1;
+    }
+    __syncthreads();
+    stage_tables_n4<n4_vn_words(D, true)>(s_tab, a, a.lut + (long long)s_passes * a.vn_it_stride);
+    __syncthreads();
+    vn_loop_n4<D, true, VEC>(a, reinterpret_cast<const uint8_t*>(s_tab), nodes, n_nodes);
+}
+
+// ------------------------------------------------------------------------------------------
+// uint8 (rows, src_pitch) -> packed nibbles (rows, pitch4); frames >= B become 0.
+// One thread per 32-bit destination word (8 frames).
+// ------------------------------------------------------------------------------------------
+template <bool ALIGNED>
+__global__ void pack_n4_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int rows, long long B,
+                               long long src_pitch, uint32_t pitch4)
+{
+    const uint32_t wpr = pitch4 >> 2;   // words per destination row
+    const long long n = (long long)rows * wpr;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / wpr;
+        const long long wd = i - r * wpr;
+        const long long f0 = wd * 8;
+        uint32_t v = 0;
+        const uint8_t* p = src + r * src_pitch + f0;
+        if (ALIGNED && f0 + 8 <= B) {
+            const uint2 x = *reinterpret_cast<const uint2*>(p);
+            // bytes b0..b3 of x.x -> nibbles 0..3, x.y -> nibbles 4..7
+            const uint32_t lo = x.x & 0x0f0f0f0fu, hi = x.y & 0x0f0f0f0fu;
+            const uint32_t l2 = (lo | (lo >> 4)) & 0x00ff00ffu, h2 = (hi | (hi >> 4)) & 0x00ff00ffu;
+            v = ((l2 | (l2 >> 8)) & 0xffffu) | (((h2 | (h2 >> 8)) & 0xffffu) << 16);
+        } else {
+#pragma unroll
+            for (int f = 0; f < 8; ++f)
+                if (f0 + f < B) v |= (uint32_t)(p[f] & 15u) << (4 * f);
+        }
+        reinterpret_cast<uint32_t*>(dst)[i] = v;
+    }
+}
+
+}  // namespace ibldpc

@@ -12,6 +12,7 @@
 
 #include "../../include/ibldpc.h"
 #include "ib_kernels.cuh"
+#include "ib_kernels_n4.cuh"
 #include "llr_kernels.cuh"
 #include "kernel_tables.h"
 
@@ -43,6 +44,8 @@ struct NodeClass {
 struct Workspace {
     uint8_t* msg = nullptr;     // IB in-place message array
     size_t msg_bytes = 0;
+    uint8_t* ch4 = nullptr;     // packed-nibble copy of the channel values (n4 path)
+    size_t ch4_bytes = 0;
     void* cin = nullptr;        // LLR inboxes
     void* vin = nullptr;
     size_t llr_bytes = 0;
@@ -84,6 +87,8 @@ struct ibldpc_decoder {
     bool use_pair = true;
     int pair_min_degree = 7;
     bool fast = false;
+    bool nib = false;     // packed-nibble fast path (ib_kernels_n4.cuh)
+    int cn_vec = 0, vn_vec = 0;   // 0 = per-degree default, 2 / 4 = forced (IBLDPC_CN_VEC / IBLDPC_VN_VEC)
     int Wc = 1, Wv = 1, Wo = 1, nrows_c = 0, nrows_v = 0, nrows_o = 0, tshift = -1;
     Workspace ws[2];
     int host_chunk = 0;   // 0 = auto: about 64 MiB of channel values per chunk
@@ -226,12 +231,16 @@ void clear_events(ibldpc_decoder* h)
     h->events.clear();
 }
 
+int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long pitch8, long long B, int imax, int early,
+                 uint8_t* out, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------
 // IB decode on padded device buffers (pitch multiple of 16, pointers 16-byte aligned)
 // ------------------------------------------------------------------------------------------
 int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long pitch, long long B, int imax,
                      int early, uint8_t* out, cudaStream_t st)
 {
+    if (h->fast && h->nib) return decode_ib_n4(h, w, ch, pitch, B, imax, early, out, st);
     int rc = ensure_ws_common(h, w);
     if (rc) return rc;
     size_t need = (size_t)h->E * (size_t)pitch;
@@ -411,6 +420,118 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
         }
         if ((rc = launch_vn(0, true))) return rc;
     }
+    CK(cudaGetLastError());
+    return IBLDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// IB decode, packed-nibble fast path: `ch` / `out` are the uint8 buffers of decode_ib_padded
+// (pitch multiple of 16); messages and channel values travel as nibbles inside.
+// ------------------------------------------------------------------------------------------
+int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long pitch8, long long B, int imax, int early,
+                 uint8_t* out, cudaStream_t st)
+{
+    int rc = ensure_ws_common(h, w);
+    if (rc) return rc;
+    const long long pitch4 = ((B + 1) / 2 + 15) / 16 * 16;
+    {
+        void* p = w.msg;
+        rc = ensure(&p, &w.msg_bytes, (size_t)h->E * (size_t)pitch4);
+        w.msg = (uint8_t*)p;
+        if (rc) return rc;
+        p = w.ch4;
+        rc = ensure(&p, &w.ch4_bytes, (size_t)h->N * (size_t)pitch4);
+        w.ch4 = (uint8_t*)p;
+        if (rc) return rc;
+    }
+    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)std::max(imax, 1), st));
+    h->last_launches = 0;
+    Prof prof{h, st};
+    {
+        const long long nwords = (long long)h->N * (pitch4 / 4);
+        const int grid = (int)std::min<long long>((nwords + 255) / 256, (long long)h->sm_count * 16);
+        if ((rc = prof.begin(2))) return rc;
+        pack_n4_kernel<true><<<grid, 256, 0, st>>>(ch, w.ch4, h->N, B, pitch8, (uint32_t)pitch4);
+        h->last_launches++;
+        if ((rc = prof.end())) return rc;
+    }
+    IbArgs a{};
+    a.sc = h->d_sc; a.deg_c = h->d_dc; a.sv = h->d_sv; a.deg_v = h->d_dv; a.tv = h->d_tv; a.vidx = h->d_vidx;
+    a.n_var = h->N; a.n_chk = h->M;
+    a.ch = w.ch4; a.msg = w.msg; a.out = out;
+    a.pitch = (uint32_t)pitch4; a.out_pitch = (uint32_t)pitch8; a.B = (int)B;
+    a.T = h->T; a.Tc = h->Tc; a.tshift = h->tshift;
+    a.flags = w.flags; a.inum = w.inum; a.early = early; a.imax = imax;
+    a.DC = h->DC; a.DV = h->DV; a.xp_col = -1;
+    const int T = h->T, TT = T * T;
+    // tile geometry of one launch: a warp covers 128*vec bytes of a row
+    auto set_tiles = [&](IbArgs& b, int vec, int* tile_groups, int* nps) {
+        b.tiles = (int)((pitch4 + 128 * vec - 1) / (128 * vec));
+        b.tpc_log2 = b.tiles >= 8 ? 3 : b.tiles > 2 ? 2 : b.tiles == 2 ? 1 : 0;
+        *tile_groups = (b.tiles + (1 << b.tpc_log2) - 1) >> b.tpc_log2;
+        *nps = kWarpsPerCta >> b.tpc_log2;
+    };
+    auto cn_vec_of = [&](int) { return h->cn_vec ? h->cn_vec : 2; };
+    auto vn_vec_of = [&](int d) { return h->vn_vec ? h->vn_vec : (d <= 6 ? 4 : 2); };
+    auto launch_cn = [&](int it) -> int {
+        IbArgs b = a;
+        b.it = it; b.iter0 = (it < 0);
+        const int blk = it + 1;   // table block: 0 = iteration-0 tables
+        b.lut = h->d_cn8 + (size_t)blk * (h->DC - 2) * TT;
+        b.match = h->match ? h->d_mc8 + (size_t)blk * h->DC * T : nullptr;
+        int r = prof.begin(it < 0 ? 2 : 0);
+        if (r) return r;
+        for (auto& c : h->cn_classes) {
+            b.nst = c.degree - 2;
+            const bool explicit_match = h->match && b.nst == 0;   // folded into the last stage otherwise
+            b.dmax_match = h->match ? c.degree : 0;
+            const int vec = cn_vec_of(c.degree);
+            int tile_groups, nps;
+            set_tiles(b, vec, &tile_groups, &nps);
+            const int smem = n4_table_bytes(n4_cn_words(c.degree, explicit_match)) + stage_scratch_bytes(b.nst, T, b.dmax_match);
+            NodeKernel k = vec == 4 ? cn_n4_kernel_v4(c.degree, explicit_match, early != 0)
+                                    : cn_n4_kernel_v2(c.degree, explicit_match, early != 0);
+            if (!k) return fail(IBLDPC_E_INVALID, "no packed check-node kernel for degree " + std::to_string(c.degree));
+            int grid;
+            if ((r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid))) return r;
+            k<<<dim3(grid, tile_groups), kThreads, smem, st>>>(b, c.d_nodes, c.count);
+            h->last_launches++; h->last_grid = grid * tile_groups; h->last_smem = smem;
+        }
+        return prof.end();
+    };
+    auto launch_vn = [&](int it, bool decide) -> int {
+        IbArgs b = a;
+        b.it = it; b.iter0 = 0;
+        if (decide) {
+            b.lut = h->d_vn8; b.vn_it_stride = (long long)h->DV * TT; b.match = nullptr;
+        } else {
+            b.lut = h->d_vn8 + (size_t)it * h->DV * TT;
+            b.match = h->match ? h->d_mv8 + (size_t)it * h->DV * T : nullptr;
+        }
+        int r = prof.begin(decide ? 2 : 1);
+        if (r) return r;
+        for (auto& c : h->vn_classes) {
+            b.nst = decide ? c.degree : c.degree - 1;
+            b.dmax_match = b.match != nullptr ? c.degree : 0;
+            const int vec = vn_vec_of(c.degree);
+            int tile_groups, nps;
+            set_tiles(b, vec, &tile_groups, &nps);
+            const int smem = n4_table_bytes(n4_vn_words(c.degree, decide)) + stage_scratch_bytes(b.nst, T, b.dmax_match);
+            NodeKernel k = vec == 4 ? vn_n4_kernel_v4(c.degree, decide) : vn_n4_kernel_v2(c.degree, decide);
+            if (!k) return fail(IBLDPC_E_INVALID, "no packed variable-node kernel for degree " + std::to_string(c.degree));
+            int grid;
+            if ((r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid))) return r;
+            k<<<dim3(grid, tile_groups), kThreads, smem, st>>>(b, c.d_nodes, c.count);
+            h->last_launches++;
+        }
+        return prof.end();
+    };
+    if ((rc = launch_cn(-1))) return rc;
+    for (int it = 0; it < imax - 1; ++it) {
+        if ((rc = launch_vn(it, false))) return rc;
+        if ((rc = launch_cn(it))) return rc;
+    }
+    if ((rc = launch_vn(0, true))) return rc;
     CK(cudaGetLastError());
     return IBLDPC_OK;
 }
@@ -778,6 +899,11 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
               (size_t)h->nrows_c * h->Wc * 128 <= smem_max && (size_t)h->nrows_v * h->Wv * 128 <= smem_max &&
               (size_t)h->nrows_o * h->Wo * 128 <= smem_max;
     if (getenv("IBLDPC_FORCE_GENERIC")) h->fast = false;
+    // packed-nibble messages need an even |T| (address terms are shifts of the packed word)
+    h->nib = h->fast && (T % 2 == 0) && getenv("IBLDPC_NO_NIBBLE") == nullptr;
+    h->cn_vec = h->vn_vec = 0;
+    if (const char* e = getenv("IBLDPC_CN_VEC")) h->cn_vec = atoi(e) == 4 ? 4 : atoi(e) == 2 ? 2 : 0;
+    if (const char* e = getenv("IBLDPC_VN_VEC")) h->vn_vec = atoi(e) == 4 ? 4 : atoi(e) == 2 ? 2 : 0;
     h->use_pair = getenv("IBLDPC_NO_PAIR") == nullptr;
     if (const char* pm = getenv("IBLDPC_PAIR_MIN_DEGREE")) h->pair_min_degree = std::max(4, atoi(pm));
     if (h->d_cn_pair) { CK(cudaFree(h->d_cn_pair)); h->d_cn_pair = nullptr; }
@@ -961,7 +1087,7 @@ int ibldpc_uniform(int device, uint64_t seed, uint64_t offset, int64_t n, double
 int ibldpc_info(ibldpc_handle h, int32_t* which4)
 {
     if (!h || !which4) return fail(IBLDPC_E_INVALID, "null argument");
-    which4[0] = h->fast ? 1 : 0;
+    which4[0] = h->fast ? (h->nib ? 2 : 1) : 0;   // 0 generic, 1 uint8 fast path, 2 packed-nibble fast path
     which4[1] = h->last_launches;
     which4[2] = h->last_grid;
     which4[3] = h->last_smem;
@@ -1011,7 +1137,7 @@ int ibldpc_destroy(ibldpc_handle h)
     for (auto& c : h->cn_classes) if (c.d_nodes) cudaFree(c.d_nodes);
     for (auto& c : h->vn_classes) if (c.d_nodes) cudaFree(c.d_nodes);
     for (auto& w : h->ws) {
-        for (void* p : {(void*)w.msg, w.cin, w.vin, (void*)w.padbuf_in, (void*)w.padbuf_out, (void*)w.stage_in,
+        for (void* p : {(void*)w.msg, (void*)w.ch4, w.cin, w.vin, (void*)w.padbuf_in, (void*)w.padbuf_out, (void*)w.stage_in,
                         (void*)w.stage_out, (void*)w.flags, (void*)w.inum})
             if (p) cudaFree(p);
         if (w.stream) cudaStreamDestroy(w.stream);

@@ -13,6 +13,11 @@ using LlrShflKernel = void (*)(LlrArgs, int);
 
 NodeKernel cn_fast_kernel_for(int d, bool match, bool early, bool pair);
 NodeKernel vn_fast_kernel_for(int d, bool decide, bool match);
+// packed-nibble fast path (ib_kernels_n4.cuh); vec = 32-bit words per lane and message (2 or 4)
+NodeKernel cn_n4_kernel_v2(int d, bool match, bool early);
+NodeKernel cn_n4_kernel_v4(int d, bool match, bool early);
+NodeKernel vn_n4_kernel_v2(int d, bool decide);
+NodeKernel vn_n4_kernel_v4(int d, bool decide);
 LlrNodeKernel llr_cn_kernel_for(bool f64, int algo, int d);
 LlrNodeKernel llr_vn_kernel_for(bool f64, int mode, int d);
 LlrSynKernel llr_syndrome_kernel_for(bool f64);

@@ -27,11 +27,28 @@ def _dev(a):
     return pkg.DeviceArray(torch.from_numpy(np.ascontiguousarray(a)).cuda())
 
 
+# Kernel families of the IB fast path (|T| <= 16), selected when the tables are uploaded:
+#   n4       packed-nibble messages (default), per-degree default vector widths
+#   n4_v24 / n4_v42  packed nibbles with the check-/variable-node vector widths forced to 2/4 and 4/2 words
+#   u8       one byte per message (IBLDPC_NO_NIBBLE=1), incl. the tail-pair check-node kernels
+IB_VARIANTS = {"n4": {}, "n4_v24": {"IBLDPC_CN_VEC": "2", "IBLDPC_VN_VEC": "4"},
+               "n4_v42": {"IBLDPC_CN_VEC": "4", "IBLDPC_VN_VEC": "2"}, "u8": {"IBLDPC_NO_NIBBLE": "1"}}
+
+
+@pytest.fixture(params=list(IB_VARIANTS))
+def ib_variant(request, monkeypatch):
+    for k, v in IB_VARIANTS[request.param].items():
+        monkeypatch.setenv(k, v)
+    return 1 if request.param == "u8" else 2     # expected ibldpc_info()[0] of the fast path
+
+
 @pytest.mark.parametrize("force_generic", [False, True])
 @pytest.mark.parametrize("case", IB_CASES)
-def test_ib_golden_device_buffers(gpu, case, force_generic, monkeypatch):
+def test_ib_golden_device_buffers(gpu, case, force_generic, monkeypatch, ib_variant):
     g = load_golden(case)
     if force_generic:
+        if ib_variant != 2 or os.environ.get("IBLDPC_CN_VEC"):
+            pytest.skip("the generic path has one variant")
         monkeypatch.setenv("IBLDPC_FORCE_GENERIC", "1")
     T, imax = int(g["T"]), int(g["imax"])
     match = bool(int(g["match"]))
@@ -42,7 +59,7 @@ def test_ib_golden_device_buffers(gpu, case, force_generic, monkeypatch):
     dec.early_termination = bool(int(g["early"]))
     out = dec.decode_OpenCL(_dev(g["ch"]), buffer_in=True, return_buffer=True)
     fast = dec.info()[0]
-    assert fast == (0 if (force_generic or T > 16) else 1)
+    assert fast == (0 if (force_generic or T > 16) else ib_variant)
     assert np.array_equal(out.get(), g["out"]), case
     if dec.early_termination:
         assert dec.last_i_num == int(g["i_num"])
@@ -78,8 +95,8 @@ def _oracle_ib(t, ch, T, imax, tb, early):
                             vn_match=tb.matching_vector_varnode, early=early)
 
 
-@pytest.mark.parametrize("B", [1, 15, 16, 100, 513, 1040])
-def test_ib_c1_vs_oracle_ragged_batches(gpu, B):
+@pytest.mark.parametrize("B", [1, 15, 16, 31, 33, 100, 513, 1040, 2049])
+def test_ib_c1_vs_oracle_ragged_batches(gpu, B, ib_variant):
     """(3,6) n=8000, random tables: every batch-size class (sub-vector, unaligned, multi-tile)."""
     H = codes.regular_random(8000, 3, 6)
     t = graph.edge_tables(H)
@@ -103,7 +120,7 @@ def test_ib_c1_vs_oracle_ragged_batches(gpu, B):
     ("wlan1296_T12", lambda: codes.wlan_80211n(54), 12),
 ])
 @pytest.mark.parametrize("match", [True, False])
-def test_ib_irregular_vs_oracle(gpu, name, H, T, match):
+def test_ib_irregular_vs_oracle(gpu, name, H, T, match, ib_variant):
     H = H()
     t = graph.edge_tables(H)
     imax, B = 7, 77
@@ -113,7 +130,7 @@ def test_ib_irregular_vs_oracle(gpu, name, H, T, match):
                  tb.matching_vector_checknode, tb.matching_vector_varnode)
     got = dec.decode_OpenCL(_dev(ch), buffer_in=True, return_buffer=True).get()
     ref, i_num = _oracle_ib(t, ch, T, imax, tb, True)
-    assert dec.info()[0] == 1
+    assert dec.info()[0] == ib_variant
     assert np.array_equal(got, ref) and dec.last_i_num == i_num
 
 
@@ -121,6 +138,7 @@ def test_ib_tail_pair_variant_all_degrees(gpu, monkeypatch):
     """The composed tail-pair check-node kernels (cn_word_pair) for every degree 4..10, forced on with
     IBLDPC_PAIR_MIN_DEGREE=4, with and without message alignment, against the oracle."""
     monkeypatch.setenv("IBLDPC_PAIR_MIN_DEGREE", "4")
+    monkeypatch.setenv("IBLDPC_NO_NIBBLE", "1")          # the tail-pair kernels belong to the uint8 family
     H = codes.random_from_degrees([2] * 40 + [3] * 40 + [4] * 16, [4] * 16 + [5] * 8 + [6] * 8 + [7] * 6 + [8] * 4 + [9] * 2 + [10] * 2, seed=4)
     t = graph.edge_tables(H)
     assert sorted(set(t.degree_chk)) == [4, 5, 6, 7, 8, 9, 10]
