@@ -6,7 +6,7 @@
 
 Workload (BASELINE.json configs[0], the configuration the metric is quoted on): regular (3,6)
 LDPC code n=8000, R=1/2, BPSK/AWGN, IB decoder |T|=16, i_max=50, early termination off,
-B=32768 frames per GPU and step, channel cluster indices drawn by the inversion method from the
+B=65536 frames per GPU and step, channel cluster indices drawn by the inversion method from the
 |T|=16 quantizer at Eb/N0 = 1.6 dB (all-zero codeword), exactly like quantize_direct_OpenCL;
 IB tables designed at 1.2 dB by the in-repo discrete density evolution.
 A "step" = decode one batch + count bit/frame errors (+ all-reduce of the 4 counters for N>1).
@@ -38,7 +38,7 @@ def workload(name):
     from informationbottleneckdecodingldpc_b200 import codes
     if name == "c1":
         return dict(name="(3,6) n=8000 R=0.5 IB |T|=16 i_max=50 ET off", H=codes.regular_random(8000, 3, 6, seed=SEED),
-                    irregular=False, B=32768, ebn0=1.6, design_ebn0=1.2)
+                    irregular=False, B=65536, ebn0=1.6, design_ebn0=1.2)
     if name == "wlan":
         return dict(name="802.11n n=1296 R=0.5 IB |T|=16 i_max=50 ET off, message alignment", H=codes.wlan_80211n(54),
                     irregular=True, B=100096, ebn0=2.0, design_ebn0=1.0)
@@ -314,18 +314,25 @@ def main():
     _lib.check(L.ibldpc_set_profiling(h, 0))
     cn_ms, vn_ms = ms3[0] / max(n3[0], 1), ms3[1] / max(n3[1], 1)
     peak, peak_src = measured_peak_gbs()
+    # Algorithmic bytes per launch as SURVEY.md 8(d) defines them (uint8 messages): CN 2E, VN 2E+N per frame.
+    # The packed-nibble kernels store two frames per byte, so the bytes they really move ("stored") are half
+    # of that; both figures are reported, and `frac` (algorithmic / peak) may exceed 1 for that reason.
+    packed = decodi.info()[0] == 2
     cn_bytes, vn_bytes = 2 * E * B, (2 * E + N) * B
+    fam = "n4" if packed else "fast"
     if ms3[0] >= ms3[1]:
-        dom, dom_ms, dom_bytes = "ib_cn_fast_kernel (check-node update + syndrome)", cn_ms, cn_bytes
+        dom, dom_ms, dom_bytes = f"ib_cn_{fam}_kernel (check-node update + syndrome)", cn_ms, cn_bytes
     else:
-        dom, dom_ms, dom_bytes = "ib_vn_fast_kernel (variable-node update)", vn_ms, vn_bytes
+        dom, dom_ms, dom_bytes = f"ib_vn_{fam}_kernel (variable-node update)", vn_ms, vn_bytes
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    stored_div = 2 if packed else 1
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tfile):
         try:
             tj = json.load(open(tfile)).get(args.workload)
-            if tj:   # measured at tj["frames_per_launch"]; DRAM traffic of these kernels is linear in B
+            if tj and tj.get("kernel", "")[:9] == dom[:9]:
+                # measured at tj["frames_per_launch"]; DRAM traffic of these kernels is linear in B
                 traffic = tj["bytes"] * B / tj["frames_per_launch"]
         except Exception:
             traffic = None
@@ -334,7 +341,11 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+        "message_storage": "packed nibbles (2 frames per byte)" if packed else "uint8",
+        "stored_bytes_per_launch": dom_bytes // stored_div, "achieved_stored": achieved / stored_div,
+        "frac_stored": achieved / stored_div / peak,
         "avg_launch_ms": dom_ms, "cn_avg_ms": cn_ms, "vn_avg_ms": vn_ms,
+        "cn_frac": cn_bytes / (cn_ms * 1e-3) / 1e9 / peak, "vn_frac": vn_bytes / (vn_ms * 1e-3) / 1e9 / peak,
         "cn_share_of_decode": ms3[0] / decode_ms, "vn_share_of_decode": ms3[1] / decode_ms,
         "whole_decode": {"bytes_per_frame": bytes_frame, "achieved_gbs": bytes_frame * B / (decode_ms * 1e-3) / 1e9,
                          "frac": bytes_frame * B / (decode_ms * 1e-3) / 1e9 / peak},
@@ -379,11 +390,11 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u4" if packed else "u8", "data": "synthetic",
             "config": {"workload": wl["name"], "frames_per_gpu_per_step": B, "n_var": N, "n_chk": M, "n_edge": E,
                        "info_bits": K_info, "i_max": IMAX, "EbN0_dB": wl["ebn0"], "tables": wl.get("tables"),
-                       "l2": "inputs_larger_than_L2 (message array %.0f MB)" % (E * B / 1e6), "parallelism": f"frames sharded x{world}",
-                       "fast_path": bool(decodi.info()[0])},
+                       "l2": "inputs_larger_than_L2 (message array %.0f MB)" % (E * B / stored_div / 1e6), "parallelism": f"frames sharded x{world}",
+                       "fast_path": bool(decodi.info()[0]), "kernel_family": "packed-nibble (n4)" if packed else "uint8"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
             "errors": {"bit": tot[0], "frame": tot[1], "frames": tot[2]},

@@ -73,7 +73,8 @@ struct IbArgs {
     // launch, and the byte offset of its expanded copy inside the dynamic shared memory
     const uint8_t* __restrict__ pair;
     uint32_t pair_off;
-    int xp_col;        // stage column stored in the shift-ready "xp" encoding (tail-pair kernels), -1 = none
+    int xp_col;        // stage column stored shift-ready for the tail-pair row ("xp" encoding in the uint8 family,
+                       // 4*x in the packed-nibble family), -1 = none
 };
 
 // ------------------------------------------------------------------------------------------

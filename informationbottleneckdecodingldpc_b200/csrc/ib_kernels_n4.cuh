@@ -107,6 +107,7 @@ __device__ __forceinline__ void stage_tables_n4(uint32_t* s_tab, const IbArgs& a
                     if (m < T) {
                         e = scratch[col * TT + t * T + m];
                         if (fold && col == a.nst - 1) e = smatch[(a.dmax_match - 1) * T + e];
+                        if (col == a.xp_col) e *= 4u;   // "x4" form: the value is the nibble shift into a tail-pair row
                     }
                 } else if (col == a.nst && a.match != nullptr && !fold) {
                     if (m < a.dmax_match) e = smatch[m * T + t];
@@ -148,9 +149,62 @@ __device__ __forceinline__ void cn_word_n4(const uint32_t (&w)[D], uint32_t (&o)
     }
 }
 
-template <int D, bool MATCH, bool EARLY, int VEC>
-__device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* tab, int s, uint32_t col, uint32_t lane4,
-                                               int valid_frames)
+// Tail-pair variant (D >= 4), see cn_word_pair in ib_kernels.cuh: all outputs w <= D-3 end with
+//   out_w = S_{D-3}( S_{D-4}(x_w, m_{D-2}), m_{D-1} ) = G(m_{D-2}, m_{D-1})[x_w],
+// G composed on the host (ibldpc_set_luts), 16 nibbles = one 64-bit row per (m_{D-2}, m_{D-1}),
+// fetched with ONE conflict-free LDS.64 per frame (kPairSlots lane slots).  The stage feeding the
+// row (column D-5) is stored as 4*x, so selecting nibble x_w is a 64-bit shift and a mask.
+// Shared-memory wavefronts per check and frame: D=6 18 -> 12, D=7 25 -> 16, D=8 33 -> 21.
+constexpr uint32_t kPairBytes = kTS * kTS * 8 * kPairSlots;   // 32 KB, placed in front of the stage tables
+
+template <int D>
+__device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab,
+                                                const uint8_t* ptab, uint32_t lane4, uint32_t slot8)
+{
+    static_assert(D >= 4, "tail-pair variant needs at least two look-up stages");
+    constexpr uint32_t W = n4_cn_words(D, false), RS = 128u * W, TRS = RS * kTS;
+    constexpr uint32_t PS = 8u * kPairSlots, TPS = PS * kTS;
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = 0;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        uint32_t ms[D];
+#pragma unroll
+        for (int k = 1; k < D; ++k) ms[k] = nib_times<TRS>(w[k], f) | lane4;
+        const uint2 g2 = *reinterpret_cast<const uint2*>(ptab + (nib_times<TPS>(w[D - 2], f) | nib_times<PS>(w[D - 1], f) | slot8));
+        const unsigned long long g = ((unsigned long long)g2.y << 32) | g2.x;
+        // prefix chain; P[D-3] comes out of column D-5, i.e. in x4 form (D >= 5)
+        uint32_t P[D];
+        P[1] = (w[0] >> (4 * f)) & 15u;
+#pragma unroll
+        for (int j = 1; j <= D - 3; ++j) {
+            const bool in_x4 = (D >= 5) && (j == D - 3);
+            P[j + 1] = lut_ld(tab, P[j] * (in_x4 ? RS / 4u : RS) + ms[j] + IB_SO(j - 1));
+        }
+        // the two outputs that skip one of the tail messages
+        o[D - 1] += lut_ld(tab, P[D - 2] * RS + ms[D - 2] + IB_SO(D - 3)) << (4 * f);
+        o[D - 2] += lut_ld(tab, P[D - 2] * RS + ms[D - 1] + IB_SO(D - 3)) << (4 * f);
+#pragma unroll
+        for (int wo = 0; wo <= D - 3; ++wo) {
+            uint32_t e;   // 4 * x_w
+            if (D >= 5 && wo == D - 3) {
+                e = P[D - 3];
+            } else if (D == 4) {
+                e = nib_times<4u>(w[wo == 0 ? 1 : 0], f);
+            } else {
+                uint32_t t = (wo == 0) ? ((w[1] >> (4 * f)) & 15u) : P[wo];
+#pragma unroll
+                for (int k = (wo == 0 ? 2 : wo + 1); k <= D - 3; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
+                e = t;   // the last look-up read column D-5
+            }
+            o[wo] += ((uint32_t)(g >> e) & 15u) << (4 * f);
+        }
+    }
+}
+
+template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR>
+__device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* tab, const uint8_t* ptab, int s, uint32_t col,
+                                               uint32_t lane4, int valid_frames)
 {
     uint32_t m[D][VEC];
     if (a.iter0) {
@@ -189,7 +243,8 @@ __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* t
             const uint32_t vmask = nv >= 8 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (4 * nv)) - 1u);
             syn |= par & vmask;
         }
-        cn_word_n4<D, MATCH>(w, o, tab, lane4);
+        if constexpr (PAIR) cn_word_n4_pair<D>(w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
+        else cn_word_n4<D, MATCH>(w, o, tab, lane4);
 #pragma unroll
         for (int k = 0; k < D; ++k) r[k][j] = o[k];
     }
@@ -198,21 +253,33 @@ __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* t
     return syn;
 }
 
-__host__ __device__ constexpr int cn_n4_min_blocks(int D, int VEC)
+__host__ __device__ constexpr int cn_n4_min_blocks(int D, int VEC, bool PAIR)
 {
-    return VEC == 2 ? (D <= 6 ? 5 : (D <= 8 ? 3 : 2)) : (D <= 6 ? 4 : (D <= 8 ? 3 : 2));
+    return PAIR ? (D <= 6 ? 3 : 2) : VEC == 2 ? (D <= 6 ? 5 : (D <= 8 ? 3 : 2)) : (D <= 6 ? 4 : (D <= 8 ? 3 : 2));
 }
 
 // send + checknode_update_iter0 (a.iter0) or checknode_update + calc_syndrome, packed nibbles.
-template <int D, bool MATCH, bool EARLY, int VEC>
-__global__ void __launch_bounds__(kThreads, cn_n4_min_blocks(D, VEC))
+// PAIR: shared memory = [tail-pair rows (kPairBytes)][stage tables][staging scratch].
+template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR>
+__global__ void __launch_bounds__(kThreads, cn_n4_min_blocks(D, VEC, PAIR))
 ib_cn_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 {
-    extern __shared__ __align__(16) uint32_t s_tab[];
+    extern __shared__ __align__(16) uint32_t s_all[];
     if (EARLY && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
+    uint32_t* s_tab = s_all + (PAIR ? kPairBytes / 4 : 0);
+    if (PAIR) {
+        // expand the composed rows (global: row a*T+b, 8 bytes) to kPairSlots lane slots per row a*16+b
+        const uint2* src = reinterpret_cast<const uint2*>(a.pair);
+        uint2* dst = reinterpret_cast<uint2*>(s_all);
+        for (int i = threadIdx.x; i < kTS * kTS * kPairSlots; i += kThreads) {
+            const int r = i / kPairSlots, ra = r / kTS, rb = r - ra * kTS;
+            dst[i] = (ra < a.T && rb < a.T) ? src[ra * a.T + rb] : make_uint2(0u, 0u);
+        }
+    }
     stage_tables_n4<n4_cn_words(D, MATCH)>(s_tab, a, a.lut);
     __syncthreads();
     const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_tab);
+    const uint8_t* ptab = reinterpret_cast<const uint8_t*>(s_all);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lane4 = lane * 4;
     const int tile = (blockIdx.y << a.tpc_log2) + (warp & ((1 << a.tpc_log2) - 1));
@@ -227,7 +294,7 @@ ib_cn_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
         while (i < n_nodes) {
             const int i2 = i + stride;
             const int s2 = i2 < n_nodes ? a.sc[nodes[i2]] : 0;
-            syn |= cn_node_n4<D, MATCH, EARLY, VEC>(a, tab, s, col, lane4, valid);
+            syn |= cn_node_n4<D, MATCH, EARLY, VEC, PAIR>(a, tab, ptab, s, col, lane4, valid);
             i = i2;
             s = s2;
         }

@@ -1,0 +1,20 @@
+// ib_n4_cn_pair.cu -- instantiations of the tail-pair check-node kernels ib_cn_n4_kernel<D, false, EARLY, 2, true>
+#include "kernel_tables.h"
+#include "ib_kernels_n4.cuh"
+namespace ibldpc {
+template <bool EARLY>
+static NodeKernel cn_n4_pair_sel(int d)
+{
+    switch (d) {
+    case 4: return ib_cn_n4_kernel<4, false, EARLY, 2, true>;
+    case 5: return ib_cn_n4_kernel<5, false, EARLY, 2, true>;
+    case 6: return ib_cn_n4_kernel<6, false, EARLY, 2, true>;
+    case 7: return ib_cn_n4_kernel<7, false, EARLY, 2, true>;
+    case 8: return ib_cn_n4_kernel<8, false, EARLY, 2, true>;
+    case 9: return ib_cn_n4_kernel<9, false, EARLY, 2, true>;
+    case 10: return ib_cn_n4_kernel<10, false, EARLY, 2, true>;
+    default: return nullptr;
+    }
+}
+NodeKernel cn_n4_pair_kernel(int d, bool early) { return early ? cn_n4_pair_sel<true>(d) : cn_n4_pair_sel<false>(d); }
+}  // namespace ibldpc

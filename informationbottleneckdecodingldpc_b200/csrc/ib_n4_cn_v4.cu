@@ -6,15 +6,15 @@ template <bool EARLY>
 static NodeKernel cn_n4_sel(int d)
 {
     switch (d) {
-    case 2: return ib_cn_n4_kernel<2, false, EARLY, 4>;
-    case 3: return ib_cn_n4_kernel<3, false, EARLY, 4>;
-    case 4: return ib_cn_n4_kernel<4, false, EARLY, 4>;
-    case 5: return ib_cn_n4_kernel<5, false, EARLY, 4>;
-    case 6: return ib_cn_n4_kernel<6, false, EARLY, 4>;
-    case 7: return ib_cn_n4_kernel<7, false, EARLY, 4>;
-    case 8: return ib_cn_n4_kernel<8, false, EARLY, 4>;
-    case 9: return ib_cn_n4_kernel<9, false, EARLY, 4>;
-    case 10: return ib_cn_n4_kernel<10, false, EARLY, 4>;
+    case 2: return ib_cn_n4_kernel<2, false, EARLY, 4, false>;
+    case 3: return ib_cn_n4_kernel<3, false, EARLY, 4, false>;
+    case 4: return ib_cn_n4_kernel<4, false, EARLY, 4, false>;
+    case 5: return ib_cn_n4_kernel<5, false, EARLY, 4, false>;
+    case 6: return ib_cn_n4_kernel<6, false, EARLY, 4, false>;
+    case 7: return ib_cn_n4_kernel<7, false, EARLY, 4, false>;
+    case 8: return ib_cn_n4_kernel<8, false, EARLY, 4, false>;
+    case 9: return ib_cn_n4_kernel<9, false, EARLY, 4, false>;
+    case 10: return ib_cn_n4_kernel<10, false, EARLY, 4, false>;
     default: return nullptr;
     }
 }
@@ -24,7 +24,7 @@ NodeKernel cn_n4_kernel_v4(int d, bool match, bool early)
 {
     if (match) {
         if (d != 2) return nullptr;
-        return early ? (NodeKernel)ib_cn_n4_kernel<2, true, true, 4> : (NodeKernel)ib_cn_n4_kernel<2, true, false, 4>;
+        return early ? (NodeKernel)ib_cn_n4_kernel<2, true, true, 4, false> : (NodeKernel)ib_cn_n4_kernel<2, true, false, 4, false>;
     }
     return early ? cn_n4_sel<true>(d) : cn_n4_sel<false>(d);
 }

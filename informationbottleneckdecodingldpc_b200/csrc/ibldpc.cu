@@ -85,7 +85,8 @@ struct ibldpc_decoder {
     uint8_t *d_cn8 = nullptr, *d_vn8 = nullptr, *d_mc8 = nullptr, *d_mv8 = nullptr;
     uint8_t* d_cn_pair = nullptr;   // [imax blocks][cn classes][T*T rows][8 bytes] composed tail-pair tables
     bool use_pair = true;
-    int pair_min_degree = 7;
+    int pair_min_degree = 7;      // uint8 family
+    int n4_pair_min_degree = 6;   // packed-nibble family
     bool fast = false;
     bool nib = false;     // packed-nibble fast path (ib_kernels_n4.cuh)
     int cn_vec = 0, vn_vec = 0;   // 0 = per-degree default, 2 / 4 = forced (IBLDPC_CN_VEC / IBLDPC_VN_VEC)
@@ -485,12 +486,24 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
             b.nst = c.degree - 2;
             const bool explicit_match = h->match && b.nst == 0;   // folded into the last stage otherwise
             b.dmax_match = h->match ? c.degree : 0;
-            const int vec = cn_vec_of(c.degree);
+            // tail-pair variant (cn_word_n4_pair): one LDS.64 of a host-composed row replaces the two last
+            // look-ups of D-2 outputs; 2 words per lane only
+            const bool pair = h->use_pair && c.degree >= h->n4_pair_min_degree && c.degree >= 4 && h->d_cn_pair != nullptr &&
+                              (h->cn_vec == 0 || h->cn_vec == 2);
+            const int vec = pair ? 2 : cn_vec_of(c.degree);
             int tile_groups, nps;
             set_tiles(b, vec, &tile_groups, &nps);
-            const int smem = n4_table_bytes(n4_cn_words(c.degree, explicit_match)) + stage_scratch_bytes(b.nst, T, b.dmax_match);
-            NodeKernel k = vec == 4 ? cn_n4_kernel_v4(c.degree, explicit_match, early != 0)
-                                    : cn_n4_kernel_v2(c.degree, explicit_match, early != 0);
+            int smem = n4_table_bytes(n4_cn_words(c.degree, explicit_match)) + stage_scratch_bytes(b.nst, T, b.dmax_match);
+            b.xp_col = -1;
+            if (pair) {
+                const size_t ci = (size_t)(&c - &h->cn_classes[0]);
+                b.pair = h->d_cn_pair + ((size_t)blk * h->cn_classes.size() + ci) * (size_t)TT * 8;
+                b.xp_col = c.degree - 5;    // column stored as 4*x (-1 for degree 4: raw messages feed the row)
+                smem += (int)kPairBytes;
+            }
+            NodeKernel k = pair ? cn_n4_pair_kernel(c.degree, early != 0)
+                           : vec == 4 ? cn_n4_kernel_v4(c.degree, explicit_match, early != 0)
+                                      : cn_n4_kernel_v2(c.degree, explicit_match, early != 0);
             if (!k) return fail(IBLDPC_E_INVALID, "no packed check-node kernel for degree " + std::to_string(c.degree));
             int grid;
             if ((r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid))) return r;
@@ -905,7 +918,7 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
     if (const char* e = getenv("IBLDPC_CN_VEC")) h->cn_vec = atoi(e) == 4 ? 4 : atoi(e) == 2 ? 2 : 0;
     if (const char* e = getenv("IBLDPC_VN_VEC")) h->vn_vec = atoi(e) == 4 ? 4 : atoi(e) == 2 ? 2 : 0;
     h->use_pair = getenv("IBLDPC_NO_PAIR") == nullptr;
-    if (const char* pm = getenv("IBLDPC_PAIR_MIN_DEGREE")) h->pair_min_degree = std::max(4, atoi(pm));
+    if (const char* pm = getenv("IBLDPC_PAIR_MIN_DEGREE")) h->pair_min_degree = h->n4_pair_min_degree = std::max(4, atoi(pm));
     if (h->d_cn_pair) { CK(cudaFree(h->d_cn_pair)); h->d_cn_pair = nullptr; }
     if (h->fast && h->use_pair) {
         // Composed tail-pair tables of the check-node kernel (cn_word_pair): for every iteration block and

@@ -12,13 +12,7 @@ def run(env, label, wl="c1", B=32768):
             return
     print(label, "FAILED", p.stderr[-400:])
 if __name__ == "__main__":
-    for wl, B in (("c1", 32768), ("c1", 65536)):
-        run({"IBLDPC_NO_NIBBLE": "1"}, "u8", wl, B)
-        run({}, "n4 default(cn2,vn4)", wl, B)
-        run({"IBLDPC_CN_VEC": "4"}, "n4 cn4 vn4", wl, B)
-        run({"IBLDPC_VN_VEC": "2"}, "n4 cn2 vn2", wl, B)
-    for wl, B in (("wlan", 65536), ("dvbs2", 4096)):
-        run({"IBLDPC_NO_NIBBLE": "1"}, "u8", wl, B)
-        run({}, "n4 default", wl, B)
-        run({"IBLDPC_CN_VEC": "4", "IBLDPC_VN_VEC": "4"}, "n4 cn4 vn4", wl, B)
-        run({"IBLDPC_CN_VEC": "2", "IBLDPC_VN_VEC": "2"}, "n4 cn2 vn2", wl, B)
+    for wl, B in (("c1", 65536), ("wlan", 65536), ("dvbs2", 4096)):
+        run({"IBLDPC_NO_PAIR": "1"}, "n4 no pair", wl, B)
+        for pm in (4, 6, 7, 8):
+            run({"IBLDPC_PAIR_MIN_DEGREE": str(pm)}, f"n4 pair from d>={pm}", wl, B)

@@ -31,8 +31,10 @@ def _dev(a):
 #   n4       packed-nibble messages (default), per-degree default vector widths
 #   n4_v24 / n4_v42  packed nibbles with the check-/variable-node vector widths forced to 2/4 and 4/2 words
 #   u8       one byte per message (IBLDPC_NO_NIBBLE=1), incl. the tail-pair check-node kernels
+#   n4_pair4 / n4_nopair  tail-pair check-node kernels from degree 4 on / never
 IB_VARIANTS = {"n4": {}, "n4_v24": {"IBLDPC_CN_VEC": "2", "IBLDPC_VN_VEC": "4"},
-               "n4_v42": {"IBLDPC_CN_VEC": "4", "IBLDPC_VN_VEC": "2"}, "u8": {"IBLDPC_NO_NIBBLE": "1"}}
+               "n4_v42": {"IBLDPC_CN_VEC": "4", "IBLDPC_VN_VEC": "2"}, "n4_pair4": {"IBLDPC_PAIR_MIN_DEGREE": "4"},
+               "n4_nopair": {"IBLDPC_NO_PAIR": "1"}, "u8": {"IBLDPC_NO_NIBBLE": "1"}}
 
 
 @pytest.fixture(params=list(IB_VARIANTS))
@@ -47,7 +49,7 @@ def ib_variant(request, monkeypatch):
 def test_ib_golden_device_buffers(gpu, case, force_generic, monkeypatch, ib_variant):
     g = load_golden(case)
     if force_generic:
-        if ib_variant != 2 or os.environ.get("IBLDPC_CN_VEC"):
+        if ib_variant != 2 or any(os.environ.get(k) for k in ("IBLDPC_CN_VEC", "IBLDPC_PAIR_MIN_DEGREE", "IBLDPC_NO_PAIR")):
             pytest.skip("the generic path has one variant")
         monkeypatch.setenv("IBLDPC_FORCE_GENERIC", "1")
     T, imax = int(g["T"]), int(g["imax"])
@@ -134,11 +136,13 @@ def test_ib_irregular_vs_oracle(gpu, name, H, T, match, ib_variant):
     assert np.array_equal(got, ref) and dec.last_i_num == i_num
 
 
-def test_ib_tail_pair_variant_all_degrees(gpu, monkeypatch):
-    """The composed tail-pair check-node kernels (cn_word_pair) for every degree 4..10, forced on with
-    IBLDPC_PAIR_MIN_DEGREE=4, with and without message alignment, against the oracle."""
+@pytest.mark.parametrize("family", ["n4", "u8"])
+def test_ib_tail_pair_variant_all_degrees(gpu, monkeypatch, family):
+    """The composed tail-pair check-node kernels (cn_word_pair / cn_word_n4_pair) for every degree 4..10,
+    forced on with IBLDPC_PAIR_MIN_DEGREE=4, with and without message alignment, against the oracle."""
     monkeypatch.setenv("IBLDPC_PAIR_MIN_DEGREE", "4")
-    monkeypatch.setenv("IBLDPC_NO_NIBBLE", "1")          # the tail-pair kernels belong to the uint8 family
+    if family == "u8":
+        monkeypatch.setenv("IBLDPC_NO_NIBBLE", "1")
     H = codes.random_from_degrees([2] * 40 + [3] * 40 + [4] * 16, [4] * 16 + [5] * 8 + [6] * 8 + [7] * 6 + [8] * 4 + [9] * 2 + [10] * 2, seed=4)
     t = graph.edge_tables(H)
     assert sorted(set(t.degree_chk)) == [4, 5, 6, 7, 8, 9, 10]
