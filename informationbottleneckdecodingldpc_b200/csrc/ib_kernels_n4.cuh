@@ -74,7 +74,7 @@ __device__ __forceinline__ uint32_t nib_times(uint32_t w, int f)
 // Host side: dynamic smem = n4_table_bytes(W) + stage_scratch_bytes(nst, T, dmax_match).
 // Message alignment is folded into the last stage exactly as in stage_tables().
 // ------------------------------------------------------------------------------------------
-template <int W>
+template <int W, int NT = kThreads>
 __device__ __forceinline__ void stage_tables_n4(uint32_t* s_tab, const IbArgs& a, const uint8_t* lut)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -85,16 +85,16 @@ __device__ __forceinline__ void stage_tables_n4(uint32_t* s_tab, const IbArgs& a
     if (((n_lut | (int)(reinterpret_cast<uintptr_t>(lut) & 3)) & 3) == 0) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(lut);
         uint32_t* dst = reinterpret_cast<uint32_t*>(scratch);
-        for (int i = threadIdx.x; i < n_lut / 4; i += kThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i < n_lut / 4; i += NT) dst[i] = src[i];
     } else {
-        for (int i = threadIdx.x; i < n_lut; i += kThreads) scratch[i] = lut[i];
+        for (int i = threadIdx.x; i < n_lut; i += NT) scratch[i] = lut[i];
     }
     uint8_t* smatch = scratch + n_lut;
     if (a.match != nullptr)
-        for (int i = threadIdx.x; i < a.dmax_match * T; i += kThreads) smatch[i] = a.match[i];
+        for (int i = threadIdx.x; i < a.dmax_match * T; i += NT) smatch[i] = a.match[i];
     __syncthreads();
     const bool fold = a.match != nullptr && a.nst >= 1;
-    for (int rw = warp; rw < total; rw += kWarpsPerCta) {
+    for (int rw = warp; rw < total; rw += NT / 32) {
         const int r = rw / W, w = rw - r * W;
         const int m = r / kTS, t = r - m * kTS;
         uint32_t v = 0;
@@ -260,8 +260,10 @@ __host__ __device__ constexpr int cn_n4_min_blocks(int D, int VEC, bool PAIR)
 
 // send + checknode_update_iter0 (a.iter0) or checknode_update + calc_syndrome, packed nibbles.
 // PAIR: shared memory = [tail-pair rows (kPairBytes)][stage tables][staging scratch].
-template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR>
-__global__ void __launch_bounds__(kThreads, cn_n4_min_blocks(D, VEC, PAIR))
+// NT = threads per CTA: the tail-pair kernels of degree <= 8 run 512 threads (2 CTAs/SM at 64 registers share
+// one 64-96 KB table set per 16 warps: 32 warps/SM instead of 24 resp. 16 with 256-thread CTAs).
+template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR, int NT = kThreads>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : cn_n4_min_blocks(D, VEC, PAIR))
 ib_cn_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 {
     extern __shared__ __align__(16) uint32_t s_all[];
@@ -271,19 +273,19 @@ ib_cn_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
         // expand the composed rows (global: row a*T+b, 8 bytes) to kPairSlots lane slots per row a*16+b
         const uint2* src = reinterpret_cast<const uint2*>(a.pair);
         uint2* dst = reinterpret_cast<uint2*>(s_all);
-        for (int i = threadIdx.x; i < kTS * kTS * kPairSlots; i += kThreads) {
+        for (int i = threadIdx.x; i < kTS * kTS * kPairSlots; i += NT) {
             const int r = i / kPairSlots, ra = r / kTS, rb = r - ra * kTS;
             dst[i] = (ra < a.T && rb < a.T) ? src[ra * a.T + rb] : make_uint2(0u, 0u);
         }
     }
-    stage_tables_n4<n4_cn_words(D, MATCH)>(s_tab, a, a.lut);
+    stage_tables_n4<n4_cn_words(D, MATCH), NT>(s_tab, a, a.lut);
     __syncthreads();
     const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_tab);
     const uint8_t* ptab = reinterpret_cast<const uint8_t*>(s_all);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lane4 = lane * 4;
     const int tile = (blockIdx.y << a.tpc_log2) + (warp & ((1 << a.tpc_log2) - 1));
-    const int nps = kWarpsPerCta >> a.tpc_log2;
+    const int nps = (NT / 32) >> a.tpc_log2;
     const int stride = gridDim.x * nps;
     const uint32_t col = ((uint32_t)tile * 32u + lane) * (4u * VEC);
     uint32_t syn = 0;

@@ -1,4 +1,4 @@
-"""A/B: packed-nibble vs uint8 fast path, C1 workload, per-phase times (scratch)."""
+"""A/B of kernel options through environment switches, per-phase times (scratch)."""
 import os, sys, json, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def run(env, label, wl="c1", B=32768):
@@ -12,7 +12,5 @@ def run(env, label, wl="c1", B=32768):
             return
     print(label, "FAILED", p.stderr[-400:])
 if __name__ == "__main__":
-    for wl, B in (("c1", 65536), ("wlan", 65536), ("dvbs2", 4096)):
-        run({"IBLDPC_NO_PAIR": "1"}, "n4 no pair", wl, B)
-        for pm in (4, 6, 7, 8):
-            run({"IBLDPC_PAIR_MIN_DEGREE": str(pm)}, f"n4 pair from d>={pm}", wl, B)
+    for wl, B in (("c1", 65536), ("wlan", 65536), ("wlan1944", 65536), ("dvbs2", 4096)):
+        run({}, "default", wl, B)
