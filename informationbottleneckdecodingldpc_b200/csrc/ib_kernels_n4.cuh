@@ -343,6 +343,56 @@ __device__ __forceinline__ void vn_word_n4(uint32_t chw, const uint32_t (&w)[D],
     }
 }
 
+// Tail-pair variant of the variable-node update (D >= 3): all outputs w <= D-2 end with
+//   out_w = S_{D-2}( S_{D-3}(x_w, y_{D-1}), y_D ) = G(y_{D-1}, y_D)[x_w]
+// (G composed on the host with the matching row of degree D folded in).  One LDS.64 per frame
+// replaces 2(D-2) look-ups; column D-4, which produces every x_w, is stored as 4*x.
+// Shared-memory wavefronts per variable node and frame: D=8 35 -> 25, D=11 65 -> 49.
+template <int D>
+__device__ __forceinline__ void vn_word_n4_pair(uint32_t chw, const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab,
+                                                const uint8_t* ptab, uint32_t lane4, uint32_t slot8)
+{
+    static_assert(D >= 3, "tail-pair variant needs two update stages");
+    constexpr uint32_t W = n4_vn_words(D, false), RS = 128u * W, TRS = RS * kTS;
+    constexpr uint32_t PS = 8u * kPairSlots, TPS = PS * kTS;
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = 0;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        uint32_t ms[D + 1];   // ms[k] for y_k, k = 1..D
+#pragma unroll
+        for (int k = 1; k <= D; ++k) ms[k] = nib_times<TRS>(w[k - 1], f) | lane4;
+        const uint2 g2 = *reinterpret_cast<const uint2*>(ptab + (nib_times<TPS>(w[D - 2], f) | nib_times<PS>(w[D - 1], f) | slot8));
+        const unsigned long long g = ((unsigned long long)g2.y << 32) | g2.x;
+        // prefix chain P[1..D-1]; P[D-2] comes out of column D-4, i.e. as 4*x (D >= 4)
+        uint32_t P[D + 1];
+        P[1] = (chw >> (4 * f)) & 15u;
+#pragma unroll
+        for (int j = 1; j <= D - 2; ++j) {
+            const bool in_x4 = (D >= 4) && (j == D - 2);
+            P[j + 1] = lut_ld(tab, P[j] * (in_x4 ? RS / 4u : RS) + ms[j] + IB_SO(j - 1));
+        }
+        // the two outputs that skip one of the tail messages
+        o[D - 2] += lut_ld(tab, P[D - 1] * RS + ms[D] + IB_SO(D - 2)) << (4 * f);       // w = D-1
+        o[D - 1] += lut_ld(tab, P[D - 1] * RS + ms[D - 1] + IB_SO(D - 2)) << (4 * f);   // w = D
+#pragma unroll
+        for (int wo = 1; wo <= D - 2; ++wo) {
+            uint32_t e;   // 4 * x_w
+            if (D >= 4 && wo == D - 2) {
+                e = P[D - 2];
+            } else if (D == 3) {
+                e = nib_times<4u>(chw, f);
+            } else {
+                uint32_t t = P[wo];
+#pragma unroll
+                for (int k = wo + 1; k <= D - 2; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
+                e = t;   // the last look-up read column D-4
+            }
+            o[wo - 1] += ((uint32_t)(g >> e) & 15u) << (4 * f);
+        }
+    }
+}
+
 template <int D, int VEC> struct VnIn4 { uint32_t c[VEC]; uint32_t m[D][VEC]; };
 
 template <int D, int VEC>
@@ -355,8 +405,8 @@ __device__ __forceinline__ void vn_load_msgs_n4(const IbArgs& a, const VnIdx<D>&
     }
 }
 
-template <int D, bool DECIDE, int VEC>
-__device__ __forceinline__ void vn_compute_store_n4(const IbArgs& a, const uint8_t* tab, const VnIdx<D>& x,
+template <int D, bool DECIDE, int VEC, bool PAIR = false>
+__device__ __forceinline__ void vn_compute_store_n4(const IbArgs& a, const uint8_t* tab, const uint8_t* ptab, const VnIdx<D>& x,
                                                     const VnIn4<D, VEC>& in, uint32_t col, uint32_t lane4)
 {
     if (!DECIDE && D == 1) {   // degree-1 variable node forwards the raw channel value (:132-136)
@@ -370,7 +420,8 @@ __device__ __forceinline__ void vn_compute_store_n4(const IbArgs& a, const uint8
         uint32_t w[D], o[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) w[k] = in.m[k][j];
-        vn_word_n4<D, DECIDE>(in.c[j], w, o, dec[2 * j], dec[2 * j + 1], tab, lane4);
+        if constexpr (PAIR) vn_word_n4_pair<D>(in.c[j], w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
+        else vn_word_n4<D, DECIDE>(in.c[j], w, o, dec[2 * j], dec[2 * j + 1], tab, lane4);
         if (!DECIDE) {
 #pragma unroll
             for (int k = 0; k < D; ++k) r[k][j] = o[k];
@@ -392,13 +443,14 @@ __device__ __forceinline__ void vn_compute_store_n4(const IbArgs& a, const uint8
 
 // Software pipeline over the node list of one degree class (row indices fetched two nodes ahead,
 // see vn_loop in ib_kernels.cuh).
-template <int D, bool DECIDE, int VEC>
-__device__ __forceinline__ void vn_loop_n4(const IbArgs& a, const uint8_t* tab, const int* __restrict__ nodes, int n_nodes)
+template <int D, bool DECIDE, int VEC, bool PAIR = false, int NT = kThreads>
+__device__ __forceinline__ void vn_loop_n4(const IbArgs& a, const uint8_t* tab, const uint8_t* ptab, const int* __restrict__ nodes,
+                                           int n_nodes)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lane4 = lane * 4;
     const int tile = (blockIdx.y << a.tpc_log2) + (warp & ((1 << a.tpc_log2) - 1));
-    const int nps = kWarpsPerCta >> a.tpc_log2;
+    const int nps = (NT / 32) >> a.tpc_log2;
     const int stride = gridDim.x * nps;
     const uint32_t col = ((uint32_t)tile * 32u + lane) * (4u * VEC);
     if (tile >= a.tiles || col >= a.pitch) return;
@@ -412,7 +464,7 @@ __device__ __forceinline__ void vn_loop_n4(const IbArgs& a, const uint8_t* tab, 
         vn_load_msgs_n4<D, VEC>(a, cur, col, buf);
         vn_load_idx<D>(a, nodes, n_nodes, inn, nn);
         inn += stride;
-        vn_compute_store_n4<D, DECIDE, VEC>(a, tab, cur, buf, col, lane4);
+        vn_compute_store_n4<D, DECIDE, VEC, PAIR>(a, tab, ptab, cur, buf, col, lane4);
         cur = nxt;
         nxt = nn;
     }
@@ -434,7 +486,32 @@ ib_vn_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
         stage_tables_n4<n4_vn_words(D, false)>(s_tab, a, a.lut);
         __syncthreads();
     }
-    vn_loop_n4<D, false, VEC>(a, reinterpret_cast<const uint8_t*>(s_tab), nodes, n_nodes);
+    vn_loop_n4<D, false, VEC>(a, reinterpret_cast<const uint8_t*>(s_tab), nullptr, nodes, n_nodes);
+}
+
+// varnode_update through the tail-pair rows (vn_word_n4_pair): shared memory =
+// [tail-pair rows (kPairBytes)][stage tables][staging scratch]; NT threads per CTA, 2 words per lane.
+__host__ __device__ constexpr int vn_n4_pair_min_blocks(int D, int NT)
+{
+    return NT == 512 ? (D <= 9 ? 2 : 1) : (D <= 5 ? 3 : (D <= 9 ? 2 : 1));
+}
+template <int D, int NT>
+__global__ void __launch_bounds__(NT, vn_n4_pair_min_blocks(D, NT))
+ib_vn_n4_pair_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
+{
+    extern __shared__ __align__(16) uint32_t s_all[];
+    if (a.early && a.it >= 1 && a.flags[a.it - 1] == 0) return;
+    uint32_t* s_tab = s_all + kPairBytes / 4;
+    const uint2* src = reinterpret_cast<const uint2*>(a.pair);
+    uint2* dst = reinterpret_cast<uint2*>(s_all);
+    for (int i = threadIdx.x; i < kTS * kTS * kPairSlots; i += NT) {
+        const int r = i / kPairSlots, ra = r / kTS, rb = r - ra * kTS;
+        dst[i] = (ra < a.T && rb < a.T) ? src[ra * a.T + rb] : make_uint2(0u, 0u);
+    }
+    stage_tables_n4<n4_vn_words(D, false), NT>(s_tab, a, a.lut);
+    __syncthreads();
+    vn_loop_n4<D, false, 2, true, NT>(a, reinterpret_cast<const uint8_t*>(s_tab), reinterpret_cast<const uint8_t*>(s_all), nodes,
+                                      n_nodes);
 }
 
 // calc_varnode_output (kernels_template_irreg.cl:249-302) with the VN table of iteration i_num-1;
@@ -451,7 +528,7 @@ __global__ void __launch_bounds__(kThreads) ib_out_n4_kernel(IbArgs a, const int
     __syncthreads();
     stage_tables_n4<n4_vn_words(D, true)>(s_tab, a, a.lut + (long long)s_passes * a.vn_it_stride);
     __syncthreads();
-    vn_loop_n4<D, true, VEC>(a, reinterpret_cast<const uint8_t*>(s_tab), nodes, n_nodes);
+    vn_loop_n4<D, true, VEC>(a, reinterpret_cast<const uint8_t*>(s_tab), nullptr, nodes, n_nodes);
 }
 
 // ------------------------------------------------------------------------------------------

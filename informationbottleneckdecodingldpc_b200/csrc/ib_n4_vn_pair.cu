@@ -1,0 +1,36 @@
+// ib_n4_vn_pair.cu -- instantiations of the tail-pair variable-node kernels ib_vn_n4_pair_kernel<D, NT>
+#include "kernel_tables.h"
+#include "ib_kernels_n4.cuh"
+namespace ibldpc {
+NodeKernel vn_n4_pair_kernel(int d, int threads)
+{
+    if (threads == 512) {
+        switch (d) {
+        case 3: return ib_vn_n4_pair_kernel<3, 512>;
+        case 4: return ib_vn_n4_pair_kernel<4, 512>;
+        case 5: return ib_vn_n4_pair_kernel<5, 512>;
+        case 6: return ib_vn_n4_pair_kernel<6, 512>;
+        case 7: return ib_vn_n4_pair_kernel<7, 512>;
+        case 8: return ib_vn_n4_pair_kernel<8, 512>;
+        case 9: return ib_vn_n4_pair_kernel<9, 512>;
+        case 10: return ib_vn_n4_pair_kernel<10, 512>;
+        case 11: return ib_vn_n4_pair_kernel<11, 512>;
+        case 12: return ib_vn_n4_pair_kernel<12, 512>;
+        default: return nullptr;
+        }
+    }
+    switch (d) {
+    case 3: return ib_vn_n4_pair_kernel<3, 256>;
+    case 4: return ib_vn_n4_pair_kernel<4, 256>;
+    case 5: return ib_vn_n4_pair_kernel<5, 256>;
+    case 6: return ib_vn_n4_pair_kernel<6, 256>;
+    case 7: return ib_vn_n4_pair_kernel<7, 256>;
+    case 8: return ib_vn_n4_pair_kernel<8, 256>;
+    case 9: return ib_vn_n4_pair_kernel<9, 256>;
+    case 10: return ib_vn_n4_pair_kernel<10, 256>;
+    case 11: return ib_vn_n4_pair_kernel<11, 256>;
+    case 12: return ib_vn_n4_pair_kernel<12, 256>;
+    default: return nullptr;
+    }
+}
+}  // namespace ibldpc

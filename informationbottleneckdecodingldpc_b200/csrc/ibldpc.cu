@@ -84,6 +84,9 @@ struct ibldpc_decoder {
     bool match = false;
     uint8_t *d_cn8 = nullptr, *d_vn8 = nullptr, *d_mc8 = nullptr, *d_mv8 = nullptr;
     uint8_t* d_cn_pair = nullptr;   // [imax blocks][cn classes][T*T rows][8 bytes] composed tail-pair tables
+    uint8_t* d_vn_pair = nullptr;   // [imax][vn classes][T*T rows][8 bytes] composed tail-pair tables of the VN update
+    int vn_pair_min_degree = 5;     // packed-nibble family (IBLDPC_VN_PAIR_MIN_DEGREE)
+    int vn_pair_threads = 0;        // 0 = per-degree default, 256 / 512 forced (IBLDPC_VN_PAIR_THREADS)
     bool use_pair = true;
     int pair_min_degree = 7;      // uint8 family
     int n4_pair_min_degree = 6;   // packed-nibble family
@@ -528,15 +531,35 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
         for (auto& c : h->vn_classes) {
             b.nst = decide ? c.degree : c.degree - 1;
             b.dmax_match = b.match != nullptr ? c.degree : 0;
-            const int vec = vn_vec_of(c.degree);
+            // tail-pair variant (vn_word_n4_pair) for the high degrees: one LDS.64 of a host-composed row replaces
+            // the two last look-ups of D-2 outputs; 2 words per lane, 512-thread CTAs share one table set
+            const bool pair = !decide && h->use_pair && h->d_vn_pair != nullptr && c.degree >= h->vn_pair_min_degree &&
+                              c.degree >= 3 && (h->vn_vec == 0 || h->vn_vec == 2);
+            const int vec = pair ? 2 : vn_vec_of(c.degree);
             int tile_groups, nps;
             set_tiles(b, vec, &tile_groups, &nps);
-            const int smem = n4_table_bytes(n4_vn_words(c.degree, decide)) + stage_scratch_bytes(b.nst, T, b.dmax_match);
-            NodeKernel k = vec == 4 ? vn_n4_kernel_v4(c.degree, decide) : vn_n4_kernel_v2(c.degree, decide);
+            int smem = n4_table_bytes(n4_vn_words(c.degree, decide)) + stage_scratch_bytes(b.nst, T, b.dmax_match);
+            int threads = kThreads;
+            b.xp_col = -1;
+            NodeKernel k;
+            if (pair) {
+                const size_t ci = (size_t)(&c - &h->vn_classes[0]);
+                b.pair = h->d_vn_pair + ((size_t)it * h->vn_classes.size() + ci) * (size_t)TT * 8;
+                b.xp_col = c.degree - 4;    // column stored as 4*x (-1 for degree 3: the channel value feeds the row)
+                smem += (int)kPairBytes;
+                // measured on B200: degrees 8-9 spill at the 64 registers a 2 x 512-thread residency allows (DVB-S2 d_v=8:
+                // 0.387 ms with 256 threads vs 0.420 ms), degree >= 10 has one table set per SM either way (WLAN d_v=11:
+                // 0.195 ms with 512 threads vs 0.229 ms)
+                threads = h->vn_pair_threads ? h->vn_pair_threads : (c.degree == 8 || c.degree == 9) ? 256 : 512;
+                nps = (threads / 32) >> b.tpc_log2;
+                k = vn_n4_pair_kernel(c.degree, threads);
+            } else {
+                k = vec == 4 ? vn_n4_kernel_v4(c.degree, decide) : vn_n4_kernel_v2(c.degree, decide);
+            }
             if (!k) return fail(IBLDPC_E_INVALID, "no packed variable-node kernel for degree " + std::to_string(c.degree));
             int grid;
-            if ((r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid))) return r;
-            k<<<dim3(grid, tile_groups), kThreads, smem, st>>>(b, c.d_nodes, c.count);
+            if ((r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid, 1.0, threads))) return r;
+            k<<<dim3(grid, tile_groups), threads, smem, st>>>(b, c.d_nodes, c.count);
             h->last_launches++;
         }
         return prof.end();
@@ -947,6 +970,34 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
             }
         if ((rc = upload(&h->d_cn_pair, pair.data(), pair.size()))) return rc;
     }
+    if (h->d_vn_pair) { CK(cudaFree(h->d_vn_pair)); h->d_vn_pair = nullptr; }
+    if (const char* e = getenv("IBLDPC_VN_PAIR_MIN_DEGREE")) h->vn_pair_min_degree = std::max(3, atoi(e));
+    if (const char* e = getenv("IBLDPC_VN_PAIR_THREADS")) h->vn_pair_threads = atoi(e) == 512 ? 512 : atoi(e) == 256 ? 256 : 0;
+    if (h->nib && h->use_pair) {
+        // Composed tail-pair tables of the variable-node update (vn_word_n4_pair): for every iteration and every
+        // variable-node degree d >= 3, G(a,b)[x] = M_d( S_{d-2}( S_{d-3}(x, a), b ) ), 16 nibbles per (a,b) row
+        // (stage 0 is indexed by the channel value; with Tc == T every stage block holds T*T entries).
+        const int TT = T * T;
+        const size_t ncls = h->vn_classes.size();
+        std::vector<uint8_t> vpair((size_t)imax * ncls * TT * 8, 0);
+        for (int it = 0; it < imax; ++it)
+            for (size_t ci = 0; ci < ncls; ++ci) {
+                const int d = h->vn_classes[ci].degree;
+                if (d < 3) continue;
+                const uint8_t* Sa = vn.data() + ((size_t)it * DV + (d - 3)) * TT;
+                const uint8_t* Sb = vn.data() + ((size_t)it * DV + (d - 2)) * TT;
+                const uint8_t* mrow = match ? mv.data() + ((size_t)it * DV + (d - 1)) * T : nullptr;
+                uint8_t* dst = vpair.data() + ((size_t)it * ncls + ci) * TT * 8;
+                for (int a = 0; a < T; ++a)
+                    for (int b = 0; b < T; ++b)
+                        for (int x = 0; x < T; ++x) {
+                            int v = Sb[Sa[x * T + a] * T + b];
+                            if (mrow) v = mrow[v];
+                            dst[(a * T + b) * 8 + (x >> 1)] |= (uint8_t)(v << ((x & 1) * 4));
+                        }
+            }
+        if ((rc = upload(&h->d_vn_pair, vpair.data(), vpair.size()))) return rc;
+    }
     h->occ_cache.clear();
     h->have_luts = true;
     return IBLDPC_OK;
@@ -1155,7 +1206,7 @@ int ibldpc_destroy(ibldpc_handle h)
     clear_events(h);
     for (int* p : {h->d_sc, h->d_dc, h->d_tc, h->d_sv, h->d_dv, h->d_tv, h->d_vidx})
         if (p) cudaFree(p);
-    for (uint8_t* p : {h->d_cn8, h->d_vn8, h->d_mc8, h->d_mv8, h->d_cn_pair})
+    for (uint8_t* p : {h->d_cn8, h->d_vn8, h->d_mc8, h->d_mv8, h->d_cn_pair, h->d_vn_pair})
         if (p) cudaFree(p);
     for (auto& c : h->cn_classes) if (c.d_nodes) cudaFree(c.d_nodes);
     for (auto& c : h->vn_classes) if (c.d_nodes) cudaFree(c.d_nodes);

@@ -18,6 +18,7 @@ NodeKernel cn_n4_kernel_v2(int d, bool match, bool early);
 NodeKernel cn_n4_kernel_v4(int d, bool match, bool early);
 NodeKernel cn_n4_pair_kernel(int d, bool early);   // tail-pair variant (2 words per lane), d >= 4
 int cn_n4_pair_threads(int d);                     // threads per CTA of that kernel
+NodeKernel vn_n4_pair_kernel(int d, int threads);   // tail-pair variable-node update, d >= 3, threads = 256 / 512
 NodeKernel vn_n4_kernel_v2(int d, bool decide);
 NodeKernel vn_n4_kernel_v4(int d, bool decide);
 LlrNodeKernel llr_cn_kernel_for(bool f64, int algo, int d);

@@ -12,5 +12,8 @@ def run(env, label, wl="c1", B=32768):
             return
     print(label, "FAILED", p.stderr[-400:])
 if __name__ == "__main__":
-    for wl, B in (("c1", 65536), ("wlan", 65536), ("wlan1944", 65536), ("dvbs2", 4096)):
-        run({}, "default", wl, B)
+    for wl, B in (("wlan", 65536), ("dvbs2", 4096), ("c1", 65536)):
+        run({"IBLDPC_VN_PAIR_MIN_DEGREE": "99"}, "no vn pair", wl, B)
+        for md in (3, 4, 5):
+            run({"IBLDPC_VN_PAIR_MIN_DEGREE": str(md)}, f"vn pair d>={md} 512thr", wl, B)
+        run({"IBLDPC_VN_PAIR_MIN_DEGREE": "5", "IBLDPC_VN_PAIR_THREADS": "256"}, "vn pair d>=5 256thr", wl, B)

@@ -31,9 +31,12 @@ def _dev(a):
 #   n4       packed-nibble messages (default), per-degree default vector widths
 #   n4_v24 / n4_v42  packed nibbles with the check-/variable-node vector widths forced to 2/4 and 4/2 words
 #   u8       one byte per message (IBLDPC_NO_NIBBLE=1), incl. the tail-pair check-node kernels
-#   n4_pair4 / n4_nopair  tail-pair check-node kernels from degree 4 on / never
+#   n4_pair4 / n4_nopair  tail-pair check-node kernels from degree 4 on / no tail-pair kernels at all
+#   n4_vpair3 / n4_vpair3_256  tail-pair variable-node kernels from degree 3 on, 512- / 256-thread CTAs
 IB_VARIANTS = {"n4": {}, "n4_v24": {"IBLDPC_CN_VEC": "2", "IBLDPC_VN_VEC": "4"},
                "n4_v42": {"IBLDPC_CN_VEC": "4", "IBLDPC_VN_VEC": "2"}, "n4_pair4": {"IBLDPC_PAIR_MIN_DEGREE": "4"},
+               "n4_vpair3": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3"},
+               "n4_vpair3_256": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3", "IBLDPC_VN_PAIR_THREADS": "256"},
                "n4_nopair": {"IBLDPC_NO_PAIR": "1"}, "u8": {"IBLDPC_NO_NIBBLE": "1"}}
 
 
@@ -49,7 +52,7 @@ def ib_variant(request, monkeypatch):
 def test_ib_golden_device_buffers(gpu, case, force_generic, monkeypatch, ib_variant):
     g = load_golden(case)
     if force_generic:
-        if ib_variant != 2 or any(os.environ.get(k) for k in ("IBLDPC_CN_VEC", "IBLDPC_PAIR_MIN_DEGREE", "IBLDPC_NO_PAIR")):
+        if ib_variant != 2 or any(os.environ.get(k) for k in ("IBLDPC_CN_VEC", "IBLDPC_PAIR_MIN_DEGREE", "IBLDPC_NO_PAIR", "IBLDPC_VN_PAIR_MIN_DEGREE")):
             pytest.skip("the generic path has one variant")
         monkeypatch.setenv("IBLDPC_FORCE_GENERIC", "1")
     T, imax = int(g["T"]), int(g["imax"])
@@ -155,6 +158,28 @@ def test_ib_tail_pair_variant_all_degrees(gpu, monkeypatch, family):
                          tb.matching_vector_checknode, tb.matching_vector_varnode)
             got = dec.decode_OpenCL(_dev(ch), buffer_in=True, return_buffer=True).get()
             ref, i_num = _oracle_ib(t, ch, T, imax, tb, True)
+            assert np.array_equal(got, ref) and dec.last_i_num == i_num
+
+
+@pytest.mark.parametrize("threads", ["256", "512"])
+def test_ib_vn_tail_pair_variant_all_degrees(gpu, monkeypatch, threads):
+    """The composed tail-pair variable-node kernels (vn_word_n4_pair) for every degree 3..12, forced on with
+    IBLDPC_VN_PAIR_MIN_DEGREE=3, both CTA sizes, with and without message alignment, against the oracle."""
+    monkeypatch.setenv("IBLDPC_VN_PAIR_MIN_DEGREE", "3")
+    monkeypatch.setenv("IBLDPC_VN_PAIR_THREADS", threads)
+    H = codes.random_from_degrees([d for d in range(3, 13) for _ in range(4)], [6] * 50, seed=6)
+    t = graph.edge_tables(H)
+    assert sorted(set(t.degree_var)) == list(range(3, 13))
+    for T in (16, 8):
+        for match in (True, False):
+            imax, B = 5, 70
+            tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=41, matching=match)
+            ch = np.random.Generator(np.random.PCG64(42)).integers(0, T, size=(t.n_var, B)).astype(np.uint8)
+            dec = _mk_ib(H, T, imax, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                         tb.matching_vector_checknode, tb.matching_vector_varnode)
+            got = dec.decode_OpenCL(_dev(ch), buffer_in=True, return_buffer=True).get()
+            ref, i_num = _oracle_ib(t, ch, T, imax, tb, True)
+            assert dec.info()[0] == 2
             assert np.array_equal(got, ref) and dec.last_i_num == i_num
 
 
