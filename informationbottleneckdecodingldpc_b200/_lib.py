@@ -11,7 +11,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libibldpc.so")
-UNITS = ["ibldpc.cu", "ib_fast_cn.cu", "ib_fast_vn.cu", "ib_n4_cn_v2.cu", "ib_n4_cn_v4.cu", "ib_n4_cn_pair.cu", "ib_n4_vn_pair.cu", "ib_n4_vn_v2.cu", "ib_n4_vn_v4.cu",
+UNITS = ["ibldpc.cu", "ib_fast_cn.cu", "ib_fast_vn.cu", "ib_n4_cn_v2.cu", "ib_n4_cn_pair.cu", "ib_n4_vn_pair.cu", "ib_n4_vn_v2.cu", "ib_n4_vn_v4.cu",
          "llr_f32.cu", "llr_f64.cu"]   # compiled in parallel
 SOURCES = [os.path.join(HERE, "csrc", f) for f in UNITS + ["ib_kernels.cuh", "ib_kernels_n4.cuh", "llr_kernels.cuh", "kernel_tables.h"]]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "ibldpc.h")

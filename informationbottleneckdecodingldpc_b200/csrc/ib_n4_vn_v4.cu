@@ -1,4 +1,5 @@
 // ib_n4_vn_v4.cu -- instantiations of ib_vn_n4_kernel<D, 4> / ib_out_n4_kernel<D, 4> (see ib_kernels_n4.cuh)
+// for D <= 6 (wider degrees spill with 4 words per lane and use the 2-word kernels)
 #include "kernel_tables.h"
 #include "ib_kernels_n4.cuh"
 namespace ibldpc {
@@ -12,12 +13,6 @@ NodeKernel vn_n4_kernel_v4(int d, bool decide)
         case 4: return ib_vn_n4_kernel<4, 4>;
         case 5: return ib_vn_n4_kernel<5, 4>;
         case 6: return ib_vn_n4_kernel<6, 4>;
-        case 7: return ib_vn_n4_kernel<7, 4>;
-        case 8: return ib_vn_n4_kernel<8, 4>;
-        case 9: return ib_vn_n4_kernel<9, 4>;
-        case 10: return ib_vn_n4_kernel<10, 4>;
-        case 11: return ib_vn_n4_kernel<11, 4>;
-        case 12: return ib_vn_n4_kernel<12, 4>;
         default: return nullptr;
         }
     }
@@ -28,12 +23,6 @@ NodeKernel vn_n4_kernel_v4(int d, bool decide)
     case 4: return ib_out_n4_kernel<4, 4>;
     case 5: return ib_out_n4_kernel<5, 4>;
     case 6: return ib_out_n4_kernel<6, 4>;
-    case 7: return ib_out_n4_kernel<7, 4>;
-    case 8: return ib_out_n4_kernel<8, 4>;
-    case 9: return ib_out_n4_kernel<9, 4>;
-    case 10: return ib_out_n4_kernel<10, 4>;
-    case 11: return ib_out_n4_kernel<11, 4>;
-    case 12: return ib_out_n4_kernel<12, 4>;
     default: return nullptr;
     }
 }

@@ -92,7 +92,7 @@ struct ibldpc_decoder {
     int n4_pair_min_degree = 6;   // packed-nibble family
     bool fast = false;
     bool nib = false;     // packed-nibble fast path (ib_kernels_n4.cuh)
-    int cn_vec = 0, vn_vec = 0;   // 0 = per-degree default, 2 / 4 = forced (IBLDPC_CN_VEC / IBLDPC_VN_VEC)
+    int vn_vec = 0;       // words per lane of the variable-node kernels: 0 = per-degree default, 2 / 4 forced (IBLDPC_VN_VEC)
     int Wc = 1, Wv = 1, Wo = 1, nrows_c = 0, nrows_v = 0, nrows_o = 0, tshift = -1;
     Workspace ws[2];
     int host_chunk = 0;   // 0 = auto: about 256 MiB of channel values per chunk
@@ -475,7 +475,6 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
         *tile_groups = (b.tiles + (1 << b.tpc_log2) - 1) >> b.tpc_log2;
         *nps = kWarpsPerCta >> b.tpc_log2;
     };
-    auto cn_vec_of = [&](int) { return h->cn_vec ? h->cn_vec : 2; };
     auto vn_vec_of = [&](int d) { return h->vn_vec ? h->vn_vec : (d <= 6 ? 4 : 2); };
     auto launch_cn = [&](int it) -> int {
         IbArgs b = a;
@@ -491,9 +490,8 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
             b.dmax_match = h->match ? c.degree : 0;
             // tail-pair variant (cn_word_n4_pair): one LDS.64 of a host-composed row replaces the two last
             // look-ups of D-2 outputs; 2 words per lane only
-            const bool pair = h->use_pair && c.degree >= h->n4_pair_min_degree && c.degree >= 4 && h->d_cn_pair != nullptr &&
-                              (h->cn_vec == 0 || h->cn_vec == 2);
-            const int vec = pair ? 2 : cn_vec_of(c.degree);
+            const bool pair = h->use_pair && c.degree >= h->n4_pair_min_degree && c.degree >= 4 && h->d_cn_pair != nullptr;
+            const int vec = 2;
             int tile_groups, nps;
             set_tiles(b, vec, &tile_groups, &nps);
             int smem = n4_table_bytes(n4_cn_words(c.degree, explicit_match)) + stage_scratch_bytes(b.nst, T, b.dmax_match);
@@ -504,9 +502,7 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
                 b.xp_col = c.degree - 5;    // column stored as 4*x (-1 for degree 4: raw messages feed the row)
                 smem += (int)kPairBytes;
             }
-            NodeKernel k = pair ? cn_n4_pair_kernel(c.degree, early != 0)
-                           : vec == 4 ? cn_n4_kernel_v4(c.degree, explicit_match, early != 0)
-                                      : cn_n4_kernel_v2(c.degree, explicit_match, early != 0);
+            NodeKernel k = pair ? cn_n4_pair_kernel(c.degree, early != 0) : cn_n4_kernel_v2(c.degree, explicit_match, early != 0);
             if (!k) return fail(IBLDPC_E_INVALID, "no packed check-node kernel for degree " + std::to_string(c.degree));
             const int threads = pair ? cn_n4_pair_threads(c.degree) : kThreads;
             nps = (threads / 32) >> b.tpc_log2;
@@ -555,6 +551,10 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
                 k = vn_n4_pair_kernel(c.degree, threads);
             } else {
                 k = vec == 4 ? vn_n4_kernel_v4(c.degree, decide) : vn_n4_kernel_v2(c.degree, decide);
+                if (!k && vec == 4) {   // 4-word kernels exist up to degree 6 only
+                    set_tiles(b, 2, &tile_groups, &nps);
+                    k = vn_n4_kernel_v2(c.degree, decide);
+                }
             }
             if (!k) return fail(IBLDPC_E_INVALID, "no packed variable-node kernel for degree " + std::to_string(c.degree));
             int grid;
@@ -939,8 +939,7 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
     if (getenv("IBLDPC_FORCE_GENERIC")) h->fast = false;
     // packed-nibble messages need an even |T| (address terms are shifts of the packed word)
     h->nib = h->fast && (T % 2 == 0) && getenv("IBLDPC_NO_NIBBLE") == nullptr;
-    h->cn_vec = h->vn_vec = 0;
-    if (const char* e = getenv("IBLDPC_CN_VEC")) h->cn_vec = atoi(e) == 4 ? 4 : atoi(e) == 2 ? 2 : 0;
+    h->vn_vec = 0;
     if (const char* e = getenv("IBLDPC_VN_VEC")) h->vn_vec = atoi(e) == 4 ? 4 : atoi(e) == 2 ? 2 : 0;
     h->use_pair = getenv("IBLDPC_NO_PAIR") == nullptr;
     if (const char* pm = getenv("IBLDPC_PAIR_MIN_DEGREE")) h->pair_min_degree = h->n4_pair_min_degree = std::max(4, atoi(pm));

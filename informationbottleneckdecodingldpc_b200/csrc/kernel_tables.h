@@ -13,9 +13,9 @@ using LlrShflKernel = void (*)(LlrArgs, int);
 
 NodeKernel cn_fast_kernel_for(int d, bool match, bool early, bool pair);
 NodeKernel vn_fast_kernel_for(int d, bool decide, bool match);
-// packed-nibble fast path (ib_kernels_n4.cuh); vec = 32-bit words per lane and message (2 or 4)
+// packed-nibble fast path (ib_kernels_n4.cuh); v2 / v4 = 32-bit words per lane and message
+// (check nodes: 2; variable nodes: 4 up to degree 6, else 2)
 NodeKernel cn_n4_kernel_v2(int d, bool match, bool early);
-NodeKernel cn_n4_kernel_v4(int d, bool match, bool early);
 NodeKernel cn_n4_pair_kernel(int d, bool early);   // tail-pair variant (2 words per lane), d >= 4
 int cn_n4_pair_threads(int d);                     // threads per CTA of that kernel
 NodeKernel vn_n4_pair_kernel(int d, int threads);   // tail-pair variable-node update, d >= 3, threads = 256 / 512

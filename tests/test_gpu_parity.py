@@ -29,12 +29,11 @@ def _dev(a):
 
 # Kernel families of the IB fast path (|T| <= 16), selected when the tables are uploaded:
 #   n4       packed-nibble messages (default), per-degree default vector widths
-#   n4_v24 / n4_v42  packed nibbles with the check-/variable-node vector widths forced to 2/4 and 4/2 words
+#   n4_vn4 / n4_vn2  packed nibbles with the variable-node vector width forced to 4 (degree <= 6) / 2 words
 #   u8       one byte per message (IBLDPC_NO_NIBBLE=1), incl. the tail-pair check-node kernels
 #   n4_pair4 / n4_nopair  tail-pair check-node kernels from degree 4 on / no tail-pair kernels at all
 #   n4_vpair3 / n4_vpair3_256  tail-pair variable-node kernels from degree 3 on, 512- / 256-thread CTAs
-IB_VARIANTS = {"n4": {}, "n4_v24": {"IBLDPC_CN_VEC": "2", "IBLDPC_VN_VEC": "4"},
-               "n4_v42": {"IBLDPC_CN_VEC": "4", "IBLDPC_VN_VEC": "2"}, "n4_pair4": {"IBLDPC_PAIR_MIN_DEGREE": "4"},
+IB_VARIANTS = {"n4": {}, "n4_vn4": {"IBLDPC_VN_VEC": "4"}, "n4_vn2": {"IBLDPC_VN_VEC": "2"}, "n4_pair4": {"IBLDPC_PAIR_MIN_DEGREE": "4"},
                "n4_vpair3": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3"},
                "n4_vpair3_256": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3", "IBLDPC_VN_PAIR_THREADS": "256"},
                "n4_nopair": {"IBLDPC_NO_PAIR": "1"}, "u8": {"IBLDPC_NO_NIBBLE": "1"}}
@@ -52,7 +51,7 @@ def ib_variant(request, monkeypatch):
 def test_ib_golden_device_buffers(gpu, case, force_generic, monkeypatch, ib_variant):
     g = load_golden(case)
     if force_generic:
-        if ib_variant != 2 or any(os.environ.get(k) for k in ("IBLDPC_CN_VEC", "IBLDPC_PAIR_MIN_DEGREE", "IBLDPC_NO_PAIR", "IBLDPC_VN_PAIR_MIN_DEGREE")):
+        if ib_variant != 2 or any(os.environ.get(k) for k in ("IBLDPC_VN_VEC", "IBLDPC_PAIR_MIN_DEGREE", "IBLDPC_NO_PAIR", "IBLDPC_VN_PAIR_MIN_DEGREE")):
             pytest.skip("the generic path has one variant")
         monkeypatch.setenv("IBLDPC_FORCE_GENERIC", "1")
     T, imax = int(g["T"]), int(g["imax"])
