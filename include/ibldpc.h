@@ -155,7 +155,7 @@ int ibldpc_set_profiling(ibldpc_handle h, int on);
 int ibldpc_phase_times(ibldpc_handle h, float *ms3, int32_t *launches3);
 
 /* Frames per chunk of the pinned-host pipeline of ibldpc_decode_ib_host; 0 (default) = automatic,
- * about 256 MiB of channel values, split into equal chunks. */
+ * equal chunks of at most ~256 MiB of channel values, first and last chunk split 1/4 + 3/4. */
 int ibldpc_set_host_chunk(ibldpc_handle h, int frames);
 
 const char *ibldpc_last_error(void);

@@ -1038,18 +1038,39 @@ int ibldpc_decode_ib_host(ibldpc_handle h, const uint8_t* ch_host, int64_t B, in
     if (!ch_host || !out_host) return fail(IBLDPC_E_INVALID, "null buffer");
     CK(cudaSetDevice(h->device));
     // Early termination is a property of the whole call (all B frames), so it cannot be chunked.
-    // Auto chunk: about 256 MiB of channel values, the batch split into equal chunks (measured on B200, C1,
-    // B=65536: 8192-frame chunks 4.2, 32768-frame chunks 4.64 Gbit/s end to end; the kernels lose efficiency
-    // on small batches faster than the un-overlapped first copy-in / last copy-out cost).
-    int64_t want = h->host_chunk;
-    if (want <= 0) {
+    // Chunk schedule of the two-slot copy/decode pipeline.  Auto: equal chunks of at most ~256 MiB of channel values
+    // (at least two when B >= 8192), with the first and the last chunk split 1/4 + 3/4 and 3/4 + 1/4 so that only a
+    // quarter chunk of copy-in and of copy-out is not overlapped with decoding.  Measured on B200, C1, B=65536:
+    // 8 x 8192 frames 4.2, 2 x 32768 4.64 Gbit/s end to end (the kernels lose efficiency on small batches, large
+    // chunks expose their first copy-in / last copy-out).  An explicit ibldpc_set_host_chunk gives equal chunks.
+    std::vector<int64_t> widths;
+    if (early_term) {
+        widths.push_back(B);
+    } else if (h->host_chunk > 0) {
+        const int64_t c = std::max<int64_t>(16, h->host_chunk / 16 * 16);
+        for (int64_t off = 0; off < B; off += c) widths.push_back(std::min<int64_t>(c, B - off));
+    } else {
         const int64_t target = std::max<int64_t>(512, ((256LL << 20) / h->N) / 512 * 512);
-        const int64_t n_chunks = (B + target - 1) / target;
-        want = ((B + n_chunks - 1) / n_chunks + 511) / 512 * 512;
+        int64_t n_chunks = (B + target - 1) / target;
+        if (n_chunks < 2 && B >= 8192) n_chunks = 2;
+        if (n_chunks < 2) {
+            widths.push_back(B);
+        } else {
+            const int64_t c = ((B + n_chunks - 1) / n_chunks + 511) / 512 * 512;
+            const int64_t q = std::max<int64_t>(512, (c / 4) / 512 * 512);
+            int64_t left = B;
+            auto take = [&](int64_t wdt) { wdt = std::min(wdt, left); if (wdt > 0) { widths.push_back(wdt); left -= wdt; } };
+            take(q);
+            take(c - q);
+            while (left > c) take(c);
+            if (left > q) take(left - q);
+            take(left);
+        }
     }
-    const int64_t chunk = early_term ? B : std::min<int64_t>(B, std::max<int64_t>(16, want / 16 * 16));
+    int64_t chunk = 0;
+    for (int64_t wdt : widths) chunk = std::max(chunk, wdt);
     const long long cpitch = (chunk + 15) / 16 * 16;
-    const int nslots = (chunk < B) ? 2 : 1;
+    const int nslots = widths.size() > 1 ? 2 : 1;
     for (int s = 0; s < nslots; ++s) {
         Workspace& w = h->ws[s];
         if (!w.stream) CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
@@ -1067,15 +1088,17 @@ int ibldpc_decode_ib_host(ibldpc_handle h, const uint8_t* ch_host, int64_t B, in
     }
     if (h->profiling) clear_events(h);
     int slot = 0;
-    for (int64_t off = 0; off < B; off += chunk, slot ^= (nslots - 1)) {
+    int64_t off = 0;
+    for (int64_t wd : widths) {
         Workspace& w = h->ws[slot];
-        const int64_t wd = std::min<int64_t>(chunk, B - off);
-        const long long pitch = (wd + 15) / 16 * 16;   // the tail chunk may be narrower
+        const long long pitch = (wd + 15) / 16 * 16;
         CK(cudaMemcpy2DAsync(w.stage_in, (size_t)pitch, ch_host + off, (size_t)B, (size_t)wd, (size_t)h->N,
                              cudaMemcpyHostToDevice, w.stream));
         if ((rc = decode_ib_padded(h, w, w.stage_in, pitch, wd, imax, early_term, w.stage_out, w.stream))) return rc;
         CK(cudaMemcpy2DAsync(out_host + off, (size_t)B, w.stage_out, (size_t)pitch, (size_t)wd, (size_t)h->N,
                              cudaMemcpyDeviceToHost, w.stream));
+        off += wd;
+        slot ^= (nslots - 1);
     }
     for (int s = 0; s < nslots; ++s) CK(cudaStreamSynchronize(h->ws[s].stream));
     if (i_num_host) CK(cudaMemcpy(i_num_host, h->ws[0].inum, sizeof(int), cudaMemcpyDeviceToHost));

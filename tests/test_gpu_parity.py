@@ -182,6 +182,31 @@ def test_ib_vn_tail_pair_variant_all_degrees(gpu, monkeypatch, threads):
             assert np.array_equal(got, ref) and dec.last_i_num == i_num
 
 
+@pytest.mark.parametrize("B,chunk", [(9001, 0), (8200, 0), (5000, 1008), (777, 0)])
+def test_ib_host_pipeline_chunk_schedules(gpu, B, chunk):
+    """ibldpc_decode_ib_host (pinned-host two-slot pipeline): the automatic ramped chunk schedule and an explicit
+    chunk size, ragged batch sizes, must give exactly what one device-buffer decode of the whole batch gives."""
+    import informationbottleneckdecodingldpc_b200 as pkg
+    from informationbottleneckdecodingldpc_b200 import _lib
+    H = codes.wlan_80211n(54)
+    t = graph.edge_tables(H)
+    T, imax = 16, 5
+    tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=51, matching=True)
+    ch = np.random.Generator(np.random.PCG64(52)).integers(0, T, size=(t.n_var, B)).astype(np.uint8)
+    dec = _mk_ib(H, T, imax, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                 tb.matching_vector_checknode, tb.matching_vector_varnode)
+    dec.early_termination = False
+    dec.host_output_dtype = np.uint8
+    full = dec.decode_OpenCL(_dev(ch), buffer_in=True, return_buffer=True).get()
+    _lib.check(_lib.lib().ibldpc_set_host_chunk(dec._ensure_handle(), chunk))
+    host_in = pkg.pinned_empty(ch.shape, np.uint8)
+    host_in[:] = ch
+    host = dec.decode_OpenCL(host_in, buffer_in=False, return_buffer=False)
+    assert np.array_equal(host, full)
+    ref, _ = _oracle_ib(t, ch[:, -40:], T, imax, tb, False)
+    assert np.array_equal(host[:, -40:], ref)
+
+
 def test_ib_dvbs2_full_size_vs_oracle(gpu):
     """DVB-S2-like n=64800 (degree-1 VN, d_v 8, d_c 6/7, matching), a few frames, 4 iterations."""
     H = codes.dvbs2_like_half_rate()
