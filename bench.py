@@ -8,7 +8,9 @@ Workload (BASELINE.json configs[0], the configuration the metric is quoted on): 
 LDPC code n=8000, R=1/2, BPSK/AWGN, IB decoder |T|=16, i_max=50, early termination off,
 B=65536 frames per GPU and step, channel cluster indices drawn by the inversion method from the
 |T|=16 quantizer at Eb/N0 = 1.6 dB (all-zero codeword), exactly like quantize_direct_OpenCL;
-IB tables designed at 1.2 dB by the in-repo discrete density evolution.
+IB tables designed at 1.2 dB by the in-repo discrete density evolution.  The decoder runs the
+packed-nibble kernel family (four-bit messages); the roofline object reports both SURVEY 8(d)'s
+algorithmic (uint8) bytes and the bytes really stored.
 A "step" = decode one batch + count bit/frame errors (+ all-reduce of the 4 counters for N>1).
 One JSON line is printed by rank 0.
 """
