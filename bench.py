@@ -230,10 +230,11 @@ def main():
     import torch.distributed as dist
     import informationbottleneckdecodingldpc_b200 as pkg
     from informationbottleneckdecodingldpc_b200 import _lib
-    from informationbottleneckdecodingldpc_b200.parallel import allreduce_counters, init_distributed
+    from informationbottleneckdecodingldpc_b200.parallel import allreduce_counters, bind_to_gpu_numa_node, init_distributed
 
     rank, world, local = init_distributed(args.gpus)
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None   # host buffers of the e2e leg local to the GPU
     wl = workload(args.workload)
     B = args.frames or wl["B"]
     t, tb = make_tables(wl)
@@ -395,7 +396,7 @@ def main():
             "vs_baseline": None, "dtype": "u4" if packed else "u8", "data": "synthetic",
             "config": {"workload": wl["name"], "frames_per_gpu_per_step": B, "n_var": N, "n_chk": M, "n_edge": E,
                        "info_bits": K_info, "i_max": IMAX, "EbN0_dB": wl["ebn0"], "tables": wl.get("tables"),
-                       "l2": "inputs_larger_than_L2 (message array %.0f MB)" % (E * B / stored_div / 1e6), "parallelism": f"frames sharded x{world}",
+                       "l2": "inputs_larger_than_L2 (message array %.0f MB)" % (E * B / stored_div / 1e6), "parallelism": f"frames sharded x{world}", "rank0_numa_node": numa_node,
                        "fast_path": bool(decodi.info()[0]), "kernel_family": "packed-nibble (n4)" if packed else "uint8"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,

@@ -30,6 +30,40 @@ def init_distributed(n_gpus: int = 1, backend: str | None = None):
     return rank, world, local
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(local_rank: int, sysfs: str = "/sys") -> int | None:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs: the PCI device's
+    numa_node and that node's cpulist), so that the pinned host buffers of the host-buffer path
+    (first touch) and the copy-issuing thread are local to the GPU's root complex.  With 8 ranks on a
+    two-socket host the default placement puts half of the DMA traffic across the socket link.
+    Returns the node, or None when the topology is not exposed (then nothing is changed)."""
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open(os.path.join(sysfs, "bus/pci/devices", bdf, "numa_node")) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(os.path.join(sysfs, "devices/system/node", f"node{node}", "cpulist")) as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_frames(total_frames: int, rank: int, world: int):
     """Contiguous frame range [lo, hi) of this rank (remainder spread over the first ranks)."""
     base, rem = divmod(int(total_frames), int(world))

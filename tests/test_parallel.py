@@ -45,3 +45,14 @@ def test_counter_allreduce_world2_gloo(tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_cpulist_parser_and_numa_binding_without_topology(tmp_path):
+    """bind_to_gpu_numa_node must be a no-op (None) when sysfs does not expose the GPU; the cpulist parser
+    handles ranges and singletons."""
+    from informationbottleneckdecodingldpc_b200 import parallel
+    assert parallel._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert parallel._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert parallel.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
+    assert os.sched_getaffinity(0) == before
