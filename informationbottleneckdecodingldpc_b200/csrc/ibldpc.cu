@@ -469,11 +469,37 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
     a.DC = h->DC; a.DV = h->DV; a.xp_col = -1;
     const int T = h->T, TT = T * T;
     // tile geometry of one launch: a warp covers 128*vec bytes of a row
-    auto set_tiles = [&](IbArgs& b, int vec, int* tile_groups, int* nps) {
+    // Launch geometry of one degree class: the grid is (CTAs per tile group) x (tile groups), a CTA's warps cover
+    // 2^tpc_log2 consecutive tiles of (warps >> tpc_log2) nodes.  floor(resident slots / tile groups) CTAs per group
+    // can leave many slots empty (802.11n, B=100096: 25 groups on 148 slots -> 125 CTAs), so the number of tiles per
+    // CTA is chosen to minimise the makespan in node steps: waves x ceil(node steps / CTAs per group) / (fraction of
+    // warps that own a real tile); ties go to the wider CTA footprint (longer contiguous runs per row).
+    auto plan_launch = [&](IbArgs& b, const void* fn, int smem, int threads, int vec, int n_nodes, int* tile_groups, int* grid) -> int {
+        int occ;
+        int r = occupancy_of(h, fn, smem, &occ, threads);
+        if (r) return r;
+        const long long slots = (long long)occ * h->sm_count;
+        const int warps = threads / 32;
         b.tiles = (int)((pitch4 + 128 * vec - 1) / (128 * vec));
-        b.tpc_log2 = b.tiles >= 8 ? 3 : b.tiles > 2 ? 2 : b.tiles == 2 ? 1 : 0;
-        *tile_groups = (b.tiles + (1 << b.tpc_log2) - 1) >> b.tpc_log2;
-        *nps = kWarpsPerCta >> b.tpc_log2;
+        double best = 0;
+        int best_tpc = -1;
+        static const bool no_plan = getenv("IBLDPC_NO_PLAN") != nullptr;   // A/B switch: widest footprint that fits the row
+        for (int tpc = 3; tpc >= 0; --tpc) {
+            if (tpc > 0 && (1 << (tpc - 1)) >= b.tiles) continue;      // wider than the row: only wasted warps
+            if (no_plan && best_tpc >= 0) break;
+            const long long tg = (b.tiles + (1 << tpc) - 1) >> tpc;
+            const long long nsteps = (n_nodes + (warps >> tpc) - 1) / (warps >> tpc);
+            const long long per = std::max<long long>(1, std::min(nsteps, slots / tg));
+            const long long waves = (per * tg + slots - 1) / slots;
+            const double used = (double)b.tiles / (double)(tg << tpc);
+            const double cost = (double)(waves * ((nsteps + per - 1) / per)) / used;
+            if (best_tpc < 0 || cost < best * 0.999) { best = cost; best_tpc = tpc; }
+        }
+        b.tpc_log2 = best_tpc;
+        *tile_groups = (b.tiles + (1 << best_tpc) - 1) >> best_tpc;
+        const long long nsteps = (n_nodes + (warps >> best_tpc) - 1) / (warps >> best_tpc);
+        *grid = (int)std::max<long long>(1, std::min(nsteps, slots / *tile_groups));
+        return IBLDPC_OK;
     };
     auto vn_vec_of = [&](int d) { return h->vn_vec ? h->vn_vec : (d <= 6 ? 4 : 2); };
     auto launch_cn = [&](int it) -> int {
@@ -492,8 +518,7 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
             // look-ups of D-2 outputs; 2 words per lane only
             const bool pair = h->use_pair && c.degree >= h->n4_pair_min_degree && c.degree >= 4 && h->d_cn_pair != nullptr;
             const int vec = 2;
-            int tile_groups, nps;
-            set_tiles(b, vec, &tile_groups, &nps);
+            int tile_groups;
             int smem = n4_table_bytes(n4_cn_words(c.degree, explicit_match)) + stage_scratch_bytes(b.nst, T, b.dmax_match);
             b.xp_col = -1;
             if (pair) {
@@ -505,9 +530,8 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
             NodeKernel k = pair ? cn_n4_pair_kernel(c.degree, early != 0) : cn_n4_kernel_v2(c.degree, explicit_match, early != 0);
             if (!k) return fail(IBLDPC_E_INVALID, "no packed check-node kernel for degree " + std::to_string(c.degree));
             const int threads = pair ? cn_n4_pair_threads(c.degree) : kThreads;
-            nps = (threads / 32) >> b.tpc_log2;
             int grid;
-            if ((r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid, 1.0, threads))) return r;
+            if ((r = plan_launch(b, (const void*)k, smem, threads, vec, c.count, &tile_groups, &grid))) return r;
             k<<<dim3(grid, tile_groups), threads, smem, st>>>(b, c.d_nodes, c.count);
             h->last_launches++; h->last_grid = grid * tile_groups; h->last_smem = smem;
         }
@@ -532,8 +556,8 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
             const bool pair = !decide && h->use_pair && h->d_vn_pair != nullptr && c.degree >= h->vn_pair_min_degree &&
                               c.degree >= 3 && (h->vn_vec == 0 || h->vn_vec == 2);
             const int vec = pair ? 2 : vn_vec_of(c.degree);
-            int tile_groups, nps;
-            set_tiles(b, vec, &tile_groups, &nps);
+            int vec_used = vec;
+            int tile_groups;
             int smem = n4_table_bytes(n4_vn_words(c.degree, decide)) + stage_scratch_bytes(b.nst, T, b.dmax_match);
             int threads = kThreads;
             b.xp_col = -1;
@@ -547,18 +571,17 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
                 // 0.387 ms with 256 threads vs 0.420 ms), degree >= 10 has one table set per SM either way (WLAN d_v=11:
                 // 0.195 ms with 512 threads vs 0.229 ms)
                 threads = h->vn_pair_threads ? h->vn_pair_threads : (c.degree == 8 || c.degree == 9) ? 256 : 512;
-                nps = (threads / 32) >> b.tpc_log2;
                 k = vn_n4_pair_kernel(c.degree, threads);
             } else {
                 k = vec == 4 ? vn_n4_kernel_v4(c.degree, decide) : vn_n4_kernel_v2(c.degree, decide);
                 if (!k && vec == 4) {   // 4-word kernels exist up to degree 6 only
-                    set_tiles(b, 2, &tile_groups, &nps);
+                    vec_used = 2;
                     k = vn_n4_kernel_v2(c.degree, decide);
                 }
             }
             if (!k) return fail(IBLDPC_E_INVALID, "no packed variable-node kernel for degree " + std::to_string(c.degree));
             int grid;
-            if ((r = grid_for(h, (const void*)k, smem, tile_groups, nps, c.count, &grid, 1.0, threads))) return r;
+            if ((r = plan_launch(b, (const void*)k, smem, threads, vec_used, c.count, &tile_groups, &grid))) return r;
             k<<<dim3(grid, tile_groups), threads, smem, st>>>(b, c.d_nodes, c.count);
             h->last_launches++;
         }
