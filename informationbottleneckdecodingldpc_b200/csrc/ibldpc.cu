@@ -501,7 +501,9 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
         *grid = (int)std::max<long long>(1, std::min(nsteps, slots / *tile_groups));
         return IBLDPC_OK;
     };
-    auto vn_vec_of = [&](int d) { return h->vn_vec ? h->vn_vec : (d <= 6 ? 4 : 2); };
+    // words per lane of the variable-node kernels: 4 up to degree 6, except for batches that fit one 2-word tile
+    // (B <= 512), where 4 words would leave half of every warp's lanes without frames
+    auto vn_vec_of = [&](int d) { return h->vn_vec ? h->vn_vec : (d <= 6 && pitch4 > 256 ? 4 : 2); };
     auto launch_cn = [&](int it) -> int {
         IbArgs b = a;
         b.it = it; b.iter0 = (it < 0);
