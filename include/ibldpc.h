@@ -158,6 +158,18 @@ int ibldpc_phase_times(ibldpc_handle h, float *ms3, int32_t *launches3);
  * equal chunks of at most ~256 MiB of channel values, first and last chunk split 1/4 + 3/4. */
 int ibldpc_set_host_chunk(ibldpc_handle h, int frames);
 
+/* Host-side planning, exposed so that the CPU test-suite can check it without a GPU (no reference counterpart:
+ * the reference leaves the OpenCL local size to the runtime, discrete_LDPC_decoder.py:211,219,235-237, and has
+ * no host pipeline).
+ * ibldpc_plan_geometry: launch geometry of one degree class of the packed-nibble kernels for `resident_ctas`
+ *   resident CTA slots of `warps_per_cta` warps, `tiles` frame tiles per row and `n_nodes` nodes:
+ *   out3 = {log2(tiles per CTA), tile groups, CTAs per tile group}.
+ * ibldpc_host_chunk_schedule: chunk widths (frames) ibldpc_decode_ib_host uses for a batch of B frames of a code
+ *   with n_var variable nodes; returns the number of chunks (> capacity: only the first `capacity` are written). */
+int ibldpc_plan_geometry(int64_t resident_ctas, int warps_per_cta, int tiles, int n_nodes, int32_t *out3);
+int ibldpc_host_chunk_schedule(int64_t B, int64_t n_var, int64_t host_chunk, int early_term, int64_t *widths,
+                               int capacity);
+
 const char *ibldpc_last_error(void);
 int ibldpc_destroy(ibldpc_handle h);
 

@@ -58,6 +58,8 @@ SIGNATURES = {
     "ibldpc_set_profiling": (_i, [_vp, _i]),
     "ibldpc_phase_times": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "ibldpc_set_host_chunk": (_i, [_vp, _i]),
+    "ibldpc_plan_geometry": (_i, [_i64, _i, _i, _i, C.POINTER(C.c_int32)]),
+    "ibldpc_host_chunk_schedule": (_i, [_i64, _i64, _i64, _i, C.POINTER(C.c_int64), _i]),
     "ibldpc_last_error": (C.c_char_p, []),
     "ibldpc_destroy": (_i, [_vp]),
 }

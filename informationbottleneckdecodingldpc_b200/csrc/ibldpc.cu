@@ -202,6 +202,74 @@ int grid_for(ibldpc_decoder* h, const void* fn, int smem, long long items, int* 
     return IBLDPC_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Host-side planning (pure functions, also exported for the CPU test-suite: ibldpc_plan_geometry,
+// ibldpc_host_chunk_schedule)
+// ------------------------------------------------------------------------------------------
+// Launch geometry of one degree class of the packed-nibble kernels: the grid is (CTAs per tile group) x (tile
+// groups), a CTA's warps cover 2^tpc_log2 consecutive tiles of (warps >> tpc_log2) nodes.
+// floor(resident slots / tile groups) CTAs per group can leave many slots empty (802.11n, B=100096: 25 groups on
+// 148 slots -> 125 CTAs), so the number of tiles per CTA is chosen to minimise the makespan in node steps:
+// waves x ceil(node steps / CTAs per group) / (fraction of warps that own a real tile); ties go to the wider CTA
+// footprint (longer contiguous runs per row).  `widest_only` = the pre-planner rule (A/B switch IBLDPC_NO_PLAN).
+void plan_geometry(long long slots, int warps, int tiles, int n_nodes, bool widest_only, int* tpc_log2, int* tile_groups,
+                   int* grid_x)
+{
+    double best = 0;
+    int best_tpc = -1;
+    for (int tpc = 3; tpc >= 0; --tpc) {
+        if ((warps >> tpc) < 1) continue;
+        if (tpc > 0 && (1 << (tpc - 1)) >= tiles) continue;      // wider than the row: only wasted warps
+        if (widest_only && best_tpc >= 0) break;
+        const long long tg = (tiles + (1 << tpc) - 1) >> tpc;
+        const long long nsteps = (n_nodes + (warps >> tpc) - 1) / (warps >> tpc);
+        const long long per = std::max<long long>(1, std::min(nsteps, slots / tg));
+        const long long waves = (per * tg + slots - 1) / slots;
+        const double used = (double)tiles / (double)(tg << tpc);
+        const double cost = (double)(waves * ((nsteps + per - 1) / per)) / used;
+        if (best_tpc < 0 || cost < best * 0.999) { best = cost; best_tpc = tpc; }
+    }
+    *tpc_log2 = best_tpc;
+    *tile_groups = (tiles + (1 << best_tpc) - 1) >> best_tpc;
+    const long long nsteps = (n_nodes + (warps >> best_tpc) - 1) / (warps >> best_tpc);
+    *grid_x = (int)std::max<long long>(1, std::min(nsteps, std::max<long long>(1, slots / *tile_groups)));
+}
+
+// Chunk schedule of the two-slot copy/decode pipeline of ibldpc_decode_ib_host.  Auto (host_chunk == 0): equal
+// chunks of at most ~256 MiB of channel values (at least two when B >= 8192), with the first and the last chunk
+// split 1/4 + 3/4 and 3/4 + 1/4 so that only a quarter chunk of copy-in and of copy-out is not overlapped with
+// decoding.  Measured on B200, C1, B=65536: 8 x 8192 frames 4.2, 2 x 32768 4.64, ramped 5.03 Gbit/s end to end
+// (the kernels lose efficiency on small batches, large chunks expose their first copy-in / last copy-out).
+// An explicit chunk size gives equal chunks; early termination is a property of the whole call: one chunk.
+std::vector<int64_t> host_chunk_schedule(int64_t B, int64_t n_var, int64_t host_chunk, bool early_term)
+{
+    std::vector<int64_t> widths;
+    if (early_term) {
+        widths.push_back(B);
+    } else if (host_chunk > 0) {
+        const int64_t c = std::max<int64_t>(16, host_chunk / 16 * 16);
+        for (int64_t off = 0; off < B; off += c) widths.push_back(std::min<int64_t>(c, B - off));
+    } else {
+        const int64_t target = std::max<int64_t>(512, ((256LL << 20) / std::max<int64_t>(n_var, 1)) / 512 * 512);
+        int64_t n_chunks = (B + target - 1) / target;
+        if (n_chunks < 2 && B >= 8192) n_chunks = 2;
+        if (n_chunks < 2) {
+            widths.push_back(B);
+        } else {
+            const int64_t c = ((B + n_chunks - 1) / n_chunks + 511) / 512 * 512;
+            const int64_t q = std::max<int64_t>(512, (c / 4) / 512 * 512);
+            int64_t left = B;
+            auto take = [&](int64_t wdt) { wdt = std::min(wdt, left); if (wdt > 0) { widths.push_back(wdt); left -= wdt; } };
+            take(q);
+            take(c - q);
+            while (left > c) take(c);
+            if (left > q) take(left - q);
+            take(left);
+        }
+    }
+    return widths;
+}
+
 struct Prof {
     ibldpc_decoder* h;
     cudaStream_t st;
@@ -469,36 +537,14 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
     a.DC = h->DC; a.DV = h->DV; a.xp_col = -1;
     const int T = h->T, TT = T * T;
     // tile geometry of one launch: a warp covers 128*vec bytes of a row
-    // Launch geometry of one degree class: the grid is (CTAs per tile group) x (tile groups), a CTA's warps cover
-    // 2^tpc_log2 consecutive tiles of (warps >> tpc_log2) nodes.  floor(resident slots / tile groups) CTAs per group
-    // can leave many slots empty (802.11n, B=100096: 25 groups on 148 slots -> 125 CTAs), so the number of tiles per
-    // CTA is chosen to minimise the makespan in node steps: waves x ceil(node steps / CTAs per group) / (fraction of
-    // warps that own a real tile); ties go to the wider CTA footprint (longer contiguous runs per row).
+    // launch geometry of one degree class (plan_geometry): tiles per CTA, tile groups, CTAs per tile group
     auto plan_launch = [&](IbArgs& b, const void* fn, int smem, int threads, int vec, int n_nodes, int* tile_groups, int* grid) -> int {
         int occ;
         int r = occupancy_of(h, fn, smem, &occ, threads);
         if (r) return r;
-        const long long slots = (long long)occ * h->sm_count;
-        const int warps = threads / 32;
+        static const bool no_plan = getenv("IBLDPC_NO_PLAN") != nullptr;
         b.tiles = (int)((pitch4 + 128 * vec - 1) / (128 * vec));
-        double best = 0;
-        int best_tpc = -1;
-        static const bool no_plan = getenv("IBLDPC_NO_PLAN") != nullptr;   // A/B switch: widest footprint that fits the row
-        for (int tpc = 3; tpc >= 0; --tpc) {
-            if (tpc > 0 && (1 << (tpc - 1)) >= b.tiles) continue;      // wider than the row: only wasted warps
-            if (no_plan && best_tpc >= 0) break;
-            const long long tg = (b.tiles + (1 << tpc) - 1) >> tpc;
-            const long long nsteps = (n_nodes + (warps >> tpc) - 1) / (warps >> tpc);
-            const long long per = std::max<long long>(1, std::min(nsteps, slots / tg));
-            const long long waves = (per * tg + slots - 1) / slots;
-            const double used = (double)b.tiles / (double)(tg << tpc);
-            const double cost = (double)(waves * ((nsteps + per - 1) / per)) / used;
-            if (best_tpc < 0 || cost < best * 0.999) { best = cost; best_tpc = tpc; }
-        }
-        b.tpc_log2 = best_tpc;
-        *tile_groups = (b.tiles + (1 << best_tpc) - 1) >> best_tpc;
-        const long long nsteps = (n_nodes + (warps >> best_tpc) - 1) / (warps >> best_tpc);
-        *grid = (int)std::max<long long>(1, std::min(nsteps, slots / *tile_groups));
+        plan_geometry((long long)occ * h->sm_count, threads / 32, b.tiles, n_nodes, no_plan, &b.tpc_log2, tile_groups, grid);
         return IBLDPC_OK;
     };
     // words per lane of the variable-node kernels: 4 up to degree 6, except for batches that fit one 2-word tile
@@ -1063,35 +1109,7 @@ int ibldpc_decode_ib_host(ibldpc_handle h, const uint8_t* ch_host, int64_t B, in
     if (!ch_host || !out_host) return fail(IBLDPC_E_INVALID, "null buffer");
     CK(cudaSetDevice(h->device));
     // Early termination is a property of the whole call (all B frames), so it cannot be chunked.
-    // Chunk schedule of the two-slot copy/decode pipeline.  Auto: equal chunks of at most ~256 MiB of channel values
-    // (at least two when B >= 8192), with the first and the last chunk split 1/4 + 3/4 and 3/4 + 1/4 so that only a
-    // quarter chunk of copy-in and of copy-out is not overlapped with decoding.  Measured on B200, C1, B=65536:
-    // 8 x 8192 frames 4.2, 2 x 32768 4.64 Gbit/s end to end (the kernels lose efficiency on small batches, large
-    // chunks expose their first copy-in / last copy-out).  An explicit ibldpc_set_host_chunk gives equal chunks.
-    std::vector<int64_t> widths;
-    if (early_term) {
-        widths.push_back(B);
-    } else if (h->host_chunk > 0) {
-        const int64_t c = std::max<int64_t>(16, h->host_chunk / 16 * 16);
-        for (int64_t off = 0; off < B; off += c) widths.push_back(std::min<int64_t>(c, B - off));
-    } else {
-        const int64_t target = std::max<int64_t>(512, ((256LL << 20) / h->N) / 512 * 512);
-        int64_t n_chunks = (B + target - 1) / target;
-        if (n_chunks < 2 && B >= 8192) n_chunks = 2;
-        if (n_chunks < 2) {
-            widths.push_back(B);
-        } else {
-            const int64_t c = ((B + n_chunks - 1) / n_chunks + 511) / 512 * 512;
-            const int64_t q = std::max<int64_t>(512, (c / 4) / 512 * 512);
-            int64_t left = B;
-            auto take = [&](int64_t wdt) { wdt = std::min(wdt, left); if (wdt > 0) { widths.push_back(wdt); left -= wdt; } };
-            take(q);
-            take(c - q);
-            while (left > c) take(c);
-            if (left > q) take(left - q);
-            take(left);
-        }
-    }
+    const std::vector<int64_t> widths = host_chunk_schedule(B, h->N, h->host_chunk, early_term != 0);
     int64_t chunk = 0;
     for (int64_t wdt : widths) chunk = std::max(chunk, wdt);
     const long long cpitch = (chunk + 15) / 16 * 16;
@@ -1243,6 +1261,25 @@ int ibldpc_phase_times(ibldpc_handle h, float* ms3, int32_t* launches3)
         launches3[e.phase] += 1;
     }
     return IBLDPC_OK;
+}
+
+int ibldpc_plan_geometry(int64_t resident_ctas, int warps_per_cta, int tiles, int n_nodes, int32_t* out3)
+{
+    if (!out3 || resident_ctas < 1 || warps_per_cta < 8 || warps_per_cta % 8 || tiles < 1 || n_nodes < 1)
+        return fail(IBLDPC_E_INVALID, "bad arguments");
+    int tpc, tg, gx;
+    plan_geometry(resident_ctas, warps_per_cta, tiles, n_nodes, false, &tpc, &tg, &gx);
+    out3[0] = tpc; out3[1] = tg; out3[2] = gx;
+    return IBLDPC_OK;
+}
+
+int ibldpc_host_chunk_schedule(int64_t B, int64_t n_var, int64_t host_chunk, int early_term, int64_t* widths, int capacity)
+{
+    if (B < 1 || n_var < 1 || host_chunk < 0 || capacity < 0 || (capacity > 0 && !widths))
+        return fail(IBLDPC_E_INVALID, "bad arguments");
+    const std::vector<int64_t> w = host_chunk_schedule(B, n_var, host_chunk, early_term != 0);
+    for (size_t i = 0; i < w.size() && (int)i < capacity; ++i) widths[i] = w[i];
+    return (int)w.size();
 }
 
 int ibldpc_destroy(ibldpc_handle h)

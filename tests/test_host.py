@@ -150,6 +150,73 @@ def test_cabi_library_exports_every_declared_symbol():
     _lib.lib()
 
 
+def test_launch_planner_geometry_invariants():
+    """ibldpc_plan_geometry (host logic, no GPU call): every choice covers all tiles and all nodes, keeps at least
+    one node per CTA step, never plans more CTAs per tile group than node steps, and for the shapes measured on
+    B200 picks the footprint that fills the resident slots."""
+    from informationbottleneckdecodingldpc_b200 import _lib
+    L = _lib.lib()
+    out = (ctypes.c_int32 * 3)()
+
+    def plan(slots, warps, tiles, nodes):
+        _lib.check(L.ibldpc_plan_geometry(slots, warps, tiles, nodes, out))
+        return out[0], out[1], out[2]
+
+    rng = np.random.default_rng(5)
+    for _ in range(2000):
+        slots = int(rng.integers(1, 8)) * 148
+        warps = int(rng.choice([8, 16]))
+        tiles = int(rng.integers(1, 400))
+        nodes = int(rng.integers(1, 70000))
+        tpc, tg, gx = plan(slots, warps, tiles, nodes)
+        assert 0 <= tpc <= 3 and (warps >> tpc) >= 1
+        assert tg == -(-tiles // (1 << tpc))                     # all tiles covered, no empty tile group
+        assert tpc == 0 or (1 << (tpc - 1)) < tiles              # footprint not wider than the row needs
+        nsteps = -(-nodes // (warps >> tpc))
+        assert 1 <= gx <= nsteps
+        assert gx * tg <= max(slots, tg)                          # one wave unless there are more tile groups than slots
+    # 802.11n n=1296 d_v=11 class, B=100096 (196 tiles of 256 B), 148 slots of 16 warps: 49 groups x 3 CTAs = 147 of 148
+    assert plan(148, 16, 196, 162) == (2, 49, 3)
+    # C1 check nodes, B=65536: 128 tiles, 296 slots: the widest footprint already fills 288 slots
+    assert plan(296, 16, 128, 4000) == (3, 16, 18)
+    assert L.ibldpc_plan_geometry(0, 16, 1, 1, out) != 0 and L.ibldpc_plan_geometry(148, 12, 1, 1, out) != 0
+
+
+def test_host_chunk_schedule_properties():
+    """ibldpc_host_chunk_schedule (host logic): chunks are positive and sum to B; early termination is never
+    chunked; the automatic schedule stays under ~256 MiB of channel values per chunk, has quarter-size first and
+    last chunks once B >= 8192, and an explicit chunk size gives equal chunks."""
+    from informationbottleneckdecodingldpc_b200 import _lib
+    L = _lib.lib()
+    buf = (ctypes.c_int64 * 4096)()
+
+    def sched(B, n_var, chunk=0, early=0):
+        n = L.ibldpc_host_chunk_schedule(B, n_var, chunk, early, buf, 4096)
+        assert 1 <= n <= 4096
+        return [int(buf[i]) for i in range(n)]
+
+    rng = np.random.default_rng(6)
+    for _ in range(500):
+        B = int(rng.integers(1, 300000))
+        n_var = int(rng.choice([24, 1296, 8000, 64800]))
+        w = sched(B, n_var)
+        assert all(x > 0 for x in w) and sum(w) == B
+        assert max(w) * n_var <= (256 << 20) + 512 * n_var
+        target = max(512, ((256 << 20) // n_var) // 512 * 512)
+        if B >= 8192 or B > target:
+            assert len(w) >= 3 and w[0] <= max(w) and w[-1] <= max(w)
+            if B >= 8192:
+                assert len(w) >= 4 and w[0] <= max(w) // 2 and w[-1] <= max(w) // 2
+        else:
+            assert w == [B]
+        assert sched(B, n_var, early=1) == [B]
+        c = int(rng.integers(16, 40000))
+        w = sched(B, n_var, chunk=c)
+        assert sum(w) == B and all(x == c // 16 * 16 for x in w[:-1]) and 0 < w[-1] <= c // 16 * 16
+    assert sched(65536, 8000) == [8192, 24576, 24576, 8192]
+    assert L.ibldpc_host_chunk_schedule(0, 8000, 0, 0, buf, 16) < 0
+
+
 def test_product_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
