@@ -158,6 +158,46 @@ int ibldpc_phase_times(ibldpc_handle h, float *ms3, int32_t *launches3);
  * equal chunks of at most ~256 MiB of channel values, first and last chunk split 1/4 + 3/4. */
 int ibldpc_set_host_chunk(ibldpc_handle h, int frames);
 
+/* ---------------------------------------------------------------------------------------------
+ * Transmit side of the BER drivers: systematic encoder, random bits, channel.
+ * --------------------------------------------------------------------------------------------- */
+#define IBLDPC_ENC_SUBSTITUTION 1 /* H_last (or a row permutation of it) is triangular */
+#define IBLDPC_ENC_DENSE 2        /* "Matrix Inverse": dense H_last^-1 from a GF(2) elimination on the host */
+
+typedef struct ibldpc_encoder *ibldpc_encoder_handle;
+
+/* What LDPCEncoder.getLDPCEncoderParamters derives from H (Discrete_LDPC_decoding/LDPC_encoder.py:196-262), in the
+ * form the GPU solver consumes.  H = [H_first | H_last], H_last the last M = n_var - n_info columns.  Host pointers.
+ *   a_rowptr/a_col        CSR of H_first (M rows, columns in [0, n_info))  -- MatrixA of the reference
+ *   substitution          step t solves parity bit var[t] from check equation eq[t]:
+ *                           p[var[t]] = s[eq[t]] ^ XOR p[oth[oth_ptr[t] .. oth_ptr[t+1])],   s = H_first x
+ *                         (forward / backward substitution and the row-reversed variants of the reference are all
+ *                         orderings of this schedule)
+ *   dense_inverse         M rows of ceil(M/32) words, bit k of row r = (H_last^-1)[r][k]; p = H_last^-1 s */
+typedef struct ibldpc_encoder_desc {
+    int32_t n_var, n_info;
+    int32_t method; /* IBLDPC_ENC_* */
+    const int32_t *a_rowptr, *a_col;
+    const int32_t *eq, *var, *oth_ptr, *oth;
+    const uint32_t *dense_inverse;
+} ibldpc_encoder_desc;
+
+/* Replaces LDPCEncoder.__init__ / setParityCheckMatrix (LDPC_encoder.py:23-38, :192-194): validates and uploads. */
+int ibldpc_encoder_create(const ibldpc_encoder_desc *desc, int device, ibldpc_encoder_handle *out);
+/* Replaces LDPCEncoder.encode / encode_c (LDPC_encoder.py:86-163) and the per-frame loop of
+ * LDPC_BPSK_Transmitter.transmit (LDPC_Transmitter.py:109-121) for a whole batch:
+ * bits_dev (n_info, B) uint8 0/1 -> codeword_dev (n_var, B) uint8, first n_info rows = the information bits. */
+int ibldpc_encode(ibldpc_encoder_handle h, const uint8_t *bits_dev, int64_t B, uint8_t *codeword_dev, void *stream);
+int ibldpc_encoder_destroy(ibldpc_encoder_handle h);
+/* Replaces np.random.randint(0, 2, (data_len, msg_at_time)) (LDPC_Transmitter.py:111): Philox4x32-10, counter =
+ * offset + element index, bit = top bit of the first output word. */
+int ibldpc_random_bits(int device, uint64_t seed, uint64_t offset, int64_t n, uint8_t *out_dev, void *stream);
+/* Replaces AWGN_channel.transmission (AWGN_channel.py:32-50, real noise) and, with bits_dev, BPSK_mapping +
+ * transmission (LDPC_Transmitter.py:127-132): y = x + sqrt(sigma_n2) n  resp.  y = (1 - 2 bit) + sqrt(sigma_n2) n,
+ * n ~ N(0,1) by Box-Muller from Philox4x32-10 (counter = offset + element index).  Exactly one of x_dev / bits_dev. */
+int ibldpc_awgn(int device, const double *x_dev, const uint8_t *bits_dev, int64_t n, double sigma_n2, uint64_t seed,
+                uint64_t offset, double *y_dev, void *stream);
+
 /* Host-side planning, exposed so that the CPU test-suite can check it without a GPU (no reference counterpart:
  * the reference leaves the OpenCL local size to the runtime, discrete_LDPC_decoder.py:211,219,235-237, and has
  * no host pipeline).

@@ -12,7 +12,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libibldpc.so")
 UNITS = ["ibldpc.cu", "ib_fast_cn.cu", "ib_fast_vn.cu", "ib_n4_cn_v2.cu", "ib_n4_cn_pair.cu", "ib_n4_vn_pair.cu", "ib_n4_vn_v2.cu", "ib_n4_vn_v4.cu",
-         "llr_f32.cu", "llr_f64.cu"]   # compiled in parallel
+         "llr_f32.cu", "llr_f64.cu", "encoder.cu"]   # compiled in parallel
 SOURCES = [os.path.join(HERE, "csrc", f) for f in UNITS + ["ib_kernels.cuh", "ib_kernels_n4.cuh", "llr_kernels.cuh", "kernel_tables.h"]]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "ibldpc.h")
 
@@ -27,6 +27,16 @@ class CodeDesc(C.Structure):
     _fields_ = [("n_var", C.c_int32), ("n_chk", C.c_int32), ("n_edge", C.c_int32),
                 ("inbox_start_chk", C.c_void_p), ("degree_chk", C.c_void_p), ("target_cells_chk", C.c_void_p),
                 ("inbox_start_var", C.c_void_p), ("degree_var", C.c_void_p), ("target_cells_var", C.c_void_p)]
+
+
+class EncoderDesc(C.Structure):
+    _fields_ = [("n_var", C.c_int32), ("n_info", C.c_int32), ("method", C.c_int32),
+                ("a_rowptr", C.c_void_p), ("a_col", C.c_void_p),
+                ("eq", C.c_void_p), ("var", C.c_void_p), ("oth_ptr", C.c_void_p), ("oth", C.c_void_p),
+                ("dense_inverse", C.c_void_p)]
+
+
+ENC_SUBSTITUTION, ENC_DENSE = 1, 2
 
 
 class LutDesc(C.Structure):
@@ -58,6 +68,11 @@ SIGNATURES = {
     "ibldpc_set_profiling": (_i, [_vp, _i]),
     "ibldpc_phase_times": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "ibldpc_set_host_chunk": (_i, [_vp, _i]),
+    "ibldpc_encoder_create": (_i, [C.POINTER(EncoderDesc), _i, C.POINTER(_vp)]),
+    "ibldpc_encode": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "ibldpc_encoder_destroy": (_i, [_vp]),
+    "ibldpc_random_bits": (_i, [_i, _u64, _u64, _i64, _vp, _vp]),
+    "ibldpc_awgn": (_i, [_i, _vp, _vp, _i64, C.c_double, _u64, _u64, _vp, _vp]),
     "ibldpc_plan_geometry": (_i, [_i64, _i, _i, _i, C.POINTER(C.c_int32)]),
     "ibldpc_host_chunk_schedule": (_i, [_i64, _i64, _i64, _i, C.POINTER(C.c_int64), _i]),
     "ibldpc_last_error": (C.c_char_p, []),

@@ -70,6 +70,11 @@ struct PhaseEvent { cudaEvent_t a, b; int phase; };
 
 }  // namespace
 
+namespace ibldpc {
+// error sink shared with encoder.cu
+int fail_msg(int code, const std::string& msg) { return fail(code, msg); }
+}  // namespace ibldpc
+
 struct ibldpc_decoder {
     int device = 0;
     int sm_count = 148;

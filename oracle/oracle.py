@@ -160,3 +160,39 @@ def quantize_llr(x, limits, card, llr_values, backend="port"):
     else:
         ref_lib().ref_quantize_llr(card, x.ravel(), lim, lv, x.shape[0], x.shape[1], out.reshape(-1))
     return out
+
+
+def gf2_solve(Hlast, S):
+    """Solve Hlast P = S over GF(2) by plain Gauss-Jordan elimination on 0/1 arrays (Hlast square and
+    invertible, S one column per frame).  Independent of the product's host analysis."""
+    A = (np.asarray(Hlast, dtype=np.uint8) & 1).copy()
+    P = (np.asarray(S, dtype=np.uint8) & 1).copy()
+    n = A.shape[0]
+    for col in range(n):
+        cand = np.nonzero(A[col:, col])[0]
+        if cand.size == 0:
+            raise ValueError("singular over GF(2)")
+        piv = col + int(cand[0])
+        if piv != col:
+            A[[col, piv]] = A[[piv, col]]
+            P[[col, piv]] = P[[piv, col]]
+        rows = np.nonzero(A[:, col])[0]
+        rows = rows[rows != col]
+        A[rows] ^= A[col]
+        P[rows] ^= P[col]
+    return P
+
+
+def encode(H, bits):
+    """Systematic encoding as the reference's LDPCEncoder defines it (Discrete_LDPC_decoding/LDPC_encoder.py:15-21,
+    :86-123): codeword = [x ; p] with H[:, K:] p = H[:, :K] x over GF(2).  ``bits`` (K, B) -> (N, B) uint8.
+    The parity vector is unique, so forward / backward substitution and the GF(2) factorisation of the
+    reference all produce this result."""
+    import scipy.sparse as sp
+    H = sp.csr_matrix(H)
+    M, N = H.shape
+    K = N - M
+    x = (np.asarray(bits, dtype=np.int64) & 1).reshape(K, -1)
+    s = (H[:, :K].astype(np.int64) @ x) & 1
+    p = gf2_solve(H[:, K:].toarray(), s.astype(np.uint8))
+    return np.concatenate([x.astype(np.uint8), p.astype(np.uint8)], axis=0)

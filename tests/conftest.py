@@ -26,6 +26,7 @@ def load_golden(name):
 
 IB_CASES = sorted(f[:-4] for f in os.listdir(GOLD) if f.startswith("ib_"))
 LLR_CASES = sorted(f[:-4] for f in os.listdir(GOLD) if f.startswith("llr_"))
+ENC_CASES = sorted(f[:-4] for f in os.listdir(GOLD) if f.startswith("enc_"))
 
 
 @pytest.fixture(scope="session")
