@@ -72,7 +72,11 @@ __global__ void gf2_spmv_kernel(const int* __restrict__ rowptr, const int* __res
 }
 
 // Substitution: for t = 0..M-1:  p[var[t]] = s[eq[t]] ^ XOR_{e in [optr[t], optr[t+1])} p[oth[e]].
-// Every p row read in step t was written by the same thread in an earlier step.
+// Every p row read in step t was written by the same thread in an earlier step.  The recursion is a chain of
+// short steps, so everything that does not depend on it -- the right-hand sides s[eq[t]] and the schedule entries
+// of the next kDepth steps -- is fetched a block ahead (independent loads, one round trip per block instead of one
+// per step); the parity bit of the previous step stays in a register (staircase codes read nothing else).
+constexpr int kTriDepth = 16;
 __global__ void gf2_trisolve_kernel(const int* __restrict__ eq, const int* __restrict__ var, const int* __restrict__ optr,
                                     const int* __restrict__ oth, const uint32_t* __restrict__ s, uint32_t* __restrict__ p,
                                     int M, int wp)
@@ -81,18 +85,34 @@ __global__ void gf2_trisolve_kernel(const int* __restrict__ eq, const int* __res
     if (w >= wp) return;
     int prev_var = -1;
     uint32_t prev_val = 0;
-    uint32_t s_next = s[(long long)eq[0] * wp + w];
-    for (int t = 0; t < M; ++t) {
-        uint32_t acc = s_next;
-        if (t + 1 < M) s_next = s[(long long)eq[t + 1] * wp + w];   // independent of the recursion: fetched ahead
-        for (int e = optr[t]; e < optr[t + 1]; ++e) {
-            const int j = oth[e];
-            acc ^= (j == prev_var) ? prev_val : p[(long long)j * wp + w];   // staircase codes: p[i-1] stays in a register
+    for (int t0 = 0; t0 < M; t0 += kTriDepth) {
+        uint32_t rhs[kTriDepth];
+        int v[kTriDepth], lo[kTriDepth + 1];
+#pragma unroll
+        for (int q = 0; q < kTriDepth; ++q) {
+            const int t = min(t0 + q, M - 1);
+            rhs[q] = s[(long long)eq[t] * wp + w];
+            v[q] = var[t];
+            lo[q] = optr[min(t0 + q, M)];      // optr has M + 1 entries
         }
-        const int v = var[t];
-        p[(long long)v * wp + w] = acc;
-        prev_var = v;
-        prev_val = acc;
+        lo[kTriDepth] = optr[min(t0 + kTriDepth, M)];
+        int j0[kTriDepth];   // first operand of every step of the block (-1 = none), fetched ahead as well
+#pragma unroll
+        for (int q = 0; q < kTriDepth; ++q) j0[q] = lo[q] < lo[q + 1] ? oth[lo[q]] : -1;
+#pragma unroll
+        for (int q = 0; q < kTriDepth; ++q) {
+            if (t0 + q < M) {
+                uint32_t acc = rhs[q];
+                if (j0[q] >= 0) acc ^= (j0[q] == prev_var) ? prev_val : p[(long long)j0[q] * wp + w];
+                for (int e = lo[q] + 1; e < lo[q + 1]; ++e) {
+                    const int j = oth[e];
+                    acc ^= (j == prev_var) ? prev_val : p[(long long)j * wp + w];
+                }
+                p[(long long)v[q] * wp + w] = acc;
+                prev_var = v[q];
+                prev_val = acc;
+            }
+        }
     }
 }
 
