@@ -137,22 +137,6 @@ class EncoderPlan:
             self.dense_inverse = gf2_inverse_packed(sp.csr_matrix(H[:, K:]).toarray())
             self.method = _lib.ENC_DENSE
 
-    def encode_host_check(self, x: np.ndarray) -> np.ndarray:
-        """numpy evaluation of the plan for ONE frame (used by tests to validate the analysis without a GPU;
-        the product path is ibldpc_encode)."""
-        x = np.asarray(x).astype(np.uint8).ravel() & 1
-        s = np.zeros(self.M, dtype=np.uint8)
-        for r in range(self.M):
-            s[r] = x[self.a_col[self.a_rowptr[r]:self.a_rowptr[r + 1]]].sum() & 1
-        p = np.zeros(self.M, dtype=np.uint8)
-        if self.method == _lib.ENC_SUBSTITUTION:
-            for t in range(self.M):
-                p[self.var[t]] = (s[self.eq[t]] + p[self.oth[self.oth_ptr[t]:self.oth_ptr[t + 1]]].sum()) & 1
-        else:
-            G = np.unpackbits(self.dense_inverse.view(np.uint8), axis=1, bitorder="little")[:, :self.M]
-            p = (G.astype(np.int64) @ s.astype(np.int64) & 1).astype(np.uint8)
-        return np.concatenate([x, p])
-
 
 class LDPCEncoder:
     """``LDPCEncoder(filename, alist_file=True)`` -- constructor and attributes of the reference class
