@@ -13,7 +13,7 @@ invertible.  The host analysis mirrors ``getLDPCEncoderParamters`` (LDPC_encoder
 All substitution variants become one schedule "step t solves parity bit var[t] from equation eq[t]";
 'Matrix Inverse' uploads the dense inverse of the last part (bit-packed rows).  Because the parity
 vector is unique, the results equal the reference's codewords bit for bit.  Two notes on the reference,
-both visible when it is run under numpy 2 (oracle/make_golden.py): its int8 ``EncodingMethod`` overflows the
+both visible when it is run under numpy 2 (oracle/make_golden_encoder.py): its int8 ``EncodingMethod`` overflows the
 column counter of ``GF2MatrixMul`` for more than 127 columns (:187), and its 'Backward Substitution' branch
 sets the substitution direction to +1 (:236), which does not solve an upper-triangular system; this
 implementation returns the valid codeword in both cases.
