@@ -258,6 +258,35 @@ __host__ __device__ constexpr int cn_n4_min_blocks(int D, int VEC, bool PAIR)
     return PAIR ? (D <= 6 ? 3 : 2) : VEC == 2 ? (D <= 6 ? 5 : (D <= 8 ? 3 : 2)) : (D <= 6 ? 4 : (D <= 8 ? 3 : 2));
 }
 
+// Node loop of one check-node launch (or of one check-node phase of the cooperative kernel): CTA -> (tile group
+// blockIdx.y, node subset), no divisions, 32-bit offsets; the next node's slot index is fetched while this node is
+// being computed.  Returns the OR of the syndrome bits this thread saw.
+template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR, int NT>
+__device__ __forceinline__ uint32_t cn_loop_n4(const IbArgs& a, const uint8_t* tab, const uint8_t* ptab,
+                                               const int* __restrict__ nodes, int n_nodes)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane4 = lane * 4;
+    const int tile = (blockIdx.y << a.tpc_log2) + (warp & ((1 << a.tpc_log2) - 1));
+    const int nps = (NT / 32) >> a.tpc_log2;
+    const int stride = gridDim.x * nps;
+    const uint32_t col = ((uint32_t)tile * 32u + lane) * (4u * VEC);
+    uint32_t syn = 0;
+    if (tile < a.tiles && col < a.pitch) {
+        const int valid = a.B - 2 * (int)col;
+        int i = blockIdx.x * nps + (warp >> a.tpc_log2);
+        int s = i < n_nodes ? a.sc[nodes[i]] : 0;
+        while (i < n_nodes) {
+            const int i2 = i + stride;
+            const int s2 = i2 < n_nodes ? a.sc[nodes[i2]] : 0;
+            syn |= cn_node_n4<D, MATCH, EARLY, VEC, PAIR>(a, tab, ptab, s, col, lane4, valid);
+            i = i2;
+            s = s2;
+        }
+    }
+    return syn;
+}
+
 // send + checknode_update_iter0 (a.iter0) or checknode_update + calc_syndrome, packed nibbles.
 // PAIR: shared memory = [tail-pair rows (kPairBytes)][stage tables][staging scratch].
 // NT = threads per CTA: the tail-pair kernels of degree <= 8 run 512 threads (2 CTAs/SM at 64 registers share
@@ -282,28 +311,10 @@ ib_cn_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
     __syncthreads();
     const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_tab);
     const uint8_t* ptab = reinterpret_cast<const uint8_t*>(s_all);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lane4 = lane * 4;
-    const int tile = (blockIdx.y << a.tpc_log2) + (warp & ((1 << a.tpc_log2) - 1));
-    const int nps = (NT / 32) >> a.tpc_log2;
-    const int stride = gridDim.x * nps;
-    const uint32_t col = ((uint32_t)tile * 32u + lane) * (4u * VEC);
-    uint32_t syn = 0;
-    if (tile < a.tiles && col < a.pitch) {
-        const int valid = a.B - 2 * (int)col;
-        int i = blockIdx.x * nps + (warp >> a.tpc_log2);
-        int s = i < n_nodes ? a.sc[nodes[i]] : 0;
-        while (i < n_nodes) {
-            const int i2 = i + stride;
-            const int s2 = i2 < n_nodes ? a.sc[nodes[i2]] : 0;
-            syn |= cn_node_n4<D, MATCH, EARLY, VEC, PAIR>(a, tab, ptab, s, col, lane4, valid);
-            i = i2;
-            s = s2;
-        }
-    }
+    const uint32_t syn = cn_loop_n4<D, MATCH, EARLY, VEC, PAIR, NT>(a, tab, ptab, nodes, n_nodes);
     if (EARLY && !a.iter0) {
         const unsigned any = __ballot_sync(0xffffffffu, syn != 0);
-        if (any != 0 && lane == 0) atomicOr(&a.flags[a.it], 1);
+        if (any != 0 && (threadIdx.x & 31) == 0) atomicOr(&a.flags[a.it], 1);
     }
 }
 

@@ -13,6 +13,7 @@
 #include "../../include/ibldpc.h"
 #include "ib_kernels.cuh"
 #include "ib_kernels_n4.cuh"
+#include "ib_coop_n4.cuh"
 #include "llr_kernels.cuh"
 #include "kernel_tables.h"
 
@@ -92,6 +93,9 @@ struct ibldpc_decoder {
     uint8_t* d_vn_pair = nullptr;   // [imax][vn classes][T*T rows][8 bytes] composed tail-pair tables of the VN update
     int vn_pair_min_degree = 5;     // packed-nibble family (IBLDPC_VN_PAIR_MIN_DEGREE)
     int vn_pair_threads = 0;        // 0 = per-degree default, 256 / 512 forced (IBLDPC_VN_PAIR_THREADS)
+    long long coop_max_frames = 4096;   // regular codes: whole-decode cooperative kernel up to this batch size
+                                        // (IBLDPC_COOP_MAX_B, 0 disables)
+    int coop_supported = -1;        // device attribute cudaDevAttrCooperativeLaunch, queried once
     bool use_pair = true;
     int pair_min_degree = 7;      // uint8 family
     int n4_pair_min_degree = 6;   // packed-nibble family
@@ -541,7 +545,41 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
     a.flags = w.flags; a.inum = w.inum; a.early = early; a.imax = imax;
     a.DC = h->DC; a.DV = h->DV; a.xp_col = -1;
     const int T = h->T, TT = T * T;
-    // tile geometry of one launch: a warp covers 128*vec bytes of a row
+    // ---- small batches of regular codes: the whole decode in one cooperative launch (ib_coop_n4.cuh)
+    if (h->cn_classes.size() == 1 && h->vn_classes.size() == 1 && B <= h->coop_max_frames && pitch4 <= 8 * 256 &&
+        (h->cn_classes[0].degree < 6 || (h->use_pair && h->d_cn_pair != nullptr))) {
+        if (h->coop_supported < 0) {
+            int v = 0;
+            CK(cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, h->device));
+            h->coop_supported = v;
+        }
+        int smem = 0;
+        CoopKernel k = h->coop_supported ? coop_kernel_for(h->cn_classes[0].degree, h->vn_classes[0].degree, early != 0, T,
+                                                           h->match, &smem)
+                                         : nullptr;
+        if (k) {
+            int occ;
+            if ((rc = occupancy_of(h, (const void*)k, smem, &occ, kCoopThreads))) return rc;
+            IbArgs b = a;
+            b.tiles = (int)((pitch4 + 255) / 256);
+            b.tpc_log2 = b.tiles > 4 ? 3 : b.tiles > 2 ? 2 : b.tiles == 2 ? 1 : 0;
+            const int nps = (kCoopThreads / 32) >> b.tpc_log2;
+            const long long want = std::max((h->cn_classes[0].count + nps - 1) / nps, (h->vn_classes[0].count + nps - 1) / nps);
+            const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)occ * h->sm_count));
+            CoopArgs c{};
+            c.cn_nodes = h->cn_classes[0].d_nodes; c.vn_nodes = h->vn_classes[0].d_nodes;
+            c.n_cn = h->cn_classes[0].count; c.n_vn = h->vn_classes[0].count;
+            c.cn8 = h->d_cn8; c.vn8 = h->d_vn8;
+            c.mc8 = h->match ? h->d_mc8 : nullptr; c.mv8 = h->match ? h->d_mv8 : nullptr;
+            c.cn_pair = h->d_cn_pair; c.DCmax = h->DC; c.DVmax = h->DV;
+            void* params[] = {&b, &c};
+            if ((rc = prof.begin(2))) return rc;
+            CK(cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(kCoopThreads), params, (size_t)smem, st));
+            h->last_launches++; h->last_grid = grid; h->last_smem = smem;
+            if ((rc = prof.end())) return rc;
+            return IBLDPC_OK;
+        }
+    }
     // launch geometry of one degree class (plan_geometry): tiles per CTA, tile groups, CTAs per tile group
     auto plan_launch = [&](IbArgs& b, const void* fn, int smem, int threads, int vec, int n_nodes, int* tile_groups, int* grid) -> int {
         int occ;
@@ -1047,6 +1085,7 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
     }
     if (h->d_vn_pair) { CK(cudaFree(h->d_vn_pair)); h->d_vn_pair = nullptr; }
     if (const char* e = getenv("IBLDPC_VN_PAIR_MIN_DEGREE")) h->vn_pair_min_degree = std::max(3, atoi(e));
+    if (const char* e = getenv("IBLDPC_COOP_MAX_B")) h->coop_max_frames = std::max(0LL, atoll(e));
     if (const char* e = getenv("IBLDPC_VN_PAIR_THREADS")) h->vn_pair_threads = atoi(e) == 512 ? 512 : atoi(e) == 256 ? 256 : 0;
     if (h->nib && h->use_pair) {
         // Composed tail-pair tables of the variable-node update (vn_word_n4_pair): for every iteration and every
