@@ -546,7 +546,10 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
     a.DC = h->DC; a.DV = h->DV; a.xp_col = -1;
     const int T = h->T, TT = T * T;
     // ---- small batches of regular codes: the whole decode in one cooperative launch (ib_coop_n4.cuh)
-    if (h->cn_classes.size() == 1 && h->vn_classes.size() == 1 && B <= h->coop_max_frames && pitch4 <= 8 * 256 &&
+    // (worth it while a phase is short: measured break-even near 100 MB of packed messages -- DVB-S2 n=64800 wins at
+    // B=512 (58 MB: 9.3 -> 6.9 ms) and loses at B=2048 (232 MB); C1 and 802.11n win up to the 4096-frame limit)
+    const bool coop_fits = B <= h->coop_max_frames && pitch4 <= 8 * 256 && (long long)h->E * pitch4 <= (96LL << 20);
+    if (h->cn_classes.size() == 1 && h->vn_classes.size() == 1 && coop_fits &&
         (h->cn_classes[0].degree < 6 || (h->use_pair && h->d_cn_pair != nullptr))) {
         if (h->coop_supported < 0) {
             int v = 0;
@@ -569,6 +572,49 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
             CoopArgs c{};
             c.cn_nodes = h->cn_classes[0].d_nodes; c.vn_nodes = h->vn_classes[0].d_nodes;
             c.n_cn = h->cn_classes[0].count; c.n_vn = h->vn_classes[0].count;
+            c.cn8 = h->d_cn8; c.vn8 = h->d_vn8;
+            c.mc8 = h->match ? h->d_mc8 : nullptr; c.mv8 = h->match ? h->d_mv8 : nullptr;
+            c.cn_pair = h->d_cn_pair; c.DCmax = h->DC; c.DVmax = h->DV;
+            void* params[] = {&b, &c};
+            if ((rc = prof.begin(2))) return rc;
+            CK(cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(kCoopThreads), params, (size_t)smem, st));
+            h->last_launches++; h->last_grid = grid; h->last_smem = smem;
+            if ((rc = prof.end())) return rc;
+            return IBLDPC_OK;
+        }
+    }
+    // ---- small batches of the irregular codes whose degree sets are instantiated (802.11n, DVB-S2)
+    if ((h->cn_classes.size() > 1 || h->vn_classes.size() > 1) && h->cn_classes.size() <= (size_t)kCoopMaxClasses &&
+        h->vn_classes.size() <= (size_t)kCoopMaxClasses && coop_fits && h->use_pair &&
+        h->d_cn_pair != nullptr) {
+        if (h->coop_supported < 0) {
+            int v = 0;
+            CK(cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, h->device));
+            h->coop_supported = v;
+        }
+        CoopClasses c{};
+        c.n_cn_cls = (int)h->cn_classes.size(); c.n_vn_cls = (int)h->vn_classes.size();
+        for (int i = 0; i < c.n_cn_cls; ++i) {
+            c.cn_deg[i] = h->cn_classes[i].degree; c.cn_cnt[i] = h->cn_classes[i].count; c.cn_nodes[i] = h->cn_classes[i].d_nodes;
+        }
+        for (int i = 0; i < c.n_vn_cls; ++i) {
+            c.vn_deg[i] = h->vn_classes[i].degree; c.vn_cnt[i] = h->vn_classes[i].count; c.vn_nodes[i] = h->vn_classes[i].d_nodes;
+        }
+        int smem = 0;
+        CoopMultiKernel k = h->coop_supported ? coop_multi_kernel_for(c.cn_deg, c.n_cn_cls, c.vn_deg, c.n_vn_cls, early != 0, T,
+                                                                      h->match, &smem)
+                                              : nullptr;
+        if (k) {
+            int occ;
+            if ((rc = occupancy_of(h, (const void*)k, smem, &occ, kCoopThreads))) return rc;
+            IbArgs b = a;
+            b.tiles = (int)((pitch4 + 255) / 256);
+            b.tpc_log2 = b.tiles > 4 ? 3 : b.tiles > 2 ? 2 : b.tiles == 2 ? 1 : 0;
+            const int nps = (kCoopThreads / 32) >> b.tpc_log2;
+            long long want = 1;
+            for (auto& cl : h->cn_classes) want = std::max<long long>(want, (cl.count + nps - 1) / nps);
+            for (auto& cl : h->vn_classes) want = std::max<long long>(want, (cl.count + nps - 1) / nps);
+            const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)occ * h->sm_count));
             c.cn8 = h->d_cn8; c.vn8 = h->d_vn8;
             c.mc8 = h->match ? h->d_mc8 : nullptr; c.mv8 = h->match ? h->d_mv8 : nullptr;
             c.cn_pair = h->d_cn_pair; c.DCmax = h->DC; c.DVmax = h->DV;
