@@ -292,7 +292,7 @@ __device__ __forceinline__ uint32_t cn_loop_n4(const IbArgs& a, const uint8_t* t
 // NT = threads per CTA: the tail-pair kernels of degree <= 8 run 512 threads (2 CTAs/SM at 64 registers share
 // one 64-96 KB table set per 16 warps: 32 warps/SM instead of 24 resp. 16 with 256-thread CTAs).
 template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR, int NT = kThreads>
-__global__ void __launch_bounds__(NT, NT == 512 ? 2 : cn_n4_min_blocks(D, VEC, PAIR))
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : NT == 512 ? 2 : cn_n4_min_blocks(D, VEC, PAIR))
 ib_cn_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 {
     extern __shared__ __align__(16) uint32_t s_all[];
@@ -487,17 +487,17 @@ __host__ __device__ constexpr int vn_n4_min_blocks(int D, int VEC)
 }
 
 // varnode_update (kernels_template_irreg.cl:103-179), packed nibbles
-template <int D, int VEC>
-__global__ void __launch_bounds__(kThreads, vn_n4_min_blocks(D, VEC))
+template <int D, int VEC, int NT = kThreads>
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : NT == 512 ? 2 : vn_n4_min_blocks(D, VEC))
 ib_vn_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 {
     extern __shared__ __align__(16) uint32_t s_tab[];
     if (a.early && a.it >= 1 && a.flags[a.it - 1] == 0) return;
     if (D > 1) {
-        stage_tables_n4<n4_vn_words(D, false)>(s_tab, a, a.lut);
+        stage_tables_n4<n4_vn_words(D, false), NT>(s_tab, a, a.lut);
         __syncthreads();
     }
-    vn_loop_n4<D, false, VEC>(a, reinterpret_cast<const uint8_t*>(s_tab), nullptr, nodes, n_nodes);
+    vn_loop_n4<D, false, VEC, false, NT>(a, reinterpret_cast<const uint8_t*>(s_tab), nullptr, nodes, n_nodes);
 }
 
 // varnode_update through the tail-pair rows (vn_word_n4_pair): shared memory =

@@ -93,6 +93,8 @@ struct ibldpc_decoder {
     uint8_t* d_vn_pair = nullptr;   // [imax][vn classes][T*T rows][8 bytes] composed tail-pair tables of the VN update
     int vn_pair_min_degree = 5;     // packed-nibble family (IBLDPC_VN_PAIR_MIN_DEGREE)
     int vn_pair_threads = 0;        // 0 = per-degree default, 256 / 512 forced (IBLDPC_VN_PAIR_THREADS)
+    int cn_threads = 0, vn_threads = 0;   // 0 = default CTA sizes (1024 where instantiated); IBLDPC_CN_THREADS=512 /
+                                          // IBLDPC_VN_THREADS=256 select the smaller CTAs (parity variants, A/B)
     long long coop_max_frames = 4096;   // regular codes: whole-decode cooperative kernel up to this batch size
                                         // (IBLDPC_COOP_MAX_B, 0 disables)
     int coop_supported = -1;        // device attribute cudaDevAttrCooperativeLaunch, queried once
@@ -666,7 +668,11 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
             }
             NodeKernel k = pair ? cn_n4_pair_kernel(c.degree, early != 0) : cn_n4_kernel_v2(c.degree, explicit_match, early != 0);
             if (!k) return fail(IBLDPC_E_INVALID, "no packed check-node kernel for degree " + std::to_string(c.degree));
-            const int threads = pair ? cn_n4_pair_threads(c.degree) : kThreads;
+            int threads = pair ? cn_n4_pair_threads(c.degree) : kThreads;
+            if (pair && h->cn_threads != 512 && cn_n4_pair_kernel_1024(c.degree, early != 0)) {
+                k = cn_n4_pair_kernel_1024(c.degree, early != 0);
+                threads = 1024;
+            }
             int grid;
             if ((r = plan_launch(b, (const void*)k, smem, threads, vec, c.count, &tile_groups, &grid))) return r;
             k<<<dim3(grid, tile_groups), threads, smem, st>>>(b, c.d_nodes, c.count);
@@ -714,6 +720,10 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
                 if (!k && vec == 4) {   // 4-word kernels exist up to degree 6 only
                     vec_used = 2;
                     k = vn_n4_kernel_v2(c.degree, decide);
+                }
+                if (!decide && vec_used == 4 && h->vn_threads != 256 && vn_n4_kernel_v4_1024(c.degree)) {
+                    k = vn_n4_kernel_v4_1024(c.degree);
+                    threads = 1024;
                 }
             }
             if (!k) return fail(IBLDPC_E_INVALID, "no packed variable-node kernel for degree " + std::to_string(c.degree));
@@ -1131,6 +1141,8 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
     }
     if (h->d_vn_pair) { CK(cudaFree(h->d_vn_pair)); h->d_vn_pair = nullptr; }
     if (const char* e = getenv("IBLDPC_VN_PAIR_MIN_DEGREE")) h->vn_pair_min_degree = std::max(3, atoi(e));
+    h->cn_threads = getenv("IBLDPC_CN_THREADS") ? atoi(getenv("IBLDPC_CN_THREADS")) : 0;
+    h->vn_threads = getenv("IBLDPC_VN_THREADS") ? atoi(getenv("IBLDPC_VN_THREADS")) : 0;
     if (const char* e = getenv("IBLDPC_COOP_MAX_B")) h->coop_max_frames = std::max(0LL, atoll(e));
     if (const char* e = getenv("IBLDPC_VN_PAIR_THREADS")) h->vn_pair_threads = atoi(e) == 512 ? 512 : atoi(e) == 256 ? 256 : 0;
     if (h->nib && h->use_pair) {

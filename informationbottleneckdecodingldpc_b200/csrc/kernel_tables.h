@@ -17,10 +17,12 @@ NodeKernel vn_fast_kernel_for(int d, bool decide, bool match);
 // (check nodes: 2; variable nodes: 4 up to degree 6, else 2)
 NodeKernel cn_n4_kernel_v2(int d, bool match, bool early);
 NodeKernel cn_n4_pair_kernel(int d, bool early);   // tail-pair variant (2 words per lane), d >= 4
-int cn_n4_pair_threads(int d);                     // threads per CTA of that kernel
+int cn_n4_pair_threads(int d);
+NodeKernel cn_n4_pair_kernel_1024(int d, bool early);   // d <= 8 (default); cn_n4_pair_kernel: 512 threads (d <= 8) / 256                     // threads per CTA of that kernel
 NodeKernel vn_n4_pair_kernel(int d, int threads);   // tail-pair variable-node update, d >= 3, threads = 256 / 512
 NodeKernel vn_n4_kernel_v2(int d, bool decide);
 NodeKernel vn_n4_kernel_v4(int d, bool decide);
+NodeKernel vn_n4_kernel_v4_1024(int d);   // update kernels of degree 2..4 in 1024-thread CTAs (default)
 LlrNodeKernel llr_cn_kernel_for(bool f64, int algo, int d);
 LlrNodeKernel llr_vn_kernel_for(bool f64, int mode, int d);
 LlrSynKernel llr_syndrome_kernel_for(bool f64);
