@@ -165,11 +165,11 @@ def test_launch_planner_geometry_invariants():
     rng = np.random.default_rng(5)
     for _ in range(2000):
         slots = int(rng.integers(1, 8)) * 148
-        warps = int(rng.choice([8, 16]))
+        warps = int(rng.choice([8, 16, 32]))
         tiles = int(rng.integers(1, 400))
         nodes = int(rng.integers(1, 70000))
         tpc, tg, gx = plan(slots, warps, tiles, nodes)
-        assert 0 <= tpc <= 3 and (warps >> tpc) >= 1
+        assert 0 <= tpc <= 5 and (warps >> tpc) >= 1
         assert tg == -(-tiles // (1 << tpc))                     # all tiles covered, no empty tile group
         assert tpc == 0 or (1 << (tpc - 1)) < tiles              # footprint not wider than the row needs
         nsteps = -(-nodes // (warps >> tpc))
@@ -177,8 +177,10 @@ def test_launch_planner_geometry_invariants():
         assert gx * tg <= max(slots, tg)                          # one wave unless there are more tile groups than slots
     # 802.11n n=1296 d_v=11 class, B=100096 (196 tiles of 256 B), 148 slots of 16 warps: 49 groups x 3 CTAs = 147 of 148
     assert plan(148, 16, 196, 162) == (2, 49, 3)
-    # C1 check nodes, B=65536: 128 tiles, 296 slots: the widest footprint already fills 288 slots
-    assert plan(296, 16, 128, 4000) == (3, 16, 18)
+    # C1, B=65536, one 1024-thread CTA per SM: all 32 warps of a CTA on consecutive tiles of one node fill all 148 slots
+    # (8 tiles per CTA would leave 4 SMs idle: 16 tile groups x 9 CTAs)
+    assert plan(148, 32, 128, 4000) == (5, 4, 37) and plan(148, 32, 64, 8000) == (5, 2, 74)
+    assert plan(296, 16, 128, 4000) == (4, 8, 37)
     assert L.ibldpc_plan_geometry(0, 16, 1, 1, out) != 0 and L.ibldpc_plan_geometry(148, 12, 1, 1, out) != 0
 
 
