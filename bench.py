@@ -69,6 +69,56 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def roofline_from_phase_times(ms3, n3, N, E, B, imax, packed, workload):
+    """The `roofline` object of the JSON line from the per-phase CUDA-event times of one profiled decode
+    (ibldpc_phase_times: ms3 = [check-node launches, variable-node launches, iteration 0 + output + packing],
+    n3 = launch counts).  Algorithmic bytes per launch as SURVEY.md 8(d) defines them (uint8 messages): CN 2E,
+    VN 2E+N per frame; the packed-nibble kernels store two frames per byte, so the bytes they really move
+    ("stored") are half of that -- both figures are reported, and `frac` (algorithmic / peak) may exceed 1 for that
+    reason.  When the whole decode ran as one cooperative launch (small batches) there are no per-phase times: the
+    dominant "kernel" is then the whole decode with SURVEY's bytes per frame."""
+    peak, peak_src = measured_peak_gbs()
+    stored_div = 2 if packed else 1
+    fam = "n4" if packed else "fast"
+    bytes_frame = algorithmic_bytes_per_frame(N, E, imax)
+    decode_ms = ms3[0] + ms3[1] + ms3[2]
+    per_phase = n3[0] > 0 and n3[1] > 0 and ms3[0] > 0 and ms3[1] > 0
+    cn_bytes, vn_bytes = 2 * E * B, (2 * E + N) * B
+    if per_phase:
+        cn_ms, vn_ms = ms3[0] / n3[0], ms3[1] / n3[1]
+        if ms3[0] >= ms3[1]:
+            dom, dom_ms, dom_bytes = f"ib_cn_{fam}_kernel (check-node update + syndrome)", cn_ms, cn_bytes
+        else:
+            dom, dom_ms, dom_bytes = f"ib_vn_{fam}_kernel (variable-node update)", vn_ms, vn_bytes
+    else:
+        cn_ms = vn_ms = None
+        dom, dom_ms, dom_bytes = "ib_decode_coop_kernel (whole decode in one cooperative launch)", decode_ms, bytes_frame * B
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tfile):
+        try:
+            tj = json.load(open(tfile)).get(workload)
+            if tj and tj.get("kernel", "")[:9] == dom[:9]:
+                # measured at tj["frames_per_launch"]; DRAM traffic of these kernels is linear in B
+                traffic = tj["bytes"] * B / tj["frames_per_launch"]
+        except Exception:
+            traffic = None
+    return {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+        "message_storage": "packed nibbles (2 frames per byte)" if packed else "uint8",
+        "stored_bytes_per_launch": dom_bytes // stored_div, "achieved_stored": achieved / stored_div,
+        "frac_stored": achieved / stored_div / peak,
+        "avg_launch_ms": dom_ms, "cn_avg_ms": cn_ms, "vn_avg_ms": vn_ms,
+        "cn_frac": cn_bytes / (cn_ms * 1e-3) / 1e9 / peak if per_phase else None,
+        "vn_frac": vn_bytes / (vn_ms * 1e-3) / 1e9 / peak if per_phase else None,
+        "cn_share_of_decode": ms3[0] / decode_ms, "vn_share_of_decode": ms3[1] / decode_ms,
+        "whole_decode": {"bytes_per_frame": bytes_frame, "achieved_gbs": bytes_frame * B / (decode_ms * 1e-3) / 1e9,
+                         "frac": bytes_frame * B / (decode_ms * 1e-3) / 1e9 / peak},
+    }
+
+
 class ClockSampler:
     """SM clock, power and throttle reasons sampled every 100 ms during the timed region, in-process through NVML
     (pynvml).  A spawned `nvidia-smi -lms` does the same job but its queries serialise with kernel launches in the
@@ -358,44 +408,9 @@ def main():
     n3 = (C.c_int32 * 3)()
     _lib.check(L.ibldpc_phase_times(h, ms3, n3))
     _lib.check(L.ibldpc_set_profiling(h, 0))
-    cn_ms, vn_ms = ms3[0] / max(n3[0], 1), ms3[1] / max(n3[1], 1)
-    peak, peak_src = measured_peak_gbs()
-    # Algorithmic bytes per launch as SURVEY.md 8(d) defines them (uint8 messages): CN 2E, VN 2E+N per frame.
-    # The packed-nibble kernels store two frames per byte, so the bytes they really move ("stored") are half
-    # of that; both figures are reported, and `frac` (algorithmic / peak) may exceed 1 for that reason.
     packed = decodi.info()[0] == 2
-    cn_bytes, vn_bytes = 2 * E * B, (2 * E + N) * B
-    fam = "n4" if packed else "fast"
-    if ms3[0] >= ms3[1]:
-        dom, dom_ms, dom_bytes = f"ib_cn_{fam}_kernel (check-node update + syndrome)", cn_ms, cn_bytes
-    else:
-        dom, dom_ms, dom_bytes = f"ib_vn_{fam}_kernel (variable-node update)", vn_ms, vn_bytes
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     stored_div = 2 if packed else 1
-    traffic = None
-    tfile = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tfile):
-        try:
-            tj = json.load(open(tfile)).get(args.workload)
-            if tj and tj.get("kernel", "")[:9] == dom[:9]:
-                # measured at tj["frames_per_launch"]; DRAM traffic of these kernels is linear in B
-                traffic = tj["bytes"] * B / tj["frames_per_launch"]
-        except Exception:
-            traffic = None
-    bytes_frame = algorithmic_bytes_per_frame(N, E, IMAX)
-    decode_ms = ms3[0] + ms3[1] + ms3[2]
-    roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-        "message_storage": "packed nibbles (2 frames per byte)" if packed else "uint8",
-        "stored_bytes_per_launch": dom_bytes // stored_div, "achieved_stored": achieved / stored_div,
-        "frac_stored": achieved / stored_div / peak,
-        "avg_launch_ms": dom_ms, "cn_avg_ms": cn_ms, "vn_avg_ms": vn_ms,
-        "cn_frac": cn_bytes / (cn_ms * 1e-3) / 1e9 / peak, "vn_frac": vn_bytes / (vn_ms * 1e-3) / 1e9 / peak,
-        "cn_share_of_decode": ms3[0] / decode_ms, "vn_share_of_decode": ms3[1] / decode_ms,
-        "whole_decode": {"bytes_per_frame": bytes_frame, "achieved_gbs": bytes_frame * B / (decode_ms * 1e-3) / 1e9,
-                         "frac": bytes_frame * B / (decode_ms * 1e-3) / 1e9 / peak},
-    }
+    roofline = roofline_from_phase_times(list(ms3), list(n3), N, E, B, IMAX, packed, args.workload)
 
     # --- end to end through the class API with HOST buffers (H2D + D2H inside the timed region)
     e2e = None

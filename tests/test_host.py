@@ -219,6 +219,27 @@ def test_host_chunk_schedule_properties():
     assert L.ibldpc_host_chunk_schedule(0, 8000, 0, 0, buf, 16) < 0
 
 
+def test_bench_roofline_object_handles_both_launch_schemes():
+    """bench.py's roofline object: per-phase launches (large batches) and the single cooperative launch (small
+    batches, no per-phase times) -- pure host arithmetic, checked here without a GPU."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    N, E, B = 8000, 24000, 65536
+    r = bench.roofline_from_phase_times([23.3, 19.3, 0.6], [49, 49, 4], N, E, B, 50, True, "c1")
+    assert r["kernel"].startswith("ib_cn_n4_kernel") and r["algorithmic_bytes_per_launch"] == 2 * E * B
+    assert r["stored_bytes_per_launch"] * 2 == r["algorithmic_bytes_per_launch"]
+    assert abs(r["frac"] - r["cn_frac"]) < 1e-12 and r["vn_frac"] > r["cn_frac"]
+    assert abs(r["achieved"] - 2 * E * B / (23.3e-3 / 49) / 1e9) < 1e-6
+    assert r["whole_decode"]["bytes_per_frame"] == 49 * (4 * E + N) + 2 * E + 3 * N == 5168000
+    r = bench.roofline_from_phase_times([0.0, 0.0, 1.0], [0, 0, 2], N, E, 512, 50, True, "c1")
+    assert r["kernel"].startswith("ib_decode_coop_kernel") and r["cn_frac"] is None and r["cn_avg_ms"] is None
+    assert abs(r["achieved"] - 5168000 * 512 / 1e-3 / 1e9) < 1e-6 and r["traffic"] is None
+    r = bench.roofline_from_phase_times([10.0, 12.0, 1.0], [49, 49, 4], N, E, B, 50, False, "c1")
+    assert r["kernel"].startswith("ib_vn_fast_kernel") and r["stored_bytes_per_launch"] == (2 * E + N) * B
+
+
 def test_product_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
