@@ -69,53 +69,73 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def roofline_from_phase_times(ms3, n3, N, E, B, imax, packed, workload):
+def roofline_from_phase_times(ms3, n3, N, E, B, imax, packed, workload, family=None):
     """The `roofline` object of the JSON line from the per-phase CUDA-event times of one profiled decode
     (ibldpc_phase_times: ms3 = [check-node launches, variable-node launches, iteration 0 + output + packing],
     n3 = launch counts).  Algorithmic bytes per launch as SURVEY.md 8(d) defines them (uint8 messages): CN 2E,
     VN 2E+N per frame; the packed-nibble kernels store two frames per byte, so the bytes they really move
     ("stored") are half of that -- both figures are reported, and `frac` (algorithmic / peak) may exceed 1 for that
-    reason.  When the whole decode ran as one cooperative launch (small batches) there are no per-phase times: the
-    dominant "kernel" is then the whole decode with SURVEY's bytes per frame."""
+    reason; `frac_stored` is the physical fraction of the HBM peak.  `bound` names the real limiter: with four-bit
+    storage the kernels are NOT HBM-bound but sit on the shared-memory look-up pipe and instruction issue (ncu,
+    profiles/README.md); the HBM peak stays the denominator SURVEY 8(d) prescribes.  When the whole decode ran as one
+    cooperative launch (small batches) there are no per-phase times: the dominant "kernel" is then the whole decode
+    with SURVEY's bytes per frame."""
     peak, peak_src = measured_peak_gbs()
+    if family is None:
+        family = 2 if packed else 1
     stored_div = 2 if packed else 1
-    fam = "n4" if packed else "fast"
+    fam = {0: "generic", 1: "fast", 2: "n4", 3: "t32"}.get(family, "n4")
     bytes_frame = algorithmic_bytes_per_frame(N, E, imax)
     decode_ms = ms3[0] + ms3[1] + ms3[2]
     per_phase = n3[0] > 0 and n3[1] > 0 and ms3[0] > 0 and ms3[1] > 0
     cn_bytes, vn_bytes = 2 * E * B, (2 * E + N) * B
     if per_phase:
+        # average duration of one check-node / variable-node PHASE (all degree classes of the phase; one launch when
+        # the fused per-phase kernels run, one launch per class otherwise); n3 counts phases
         cn_ms, vn_ms = ms3[0] / n3[0], ms3[1] / n3[1]
         if ms3[0] >= ms3[1]:
-            dom, dom_ms, dom_bytes = f"ib_cn_{fam}_kernel (check-node update + syndrome)", cn_ms, cn_bytes
+            dom, dom_ms, dom_bytes = f"ib_cn_{fam} (check-node update + syndrome)", cn_ms, cn_bytes
         else:
-            dom, dom_ms, dom_bytes = f"ib_vn_{fam}_kernel (variable-node update)", vn_ms, vn_bytes
+            dom, dom_ms, dom_bytes = f"ib_vn_{fam} (variable-node update)", vn_ms, vn_bytes
     else:
         cn_ms = vn_ms = None
         dom, dom_ms, dom_bytes = "ib_decode_coop_kernel (whole decode in one cooperative launch)", decode_ms, bytes_frame * B
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, "profiles/traffic.json has no capture for this workload"
     tfile = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tfile):
         try:
             tj = json.load(open(tfile)).get(workload)
-            if tj and tj.get("kernel", "")[:9] == dom[:9]:
-                # measured at tj["frames_per_launch"]; DRAM traffic of these kernels is linear in B
-                traffic = tj["bytes"] * B / tj["frames_per_launch"]
-        except Exception:
-            traffic = None
+            if tj and tj.get("kernel", "")[:5] == dom[:5]:
+                if tj.get("source_hash") == source_hash():
+                    # measured at tj["frames_per_launch"]; DRAM traffic of these kernels is linear in B
+                    traffic = tj["bytes"] * B / tj["frames_per_launch"]
+                    traffic_note = "ncu dram__bytes_read.sum + dram__bytes_write.sum, " + tj.get("source", "")
+                else:
+                    traffic_note = ("stale: captured on kernel sources %s, current sources are %s -- re-run "
+                                    "profiles/capture_traffic.py" % (tj.get("source_hash"), source_hash()))
+        except Exception as e:   # noqa: BLE001
+            traffic_note = f"profiles/traffic.json unreadable: {e}"
+    if family in (1, 2):
+        bound = ("shared-memory look-up pipe + instruction issue (l1tex data-pipe 83-92 %, issue 82 %, DRAM 37-54 % in ncu); "
+                 "HBM peak is the roofline denominator of SURVEY 8(d)") if packed else "hbm / shared-memory look-up pipe"
+    elif family == 3:
+        bound = "shared-memory look-up pipe (unstriped 32x32 byte tables, bank conflicts)"
+    else:
+        bound = "L1/L2 table gathers (generic path: tables in global memory)"
     return {
-        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+        "bound": bound, "denominator": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "frac_stored": achieved / stored_div / peak,
+        "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
         "message_storage": "packed nibbles (2 frames per byte)" if packed else "uint8",
         "stored_bytes_per_launch": dom_bytes // stored_div, "achieved_stored": achieved / stored_div,
-        "frac_stored": achieved / stored_div / peak,
         "avg_launch_ms": dom_ms, "cn_avg_ms": cn_ms, "vn_avg_ms": vn_ms,
         "cn_frac": cn_bytes / (cn_ms * 1e-3) / 1e9 / peak if per_phase else None,
         "vn_frac": vn_bytes / (vn_ms * 1e-3) / 1e9 / peak if per_phase else None,
         "cn_share_of_decode": ms3[0] / decode_ms, "vn_share_of_decode": ms3[1] / decode_ms,
         "whole_decode": {"bytes_per_frame": bytes_frame, "achieved_gbs": bytes_frame * B / (decode_ms * 1e-3) / 1e9,
-                         "frac": bytes_frame * B / (decode_ms * 1e-3) / 1e9 / peak},
+                         "frac": bytes_frame * B / (decode_ms * 1e-3) / 1e9 / peak,
+                         "frac_stored": bytes_frame * B / (decode_ms * 1e-3) / 1e9 / peak / stored_div},
     }
 
 
@@ -209,18 +229,18 @@ class ClockSampler:
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def make_tables(wl):
+def make_tables(wl, T_=T):
     """IB tables designed by discrete density evolution (decoder_config_generation.py, the in-repo
     stand-in for the reference's design chain); irregular codes with message alignment."""
     from informationbottleneckdecodingldpc_b200 import graph, luts
     t = graph.edge_tables(wl["H"])
     if not wl["irregular"]:
         from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_regular_config
-        tb, _ = generate_regular_config(wl["design_ebn0"], t.d_v_max, t.d_c_max, T, IMAX)
+        tb, _ = generate_regular_config(wl["design_ebn0"], t.d_v_max, t.d_c_max, T_, IMAX)
         wl["tables"] = "IB tables, discrete density evolution at Eb/N0 = %.1f dB (in-repo design)" % wl["design_ebn0"]
     else:
         from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_irregular_config
-        tb, _ = generate_irregular_config(wl["design_ebn0"], wl["H"], T, IMAX)
+        tb, _ = generate_irregular_config(wl["design_ebn0"], wl["H"], T_, IMAX)
         wl["tables"] = ("IB tables + message alignment, degree-mixed density evolution at Eb/N0 = %.1f dB "
                         "(in-repo design)" % wl["design_ebn0"])
     return t, tb
@@ -231,14 +251,14 @@ def use_all_host_threads():
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 
 
-def cpu_reference_run(wl, frames, seed=SEED):
+def cpu_reference_run(wl, frames, seed=SEED, T_=T):
     """The reference's own kernels (oracle/_ref) -- or the C port when that library is absent -- on
     `frames` frames of the workload, all host threads.  Returns (seconds, kind, cores)."""
     from oracle import oracle
     from informationbottleneckdecodingldpc_b200 import AWGN_Channel_Quantizer
-    t, tb = make_tables(wl)
+    t, tb = make_tables(wl, T_)
     R = 1 - t.n_chk / t.n_var
-    q = AWGN_Channel_Quantizer(10 ** (-wl["ebn0"] / 10) / (2 * R), 3, T, 2000)
+    q = AWGN_Channel_Quantizer(10 ** (-wl["ebn0"] / 10) / (2 * R), 3, T_, 2000)
     rng = np.random.Generator(np.random.PCG64(seed))
     u = rng.random(size=(t.n_var, frames))
     ch = ((u[:, :, None] - q.cdf_t_given_x_equals_zero) > 0).sum(2) - 1
@@ -249,7 +269,7 @@ def cpu_reference_run(wl, frames, seed=SEED):
             cores = int(oracle.ref_lib().ref_num_threads())
         except Exception:
             pass
-    kw = dict(T=T, imax=IMAX, cn_lut=tb.Trellis_checknodevector_a, vn_lut=tb.Trellis_varnodevector_a,
+    kw = dict(T=T_, imax=IMAX, cn_lut=tb.Trellis_checknodevector_a, vn_lut=tb.Trellis_varnodevector_a,
               cn_match=tb.matching_vector_checknode, vn_match=tb.matching_vector_varnode, early=False)
     t0 = time.perf_counter()
     try:
@@ -261,11 +281,11 @@ def cpu_reference_run(wl, frames, seed=SEED):
     return time.perf_counter() - t0, kind, cores, t
 
 
-def size_cpu_sample(wl, target_s):
+def size_cpu_sample(wl, target_s, T_=T):
     """Calibrate on a small batch, then pick a frame count worth about `target_s` seconds."""
     cores = os.cpu_count() or 1
     cal = max(2, min(2 * cores, 64))
-    dt, _, _, _ = cpu_reference_run(wl, cal)
+    dt, _, _, _ = cpu_reference_run(wl, cal, T_=T_)
     return int(max(cal, min(16384, cal * target_s / max(dt, 1e-3)))) // 1 or cal
 
 
@@ -301,6 +321,232 @@ def run_reference_arm(args):
     return 0
 
 
+def source_hash():
+    """sha256 (16 hex digits) over the kernel sources: ties profiles/traffic.json to the kernels it was captured on."""
+    import hashlib
+    from informationbottleneckdecodingldpc_b200 import _lib
+    h = hashlib.sha256()
+    for f in sorted(_lib.SOURCES):
+        if f.endswith((".cu", ".cuh", ".h")) and os.path.exists(f):
+            h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def sample_columns(B, n=32, seed=7):
+    """Frame columns of a batch for the oracle parity sample: first, middle and last 8 + 8 random ones."""
+    n = min(n, B)
+    if B <= n:
+        return np.arange(B)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    q = n // 4
+    cols = np.r_[0:q, B // 2 - q // 2:B // 2 - q // 2 + q, B - q:B, rng.integers(0, B, n - 3 * q)]
+    return np.unique(np.clip(cols, 0, B - 1))
+
+
+def parity_sample_ib(decodi, ch, out, t, tb, wl, T_):
+    """Decoded columns of the TIMED batch geometry against the CPU oracle on the same inputs (bit-exact bar)."""
+    from oracle import oracle
+    import torch
+    cols = sample_columns(ch.shape[1])
+    idx = torch.from_numpy(cols).to(ch.tensor.device)
+    ch_s = ch.tensor.index_select(1, idx).cpu().numpy()
+    got = out.tensor.index_select(1, idx).cpu().numpy()
+    t0 = time.perf_counter()
+    ref, _ = oracle.ib_decode(t, ch_s, T=T_, imax=IMAX, cn_lut=tb.Trellis_checknodevector_a, vn_lut=tb.Trellis_varnodevector_a,
+                              cn_match=tb.matching_vector_checknode, vn_match=tb.matching_vector_varnode, early=False)
+    eq = bool(np.array_equal(got, ref.astype(np.uint8)))
+    return {"frames": int(cols.size), "equal": eq, "checker": "oracle/ldpc_oracle.c (pinned to the reference kernels)",
+            "mismatching_symbols": int((got != ref.astype(np.uint8)).sum()), "oracle_s": round(time.perf_counter() - t0, 2),
+            "batch": int(ch.shape[1])}
+
+
+def build_ib(pkg, wl, B, rank, T_=T):
+    t, tb = make_tables(wl, T_)
+    N, M = t.n_var, t.n_chk
+    R = (N - M) / N
+    quanti = pkg.AWGN_Channel_Quantizer(10 ** (-wl["ebn0"] / 10) / (2 * R), 3, T_, 2000)
+    quanti.seed = SEED
+    quanti.set_stream(rank)                      # independent Philox sub-stream per rank
+    quanti.init_OpenCL_quanti(N, B, return_buffer_only=True)
+    if wl["irregular"]:
+        decodi = pkg.Discrete_LDPC_Decoder_class_irregular(wl["H"], IMAX, T_, T_, tb.Trellis_checknodevector_a,
+                                                           tb.Trellis_varnodevector_a, tb.matching_vector_checknode,
+                                                           tb.matching_vector_varnode, B)
+    else:
+        decodi = pkg.Discrete_LDPC_Decoder_class(wl["H"], IMAX, T_, T_, tb.Trellis_checknodevector_a,
+                                                 tb.Trellis_varnodevector_a, B)
+    decodi.init_OpenCL_decoding(B, quanti.context)
+    decodi.early_termination = False
+    return t, tb, quanti, decodi
+
+
+def phase_roofline(decodi, ch, N, E, B, workload_name):
+    """Per-launch CUDA-event times of one profiled decode -> the `roofline` object."""
+    import ctypes as C
+    from informationbottleneckdecodingldpc_b200 import _lib
+    h = decodi._ensure_handle()
+    L = _lib.lib()
+    _lib.check(L.ibldpc_set_profiling(h, 1))
+    decodi.decode_OpenCL(ch, buffer_in=True, return_buffer=True)
+    ms3 = (C.c_float * 3)()
+    n3 = (C.c_int32 * 3)()
+    _lib.check(L.ibldpc_phase_times(h, ms3, n3))
+    _lib.check(L.ibldpc_set_profiling(h, 0))
+    fam = decodi.info()[0]
+    return roofline_from_phase_times(list(ms3), list(n3), N, E, B, IMAX, fam == 2, workload_name, family=fam)
+
+
+def time_steps(step, steps, warmup):
+    import torch
+    for _ in range(max(warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        last = step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), last
+
+
+def leg_ib(pkg, name, steps, rank, T_=T, frames=0):
+    """Short leg of another BASELINE configuration: value, roofline fractions and an oracle parity sample."""
+    import torch
+    wl = workload(name)
+    B = frames or wl["B"]
+    t, tb, quanti, decodi = build_ib(pkg, wl, B, rank, T_)
+    N, M, E = t.n_var, t.n_chk, t.n_edge
+    ch = quanti.quantize_direct_OpenCL(N, B)
+    ms, out = time_steps(lambda: decodi.decode_OpenCL(ch, buffer_in=True, return_buffer=True), steps, 1)
+    launches = decodi.info()[1]
+    roof = phase_roofline(decodi, ch, N, E, B, name)
+    par = parity_sample_ib(decodi, ch, out, t, tb, wl, T_)
+    fam = decodi.info()[0]
+    res = {"workload": wl["name"] if T_ == T else wl["name"].replace("|T|=16", f"|T|={T_}"), "frames_per_step": B, "steps": steps,
+           "value": (N - M) * B * steps / (ms * 1e-3) / 1e9, "unit": "Gbit/s", "ms_per_step": ms / steps,
+           "kernel_family": {0: "generic (tables in global memory)", 1: "uint8 shared-memory", 2: "packed-nibble (n4)",
+                             3: "|T|<=32 shared-memory bytes (t32)"}.get(fam, str(fam)),
+           "gpu_launches_per_step": launches, "tables": wl.get("tables"),
+           "roofline": {k: roof[k] for k in ("bound", "kernel", "frac", "frac_stored", "avg_launch_ms", "cn_frac", "vn_frac")}
+           | {"whole_decode_frac": roof["whole_decode"]["frac"], "whole_decode_frac_stored": roof["whole_decode"]["frac_stored"]},
+           "parity_sample": par}
+    del decodi, ch, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def leg_llr(pkg, algo, steps, rank, B=16384):
+    """min-sum / BP benchmark decoders on the (3,6) n=8000 graph in float64 (the reference's arithmetic; the only
+    precision that meets the >= 99.99 % identical-frames bar, tests/test_gpu_parity.py)."""
+    import torch
+    from oracle import oracle
+    from informationbottleneckdecodingldpc_b200 import graph
+    wl = workload("c1")
+    t = graph.edge_tables(wl["H"])
+    N, M, E = t.n_var, t.n_chk, t.n_edge
+    R = (N - M) / N
+    quanti = pkg.AWGN_Channel_Quantizer(10 ** (-wl["ebn0"] / 10) / (2 * R), 3, T, 2000)
+    quanti.seed = SEED
+    quanti.set_stream(rank)
+    quanti.llr_dtype = np.float64
+    quanti.init_OpenCL_quanti(N, B, return_buffer_only=True)
+    cls = pkg.Min_Sum_Decoder_class_irregular if algo == "minsum" else pkg.BeliefPropagationDecoderClassIrregular
+    decodi = cls(wl["H"], IMAX, T, B)
+    decodi.init_OpenCL_decoding(B, quanti.context)
+    decodi.early_termination = False
+    ch = quanti.quantize_direct_OpenCL_LLR(N, B)
+    ms, out = time_steps(lambda: decodi.decode(ch, buffer_in=True, return_buffer=True), steps, 1)
+    launches = decodi.info()[1]
+    cols = sample_columns(B, 16)
+    idx = torch.from_numpy(cols).to(ch.tensor.device)
+    ch_s = ch.tensor.index_select(1, idx).cpu().numpy()
+    got = out.tensor.index_select(1, idx).cpu().numpy()
+    ref, _ = oracle.llr_decode(t, ch_s, algo=algo, imax=IMAX, early=False)
+    same = ((got < 0) == (ref < 0)).all(axis=0)
+    peak, _src = measured_peak_gbs()
+    bytes_frame = (IMAX - 1) * (32 * E + 8 * N) + 8 * (2 * E + 3 * N)
+    res = {"workload": f"(3,6) n=8000 {'min-sum' if algo == 'minsum' else 'belief propagation'} float64 i_max=50 ET off",
+           "frames_per_step": B, "steps": steps, "value": (N - M) * B * steps / (ms * 1e-3) / 1e9, "unit": "Gbit/s",
+           "ms_per_step": ms / steps, "dtype": "f64", "gpu_launches_per_step": launches,
+           "roofline": {"bound": "hbm" if algo == "minsum" else "fp64 transcendental (exp/log) pipe",
+                        "bytes_per_frame": bytes_frame,
+                        "whole_decode_frac": bytes_frame * B * steps / (ms * 1e-3) / 1e9 / peak},
+           "parity_sample": {"frames": int(cols.size), "identical_hard_decision_frames": int(same.sum()),
+                             "equal": bool(same.all()), "max_abs_llr_diff": float(np.abs(got - ref).max()),
+                             "tolerance": "identical hard decisions on >= 99.99 % of frames (north_star); sample must be all-equal"}}
+    del decodi, ch, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def e2e_contracts(pkg, decodi, ch, N, K_info, B, T_, world, steps, rows_counted, dist):
+    """The same metric through the class API with HOST buffers, copies inside the timed region, three contracts:
+      packed        decode_packed: pinned nibble-packed cluster indices in, bit-packed hard decisions of the counted rows out
+      uint8_pinned  decode_OpenCL(pinned uint8 numpy) -> uint8 numpy (round 1's e2e)
+      int32_numpy   decode_OpenCL(int32 numpy) -> int32 numpy: the reference's own contract
+                    (discrete_LDPC_decoder.py:207-209, :292-295), pageable memory, host-side casts included."""
+    import torch
+    host_u8 = pkg.pinned_empty((N, B), np.uint8)
+    host_u8[:] = ch.get()
+    res = {}
+
+    def timed(fn, reps):
+        for _ in range(2):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tm = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return K_info * B * world * reps / float(tm.item()) / 1e9
+
+    # packed
+    host_p = pkg.pinned_empty((N, (B + 1) // 2), np.uint8)
+    decodi.pack_channel_values(host_u8, out=host_p)
+    sink = [0]
+
+    def run_packed():
+        bits = decodi.decode_packed(host_p, B, rows=rows_counted)
+        sink[0] += int(bits[0, 0])               # touch the result on the host
+
+    v = timed(run_packed, steps)
+    res["packed"] = {"value": v, "h2d_bytes_per_step": int(host_p.size), "d2h_bytes_per_step": int(rows_counted) * ((B + 7) // 8),
+                     "api": "decode_packed(pinned nibble-packed uint8) -> bit-packed hard decisions -> ibldpc_decode_ib_host_packed"}
+    # check the packed result against the device-buffer decode of the same inputs
+    bits = decodi.unpack_bits(decodi.decode_packed(host_p, B, rows=rows_counted), B)
+    dev_out = decodi.decode_OpenCL(ch, buffer_in=True, return_buffer=True).tensor[:rows_counted]
+    res["packed"]["matches_device_path"] = bool(np.array_equal(bits, (dev_out < T_ // 2).cpu().numpy().astype(np.uint8)))
+
+    decodi.host_output_dtype = np.uint8
+
+    def run_u8():
+        r = decodi.decode_OpenCL(host_u8, buffer_in=False, return_buffer=False)
+        sink[0] += int(r[0, 0])
+
+    v = timed(run_u8, steps)
+    res["uint8_pinned"] = {"value": v, "h2d_bytes_per_step": int(N) * int(B), "d2h_bytes_per_step": int(N) * int(B),
+                           "api": "decode_OpenCL(pinned uint8 numpy, buffer_in=False, return_buffer=False) -> ibldpc_decode_ib_host"}
+    decodi.host_output_dtype = np.int32
+    host_i32 = host_u8.astype(np.int32)
+
+    def run_i32():
+        r = decodi.decode_OpenCL(host_i32, buffer_in=False, return_buffer=False)
+        sink[0] += int(r[0, 0])
+
+    v = timed(run_i32, max(2, steps // 3))
+    res["int32_numpy"] = {"value": v, "h2d_bytes_per_step": int(N) * int(B), "d2h_bytes_per_step": int(N) * int(B),
+                          "host_bytes_touched_per_step": 8 * int(N) * int(B),
+                          "api": "decode_OpenCL(int32 numpy, pageable) -> int32 numpy (class default, the reference's contract) -> ibldpc_decode_ib_host_i32"}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -308,9 +554,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c1", choices=["c1", "wlan", "wlan1944", "dvbs2"])
+    ap.add_argument("--card", type=int, default=T, help="|T| of channel and decoder (16 = BASELINE; 32 = the reference's WLAN design)")
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU and step (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the short legs of the other BASELINE configurations")
+    ap.add_argument("--leg-steps", type=int, default=3)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)
@@ -322,32 +571,18 @@ def main():
     import torch
     import torch.distributed as dist
     import informationbottleneckdecodingldpc_b200 as pkg
-    from informationbottleneckdecodingldpc_b200 import _lib
-    from informationbottleneckdecodingldpc_b200.parallel import allreduce_counters, bind_to_gpu_numa_node, init_distributed
+    from informationbottleneckdecodingldpc_b200.parallel import bind_to_gpu_numa_node, counter_allreduce_fn, init_distributed
 
     rank, world, local = init_distributed(args.gpus)
     torch.cuda.set_device(local)
     numa_node = bind_to_gpu_numa_node(local) if world > 1 else None   # host buffers of the e2e leg local to the GPU
     wl = workload(args.workload)
     B = args.frames or wl["B"]
-    t, tb = make_tables(wl)
+    T_ = args.card
+    # --- objects the BER drivers build (Regular_LDPC_Decoding/BPSK/BER_simulation_OpenCL.py:76-91)
+    t, tb, quanti, decodi = build_ib(pkg, wl, B, rank, T_)
     N, M, E = t.n_var, t.n_chk, t.n_edge
     K_info = N - M
-    R = K_info / N
-    # --- objects the BER drivers build (Regular_LDPC_Decoding/BPSK/BER_simulation_OpenCL.py:76-91)
-    quanti = pkg.AWGN_Channel_Quantizer(10 ** (-wl["ebn0"] / 10) / (2 * R), 3, T, 2000)
-    quanti.seed = SEED
-    quanti._offset = rank * (1 << 40)            # disjoint Philox sub-streams per rank
-    quanti.init_OpenCL_quanti(N, B, return_buffer_only=True)
-    if wl["irregular"]:
-        decodi = pkg.Discrete_LDPC_Decoder_class_irregular(wl["H"], IMAX, T, T, tb.Trellis_checknodevector_a,
-                                                           tb.Trellis_varnodevector_a, tb.matching_vector_checknode,
-                                                           tb.matching_vector_varnode, B)
-    else:
-        decodi = pkg.Discrete_LDPC_Decoder_class(wl["H"], IMAX, T, T, tb.Trellis_checknodevector_a,
-                                                 tb.Trellis_varnodevector_a, B)
-    decodi.init_OpenCL_decoding(B, quanti.context)
-    decodi.early_termination = False
     ch = quanti.quantize_direct_OpenCL(N, B)      # resident in HBM before the timed region
     torch.cuda.synchronize()
 
@@ -356,16 +591,17 @@ def main():
     # the totals one batch late, so the GPU never idles on the host.
     from informationbottleneckdecodingldpc_b200.engine import count_errors_async
     totals = torch.zeros(4, dtype=torch.int64, device="cuda")
+    base = torch.tensor([0, 0, B, IMAX * B], dtype=torch.int64, device="cuda")
     rows_counted = N if not wl["irregular"] else int(decodi.data_len)
+    allreduce = counter_allreduce_fn(decodi) if world > 1 else None
+    abi_allreduce = bool(getattr(decodi, "_nccl_ready", False))
 
     def step():
         out = decodi.decode_OpenCL(ch, buffer_in=True, return_buffer=True)
-        c = torch.zeros(4, dtype=torch.int64, device="cuda")
-        count_errors_async(out, rows_counted, T // 2, c)
-        c[2] += B
-        c[3] += IMAX * B
+        c = base.clone()
+        count_errors_async(out, rows_counted, T_ // 2, c)
         if world > 1:
-            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            allreduce(c)
         totals.add_(c)
         return out
 
@@ -382,7 +618,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step()
+        out_last = step()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -398,53 +634,43 @@ def main():
     frames_total = B * world * args.steps
     value = K_info * frames_total / (ms * 1e-3) / 1e9
 
+    # --- parity sample at the timed geometry (rank 0): 32 decoded columns of the last timed batch vs the CPU oracle
+    parity = parity_sample_ib(decodi, ch, out_last, t, tb, wl, T_) if rank == 0 else None
+
     # --- roofline of the dominant kernel: per-launch CUDA-event times on the launch stream
-    h = decodi._ensure_handle()
-    L = _lib.lib()
-    import ctypes as C
-    _lib.check(L.ibldpc_set_profiling(h, 1))
-    decodi.decode_OpenCL(ch, buffer_in=True, return_buffer=True)
-    ms3 = (C.c_float * 3)()
-    n3 = (C.c_int32 * 3)()
-    _lib.check(L.ibldpc_phase_times(h, ms3, n3))
-    _lib.check(L.ibldpc_set_profiling(h, 0))
-    packed = decodi.info()[0] == 2
+    fam = decodi.info()[0]
+    packed = fam == 2
     stored_div = 2 if packed else 1
-    roofline = roofline_from_phase_times(list(ms3), list(n3), N, E, B, IMAX, packed, args.workload)
+    roofline = phase_roofline(decodi, ch, N, E, B, args.workload)
 
     # --- end to end through the class API with HOST buffers (H2D + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
-        host_in = pkg.pinned_empty((N, B), np.uint8)
-        host_in[:] = ch.get()
-        decodi.host_output_dtype = np.uint8
-        for _ in range(2):
-            decodi.decode_OpenCL(host_in, buffer_in=False, return_buffer=False)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            res = decodi.decode_OpenCL(host_in, buffer_in=False, return_buffer=False)
-            _bit = int((res[:8] < T // 2).sum())      # touch the result on the host
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tm = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        dt = float(tm.item())
-        e2e = {"value": K_info * B * world * args.steps / dt / 1e9, "unit": "Gbit/s",
-               "h2d_bytes_per_step": int(N) * int(B), "d2h_bytes_per_step": int(N) * int(B),
-               "api": "Discrete_LDPC_Decoder_class.decode_OpenCL(numpy uint8 pinned, buffer_in=False, return_buffer=False)"
-                      " -> ibldpc_decode_ib_host"}
+        contracts = e2e_contracts(pkg, decodi, ch, N, K_info, B, T_, world, args.steps, rows_counted, dist)
+        head = contracts["packed"] if T_ <= 16 else contracts["uint8_pinned"]
+        e2e = {"value": head["value"], "unit": "Gbit/s", "h2d_bytes_per_step": head["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": head["d2h_bytes_per_step"], "api": head["api"],
+               "contract": "packed" if T_ <= 16 else "uint8_pinned", "contracts": contracts}
 
+    legs = None
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        use_all_host_threads()
-        frames = size_cpu_sample(wl, 12.0)
-        dtc, kind, cores, _ = cpu_reference_run(wl, frames)
-        cpu = {"value": K_info * frames / dtc / 1e9, "unit": "Gbit/s", "cores": cores, "kind": kind,
-               "sample": f"{frames} frames of the workload (same tables, i_max={IMAX}, ET off) in {dtc:.1f} s"}
+    if rank == 0 and world == 1:
+        del out_last
+        if not args.no_legs and args.workload == "c1" and T_ == T:
+            del ch, decodi
+            torch.cuda.empty_cache()
+            legs = {}
+            for name in ("wlan", "wlan1944", "dvbs2"):
+                legs[name] = leg_ib(pkg, name, args.leg_steps, rank)
+            legs["wlan_T32"] = leg_ib(pkg, "wlan", args.leg_steps, rank, T_=32, frames=32768)
+            legs["minsum_f64"] = leg_llr(pkg, "minsum", args.leg_steps, rank)
+            legs["bp_f64"] = leg_llr(pkg, "bp", args.leg_steps, rank)
+        if not args.no_cpu_baseline:
+            use_all_host_threads()
+            frames = size_cpu_sample(wl, 12.0, T_)
+            dtc, kind, cores, _ = cpu_reference_run(wl, frames, T_=T_)
+            cpu = {"value": K_info * frames / dtc / 1e9, "unit": "Gbit/s", "cores": cores, "kind": kind,
+                   "sample": f"{frames} frames of the workload (same tables, i_max={IMAX}, ET off) in {dtc:.1f} s"}
 
     if rank == 0:
         tot = totals.tolist()
@@ -452,12 +678,14 @@ def main():
             "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u4" if packed else "u8", "data": "synthetic",
-            "config": {"workload": wl["name"], "frames_per_gpu_per_step": B, "n_var": N, "n_chk": M, "n_edge": E,
+            "config": {"workload": wl["name"] if T_ == T else wl["name"].replace("|T|=16", f"|T|={T_}"),
+                       "frames_per_gpu_per_step": B, "n_var": N, "n_chk": M, "n_edge": E,
                        "info_bits": K_info, "i_max": IMAX, "EbN0_dB": wl["ebn0"], "tables": wl.get("tables"),
                        "l2": "inputs_larger_than_L2 (message array %.0f MB)" % (E * B / stored_div / 1e6), "parallelism": f"frames sharded x{world}", "rank0_numa_node": numa_node,
-                       "fast_path": bool(decodi.info()[0]), "kernel_family": "packed-nibble (n4)" if packed else "uint8"},
+                       "fast_path": bool(fam), "kernel_family": {0: "generic", 1: "uint8", 2: "packed-nibble (n4)", 3: "t32"}.get(fam),
+                       "counter_allreduce": "ibldpc_allreduce_counters (C ABI, NCCL)" if abi_allreduce else ("torch.distributed NCCL" if world > 1 else None)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "parity_sample": parity, "cpu_baseline": cpu, "workloads": legs,
             "errors": {"bit": tot[0], "frame": tot[1], "frames": tot[2]},
             "frames_per_s": frames_total / (ms * 1e-3), "ms_per_step_by_rank": [m / args.steps for m in rank_ms],
         }

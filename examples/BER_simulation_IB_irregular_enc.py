@@ -41,7 +41,7 @@ AD_max_abs, cardinality_Y_channel, cardinality_T_channel, cardinality_T_decoder_
 cfg, _ = generate_irregular_config(1.0, H, cardinality_T_decoder_ops, imax)
 transi = pkg.LDPC_BPSK_Transmitter(H, msg_at_time)
 transi.return_buffer_only = True
-transi._offset = rank * (1 << 44)                       # disjoint Philox sub-streams per rank
+transi.set_stream(rank)                               # independent Philox sub-stream per rank
 decodi = pkg.Discrete_LDPC_Decoder_class_irregular(H, imax, cardinality_T_channel, cardinality_T_decoder_ops,
                                                    cfg.Trellis_checknodevector_a, cfg.Trellis_varnodevector_a,
                                                    cfg.matching_vector_checknode, cfg.matching_vector_varnode, msg_at_time)
@@ -51,7 +51,7 @@ if rank == 0:
 for EbN0_dB in (args.ebn0 or ([0.8, 1.0, 1.2] if args.code == "dvbs2" else [1.0, 1.5, 2.0, 2.5])):
     sigma_n2 = 10 ** (-EbN0_dB / 10) / (2 * transi.R_c)
     chani = pkg.AWGN_channel(sigma_n2)
-    chani._offset = rank * (1 << 44)
+    chani.set_stream(rank)
     quanti = pkg.AWGN_Channel_Quantizer(sigma_n2, AD_max_abs, cardinality_T_channel, cardinality_Y_channel)
     quanti.init_OpenCL_quanti(N_var, msg_at_time, return_buffer_only=True)
     decodi.init_OpenCL_decoding(msg_at_time, quanti.context)

@@ -35,7 +35,7 @@ R_c = 0.5
 for EbN0_dB in np.arange(1.0, 1.81, 0.2):
     sigma_n2 = 10 ** (-EbN0_dB / 10) / (2 * R_c)
     quanti = pkg.AWGN_Channel_Quantizer(sigma_n2, AD_max_abs, cardinality_T_channel, cardinality_Y_channel)
-    quanti._offset = rank * (1 << 44)
+    quanti.set_stream(rank)
     quanti.init_OpenCL_quanti(N_var, msg_at_time, return_buffer_only=True)
     decodi.init_OpenCL_decoding(msg_at_time, quanti.context)
     res = ber_point(decodi, quanti, msg_at_time, min_errors=min_errors, max_frames=400 * msg_at_time * world)

@@ -96,6 +96,31 @@ int ibldpc_decode_ib(ibldpc_handle h, const uint8_t *ch_dev, int64_t B, int imax
 int ibldpc_decode_ib_host(ibldpc_handle h, const uint8_t *ch_host, int64_t B, int imax, int early_term,
                           uint8_t *out_host, int32_t *i_num_host);
 
+/* i_num of the last decode issued on this handle, read back lazily: synchronises the stream of that decode.  Lets
+ * BER loops call ibldpc_decode_ib with i_num_host == NULL (fully asynchronous) and still query the reference's
+ * i_num afterwards.  Returns IBLDPC_E_INVALID if the channel buffer of that decode held a value >= card_channel
+ * (such values are clamped on the device, never used as table indices). */
+int ibldpc_last_i_num(ibldpc_handle h, int32_t *i_num_host);
+
+/* The reference's own host contract (numpy int32 in, numpy int32 out: discrete_LDPC_decoder.py:207-209 casts
+ * received_blocks to int32 for the upload, :292-295 returns the int32 output array).  ch_host / out_host: int32
+ * (n_var, B).  The narrowing to one byte per cluster index and the widening back run on host threads
+ * (IBLDPC_HOST_THREADS, default min(16, cores)) chunk by chunk through pinned staging buffers owned by the handle,
+ * overlapped with the copies and the decode of the neighbouring chunk.  Values outside [0, card_channel) are an
+ * error. */
+int ibldpc_decode_ib_host_i32(ibldpc_handle h, const int32_t *ch_host, int64_t B, int imax, int early_term,
+                              int32_t *out_host, int32_t *i_num_host);
+
+/* Packed host buffers (opt-in; what the BER drivers actually consume is one hard decision per information bit,
+ * Irregular_LDPC_Decoding/WLAN/BER_simulation_OpenCL_enc.py:134, discrete_LDPC_decoder_irreg.py:343-349):
+ *   ch4_host   (n_var, ceil(B/2)) bytes, frame f of a row in nibble (f & 1) of byte f >> 1 (low nibble = even frame)
+ *   bits_host  (rows, ceil(B/8)) bytes, bit (f & 7) of byte f >> 3 = decoded bit (cluster < card_decoder / 2) of the
+ *              first `rows` rows (rows = data_len for the irregular decoders, n_var for the regular one)
+ * Host->device traffic is half, device->host traffic 1/16 (rows = n_var / 2) of ibldpc_decode_ib_host.
+ * Needs card_channel, card_decoder <= 16. */
+int ibldpc_decode_ib_host_packed(ibldpc_handle h, const uint8_t *ch4_host, int64_t B, int imax, int early_term,
+                                 uint8_t *bits_host, int64_t rows, int32_t *i_num_host);
+
 /* Replaces decode_OpenCL_min_sum (min_sum_decoder_irreg.py:221-287) and
  * decode_OpenCL_belief_propagation (bp_decoder_irreg.py:221-286).  ch_dev / out_dev are
  * (n_var, B) LLR arrays of `dtype` (IBLDPC_F32: fp32 messages, the fast path;
@@ -122,6 +147,10 @@ int ibldpc_count_errors_u8_async(int device, const uint8_t *out_dev, int64_t row
 int ibldpc_count_errors_llr(int device, const void *out_dev, int dtype, int64_t rows, int64_t B,
                             const uint8_t *ref_bits_dev, int64_t *counters_host, void *stream);
 
+/* Asynchronous twin of ibldpc_count_errors_llr (counters_dev[0] += bit errors, [1] += frame errors). */
+int ibldpc_count_errors_llr_async(int device, const void *out_dev, int dtype, int64_t rows, int64_t B,
+                                  const uint8_t *ref_bits_dev, int64_t *counters_dev, void *stream);
+
 /* Replaces the `quantize` kernel (AWGN_Channel_Transmission/kernels_quanti_template.cl:2-27)
  * as launched by quantize_OpenCL (AWGN_Quantizer_BPSK.py:183-199):
  * cluster = #{w in [1,card) : x - limits[w] > 0}, float64 compare.  limits_host: card doubles. */
@@ -143,8 +172,23 @@ int ibldpc_sample_direct_llr(int device, const double *cdf_host, int card, const
                              void *stream);
 int ibldpc_uniform(int device, uint64_t seed, uint64_t offset, int64_t n, double *out_dev, void *stream);
 
-/* Introspection for tests / benchmarks: which[0] = 1 if the shared-memory fast path is
- * active for the loaded tables (0 = generic path), which[1] = kernels launched by the
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: frames are sharded over one process per GPU; the only collective of the path is the
+ * sum of the per-batch counters {bit errors, frame errors, frames, iterations} so that every rank takes the same
+ * `while errors < min_errors` decision (Regular_LDPC_Decoding/BPSK/BER_simulation_OpenCL.py:98).
+ * NCCL is bound at run time (libnccl.so.2 of the host process, or IBLDPC_NCCL_LIB).
+ *   ibldpc_nccl_unique_id     rank 0: 128-byte ncclUniqueId to hand to the other ranks (pipe / file / env)
+ *   ibldpc_nccl_init          every rank: join the communicator of `world` ranks on the handle's GPU
+ *   ibldpc_allreduce_counters in-place sum of n int64 device counters over all ranks, asynchronous on `stream`
+ *   ibldpc_nccl_finalize      destroy the communicator (also done by ibldpc_destroy)
+ * --------------------------------------------------------------------------------------------- */
+int ibldpc_nccl_unique_id(uint8_t *id128);
+int ibldpc_nccl_init(ibldpc_handle h, const uint8_t *id128, int rank, int world);
+int ibldpc_allreduce_counters(ibldpc_handle h, int64_t *counters_dev, int n, void *stream);
+int ibldpc_nccl_finalize(ibldpc_handle h);
+
+/* Introspection for tests / benchmarks: which[0] = kernel family of the loaded tables (0 = generic path: tables in
+ * global memory; 1 = uint8 shared-memory fast path; 2 = packed-nibble fast path), which[1] = kernels launched by the
  * last decode call, which[2] = persistent grid size, which[3] = dynamic smem bytes. */
 int ibldpc_info(ibldpc_handle h, int32_t *which4);
 

@@ -20,9 +20,10 @@ from .. import _lib
 from ..design import symmetric_mi_quantizer
 from ..device_array import DeviceArray, as_tensor
 from ..engine import current_device, stream_ptr
+from ..rng import PhiloxStream
 
 
-class AWGN_Channel_Quantizer:
+class AWGN_Channel_Quantizer(PhiloxStream):
     """Reference signature: AWGN_Quantizer_BPSK.py:46."""
 
     def __init__(self, sigma_n2_, AD_max_abs_, cardinality_T_, cardinality_Y_, dont_calc=False):
@@ -35,8 +36,9 @@ class AWGN_Channel_Quantizer:
         self.y_vec = np.linspace(-self.AD_max_abs, +self.AD_max_abs, self.cardinality_Y)
         self.x_vec = np.array([-1, 1])
         self.delta = self.y_vec[1] - self.y_vec[0]
-        self.seed = 20181001          # Philox key of the direct-sampling methods
+        self.seed = 20181001          # Philox seed of the direct-sampling methods (key = rng.stream_key(seed, stream))
         self._offset = 0              # Philox counter: advances by N_var*msg_at_time per call
+        self._stream = None           # sub-stream: set_stream(rank); default = rank of the process group, else 0
         self.llr_dtype = np.float64   # dtype of quantize_direct_OpenCL_LLR buffers (np.float32 = fast path)
         self.return_buffer_only = False
         self.context = None
@@ -126,7 +128,7 @@ class AWGN_Channel_Quantizer:
         out = torch.empty((int(N_var), int(msg_at_time)), dtype=torch.uint8, device=f"cuda:{dev}")
         cdf = np.ascontiguousarray(self.cdf_t_given_x_equals_zero, dtype=np.float64)
         _lib.check(_lib.lib().ibldpc_sample_direct(dev, C.c_void_p(cdf.ctypes.data), int(self.cardinality_T) + 1,
-                                                   int(self.seed), int(self._offset), n, C.c_void_p(out.data_ptr()),
+                                                   int(self._philox_key()), int(self._offset), n, C.c_void_p(out.data_ptr()),
                                                    C.c_void_p(stream_ptr())))
         self._offset += n
         if self.return_buffer_only:
@@ -143,7 +145,7 @@ class AWGN_Channel_Quantizer:
         cdf = np.ascontiguousarray(self.cdf_t_given_x_equals_zero, dtype=np.float64)
         llr = np.ascontiguousarray(np.append(self.output_LLRs, self.output_LLRs[-1]), dtype=np.float64)
         _lib.check(_lib.lib().ibldpc_sample_direct_llr(dev, C.c_void_p(cdf.ctypes.data), int(self.cardinality_T) + 1,
-                                                       C.c_void_p(llr.ctypes.data), int(self.seed), int(self._offset), n,
+                                                       C.c_void_p(llr.ctypes.data), int(self._philox_key()), int(self._offset), n,
                                                        _lib.F32 if f32 else _lib.F64, C.c_void_p(out.data_ptr()),
                                                        C.c_void_p(stream_ptr())))
         self._offset += n

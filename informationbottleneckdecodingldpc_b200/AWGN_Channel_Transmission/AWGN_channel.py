@@ -16,9 +16,10 @@ import torch
 from .. import _lib
 from ..device_array import DeviceArray, as_tensor
 from ..engine import current_device, stream_ptr
+from ..rng import PhiloxStream
 
 
-class AWGN_channel:
+class AWGN_channel(PhiloxStream):
     def __init__(self, sigma_n2_, complex=False):
         if complex:
             raise NotImplementedError("complex noise is only used by the reference's QAM transmitter")
@@ -26,6 +27,7 @@ class AWGN_channel:
         self.complex = False
         self.seed = 20181001 ^ 0x5DEECE66D
         self._offset = 0
+        self._stream = None           # sub-stream: set_stream(rank); default = rank of the process group, else 0
 
     def _run(self, x_t, bits_t, shape):
         dev = current_device()
@@ -33,7 +35,7 @@ class AWGN_channel:
         out = torch.empty(tuple(shape), dtype=torch.float64, device=f"cuda:{dev}")
         _lib.check(_lib.lib().ibldpc_awgn(dev, C.c_void_p(x_t.data_ptr()) if x_t is not None else None,
                                           C.c_void_p(bits_t.data_ptr()) if bits_t is not None else None, n, self.sigma_n2,
-                                          int(self.seed), int(self._offset), C.c_void_p(out.data_ptr()),
+                                          int(self._philox_key()), int(self._offset), C.c_void_p(out.data_ptr()),
                                           C.c_void_p(stream_ptr())))
         self._offset += n
         return out

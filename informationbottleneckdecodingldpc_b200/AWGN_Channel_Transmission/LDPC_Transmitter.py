@@ -26,9 +26,10 @@ from ..device_array import DeviceArray
 from ..Discrete_LDPC_decoding.LDPC_encoder import LDPCEncoder
 from ..engine import current_device, stream_ptr
 from ..graph import code_rate_from_degrees, load_check_matrix
+from ..rng import PhiloxStream
 
 
-class LDPC_BPSK_Transmitter:
+class LDPC_BPSK_Transmitter(PhiloxStream):
     def __init__(self, filename_H_, msg_at_time=1):
         self.filename_H = filename_H_
         if isinstance(filename_H_, (str, os.PathLike)):
@@ -42,7 +43,8 @@ class LDPC_BPSK_Transmitter:
         self.msg_at_time = int(msg_at_time)
         self.return_buffer_only = False
         self.seed = 20181001
-        self._offset = 0          # Philox counter offset: consecutive calls draw disjoint sub-streams
+        self._offset = 0          # Philox counter offset: consecutive calls draw disjoint ranges of the stream
+        self._stream = None       # sub-stream: set_stream(rank); default = rank of the process group, else 0
 
     def set_code_parameters(self):
         H = self.H_sparse
@@ -59,7 +61,7 @@ class LDPC_BPSK_Transmitter:
         dev = current_device()
         n = self.data_len * self.msg_at_time
         t = torch.empty((self.data_len, self.msg_at_time), dtype=torch.uint8, device=f"cuda:{dev}")
-        _lib.check(_lib.lib().ibldpc_random_bits(dev, int(self.seed), int(self._offset), n, C.c_void_p(t.data_ptr()),
+        _lib.check(_lib.lib().ibldpc_random_bits(dev, int(self._philox_key()), int(self._offset), n, C.c_void_p(t.data_ptr()),
                                                  C.c_void_p(stream_ptr())))
         self._offset += n
         return t

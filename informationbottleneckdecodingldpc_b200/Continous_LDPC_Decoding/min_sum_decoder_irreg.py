@@ -55,11 +55,11 @@ class _LlrDecoderBase(GraphDecoderBase):
             tdt = torch.float64 if self.precision == 'f64' else torch.float32
             ch = self._device_input(torch.from_numpy(np.ascontiguousarray(rb)).cuda(), tdt)
         out = torch.empty_like(ch)
-        inum = C.c_int32(0)
+        # asynchronous on the current stream; i_num is read back lazily (self.last_i_num)
         _lib.check(_lib.lib().ibldpc_decode_llr(
             h, self._algo, _lib.F32 if tdt == torch.float32 else _lib.F64, C.c_void_p(ch.data_ptr()), ch.shape[1],
-            int(self.imax), int(bool(early)), C.c_void_p(out.data_ptr()), C.byref(inum), C.c_void_p(stream_ptr())))
-        self.last_i_num = int(inum.value)
+            int(self.imax), int(bool(early)), C.c_void_p(out.data_ptr()), None, C.c_void_p(stream_ptr())))
+        self._inum_pending = True
         if return_buffer:
             return DeviceArray(out)
         return out.cpu().numpy().astype(np.float64)

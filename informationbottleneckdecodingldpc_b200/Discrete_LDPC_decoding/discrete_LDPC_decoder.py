@@ -48,6 +48,7 @@ class Discrete_LDPC_Decoder_class(GraphDecoderBase):
         self.last_i_num = None
         self._luts_uploaded = False
         self._host_out = None
+        self._host_bits = None
 
     # ---- tables ------------------------------------------------------------------------
     def update_trellis_vectors(self, Trellis_checknode_vector_a_, Trellis_varnode_vector_a_):
@@ -111,33 +112,57 @@ class Discrete_LDPC_Decoder_class(GraphDecoderBase):
             ch = self._device_input(received_blocks, torch.uint8)
             B = ch.shape[1]
             out = torch.empty_like(ch)
-            want_inum = bool(early) or not return_buffer
+            # asynchronous on the current stream: i_num stays on the device until someone reads self.last_i_num
             _lib.check(L.ibldpc_decode_ib(h, C.c_void_p(ch.data_ptr()), B, int(self.imax), int(bool(early)),
-                                          C.c_void_p(out.data_ptr()), C.byref(inum) if want_inum else None,
-                                          C.c_void_p(stream_ptr())))
-            self.last_i_num = int(inum.value) if want_inum else int(self.imax)
+                                          C.c_void_p(out.data_ptr()), None, C.c_void_p(stream_ptr())))
+            self._inum_pending = True
             if return_buffer:
                 return DeviceArray(out)
-            return out.cpu().numpy().astype(self.host_output_dtype, copy=False)
+            res = out.cpu().numpy().astype(self.host_output_dtype, copy=False)
+            self.last_i_num          # resolves i_num and raises on out-of-range cluster indices
+            return res
         # host buffers
         rb = np.asarray(received_blocks)
         if rb.ndim == 1:
             rb = rb[:, None]
         if rb.shape[0] != self.N_v:
             raise ValueError(f"expected {self.N_v} rows (variable nodes), got {rb.shape[0]}")
-        if rb.dtype != np.uint8:
-            if rb.size and (rb.min() < 0 or rb.max() >= int(self.cardinality_T_channel)):
-                raise ValueError("channel cluster indices must lie in [0, cardinality_T_channel)")
-            rb = rb.astype(np.uint8)
-        rb = np.ascontiguousarray(rb)
         B = rb.shape[1]
+        current_device()
+        if rb.dtype != np.uint8:
+            # the reference's own contract: integer numpy in, int32 numpy out (discrete_LDPC_decoder.py:207-209,
+            # :292-295).  Narrowing / widening run on host threads inside the library, overlapped with the copies.
+            if rb.dtype != np.int32:
+                if rb.size and not np.issubdtype(rb.dtype, np.integer) and np.any(rb != np.floor(rb)):
+                    raise ValueError("channel cluster indices must be integers")
+                if rb.size and (rb.min() < 0 or rb.max() >= int(self.cardinality_T_channel)):
+                    raise ValueError("channel cluster indices must lie in [0, cardinality_T_channel)")
+                rb = rb.astype(np.int32)
+            rb = np.ascontiguousarray(rb)
+            out32 = np.empty(rb.shape, dtype=np.int32)
+            try:
+                _lib.check(L.ibldpc_decode_ib_host_i32(h, C.c_void_p(rb.ctypes.data), B, int(self.imax), int(bool(early)),
+                                                       C.c_void_p(out32.ctypes.data), C.byref(inum)))
+            except RuntimeError as e:
+                if "cluster indices" in str(e):
+                    raise ValueError(str(e)) from None
+                raise
+            self.last_i_num = int(inum.value)
+            if return_buffer:
+                return DeviceArray(torch.from_numpy(out32).to(torch.uint8).cuda())
+            return out32 if np.dtype(self.host_output_dtype) == np.int32 else out32.astype(self.host_output_dtype)
+        rb = np.ascontiguousarray(rb)
         if self._host_out is None or self._host_out.shape != rb.shape:
             from ..device_array import pinned_empty
             self._host_out = pinned_empty(rb.shape, np.uint8)
         out = self._host_out
-        current_device()
-        _lib.check(L.ibldpc_decode_ib_host(h, C.c_void_p(rb.ctypes.data), B, int(self.imax), int(bool(early)),
-                                           C.c_void_p(out.ctypes.data), C.byref(inum)))
+        try:
+            _lib.check(L.ibldpc_decode_ib_host(h, C.c_void_p(rb.ctypes.data), B, int(self.imax), int(bool(early)),
+                                               C.c_void_p(out.ctypes.data), C.byref(inum)))
+        except RuntimeError as e:
+            if "cluster indices" in str(e):
+                raise ValueError(str(e)) from None
+            raise
         self.last_i_num = int(inum.value)
         if return_buffer:
             return DeviceArray(torch.from_numpy(out).cuda())
@@ -146,6 +171,52 @@ class Discrete_LDPC_Decoder_class(GraphDecoderBase):
         return out.astype(self.host_output_dtype)
 
     decode = decode_OpenCL
+
+    # ---- packed host buffers (opt-in): half the H2D bytes, 1/16 of the D2H bytes ------------------------------
+    @staticmethod
+    def pack_channel_values(received_blocks, out=None):
+        """(N_v, B) cluster indices (< 16) -> (N_v, ceil(B/2)) uint8, frame f in nibble f & 1 of byte f >> 1."""
+        rb = np.asarray(received_blocks)
+        if rb.ndim == 1:
+            rb = rb[:, None]
+        rb = rb.astype(np.uint8, copy=False)
+        if rb.shape[1] % 2:
+            rb = np.concatenate([rb, np.zeros((rb.shape[0], 1), np.uint8)], axis=1)
+        res = (rb[:, 0::2] | (rb[:, 1::2] << 4)).astype(np.uint8)
+        if out is not None:
+            out[...] = res
+            return out
+        return res
+
+    @staticmethod
+    def unpack_bits(bits, B):
+        """(rows, ceil(B/8)) bit-packed hard decisions -> (rows, B) uint8 0/1."""
+        return np.unpackbits(np.asarray(bits, dtype=np.uint8), axis=1, bitorder="little")[:, :B]
+
+    def decode_packed(self, packed_blocks, B, rows=None, early_termination=None):
+        """Host path for BER loops: ``packed_blocks`` = nibble-packed cluster indices (``pack_channel_values``;
+        ideally in pinned memory, ``pinned_empty``), result = bit-packed hard decisions (cluster < |T|/2, the decoded
+        bit of ``return_errors_all_zero`` and of the _enc drivers' comparison,
+        WLAN/BER_simulation_OpenCL_enc.py:134) of the first ``rows`` rows (default: ``data_len`` for irregular
+        decoders, all rows otherwise) as a (rows, ceil(B/8)) uint8 array owned by the decoder (overwritten by the
+        next call).  Same kernels and stop rule as ``decode_OpenCL``; only the host formats differ."""
+        h = self._upload_luts()
+        early = self.early_termination if early_termination is None else early_termination
+        pk = np.ascontiguousarray(packed_blocks, dtype=np.uint8)
+        B = int(B)
+        if pk.shape != (self.N_v, (B + 1) // 2):
+            raise ValueError(f"expected packed shape {(self.N_v, (B + 1) // 2)}, got {pk.shape}")
+        rows = (int(self.data_len) if self._irregular else self.N_v) if rows is None else int(rows)
+        shape = (rows, (B + 7) // 8)
+        if self._host_bits is None or self._host_bits.shape != shape:
+            from ..device_array import pinned_empty
+            self._host_bits = pinned_empty(shape, np.uint8)
+        inum = C.c_int32(0)
+        current_device()
+        _lib.check(_lib.lib().ibldpc_decode_ib_host_packed(h, C.c_void_p(pk.ctypes.data), B, int(self.imax), int(bool(early)),
+                                                           C.c_void_p(self._host_bits.ctypes.data), rows, C.byref(inum)))
+        self.last_i_num = int(inum.value)
+        return self._host_bits
 
     def return_errors_all_zero(self, varnode_output_buffer):
         """Number of decoded 1-bits, all-zero codeword assumed, over ALL rows

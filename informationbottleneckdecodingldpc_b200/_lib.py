@@ -12,8 +12,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libibldpc.so")
 UNITS = ["ibldpc.cu", "ib_fast_cn.cu", "ib_fast_vn.cu", "ib_n4_cn_v2.cu", "ib_n4_cn_pair.cu", "ib_n4_vn_pair.cu", "ib_n4_vn_v2.cu", "ib_n4_vn_v4.cu", "ib_n4_coop.cu",
-         "llr_f32.cu", "llr_f64.cu", "encoder.cu"]   # compiled in parallel
-SOURCES = [os.path.join(HERE, "csrc", f) for f in UNITS + ["ib_kernels.cuh", "ib_kernels_n4.cuh", "ib_coop_n4.cuh", "llr_kernels.cuh", "kernel_tables.h"]]
+         "llr_f32.cu", "llr_f64.cu", "encoder.cu", "nccl_abi.cu"]   # compiled in parallel
+SOURCES = [os.path.join(HERE, "csrc", f) for f in UNITS + ["ib_kernels.cuh", "ib_kernels_n4.cuh", "ib_coop_n4.cuh", "llr_kernels.cuh", "kernel_tables.h", "ibldpc_internal.h"]]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "ibldpc.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -55,10 +55,18 @@ SIGNATURES = {
     "ibldpc_set_luts": (_i, [_vp, C.POINTER(LutDesc)]),
     "ibldpc_decode_ib": (_i, [_vp, _vp, _i64, _i, _i, _vp, C.POINTER(C.c_int32), _vp]),
     "ibldpc_decode_ib_host": (_i, [_vp, _vp, _i64, _i, _i, _vp, C.POINTER(C.c_int32)]),
+    "ibldpc_last_i_num": (_i, [_vp, C.POINTER(C.c_int32)]),
+    "ibldpc_decode_ib_host_i32": (_i, [_vp, _vp, _i64, _i, _i, _vp, C.POINTER(C.c_int32)]),
+    "ibldpc_decode_ib_host_packed": (_i, [_vp, _vp, _i64, _i, _i, _vp, _i64, C.POINTER(C.c_int32)]),
     "ibldpc_decode_llr": (_i, [_vp, _i, _i, _vp, _i64, _i, _i, _vp, C.POINTER(C.c_int32), _vp]),
     "ibldpc_count_errors_u8": (_i, [_i, _vp, _i64, _i64, _i, _vp, C.POINTER(C.c_int64), _vp]),
     "ibldpc_count_errors_u8_async": (_i, [_i, _vp, _i64, _i64, _i, _vp, _vp, _vp]),
     "ibldpc_count_errors_llr": (_i, [_i, _vp, _i, _i64, _i64, _vp, C.POINTER(C.c_int64), _vp]),
+    "ibldpc_count_errors_llr_async": (_i, [_i, _vp, _i, _i64, _i64, _vp, _vp, _vp]),
+    "ibldpc_nccl_unique_id": (_i, [_vp]),
+    "ibldpc_nccl_init": (_i, [_vp, _vp, _i, _i]),
+    "ibldpc_allreduce_counters": (_i, [_vp, _vp, _i, _vp]),
+    "ibldpc_nccl_finalize": (_i, [_vp]),
     "ibldpc_quantize": (_i, [_i, _vp, _i64, _vp, _i, _vp, _vp]),
     "ibldpc_quantize_llr": (_i, [_i, _vp, _i64, _vp, _i, _vp, _i, _vp, _vp]),
     "ibldpc_sample_direct": (_i, [_i, _vp, _i, _u64, _u64, _i64, _vp, _vp]),
@@ -104,7 +112,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
         objs = list(pool.map(compile_unit, UNITS))
-    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs + ["-ldl"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

@@ -544,14 +544,18 @@ __global__ void __launch_bounds__(kThreads) ib_out_n4_kernel(IbArgs a, const int
 
 // ------------------------------------------------------------------------------------------
 // uint8 (rows, src_pitch) -> packed nibbles (rows, pitch4); frames >= B become 0.
-// One thread per 32-bit destination word (8 frames).
+// One thread per 32-bit destination word (8 frames).  Values >= T (not a cluster index of this decoder) are
+// clamped to T-1 so that no look-up leaves its table, and reported through *bad (checked by the host at its next
+// synchronisation point: ibldpc_last_i_num / the host-buffer entry points).
 // ------------------------------------------------------------------------------------------
 template <bool ALIGNED>
 __global__ void pack_n4_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int rows, long long B,
-                               long long src_pitch, uint32_t pitch4)
+                               long long src_pitch, uint32_t pitch4, int T, int* __restrict__ bad)
 {
     const uint32_t wpr = pitch4 >> 2;   // words per destination row
     const long long n = (long long)rows * wpr;
+    const uint32_t kadd = (uint32_t)(128 - T) * 0x01010101u;
+    bool any_bad = false;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / wpr;
         const long long wd = i - r * wpr;
@@ -560,16 +564,82 @@ __global__ void pack_n4_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
         const uint8_t* p = src + r * src_pitch + f0;
         if (ALIGNED && f0 + 8 <= B) {
             const uint2 x = *reinterpret_cast<const uint2*>(p);
-            // bytes b0..b3 of x.x -> nibbles 0..3, x.y -> nibbles 4..7
-            const uint32_t lo = x.x & 0x0f0f0f0fu, hi = x.y & 0x0f0f0f0fu;
-            const uint32_t l2 = (lo | (lo >> 4)) & 0x00ff00ffu, h2 = (hi | (hi >> 4)) & 0x00ff00ffu;
-            v = ((l2 | (l2 >> 8)) & 0xffffu) | (((h2 | (h2 >> 8)) & 0xffffu) << 16);
+            // a byte >= T has bit 7 set either by itself or after adding 128-T (a carry out of a byte only
+            // happens when that byte was >= 128 already, i.e. the word is reported anyway)
+            const bool ok = (((x.x | (x.x + kadd)) | (x.y | (x.y + kadd))) & 0x80808080u) == 0u;
+            if (ok) {
+                // bytes b0..b3 of x.x -> nibbles 0..3, x.y -> nibbles 4..7
+                const uint32_t lo = x.x & 0x0f0f0f0fu, hi = x.y & 0x0f0f0f0fu;
+                const uint32_t l2 = (lo | (lo >> 4)) & 0x00ff00ffu, h2 = (hi | (hi >> 4)) & 0x00ff00ffu;
+                v = ((l2 | (l2 >> 8)) & 0xffffu) | (((h2 | (h2 >> 8)) & 0xffffu) << 16);
+            } else {
+                any_bad = true;
+#pragma unroll
+                for (int f = 0; f < 8; ++f) v |= (uint32_t)min((int)p[f], T - 1) << (4 * f);
+            }
         } else {
 #pragma unroll
             for (int f = 0; f < 8; ++f)
-                if (f0 + f < B) v |= (uint32_t)(p[f] & 15u) << (4 * f);
+                if (f0 + f < B) {
+                    const int x = p[f];
+                    any_bad |= x >= T;
+                    v |= (uint32_t)min(x, T - 1) << (4 * f);
+                }
         }
         reinterpret_cast<uint32_t*>(dst)[i] = v;
+    }
+    if (any_bad) atomicOr(bad, 1);
+}
+
+// Range check of a uint8 cluster buffer for the kernel families that read it in place (uint8 family, generic path).
+static __global__ void range_check_u8_kernel(const uint8_t* __restrict__ src, int rows, long long B, long long pitch, int T,
+                                      int* __restrict__ bad)
+{
+    const long long n = (long long)rows * B;
+    bool any_bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / B, c = i - r * B;
+        any_bad |= src[r * pitch + c] >= T;
+    }
+    if (any_bad) atomicOr(bad, 1);
+}
+
+// packed nibbles (rows, pitch4) -> uint8 (rows, dst_pitch): the inverse of pack_n4_kernel, for the kernel families
+// that read uint8 when the caller hands in packed host buffers.
+static __global__ void unpack_n4_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int rows, long long B,
+                                 long long dst_pitch, uint32_t pitch4)
+{
+    const long long n = (long long)rows * dst_pitch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / dst_pitch, f = i - r * dst_pitch;
+        dst[i] = f < B ? (uint8_t)((src[r * pitch4 + (f >> 1)] >> (4 * (f & 1))) & 15u) : (uint8_t)0;
+    }
+}
+
+// Hard decisions of the first `rows` rows of a decided-cluster buffer, bit-packed: bit (f & 7) of byte f >> 3 of
+// row r = (out[r][f] < threshold), i.e. the decoded bit of return_errors_all_zero (discrete_LDPC_decoder.py:297-300)
+// and of the _enc drivers' comparison (WLAN/BER_simulation_OpenCL_enc.py:134).  One thread per 32 frames.
+static __global__ void harddecision_bits_kernel(const uint8_t* __restrict__ out, int rows, long long B, long long pitch,
+                                         int threshold, uint32_t* __restrict__ bits, long long words_per_row)
+{
+    const long long n = (long long)rows * words_per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / words_per_row, wd = i - r * words_per_row;
+        const long long f0 = wd * 32;
+        const uint8_t* p = out + r * pitch + f0;
+        uint32_t v = 0;
+        if (f0 + 32 <= B && (pitch & 15) == 0) {
+            const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);
+            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v |= (((w[q] >> (8 * k)) & 0xffu) < (uint32_t)threshold ? 1u : 0u) << (4 * q + k);
+        } else {
+            for (int f = 0; f < 32; ++f)
+                if (f0 + f < B) v |= (p[f] < threshold ? 1u : 0u) << f;
+        }
+        bits[i] = v;
     }
 }
 

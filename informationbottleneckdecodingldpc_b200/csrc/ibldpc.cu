@@ -6,11 +6,12 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
 
-#include "../../include/ibldpc.h"
+#include "ibldpc_internal.h"
 #include "ib_kernels.cuh"
 #include "ib_kernels_n4.cuh"
 #include "ib_coop_n4.cuh"
@@ -36,83 +37,12 @@ int fail(int code, const std::string& msg)
             return fail(IBLDPC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
     } while (0)
 
-struct NodeClass {
-    int degree = 0;
-    int count = 0;
-    int* d_nodes = nullptr;
-};
-
-struct Workspace {
-    uint8_t* msg = nullptr;     // IB in-place message array
-    size_t msg_bytes = 0;
-    uint8_t* ch4 = nullptr;     // packed-nibble copy of the channel values (n4 path)
-    size_t ch4_bytes = 0;
-    void* cin = nullptr;        // LLR inboxes
-    void* vin = nullptr;
-    size_t llr_bytes = 0;
-    uint8_t* padbuf_in = nullptr;   // padded copies of caller buffers when B is not vector-aligned
-    uint8_t* padbuf_out = nullptr;
-    size_t pad_bytes = 0;
-    uint8_t* stage_in = nullptr;    // device staging of the host-buffer path
-    uint8_t* stage_out = nullptr;
-    size_t stage_bytes = 0;
-    int* flags = nullptr;           // [kMaxIter]
-    int* inum = nullptr;
-    cudaStream_t stream = nullptr;  // host-path stream
-    // degree classes of one phase run concurrently on these (fork/join around every phase)
-    cudaStream_t aux[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t fork_ev = nullptr, join_ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-};
-
-constexpr int kMaxIter = 4096;
-
-
-struct PhaseEvent { cudaEvent_t a, b; int phase; };
-
 }  // namespace
 
 namespace ibldpc {
 // error sink shared with encoder.cu
 int fail_msg(int code, const std::string& msg) { return fail(code, msg); }
 }  // namespace ibldpc
-
-struct ibldpc_decoder {
-    int device = 0;
-    int sm_count = 148;
-    int N = 0, M = 0, E = 0;
-    int dc_max = 0, dv_max = 0, dc_min = 0, dv_min = 0;
-    int *d_sc = nullptr, *d_dc = nullptr, *d_tc = nullptr, *d_sv = nullptr, *d_dv = nullptr, *d_tv = nullptr,
-        *d_vidx = nullptr;
-    std::vector<NodeClass> cn_classes, vn_classes;
-    // LUTs
-    bool have_luts = false;
-    int T = 0, Tc = 0, lut_imax = 0, DC = 0, DV = 0;
-    bool match = false;
-    uint8_t *d_cn8 = nullptr, *d_vn8 = nullptr, *d_mc8 = nullptr, *d_mv8 = nullptr;
-    uint8_t* d_cn_pair = nullptr;   // [imax blocks][cn classes][T*T rows][8 bytes] composed tail-pair tables
-    uint8_t* d_vn_pair = nullptr;   // [imax][vn classes][T*T rows][8 bytes] composed tail-pair tables of the VN update
-    int vn_pair_min_degree = 5;     // packed-nibble family (IBLDPC_VN_PAIR_MIN_DEGREE)
-    int vn_pair_threads = 0;        // 0 = per-degree default, 256 / 512 forced (IBLDPC_VN_PAIR_THREADS)
-    int cn_threads = 0, vn_threads = 0;   // 0 = default CTA sizes (1024 where instantiated); IBLDPC_CN_THREADS=512 /
-                                          // IBLDPC_VN_THREADS=256 select the smaller CTAs (parity variants, A/B)
-    long long coop_max_frames = 4096;   // regular codes: whole-decode cooperative kernel up to this batch size
-                                        // (IBLDPC_COOP_MAX_B, 0 disables)
-    int coop_supported = -1;        // device attribute cudaDevAttrCooperativeLaunch, queried once
-    bool use_pair = true;
-    int pair_min_degree = 7;      // uint8 family
-    int n4_pair_min_degree = 6;   // packed-nibble family
-    bool fast = false;
-    bool nib = false;     // packed-nibble fast path (ib_kernels_n4.cuh)
-    int vn_vec = 0;       // words per lane of the variable-node kernels: 0 = per-degree default, 2 / 4 forced (IBLDPC_VN_VEC)
-    int Wc = 1, Wv = 1, Wo = 1, nrows_c = 0, nrows_v = 0, nrows_o = 0, tshift = -1;
-    Workspace ws[2];
-    int host_chunk = 0;   // 0 = auto: about 256 MiB of channel values per chunk
-    // introspection
-    int last_launches = 0, last_grid = 0, last_smem = 0;
-    bool profiling = false;
-    std::vector<PhaseEvent> events;
-    std::map<std::pair<const void*, int>, int> occ_cache;
-};
 
 namespace {
 
@@ -155,7 +85,8 @@ int ensure(void** p, size_t* have, size_t need, bool zero = false)
 int ensure_ws_common(ibldpc_decoder* h, Workspace& w)
 {
     if (!w.flags) {
-        CK(cudaMalloc((void**)&w.flags, sizeof(int) * kMaxIter));
+        CK(cudaMalloc((void**)&w.flags, sizeof(int) * (kMaxIter + 1)));   // [0] = input-range flag, [1..] = per-pass syndrome flags
+        CK(cudaMemset(w.flags, 0, sizeof(int) * (kMaxIter + 1)));
         CK(cudaMalloc((void**)&w.inum, sizeof(int)));
     }
     (void)h;
@@ -315,17 +246,20 @@ void clear_events(ibldpc_decoder* h)
 }
 
 int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long pitch8, long long B, int imax, int early,
-                 uint8_t* out, cudaStream_t st);
+                 uint8_t* out, cudaStream_t st, bool ch_packed);
 
 // ------------------------------------------------------------------------------------------
 // IB decode on padded device buffers (pitch multiple of 16, pointers 16-byte aligned)
 // ------------------------------------------------------------------------------------------
 int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long pitch, long long B, int imax,
-                     int early, uint8_t* out, cudaStream_t st)
+                     int early, uint8_t* out, cudaStream_t st, bool ch_packed = false)
 {
-    if (h->fast && h->nib) return decode_ib_n4(h, w, ch, pitch, B, imax, early, out, st);
+    h->last_stream = st;
+    h->last_ws = (int)(&w - &h->ws[0]);
+    if (h->fast && h->nib) return decode_ib_n4(h, w, ch, pitch, B, imax, early, out, st, ch_packed);
     int rc = ensure_ws_common(h, w);
     if (rc) return rc;
+    if (ch_packed) return fail(IBLDPC_E_STATE, "packed channel buffers need the packed-nibble kernel family");
     size_t need = (size_t)h->E * (size_t)pitch;
     {
         void* p = w.msg;
@@ -333,7 +267,12 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
         w.msg = (uint8_t*)p;
         if (rc) return rc;
     }
-    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)std::max(imax, 1), st));
+    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)(std::max(imax, 1) + 1), st));
+    {   // these families read the caller's uint8 buffer in place: report cluster indices >= |T_channel|
+        const long long n = (long long)h->N * B;
+        const int grid = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 16);
+        range_check_u8_kernel<<<grid, 256, 0, st>>>(ch, h->N, B, pitch, h->Tc, w.flags);
+    }
     IbArgs a{};
     a.sc = h->d_sc; a.deg_c = h->d_dc; a.sv = h->d_sv; a.deg_v = h->d_dv; a.tv = h->d_tv; a.vidx = h->d_vidx;
     a.n_var = h->N; a.n_chk = h->M;
@@ -343,7 +282,7 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
     const int tile_groups = (a.tiles + (1 << a.tpc_log2) - 1) >> a.tpc_log2;
     const int nps = kWarpsPerCta >> a.tpc_log2;
     a.T = h->T; a.Tc = h->Tc; a.tshift = h->tshift;
-    a.flags = w.flags; a.inum = w.inum; a.early = early; a.imax = imax;
+    a.flags = w.flags + 1; a.inum = w.inum; a.early = early; a.imax = imax;
     a.DC = h->DC; a.DV = h->DV; a.xp_col = -1;
     const int T = h->T, Tc = h->Tc, TT = T * T;
     h->last_launches = 0;
@@ -512,7 +451,7 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
 // (pitch multiple of 16); messages and channel values travel as nibbles inside.
 // ------------------------------------------------------------------------------------------
 int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long pitch8, long long B, int imax, int early,
-                 uint8_t* out, cudaStream_t st)
+                 uint8_t* out, cudaStream_t st, bool ch_packed)
 {
     int rc = ensure_ws_common(h, w);
     if (rc) return rc;
@@ -527,14 +466,14 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
         w.ch4 = (uint8_t*)p;
         if (rc) return rc;
     }
-    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)std::max(imax, 1), st));
+    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)(std::max(imax, 1) + 1), st));
     h->last_launches = 0;
     Prof prof{h, st};
-    {
+    if (!ch_packed) {   // ch_packed: the caller already filled w.ch4 (packed host path)
         const long long nwords = (long long)h->N * (pitch4 / 4);
         const int grid = (int)std::min<long long>((nwords + 255) / 256, (long long)h->sm_count * 16);
         if ((rc = prof.begin(2))) return rc;
-        pack_n4_kernel<true><<<grid, 256, 0, st>>>(ch, w.ch4, h->N, B, pitch8, (uint32_t)pitch4);
+        pack_n4_kernel<true><<<grid, 256, 0, st>>>(ch, w.ch4, h->N, B, pitch8, (uint32_t)pitch4, h->T, w.flags);
         h->last_launches++;
         if ((rc = prof.end())) return rc;
     }
@@ -544,7 +483,7 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
     a.ch = w.ch4; a.msg = w.msg; a.out = out;
     a.pitch = (uint32_t)pitch4; a.out_pitch = (uint32_t)pitch8; a.B = (int)B;
     a.T = h->T; a.Tc = h->Tc; a.tshift = h->tshift;
-    a.flags = w.flags; a.inum = w.inum; a.early = early; a.imax = imax;
+    a.flags = w.flags + 1; a.inum = w.inum; a.early = early; a.imax = imax;
     a.DC = h->DC; a.DV = h->DV; a.xp_col = -1;
     const int T = h->T, TT = T * T;
     // ---- small batches of regular codes: the whole decode in one cooperative launch (ib_coop_n4.cuh)
@@ -744,6 +683,32 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
     return IBLDPC_OK;
 }
 
+// i_num and the input-range flag of the last decode on workspace `w` (synchronises `st`)
+int read_back_status(Workspace& w, cudaStream_t st, int32_t* i_num_host)
+{
+    int host2[2] = {0, 0};
+    CK(cudaMemcpyAsync(&host2[0], w.inum, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&host2[1], w.flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (i_num_host) *i_num_host = host2[0];
+    if (host2[1] != 0)
+        return fail(IBLDPC_E_INVALID, "channel cluster indices must lie in [0, cardinality_T_channel): the decode clamped out-of-range values");
+    return IBLDPC_OK;
+}
+
+int ensure_n4_buffers(ibldpc_decoder* h, Workspace& w, long long B)
+{
+    const long long pitch4 = ((B + 1) / 2 + 15) / 16 * 16;
+    void* p = w.msg;
+    int rc = ensure(&p, &w.msg_bytes, (size_t)h->E * (size_t)pitch4);
+    w.msg = (uint8_t*)p;
+    if (rc) return rc;
+    p = w.ch4;
+    rc = ensure(&p, &w.ch4_bytes, (size_t)h->N * (size_t)pitch4);
+    w.ch4 = (uint8_t*)p;
+    return rc;
+}
+
 int check_decode_args(ibldpc_decoder* h, int64_t B, int imax)
 {
     if (!h) return fail(IBLDPC_E_INVALID, "null handle");
@@ -808,13 +773,13 @@ int decode_llr_padded(ibldpc_decoder* h, Workspace& w, const F* ch, long long pi
             return fail(IBLDPC_E_NOMEM, "cudaMalloc of LLR message arrays failed");
         w.llr_bytes = need;
     }
-    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)std::max(imax, 1), st));
+    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)(std::max(imax, 1) + 1), st));
     LlrArgs a{};
     a.sc = h->d_sc; a.deg_c = h->d_dc; a.tc = h->d_tc; a.sv = h->d_sv; a.deg_v = h->d_dv; a.tv = h->d_tv;
     a.n_var = h->N; a.n_chk = h->M;
     a.ch = ch; a.cin = w.cin; a.vin = w.vin; a.out = out;
     a.pitch = pitch; a.B = (int)B; a.tiles = (int)((pitch + 32 * V - 1) / (32 * V));
-    a.flags = w.flags; a.inum = w.inum; a.early = early; a.imax = imax;
+    a.flags = w.flags + 1; a.inum = w.inum; a.early = early; a.imax = imax;
     h->last_launches = 0;
     auto run_vn = [&](int mode, int it) -> int {
         LlrArgs b = a;
@@ -896,6 +861,8 @@ int decode_llr_typed(ibldpc_decoder* h, int algo, const F* ch, int64_t B, int im
                                     : decode_llr_padded<F, 1>(h, w, chp, pitch, B, imax, early, outp, st);
     if (rc) return rc;
     if (!aligned && (rc = launch_unpad<F>(outp, out, h->N, B, pitch, st))) return rc;
+    h->last_stream = st;
+    h->last_ws = 0;
     if (i_num_host) {
         CK(cudaMemcpyAsync(i_num_host, w.inum, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -911,7 +878,8 @@ int quantize_common(int device, const double* x_dev, int64_t n, const double* li
     if (out_kind != 3 && !limits_host) return fail(IBLDPC_E_INVALID, "limits missing");
     if ((out_kind == 1 || out_kind == 2) && !llr_host) return fail(IBLDPC_E_INVALID, "LLR vector missing");
     if (n == 0) return IBLDPC_OK;
-    CK(cudaSetDevice(device));
+    DeviceGuard guard_(device);
+    CK(guard_.err);
     cudaStream_t st = (cudaStream_t)stream;
     double* d_tab = nullptr;
     CK(cudaMallocAsync((void**)&d_tab, sizeof(double) * 2 * card, st));
@@ -938,7 +906,8 @@ int count_errors_common(int device, const E* out_dev, int64_t rows, int64_t B, E
                         int64_t* counters_host, int64_t* counters_dev, void* stream)
 {
     if (!out_dev || (!counters_host && !counters_dev) || rows < 0 || B <= 0) return fail(IBLDPC_E_INVALID, "bad arguments");
-    CK(cudaSetDevice(device));
+    DeviceGuard guard_(device);
+    CK(guard_.err);
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* d_cnt = (unsigned long long*)counters_dev;   // async variant: accumulate in place
     int* d_fe = nullptr;
@@ -966,6 +935,22 @@ int count_errors_common(int device, const E* out_dev, int64_t rows, int64_t B, E
     return IBLDPC_OK;
 }
 
+}  // namespace
+
+namespace {
+template <typename Fn>
+void parallel_rows(int64_t rows, int nthreads, Fn fn)
+{
+    nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, rows));
+    if (nthreads == 1) { fn(0, rows); return; }
+    std::vector<std::thread> pool;
+    const int64_t per = (rows + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        const int64_t lo = t * per, hi = std::min<int64_t>(rows, lo + per);
+        if (lo < hi) pool.emplace_back([=] { fn(lo, hi); });
+    }
+    for (auto& th : pool) th.join();
+}
 }  // namespace
 
 // ==========================================================================================
@@ -1008,7 +993,8 @@ int ibldpc_create(const ibldpc_code_desc* code, int device, ibldpc_handle* out)
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(IBLDPC_E_INVALID, "no such CUDA device");
-    CK(cudaSetDevice(device));
+    DeviceGuard guard_(device);
+    CK(guard_.err);
     ibldpc_decoder* h = new ibldpc_decoder();
     h->device = device;
     h->N = N; h->M = M; h->E = E;
@@ -1078,8 +1064,12 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
         if ((rc = to_u8(L->cn_match, (long long)imax * DC * T, mc, "matching_vector_checknode"))) return rc;
         if ((rc = to_u8(L->vn_match, (long long)imax * DV * T, mv, "matching_vector_varnode"))) return rc;
     }
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
+    CK(guard_.err);
     CK(cudaDeviceSynchronize());
+    // from here on the old tables are gone: a failure below must not leave a decodable handle behind
+    h->have_luts = false;
+    h->fast = h->nib = h->t32 = false;
     for (uint8_t** p : {&h->d_cn8, &h->d_vn8, &h->d_mc8, &h->d_mv8}) {
         if (*p) CK(cudaFree(*p));
         *p = nullptr;
@@ -1181,7 +1171,8 @@ int ibldpc_decode_ib(ibldpc_handle h, const uint8_t* ch_dev, int64_t B, int imax
     int rc = check_decode_args(h, B, imax);
     if (rc) return rc;
     if (!ch_dev || !out_dev) return fail(IBLDPC_E_INVALID, "null buffer");
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
+    CK(guard_.err);
     cudaStream_t st = (cudaStream_t)stream;
     Workspace& w = h->ws[0];
     if (h->profiling) clear_events(h);
@@ -1196,11 +1187,18 @@ int ibldpc_decode_ib(ibldpc_handle h, const uint8_t* ch_dev, int64_t B, int imax
         if ((rc = decode_ib_padded(h, w, w.padbuf_in, pitch, B, imax, early_term, w.padbuf_out, st))) return rc;
         if ((rc = launch_unpad<uint8_t>(w.padbuf_out, out_dev, h->N, B, pitch, st))) return rc;
     }
-    if (i_num_host) {
-        CK(cudaMemcpyAsync(i_num_host, w.inum, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-    }
+    if (i_num_host) return read_back_status(w, st, i_num_host);
     return IBLDPC_OK;
+}
+
+int ibldpc_last_i_num(ibldpc_handle h, int32_t* i_num_host)
+{
+    if (!h || !i_num_host) return fail(IBLDPC_E_INVALID, "null argument");
+    Workspace& w = h->ws[h->last_ws];
+    if (!w.inum) return fail(IBLDPC_E_STATE, "no decode has been issued on this handle");
+    DeviceGuard guard_(h->device);
+    CK(guard_.err);
+    return read_back_status(w, h->last_stream, i_num_host);
 }
 
 int ibldpc_decode_ib_host(ibldpc_handle h, const uint8_t* ch_host, int64_t B, int imax, int early_term,
@@ -1209,7 +1207,8 @@ int ibldpc_decode_ib_host(ibldpc_handle h, const uint8_t* ch_host, int64_t B, in
     int rc = check_decode_args(h, B, imax);
     if (rc) return rc;
     if (!ch_host || !out_host) return fail(IBLDPC_E_INVALID, "null buffer");
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
+    CK(guard_.err);
     // Early termination is a property of the whole call (all B frames), so it cannot be chunked.
     const std::vector<int64_t> widths = host_chunk_schedule(B, h->N, h->host_chunk, early_term != 0);
     int64_t chunk = 0;
@@ -1245,8 +1244,198 @@ int ibldpc_decode_ib_host(ibldpc_handle h, const uint8_t* ch_host, int64_t B, in
         off += wd;
         slot ^= (nslots - 1);
     }
-    for (int s = 0; s < nslots; ++s) CK(cudaStreamSynchronize(h->ws[s].stream));
-    if (i_num_host) CK(cudaMemcpy(i_num_host, h->ws[0].inum, sizeof(int), cudaMemcpyDeviceToHost));
+    for (int s = nslots - 1; s >= 0; --s)
+        if ((rc = read_back_status(h->ws[s], h->ws[s].stream, s == 0 ? i_num_host : nullptr))) return rc;
+    return IBLDPC_OK;
+}
+
+// ---- packed host buffers: nibble-packed channel values in, bit-packed hard decisions of the first `rows` rows out
+int ibldpc_decode_ib_host_packed(ibldpc_handle h, const uint8_t* ch4_host, int64_t B, int imax, int early_term,
+                                 uint8_t* bits_host, int64_t rows, int32_t* i_num_host)
+{
+    int rc = check_decode_args(h, B, imax);
+    if (rc) return rc;
+    if (!ch4_host || !bits_host) return fail(IBLDPC_E_INVALID, "null buffer");
+    if (rows < 0 || rows > h->N) return fail(IBLDPC_E_INVALID, "rows must lie in [0, n_var]");
+    if (h->T > 16 || h->Tc > 16) return fail(IBLDPC_E_INVALID, "packed host buffers need cardinalities <= 16 (one nibble per cluster index)");
+    DeviceGuard guard_(h->device);
+    CK(guard_.err);
+    const std::vector<int64_t> widths = host_chunk_schedule(B, h->N, h->host_chunk, early_term != 0);
+    int64_t chunk = 0;
+    for (int64_t wdt : widths) chunk = std::max(chunk, wdt);
+    const long long cpitch = (chunk + 15) / 16 * 16;
+    const int nslots = widths.size() > 1 ? 2 : 1;
+    const bool nib = h->fast && h->nib;
+    const size_t src_pitch = (size_t)((B + 1) / 2), dst_pitch = (size_t)((B + 7) / 8);
+    for (int s = 0; s < nslots; ++s) {
+        Workspace& w = h->ws[s];
+        if (!w.stream) CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+        if ((rc = ensure_ws_common(h, w))) return rc;
+        if ((rc = ensure_n4_buffers(h, w, chunk))) return rc;
+        const size_t need = (size_t)h->N * cpitch;
+        if (w.stage_bytes < need) {
+            if (w.stage_in) CK(cudaFree(w.stage_in));
+            if (w.stage_out) CK(cudaFree(w.stage_out));
+            w.stage_in = w.stage_out = nullptr;
+            w.stage_bytes = 0;
+            if (cudaMalloc((void**)&w.stage_in, need) != cudaSuccess || cudaMalloc((void**)&w.stage_out, need) != cudaSuccess)
+                return fail(IBLDPC_E_NOMEM, "cudaMalloc of staging buffers failed");
+            CK(cudaMemset(w.stage_in, 0, need));
+            w.stage_bytes = need;
+        }
+        void* p = w.stage_bits;
+        rc = ensure(&p, &w.stage_bits_bytes, (size_t)std::max<int64_t>(rows, 1) * (size_t)((chunk + 31) / 32) * 4);
+        w.stage_bits = (uint8_t*)p;
+        if (rc) return rc;
+    }
+    if (h->profiling) clear_events(h);
+    int slot = 0;
+    int64_t off = 0;
+    for (int64_t wd : widths) {
+        Workspace& w = h->ws[slot];
+        if (off % 8) return fail(IBLDPC_E_INVALID, "host chunk size must be a multiple of 8 frames");
+        const long long pitch = (wd + 15) / 16 * 16;
+        const long long pitch4 = ((wd + 1) / 2 + 15) / 16 * 16;
+        CK(cudaMemcpy2DAsync(w.ch4, (size_t)pitch4, ch4_host + off / 2, src_pitch, (size_t)((wd + 1) / 2), (size_t)h->N,
+                             cudaMemcpyHostToDevice, w.stream));
+        if (nib) {
+            if ((rc = decode_ib_padded(h, w, nullptr, pitch, wd, imax, early_term, w.stage_out, w.stream, true))) return rc;
+        } else {
+            const long long n = (long long)h->N * pitch;
+            unpack_n4_kernel<<<(int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 16), 256, 0, w.stream>>>(
+                w.ch4, w.stage_in, h->N, wd, pitch, (uint32_t)pitch4);
+            if ((rc = decode_ib_padded(h, w, w.stage_in, pitch, wd, imax, early_term, w.stage_out, w.stream))) return rc;
+        }
+        if (rows > 0) {
+            const long long wpr = (wd + 31) / 32;
+            const long long n = rows * wpr;
+            harddecision_bits_kernel<<<(int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 16), 256, 0, w.stream>>>(
+                w.stage_out, (int)rows, wd, pitch, h->T / 2, reinterpret_cast<uint32_t*>(w.stage_bits), wpr);
+            h->last_launches++;
+            CK(cudaMemcpy2DAsync(bits_host + off / 8, dst_pitch, w.stage_bits, (size_t)wpr * 4, (size_t)((wd + 7) / 8), (size_t)rows,
+                                 cudaMemcpyDeviceToHost, w.stream));
+        }
+        off += wd;
+        slot ^= (nslots - 1);
+    }
+    CK(cudaGetLastError());
+    for (int s = nslots - 1; s >= 0; --s)
+        if ((rc = read_back_status(h->ws[s], h->ws[s].stream, s == 0 ? i_num_host : nullptr))) return rc;
+    return IBLDPC_OK;
+}
+
+// ---- the reference's own host contract: int32 cluster indices in, int32 cluster indices out
+// (discrete_LDPC_decoder.py:207-209 uploads received_blocks.astype(np.int32), :292-295 returns the int32 output).
+// The narrowing to uint8 / widening to int32 runs on host threads, chunk by chunk, into pinned staging buffers,
+// overlapped with the copies and the decode of the neighbouring chunk.
+
+int ibldpc_decode_ib_host_i32(ibldpc_handle h, const int32_t* ch_host, int64_t B, int imax, int early_term,
+                              int32_t* out_host, int32_t* i_num_host)
+{
+    int rc = check_decode_args(h, B, imax);
+    if (rc) return rc;
+    if (!ch_host || !out_host) return fail(IBLDPC_E_INVALID, "null buffer");
+    DeviceGuard guard_(h->device);
+    CK(guard_.err);
+    const std::vector<int64_t> widths = host_chunk_schedule(B, h->N, h->host_chunk, early_term != 0);
+    int64_t chunk = 0;
+    for (int64_t wdt : widths) chunk = std::max(chunk, wdt);
+    const long long cpitch = (chunk + 15) / 16 * 16;
+    const int nslots = widths.size() > 1 ? 2 : 1;
+    const size_t need = (size_t)h->N * cpitch;
+    for (int s = 0; s < nslots; ++s) {
+        Workspace& w = h->ws[s];
+        if (!w.stream) CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+        if (!w.done_ev) CK(cudaEventCreateWithFlags(&w.done_ev, cudaEventDisableTiming));
+        if (w.stage_bytes < need) {
+            if (w.stage_in) CK(cudaFree(w.stage_in));
+            if (w.stage_out) CK(cudaFree(w.stage_out));
+            w.stage_in = w.stage_out = nullptr;
+            w.stage_bytes = 0;
+            if (cudaMalloc((void**)&w.stage_in, need) != cudaSuccess || cudaMalloc((void**)&w.stage_out, need) != cudaSuccess)
+                return fail(IBLDPC_E_NOMEM, "cudaMalloc of staging buffers failed");
+            CK(cudaMemset(w.stage_in, 0, need));
+            w.stage_bytes = need;
+        }
+        if (w.pin_bytes < need) {
+            if (w.pin_in) CK(cudaFreeHost(w.pin_in));
+            if (w.pin_out) CK(cudaFreeHost(w.pin_out));
+            w.pin_in = w.pin_out = nullptr;
+            w.pin_bytes = 0;
+            if (cudaHostAlloc((void**)&w.pin_in, need, cudaHostAllocDefault) != cudaSuccess ||
+                cudaHostAlloc((void**)&w.pin_out, need, cudaHostAllocDefault) != cudaSuccess)
+                return fail(IBLDPC_E_NOMEM, "cudaHostAlloc of pinned staging buffers failed");
+            w.pin_bytes = need;
+        }
+    }
+    if (h->profiling) clear_events(h);
+    static const int nthreads = [] {
+        if (const char* e = getenv("IBLDPC_HOST_THREADS")) return std::max(1, atoi(e));
+        return (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    }();
+    const int N = h->N, Tc = h->Tc;
+    struct Pending { bool busy = false; int64_t off = 0, wd = 0; long long pitch = 0; };
+    Pending pend[2];
+    auto drain = [&](int s) -> int {
+        Pending& q = pend[s];
+        if (!q.busy) return IBLDPC_OK;
+        Workspace& w = h->ws[s];
+        CK(cudaEventSynchronize(w.done_ev));
+        const uint8_t* src = w.pin_out;
+        const int64_t off = q.off, wd = q.wd;
+        const long long pitch = q.pitch;
+        parallel_rows(N, nthreads, [=](int64_t lo, int64_t hi) {
+            for (int64_t r = lo; r < hi; ++r) {
+                const uint8_t* a = src + r * pitch;
+                int32_t* o = out_host + r * B + off;
+                for (int64_t f = 0; f < wd; ++f) o[f] = a[f];
+            }
+        });
+        q.busy = false;
+        return IBLDPC_OK;
+    };
+    int slot = 0;
+    int64_t off = 0;
+    for (int64_t wd : widths) {
+        Workspace& w = h->ws[slot];
+        if ((rc = drain(slot))) return rc;
+        const long long pitch = (wd + 15) / 16 * 16;
+        std::vector<int> bad((size_t)nthreads + 1, 0);
+        uint8_t* dst = w.pin_in;
+        int* badp = bad.data();
+        const int64_t per = (N + nthreads - 1) / nthreads;
+        parallel_rows(N, nthreads, [=](int64_t lo, int64_t hi) {
+            int any = 0;
+            for (int64_t r = lo; r < hi; ++r) {
+                const int32_t* a = ch_host + r * B + off;
+                uint8_t* o = dst + r * pitch;
+                for (int64_t f = 0; f < wd; ++f) {
+                    const int32_t v = a[f];
+                    any |= (v < 0) | (v >= Tc);
+                    o[f] = (uint8_t)v;
+                }
+                for (int64_t f = wd; f < pitch; ++f) o[f] = 0;
+            }
+            badp[lo / per] = any;
+        });
+        for (int b : bad)
+            if (b) {
+                for (int s = 0; s < nslots; ++s) cudaStreamSynchronize(h->ws[s].stream);
+                return fail(IBLDPC_E_INVALID, "channel cluster indices must lie in [0, cardinality_T_channel)");
+            }
+        CK(cudaMemcpyAsync(w.stage_in, w.pin_in, (size_t)N * pitch, cudaMemcpyHostToDevice, w.stream));
+        if ((rc = decode_ib_padded(h, w, w.stage_in, pitch, wd, imax, early_term, w.stage_out, w.stream))) return rc;
+        CK(cudaMemcpyAsync(w.pin_out, w.stage_out, (size_t)N * pitch, cudaMemcpyDeviceToHost, w.stream));
+        CK(cudaEventRecord(w.done_ev, w.stream));
+        pend[slot].busy = true; pend[slot].off = off; pend[slot].wd = wd; pend[slot].pitch = pitch;
+        off += wd;
+        slot ^= (nslots - 1);
+    }
+    // drain in issue order: `slot` now names the older of the two pending chunks
+    if ((rc = drain(slot))) return rc;
+    if (nslots > 1 && (rc = drain(slot ^ 1))) return rc;
+    for (int s = nslots - 1; s >= 0; --s)
+        if ((rc = read_back_status(h->ws[s], h->ws[s].stream, s == 0 ? i_num_host : nullptr))) return rc;
     return IBLDPC_OK;
 }
 
@@ -1258,7 +1447,8 @@ int ibldpc_decode_llr(ibldpc_handle h, int algo, int dtype, const void* ch_dev, 
     if (B <= 0 || B > 0x7fffffffLL - 1024) return fail(IBLDPC_E_INVALID, "bad B");
     if (imax < 1 || imax >= kMaxIter) return fail(IBLDPC_E_INVALID, "imax out of range");
     if (algo != IBLDPC_ALGO_MINSUM && algo != IBLDPC_ALGO_BP) return fail(IBLDPC_E_INVALID, "unknown algorithm");
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
+    CK(guard_.err);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == IBLDPC_F32)
         return decode_llr_typed<float>(h, algo, (const float*)ch_dev, B, imax, early_term, (float*)out_dev, i_num_host, st);
@@ -1289,6 +1479,17 @@ int ibldpc_count_errors_llr(int device, const void* out_dev, int dtype, int64_t 
         return count_errors_common<float>(device, (const float*)out_dev, rows, B, 0.f, ref_bits_dev, counters_host, nullptr, stream);
     if (dtype == IBLDPC_F64)
         return count_errors_common<double>(device, (const double*)out_dev, rows, B, 0.0, ref_bits_dev, counters_host, nullptr, stream);
+    return fail(IBLDPC_E_INVALID, "dtype must be IBLDPC_F32 or IBLDPC_F64");
+}
+
+int ibldpc_count_errors_llr_async(int device, const void* out_dev, int dtype, int64_t rows, int64_t B,
+                                  const uint8_t* ref_bits_dev, int64_t* counters_dev, void* stream)
+{
+    if (!counters_dev) return fail(IBLDPC_E_INVALID, "null device counters");
+    if (dtype == IBLDPC_F32)
+        return count_errors_common<float>(device, (const float*)out_dev, rows, B, 0.f, ref_bits_dev, nullptr, counters_dev, stream);
+    if (dtype == IBLDPC_F64)
+        return count_errors_common<double>(device, (const double*)out_dev, rows, B, 0.0, ref_bits_dev, nullptr, counters_dev, stream);
     return fail(IBLDPC_E_INVALID, "dtype must be IBLDPC_F32 or IBLDPC_F64");
 }
 
@@ -1353,7 +1554,8 @@ int ibldpc_set_host_chunk(ibldpc_handle h, int frames)
 int ibldpc_phase_times(ibldpc_handle h, float* ms3, int32_t* launches3)
 {
     if (!h || !ms3 || !launches3) return fail(IBLDPC_E_INVALID, "null argument");
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
+    CK(guard_.err);
     CK(cudaDeviceSynchronize());
     for (int i = 0; i < 3; ++i) { ms3[i] = 0.f; launches3[i] = 0; }
     for (auto& e : h->events) {
@@ -1387,8 +1589,9 @@ int ibldpc_host_chunk_schedule(int64_t B, int64_t n_var, int64_t host_chunk, int
 int ibldpc_destroy(ibldpc_handle h)
 {
     if (!h) return IBLDPC_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard_(h->device);
     cudaDeviceSynchronize();
+    ibldpc_nccl_finalize(h);
     clear_events(h);
     for (int* p : {h->d_sc, h->d_dc, h->d_tc, h->d_sv, h->d_dv, h->d_tv, h->d_vidx})
         if (p) cudaFree(p);
@@ -1400,6 +1603,11 @@ int ibldpc_destroy(ibldpc_handle h)
         for (void* p : {(void*)w.msg, (void*)w.ch4, w.cin, w.vin, (void*)w.padbuf_in, (void*)w.padbuf_out, (void*)w.stage_in,
                         (void*)w.stage_out, (void*)w.flags, (void*)w.inum})
             if (p) cudaFree(p);
+        for (void* p : {(void*)w.stage_bits, (void*)w.pf_msg2, (void*)w.pf_ch2, (void*)w.pf_idx})
+            if (p) cudaFree(p);
+        if (w.pin_in) cudaFreeHost(w.pin_in);
+        if (w.pin_out) cudaFreeHost(w.pin_out);
+        if (w.done_ev) cudaEventDestroy(w.done_ev);
         if (w.stream) cudaStreamDestroy(w.stream);
         if (w.fork_ev) cudaEventDestroy(w.fork_ev);
         for (int i = 0; i < 7; ++i) {

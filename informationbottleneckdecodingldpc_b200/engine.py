@@ -113,9 +113,36 @@ class GraphDecoderBase:
             t = t[:, None]
         if t.shape[0] != self.N_v:
             raise ValueError(f"expected {self.N_v} rows (variable nodes), got {t.shape[0]}")
+        if self._handle_device is not None and t.device.index != self._handle_device:
+            raise ValueError(f"buffer lives on cuda:{t.device.index} but this decoder was initialised on "
+                             f"cuda:{self._handle_device} (one decoder object per GPU)")
         if t.dtype != torch_dtype:
+            if torch_dtype == torch.uint8 and t.numel():
+                # cluster indices handed over as int32 / int64 like the reference's buffers: a value outside
+                # [0, |T_channel|) must not wrap around in the uint8 cast (uint8 buffers are range-checked on the
+                # device by the decode itself)
+                lo, hi = int(t.min()), int(t.max())
+                if lo < 0 or hi >= int(getattr(self, "cardinality_T_channel", 256)):
+                    raise ValueError("channel cluster indices must lie in [0, cardinality_T_channel)")
             t = t.to(torch_dtype)
         return t.contiguous()
+
+    # ---- i_num of the last decode, read back lazily ------------------------------------------
+    @property
+    def last_i_num(self):
+        """The reference's ``i_num`` of the last decode.  Device-buffer decodes are asynchronous: the value is read
+        back (one stream synchronisation) only when this attribute is looked at."""
+        if getattr(self, "_inum_pending", False):
+            v = C.c_int32(0)
+            self._inum_pending = False
+            _lib.check(_lib.lib().ibldpc_last_i_num(self._handle, C.byref(v)))
+            self._last_i_num = int(v.value)
+        return getattr(self, "_last_i_num", None)
+
+    @last_i_num.setter
+    def last_i_num(self, value):
+        self._inum_pending = False
+        self._last_i_num = value
 
 
 def count_errors(buf, rows: int, threshold=None, ref_bits=None):
@@ -146,19 +173,27 @@ def count_errors(buf, rows: int, threshold=None, ref_bits=None):
 
 
 def count_errors_async(buf, rows: int, threshold: int, counters: torch.Tensor, ref_bits=None) -> None:
-    """Asynchronous twin for cluster buffers: ``counters`` is an int64 CUDA tensor whose elements 0/1
+    """Asynchronous twin (cluster or LLR buffers): ``counters`` is an int64 CUDA tensor whose elements 0/1
     are incremented by the bit / frame errors on the current stream; nothing is read back."""
     t = as_tensor(buf)
     if t.dim() == 1:
         t = t[:, None]
     t = t.contiguous()
-    if t.dtype != torch.uint8 or counters.dtype != torch.int64 or not counters.is_cuda or counters.numel() < 2:
-        raise TypeError("count_errors_async needs a uint8 buffer and an int64 CUDA counter tensor")
+    if counters.dtype != torch.int64 or not counters.is_cuda or counters.numel() < 2:
+        raise TypeError("count_errors_async needs an int64 CUDA counter tensor")
     ref_ptr = None
     if ref_bits is not None:
         r = as_tensor(ref_bits).to(torch.uint8).contiguous()
         ref_ptr = C.c_void_p(r.data_ptr())
     dev = t.device.index if t.device.index is not None else current_device()
-    _lib.check(_lib.lib().ibldpc_count_errors_u8_async(dev, C.c_void_p(t.data_ptr()), int(min(rows, t.shape[0])), t.shape[1],
-                                                       int(threshold), ref_ptr, C.c_void_p(counters.data_ptr()),
-                                                       C.c_void_p(stream_ptr())))
+    if t.dtype == torch.uint8:
+        _lib.check(_lib.lib().ibldpc_count_errors_u8_async(dev, C.c_void_p(t.data_ptr()), int(min(rows, t.shape[0])), t.shape[1],
+                                                           int(threshold), ref_ptr, C.c_void_p(counters.data_ptr()),
+                                                           C.c_void_p(stream_ptr())))
+    elif t.dtype in (torch.float32, torch.float64):   # LLR buffers: bit = (LLR < 0), `threshold` is ignored
+        _lib.check(_lib.lib().ibldpc_count_errors_llr_async(dev, C.c_void_p(t.data_ptr()),
+                                                            _lib.F32 if t.dtype == torch.float32 else _lib.F64,
+                                                            int(min(rows, t.shape[0])), t.shape[1], ref_ptr,
+                                                            C.c_void_p(counters.data_ptr()), C.c_void_p(stream_ptr())))
+    else:
+        raise TypeError(f"unsupported buffer dtype {t.dtype}")

@@ -82,3 +82,60 @@ def allreduce_counters(counters, world: int | None = None):
     t = torch.tensor(vals, dtype=torch.int64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return [int(x) for x in t.tolist()]
+
+
+# ---- the same all-reduce through the C ABI (ibldpc_nccl_*: NCCL bound at run time by libibldpc.so) ----------------
+def nccl_library_path() -> str | None:
+    """Path of the NCCL shared library PyTorch ships (None if it cannot be located): lets libibldpc.so dlopen the
+    very copy the process already uses when the bare soname does not resolve."""
+    import glob
+    base = os.path.dirname(os.path.dirname(torch.__file__))
+    for pat in ("nvidia/nccl/lib/libnccl.so.2", "torch/lib/libnccl.so.2"):
+        hits = glob.glob(os.path.join(base, pat))
+        if hits:
+            return hits[0]
+    return None
+
+
+def init_counter_allreduce(decoder) -> bool:
+    """Create the library-side NCCL communicator of ``decoder``'s handle (``ibldpc_nccl_init``): rank 0 draws the
+    unique id, torch.distributed broadcasts its 128 bytes.  Returns False when there is no process group."""
+    import ctypes as C
+    from . import _lib
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return False
+    if "IBLDPC_NCCL_LIB" not in os.environ:
+        p = nccl_library_path()
+        if p:
+            os.environ["IBLDPC_NCCL_LIB"] = p
+    L = _lib.lib()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ident = (C.c_uint8 * 128)()
+    if rank == 0:
+        _lib.check(L.ibldpc_nccl_unique_id(ident))
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+    _lib.check(L.ibldpc_nccl_init(decoder._ensure_handle(), ident, rank, world))
+    decoder._nccl_ready = True
+    return True
+
+
+def counter_allreduce_fn(decoder):
+    """In-place sum of an int64 CUDA counter tensor over all ranks, on the current stream.  Uses the library's own
+    communicator (C ABI) when IBLDPC_ABI_ALLREDUCE=1 or the decoder's communicator is already initialised, else
+    torch.distributed (the plumbing default)."""
+    import ctypes as C
+    from . import _lib
+    use_abi = getattr(decoder, "_nccl_ready", False) or os.environ.get("IBLDPC_ABI_ALLREDUCE") == "1"
+    if use_abi and not getattr(decoder, "_nccl_ready", False):
+        use_abi = init_counter_allreduce(decoder)
+    if not use_abi:
+        return lambda c: dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    L = _lib.lib()
+
+    def fn(c):
+        _lib.check(L.ibldpc_allreduce_counters(decoder._ensure_handle(), C.c_void_p(c.data_ptr()), int(c.numel()),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return fn

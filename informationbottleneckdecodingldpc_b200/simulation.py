@@ -28,6 +28,13 @@ def ber_point(decoder, quantizer, msg_at_time: int, min_errors: int = 7000, max_
     rows = N if (count_all_rows or (count_all_rows is None and not irregular)) else int(decoder.data_len)
     thr = int(getattr(decoder, "cardinality_T_decoder_ops", 2) / 2)
     totals = torch.zeros(4, dtype=torch.int64, device="cuda")
+    base = torch.tensor([0, 0, msg_at_time, 0], dtype=torch.int64, device="cuda")
+    if world > 1:
+        # every rank draws its own channel realisations: sub-stream = rank unless the caller chose one
+        if getattr(quantizer, "_stream", 0) is None:
+            quantizer.set_stream(dist.get_rank())
+        from .parallel import counter_allreduce_fn
+        allreduce = counter_allreduce_fn(decoder)
     pending = None          # (event, pinned host copy) of the previous batch's running totals
     host = torch.zeros(4, dtype=torch.int64).pin_memory()
     side = torch.cuda.Stream()
@@ -37,18 +44,13 @@ def ber_point(decoder, quantizer, msg_at_time: int, min_errors: int = 7000, max_
         if llr:
             rec = quantizer.quantize_direct_OpenCL_LLR(N, msg_at_time)
             out = decoder.decode(rec, buffer_in=True, return_buffer=True)
-            c = torch.zeros(4, dtype=torch.int64, device="cuda")
-            neg = (out.tensor[:rows] < 0)
-            c[0] = neg.sum()
-            c[1] = neg.any(dim=0).sum()
         else:
             rec = quantizer.quantize_direct_OpenCL(N, msg_at_time)
             out = decoder.decode_OpenCL(rec, buffer_in=True, return_buffer=True)
-            c = torch.zeros(4, dtype=torch.int64, device="cuda")
-            count_errors_async(out, rows, thr, c)
-        c[2] += msg_at_time
+        c = base.clone()                         # {0, 0, msg_at_time, 0}
+        count_errors_async(out, rows, thr, c)    # library kernel for cluster and LLR buffers alike
         if world > 1:
-            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            allreduce(c)
         totals.add_(c)
         # read back the totals of the previous batch (already complete) without stalling this one
         if pending is not None:

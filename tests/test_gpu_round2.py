@@ -1,0 +1,283 @@
+"""GPU suite, round 2 additions: packed / int32 host contracts, lazy i_num, input-range reporting, asynchronous LLR
+error counters, the C-ABI counter all-reduce, the pipelined multi-GPU BER loop and the timed bench geometry."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from informationbottleneckdecodingldpc_b200 import codes, graph, luts
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_ib(t, ch, T, imax, tb, early):
+    from oracle import oracle
+    return oracle.ib_decode(t, ch, T=T, imax=imax, cn_lut=tb.Trellis_checknodevector_a, vn_lut=tb.Trellis_varnodevector_a,
+                            cn_match=tb.matching_vector_checknode, vn_match=tb.matching_vector_varnode, early=early)
+
+
+def _wlan_decoder(T=16, imax=6, B=64, seed=3):
+    import informationbottleneckdecodingldpc_b200 as pkg
+    H = codes.wlan_80211n(54)
+    t = graph.edge_tables(H)
+    tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=seed, matching=True)
+    dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                    tb.matching_vector_checknode, tb.matching_vector_varnode, B)
+    dec.init_OpenCL_decoding(B)
+    return H, t, tb, dec
+
+
+@pytest.mark.parametrize("B,chunk", [(100, 0), (777, 0), (9001, 0), (5000, 1008), (64, 0)])
+def test_packed_host_contract_matches_oracle(gpu, B, chunk):
+    """nibble-packed channel values in, bit-packed hard decisions of the first data_len rows out."""
+    from informationbottleneckdecodingldpc_b200 import _lib
+    H, t, tb, dec = _wlan_decoder(B=B)
+    dec.early_termination = False
+    rng = np.random.Generator(np.random.PCG64(B))
+    ch = rng.integers(0, 16, size=(t.n_var, B)).astype(np.uint8)
+    if chunk:
+        _lib.check(_lib.lib().ibldpc_set_host_chunk(dec._ensure_handle(), chunk))
+    packed = dec.pack_channel_values(ch)
+    assert packed.shape == (t.n_var, (B + 1) // 2)
+    bits = dec.unpack_bits(dec.decode_packed(packed, B), B)
+    sel = np.r_[0:min(B, 8), max(B - 8, 0):B]
+    ref, _ = _oracle_ib(t, np.ascontiguousarray(ch[:, sel]), 16, 6, tb, False)
+    rows = int(dec.data_len)
+    assert bits.shape == (rows, B)
+    assert np.array_equal(bits[:, sel], (ref[:rows] < 8).astype(np.uint8))
+    # and against the device-buffer path on every frame
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    out = dec.decode_OpenCL(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True).get()
+    assert np.array_equal(bits, (out[:rows] < 8).astype(np.uint8))
+
+
+def test_packed_host_contract_early_termination_and_uint8_family(gpu, monkeypatch):
+    H, t, tb, dec = _wlan_decoder(B=48)
+    tbm = luts.minsum_like_tables(16, t.d_c_max, t.d_v_max, 6)
+    dec.update_trellis_vectors(tbm.Trellis_checknodevector_a, tbm.Trellis_varnodevector_a)
+    dec.matching_vector_checknode, dec.matching_vector_varnode = tbm.matching_vector_checknode, tbm.matching_vector_varnode
+    ch = np.full((t.n_var, 48), 15, dtype=np.uint8)       # strongly "bit 0": converges at once
+    bits = dec.unpack_bits(dec.decode_packed(dec.pack_channel_values(ch), 48), 48)
+    ref, inum = _oracle_ib(t, ch, 16, 6, tbm, True)
+    assert dec.last_i_num == inum and not bits.any()
+    monkeypatch.setenv("IBLDPC_NO_NIBBLE", "1")            # uint8 family: the library unpacks on the device
+    H, t, tb, dec2 = _wlan_decoder(B=48)
+    rng = np.random.Generator(np.random.PCG64(9))
+    ch = rng.integers(0, 16, size=(t.n_var, 48)).astype(np.uint8)
+    bits = dec2.unpack_bits(dec2.decode_packed(dec2.pack_channel_values(ch), 48), 48)
+    ref, _ = _oracle_ib(t, ch, 16, 6, tb, True)
+    assert dec2.info()[0] == 1
+    assert np.array_equal(bits, (ref[:int(dec2.data_len)] < 8).astype(np.uint8))
+
+
+@pytest.mark.parametrize("B", [1, 33, 1000, 9001])
+def test_int32_host_contract(gpu, B):
+    """The reference's own contract: int numpy in -> int32 numpy out (discrete_LDPC_decoder.py:207-209, :292-295)."""
+    H, t, tb, dec = _wlan_decoder(B=B)
+    dec.early_termination = True
+    rng = np.random.Generator(np.random.PCG64(B))
+    ch = rng.integers(0, 16, size=(t.n_var, B)).astype(np.int32)
+    out = dec.decode_OpenCL(ch)
+    assert out.dtype == np.int32 and out.shape == ch.shape
+    sel = np.arange(B) if B <= 64 else np.r_[0:8, B - 8:B]
+    if B <= 64:
+        ref, inum = _oracle_ib(t, ch, 16, 6, tb, True)
+        assert dec.last_i_num == inum
+        assert np.array_equal(out, ref)
+    else:
+        dec.early_termination = False
+        out = dec.decode_OpenCL(ch.astype(np.int64))        # int64 (quantize_on_host output) takes the same path
+        ref, _ = _oracle_ib(t, np.ascontiguousarray(ch[:, sel]), 16, 6, tb, False)
+        assert np.array_equal(out[:, sel], ref)
+    bad = ch.copy()
+    bad[5, B // 2] = 16
+    with pytest.raises(ValueError):
+        dec.decode_OpenCL(bad)
+    bad[5, B // 2] = -1
+    with pytest.raises(ValueError):
+        dec.decode_OpenCL(bad)
+
+
+def test_out_of_range_cluster_indices_are_reported_not_dereferenced(gpu, monkeypatch):
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    for env in ({}, {"IBLDPC_NO_NIBBLE": "1"}, {"IBLDPC_FORCE_GENERIC": "1"}):
+        for k in ("IBLDPC_NO_NIBBLE", "IBLDPC_FORCE_GENERIC"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        H, t, tb, dec = _wlan_decoder(B=40)
+        ch = np.zeros((t.n_var, 40), dtype=np.uint8)
+        ch[7, 3] = 200
+        with pytest.raises(ValueError):
+            dec.decode_OpenCL(ch)                                        # host uint8 path
+        out = dec.decode_OpenCL(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True)
+        with pytest.raises(RuntimeError):
+            dec.last_i_num                                               # device path: reported at the lazy read-back
+        torch.cuda.synchronize()                                         # and the context is still healthy
+        ch[7, 3] = 1
+        dec.decode_OpenCL(ch)
+        with pytest.raises(ValueError):                                  # int32 device buffers are checked before the cast
+            dec.decode_OpenCL(pkg.DeviceArray(torch.full((t.n_var, 8), 300, dtype=torch.int32, device="cuda")), buffer_in=True)
+        del out
+
+
+def test_device_buffer_decode_is_asynchronous_and_i_num_is_lazy(gpu):
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    H = codes.regular_random(8000, 3, 6)
+    t = graph.edge_tables(H)
+    tb = luts.minsum_like_tables(16, 6, 3, 50)
+    dec = pkg.Discrete_LDPC_Decoder_class(H, 50, 16, 16, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a, 8192)
+    dec.init_OpenCL_decoding(8192)
+    rng = np.random.Generator(np.random.PCG64(1))
+    ch = pkg.DeviceArray(torch.from_numpy(rng.integers(0, 16, size=(8000, 8192)).astype(np.uint8)).cuda())
+    dec.decode_OpenCL(ch, buffer_in=True, return_buffer=True)            # warm-up (allocations)
+    torch.cuda.synchronize()
+    ev = torch.cuda.Event()
+    dec.decode_OpenCL(ch, buffer_in=True, return_buffer=True)            # early termination on (class default)
+    ev.record()
+    assert not ev.query(), "decode_OpenCL(buffer_in=True, return_buffer=True) must not synchronise the stream"
+    assert dec._inum_pending
+    assert 2 <= dec.last_i_num <= 50 and not dec._inum_pending
+
+
+def test_llr_async_error_counters(gpu):
+    import torch
+    from informationbottleneckdecodingldpc_b200.engine import count_errors, count_errors_async
+    rng = np.random.Generator(np.random.PCG64(2))
+    for dt in (np.float32, np.float64):
+        x = rng.normal(1.0, 1.0, size=(100, 333)).astype(dt)
+        t = torch.from_numpy(x).cuda()
+        c = torch.tensor([5, 7, 0, 0], dtype=torch.int64, device="cuda")
+        count_errors_async(t, 60, 0, c)
+        count_errors_async(t, 60, 0, c)
+        bit, frame = int((x[:60] < 0).sum()), int((x[:60] < 0).any(axis=0).sum())
+        assert c.tolist() == [5 + 2 * bit, 7 + 2 * frame, 0, 0]
+        assert count_errors(t, 60) == (bit, frame)
+
+
+def test_cabi_counter_allreduce_single_rank(gpu):
+    """ibldpc_nccl_unique_id / _init / ibldpc_allreduce_counters with a one-rank communicator (the 2-rank case is
+    covered by test_ber_point_two_ranks when two GPUs are visible)."""
+    import torch
+    from informationbottleneckdecodingldpc_b200 import _lib
+    from informationbottleneckdecodingldpc_b200.parallel import nccl_library_path
+    p = nccl_library_path()
+    if p:
+        os.environ.setdefault("IBLDPC_NCCL_LIB", p)
+    H, t, tb, dec = _wlan_decoder(B=16)
+    L = _lib.lib()
+    ident = (C.c_uint8 * 128)()
+    _lib.check(L.ibldpc_nccl_unique_id(ident))
+    assert any(ident)
+    h = dec._ensure_handle()
+    c = torch.tensor([3, 1, 16, 96], dtype=torch.int64, device="cuda")
+    assert L.ibldpc_allreduce_counters(h, C.c_void_p(c.data_ptr()), 4, None) < 0      # before init: state error
+    _lib.check(L.ibldpc_nccl_init(h, ident, 0, 1))
+    _lib.check(L.ibldpc_allreduce_counters(h, C.c_void_p(c.data_ptr()), 4, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert c.tolist() == [3, 1, 16, 96]
+    _lib.check(L.ibldpc_nccl_finalize(h))
+
+
+def test_philox_substreams_differ_on_the_device(gpu):
+    import informationbottleneckdecodingldpc_b200 as pkg
+    qs = []
+    for stream in (0, 1, 2):
+        q = pkg.AWGN_Channel_Quantizer(0.8, 3, 16, 2000)
+        q.set_stream(stream)
+        q.init_OpenCL_quanti(64, 256, return_buffer_only=True)
+        qs.append(q.quantize_direct_OpenCL(64, 256).get())
+    assert not np.array_equal(qs[0], qs[1]) and not np.array_equal(qs[1], qs[2])
+    assert abs(float((qs[0] == qs[1]).mean()) - float((qs[0] == np.roll(qs[0], 1, axis=1)).mean())) < 0.03   # independent draws
+    q = pkg.AWGN_Channel_Quantizer(0.8, 3, 16, 2000)
+    q.init_OpenCL_quanti(64, 256, return_buffer_only=True)           # no process group: stream 0 = the seed itself
+    assert np.array_equal(q.quantize_direct_OpenCL(64, 256).get(), qs[0])
+
+
+def _ber_setup(llr):
+    import informationbottleneckdecodingldpc_b200 as pkg
+    from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_irregular_config
+    H = codes.wlan_80211n(54)
+    if llr:
+        dec = pkg.Min_Sum_Decoder_class_irregular(H, 20, 16, 512)
+    else:
+        tb, _ = generate_irregular_config(1.0, H, 16, 20)
+        dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, 20, 16, 16, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                        tb.matching_vector_checknode, tb.matching_vector_varnode, 512)
+    q = pkg.AWGN_Channel_Quantizer(10 ** (-1.5 / 10) / (2 * 0.5), 3, 16, 2000)
+    q.init_OpenCL_quanti(1296, 512, return_buffer_only=True)
+    dec.init_OpenCL_decoding(512, q.context)
+    return dec, q
+
+
+@pytest.mark.parametrize("llr", [False, True])
+def test_ber_point_equals_the_synchronous_reference_loop(gpu, llr):
+    """simulation.ber_point (pipelined, counters one batch late) against the plain loop of the reference drivers
+    (WLAN/BER_simulation_OpenCL.py:124-131) on the same Philox stream: the pipelined loop decodes the same batches
+    plus at most two more."""
+    from informationbottleneckdecodingldpc_b200.simulation import ber_point
+    dec, q = _ber_setup(llr)
+    min_errors = 400
+    res = ber_point(dec, q, 512, min_errors=min_errors, llr=llr)
+    q.set_stream(0)                                       # rewind the same sub-stream
+    errors, fer, batches, per_batch = 0, 0, 0, []
+    while batches * 512 < res["frames"]:
+        rec = q.quantize_direct_OpenCL_LLR(1296, 512) if llr else q.quantize_direct_OpenCL(1296, 512)
+        out = dec.decode(rec, buffer_in=True, return_buffer=True)
+        b, f = dec.count_errors(out)
+        assert b == dec.return_errors_all_zero(out)
+        errors += b
+        fer += f
+        batches += 1
+        per_batch.append(b)
+    assert (res["bit_errors"], res["frame_errors"], res["frames"]) == (errors, fer, batches * 512)
+    need = next(i + 1 for i in range(batches) if sum(per_batch[:i + 1]) >= min_errors)
+    assert need <= batches <= need + 2, (need, batches)
+    assert abs(res["ber"] - errors / (batches * 512 * int(dec.data_len))) < 1e-12
+
+
+def test_ber_point_two_ranks(gpu):
+    """2-rank torchrun: disjoint sub-streams per rank, NCCL all-reduced counters (once through torch.distributed, once
+    through the library's own communicator), identical totals on both ranks."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = os.path.join(ROOT, "tests", "_ber_two_ranks.py")
+    for abi in ("0", "1"):
+        env = dict(os.environ, IBLDPC_ABI_ALLREDUCE=abi)
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                            "--master-port", "29631", script], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "TWO_RANK_OK" in r.stdout
+
+
+def test_timed_bench_geometry_is_bit_exact(gpu):
+    """The launch plan bench.py times (C1, B = 65536: 1024-thread CTAs, 37 x 4 / 74 x 2 grids) against the oracle on 32
+    columns, and frame independence across the whole batch (every column equals its copy at another position)."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_regular_config
+    H = codes.regular_random(8000, 3, 6)
+    t = graph.edge_tables(H)
+    tb, _ = generate_regular_config(1.2, 3, 6, 16, 50)
+    B = 65536
+    dec = pkg.Discrete_LDPC_Decoder_class(H, 50, 16, 16, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a, B)
+    dec.init_OpenCL_decoding(B)
+    dec.early_termination = False
+    q = pkg.AWGN_Channel_Quantizer(10 ** (-1.6 / 10) / (2 * 0.5), 3, 16, 2000)
+    q.init_OpenCL_quanti(8000, B, return_buffer_only=True)
+    ch = q.quantize_direct_OpenCL(8000, B)
+    # plant copies: columns of the second half repeat those of the first half in reversed order
+    ch.tensor[:, B // 2:] = ch.tensor[:, :B // 2].flip(1)
+    out = dec.decode_OpenCL(ch, buffer_in=True, return_buffer=True)
+    assert torch.equal(out.tensor[:, B // 2:], out.tensor[:, :B // 2].flip(1))
+    cols = np.r_[0:8, 8191:8199, 32760:32776]
+    ref, _ = _oracle_ib(t, ch.tensor[:, torch.from_numpy(cols).cuda()].cpu().numpy(), 16, 50, tb, False)
+    assert np.array_equal(out.tensor[:, torch.from_numpy(cols).cuda()].cpu().numpy(), ref.astype(np.uint8))

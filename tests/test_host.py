@@ -228,7 +228,8 @@ def test_bench_roofline_object_handles_both_launch_schemes():
     spec.loader.exec_module(bench)
     N, E, B = 8000, 24000, 65536
     r = bench.roofline_from_phase_times([23.3, 19.3, 0.6], [49, 49, 4], N, E, B, 50, True, "c1")
-    assert r["kernel"].startswith("ib_cn_n4_kernel") and r["algorithmic_bytes_per_launch"] == 2 * E * B
+    assert r["kernel"].startswith("ib_cn_n4") and r["algorithmic_bytes_per_launch"] == 2 * E * B
+    assert "look-up" in r["bound"] and r["denominator"] == "hbm" and abs(r["frac_stored"] * 2 - r["frac"]) < 1e-12
     assert r["stored_bytes_per_launch"] * 2 == r["algorithmic_bytes_per_launch"]
     assert abs(r["frac"] - r["cn_frac"]) < 1e-12 and r["vn_frac"] > r["cn_frac"]
     assert abs(r["achieved"] - 2 * E * B / (23.3e-3 / 49) / 1e9) < 1e-6
@@ -237,7 +238,8 @@ def test_bench_roofline_object_handles_both_launch_schemes():
     assert r["kernel"].startswith("ib_decode_coop_kernel") and r["cn_frac"] is None and r["cn_avg_ms"] is None
     assert abs(r["achieved"] - 5168000 * 512 / 1e-3 / 1e9) < 1e-6 and r["traffic"] is None
     r = bench.roofline_from_phase_times([10.0, 12.0, 1.0], [49, 49, 4], N, E, B, 50, False, "c1")
-    assert r["kernel"].startswith("ib_vn_fast_kernel") and r["stored_bytes_per_launch"] == (2 * E + N) * B
+    assert r["kernel"].startswith("ib_vn_fast") and r["stored_bytes_per_launch"] == (2 * E + N) * B
+    assert r["whole_decode"]["frac_stored"] == r["whole_decode"]["frac"]
 
 
 def test_product_fails_loudly_without_gpu():
@@ -314,3 +316,35 @@ def test_irregular_design_tool_with_message_alignment():
     mi = ex["ext_mi_varnode_in_iter"]
     assert mi[-1] > 0.95 and mi[-1] > mi[0] + 0.25 and np.all(np.diff(mi) > -1e-6)
     assert abs(ex["lambda_vec"].sum() - 1) < 1e-12 and abs(ex["rho_vec"].sum() - 1) < 1e-12
+
+
+def test_philox_substreams_are_disjoint_per_rank():
+    """every rank of a multi-process BER run must draw its own channel realisations."""
+    from informationbottleneckdecodingldpc_b200 import AWGN_Channel_Quantizer, rng
+    keys = {rng.stream_key(20181001, r) for r in range(64)}
+    assert len(keys) == 64 and rng.stream_key(20181001, 0) == 20181001
+    assert all(0 <= k < 2 ** 64 for k in keys)
+    for seed in (0, 1, 2 ** 63, 2 ** 64 - 1):
+        assert rng.stream_key(seed, 0) == seed and rng.stream_key(seed, 5) != seed
+    a = AWGN_Channel_Quantizer(0.8, 3, 16, 2000, dont_calc=True)
+    b = AWGN_Channel_Quantizer(0.8, 3, 16, 2000, dont_calc=True)
+    a.set_stream(0)
+    b.set_stream(1)
+    assert a._philox_key() != b._philox_key() and a._offset == b._offset == 0
+    c = AWGN_Channel_Quantizer(0.8, 3, 16, 2000, dont_calc=True)
+    assert c._stream is None and c.stream == 0          # no process group here: stream 0
+
+
+def test_run_driver_overrides_and_shadowing():
+    from informationbottleneckdecodingldpc_b200 import run_driver
+    src = "a = 1\nif True:\n    min_errors = 7000\n    x = min_errors == 3\nmin_errors = 9\n"
+    out = run_driver.apply_overrides(src, {"min_errors": 200})
+    assert out == "a = 1\nif True:\n    min_errors = 200\n    x = min_errors == 3\nmin_errors = 9\n"
+    with pytest.raises(KeyError):
+        run_driver.apply_overrides(src, {"nope": 1})
+    run_driver.install_shadow()
+    import importlib
+    m = importlib.import_module("Discrete_LDPC_decoding.discrete_LDPC_decoder_irreg")
+    assert m.Discrete_LDPC_Decoder_class_irregular.__module__.startswith("informationbottleneckdecodingldpc_b200")
+    from AWGN_Channel_Transmission.LDPC_Transmitter import LDPC_BPSK_Transmitter  # noqa: F401
+    from Continous_LDPC_Decoding.min_sum_decoder_irreg import Min_Sum_Decoder_class_irregular  # noqa: F401
