@@ -36,9 +36,19 @@ class LDPC_BPSK_Transmitter(PhiloxStream):
             self.H_sparse = load_check_matrix(str(filename_H_))
         else:
             self.H_sparse = sp.csr_matrix(filename_H_)
-        self.encoder = LDPCEncoder(self.H_sparse)
         self.set_code_parameters()
-        self.data_len = int(self.encoder.K)
+        try:
+            self.encoder = LDPCEncoder(self.H_sparse)
+            self.data_len = int(self.encoder.K)
+        except ValueError as e:
+            # The reference prints 'Not invertible Matrix' and carries on (LDPC_encoder.py:246-247); its all-zero
+            # codeword drivers build a transmitter only to read R_c (Regular_LDPC_Decoding/BPSK/
+            # BER_simulation_OpenCL.py:76,85).  Same here: the object stays usable for the code parameters and
+            # transmit() reports why it cannot encode.
+            print("Not invertible Matrix")
+            self.encoder = None
+            self._encoder_error = str(e)
+            self.data_len = int(self.N_v - self.N_c)
         self.last_transmitted_bits = []
         self.msg_at_time = int(msg_at_time)
         self.return_buffer_only = False
@@ -68,6 +78,8 @@ class LDPC_BPSK_Transmitter(PhiloxStream):
 
     def transmit_bits(self, uncoded_msgs=None):
         """Coded bits (codeword_len, msg_at_time) uint8 on the device; ``last_transmitted_bits`` is updated."""
+        if self.encoder is None:
+            raise ValueError(f"this parity-check matrix has no systematic encoder: {self._encoder_error}")
         bits = self.random_bits() if uncoded_msgs is None else uncoded_msgs
         coded = self.encoder.encode_batch(bits)
         if self.return_buffer_only:

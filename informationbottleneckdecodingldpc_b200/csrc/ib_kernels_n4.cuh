@@ -122,11 +122,13 @@ __device__ __forceinline__ void stage_tables_n4(uint32_t* s_tab, const IbArgs& a
 // ------------------------------------------------------------------------------------------
 // check node, 8 frames (one 32-bit word per message)
 // ------------------------------------------------------------------------------------------
-template <int D, bool MATCH>
+// WT / CB: words per table row and first stage column of this degree class inside a table image shared by several
+// classes (fused per-phase kernels, ib_phase_n4.cuh); WT = 0 selects the class's own layout (column 0, n4_*_words).
+template <int D, bool MATCH, int WT = 0, int CB = 0>
 __device__ __forceinline__ void cn_word_n4(const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab, uint32_t lane4)
 {
-    constexpr uint32_t W = n4_cn_words(D, MATCH), RS = 128u * W, TRS = RS * kTS;
-    const uint32_t match_off = (uint32_t)(D - 1) * TRS + IB_SO(D - 2) + lane4;
+    constexpr uint32_t W = WT ? WT : n4_cn_words(D, MATCH), RS = 128u * W, TRS = RS * kTS;
+    const uint32_t match_off = (uint32_t)(D - 1) * TRS + IB_SO(CB + D - 2) + lane4;
 #pragma unroll
     for (int k = 0; k < D; ++k) o[k] = 0;
 #pragma unroll
@@ -137,12 +139,12 @@ __device__ __forceinline__ void cn_word_n4(const uint32_t (&w)[D], uint32_t (&o)
         uint32_t P[D > 1 ? D : 2];
         P[1] = (w[0] >> (4 * f)) & 15u;
 #pragma unroll
-        for (int j = 1; j <= D - 2; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(j - 1));
+        for (int j = 1; j <= D - 2; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(CB + j - 1));
 #pragma unroll
         for (int wo = 0; wo < D; ++wo) {
             uint32_t t = (wo == 0) ? ((w[1] >> (4 * f)) & 15u) : P[wo];
 #pragma unroll
-            for (int k = (wo == 0 ? 2 : wo + 1); k < D; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
+            for (int k = (wo == 0 ? 2 : wo + 1); k < D; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(CB + k - 2));
             if (MATCH) t = lut_ld(tab, t * RS + match_off);
             o[wo] += t << (4 * f);
         }
@@ -157,12 +159,12 @@ __device__ __forceinline__ void cn_word_n4(const uint32_t (&w)[D], uint32_t (&o)
 // Shared-memory wavefronts per check and frame: D=6 18 -> 12, D=7 25 -> 16, D=8 33 -> 21.
 constexpr uint32_t kPairBytes = kTS * kTS * 8 * kPairSlots;   // 32 KB, placed in front of the stage tables
 
-template <int D>
+template <int D, int WT = 0, int CB = 0>
 __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab,
                                                 const uint8_t* ptab, uint32_t lane4, uint32_t slot8)
 {
     static_assert(D >= 4, "tail-pair variant needs at least two look-up stages");
-    constexpr uint32_t W = n4_cn_words(D, false), RS = 128u * W, TRS = RS * kTS;
+    constexpr uint32_t W = WT ? WT : n4_cn_words(D, false), RS = 128u * W, TRS = RS * kTS;
     constexpr uint32_t PS = 8u * kPairSlots, TPS = PS * kTS;
 #pragma unroll
     for (int k = 0; k < D; ++k) o[k] = 0;
@@ -179,11 +181,11 @@ __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t
 #pragma unroll
         for (int j = 1; j <= D - 3; ++j) {
             const bool in_x4 = (D >= 5) && (j == D - 3);
-            P[j + 1] = lut_ld(tab, P[j] * (in_x4 ? RS / 4u : RS) + ms[j] + IB_SO(j - 1));
+            P[j + 1] = lut_ld(tab, P[j] * (in_x4 ? RS / 4u : RS) + ms[j] + IB_SO(CB + j - 1));
         }
         // the two outputs that skip one of the tail messages
-        o[D - 1] += lut_ld(tab, P[D - 2] * RS + ms[D - 2] + IB_SO(D - 3)) << (4 * f);
-        o[D - 2] += lut_ld(tab, P[D - 2] * RS + ms[D - 1] + IB_SO(D - 3)) << (4 * f);
+        o[D - 1] += lut_ld(tab, P[D - 2] * RS + ms[D - 2] + IB_SO(CB + D - 3)) << (4 * f);
+        o[D - 2] += lut_ld(tab, P[D - 2] * RS + ms[D - 1] + IB_SO(CB + D - 3)) << (4 * f);
 #pragma unroll
         for (int wo = 0; wo <= D - 3; ++wo) {
             uint32_t e;   // 4 * x_w
@@ -194,7 +196,7 @@ __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t
             } else {
                 uint32_t t = (wo == 0) ? ((w[1] >> (4 * f)) & 15u) : P[wo];
 #pragma unroll
-                for (int k = (wo == 0 ? 2 : wo + 1); k <= D - 3; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
+                for (int k = (wo == 0 ? 2 : wo + 1); k <= D - 3; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(CB + k - 2));
                 e = t;   // the last look-up read column D-5
             }
             o[wo] += ((uint32_t)(g >> e) & 15u) << (4 * f);
@@ -202,7 +204,7 @@ __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t
     }
 }
 
-template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR>
+template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR, int WT = 0, int CB = 0>
 __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* tab, const uint8_t* ptab, int s, uint32_t col,
                                                uint32_t lane4, int valid_frames)
 {
@@ -243,8 +245,8 @@ __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* t
             const uint32_t vmask = nv >= 8 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (4 * nv)) - 1u);
             syn |= par & vmask;
         }
-        if constexpr (PAIR) cn_word_n4_pair<D>(w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
-        else cn_word_n4<D, MATCH>(w, o, tab, lane4);
+        if constexpr (PAIR) cn_word_n4_pair<D, WT, CB>(w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
+        else cn_word_n4<D, MATCH, WT, CB>(w, o, tab, lane4);
 #pragma unroll
         for (int k = 0; k < D; ++k) r[k][j] = o[k];
     }
@@ -321,11 +323,11 @@ ib_cn_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 // ------------------------------------------------------------------------------------------
 // variable node: channel value + D inbox messages, 8 frames
 // ------------------------------------------------------------------------------------------
-template <int D, bool DECIDE>
+template <int D, bool DECIDE, int WT = 0, int CB = 0>
 __device__ __forceinline__ void vn_word_n4(uint32_t chw, const uint32_t (&w)[D], uint32_t (&o)[D], uint32_t& dec_lo,
                                            uint32_t& dec_hi, const uint8_t* tab, uint32_t lane4)
 {
-    constexpr uint32_t W = n4_vn_words(D, DECIDE), RS = 128u * W, TRS = RS * kTS;
+    constexpr uint32_t W = WT ? WT : n4_vn_words(D, DECIDE), RS = 128u * W, TRS = RS * kTS;
 #pragma unroll
     for (int k = 0; k < D; ++k) o[k] = 0;
     dec_lo = dec_hi = 0;
@@ -337,9 +339,9 @@ __device__ __forceinline__ void vn_word_n4(uint32_t chw, const uint32_t (&w)[D],
         uint32_t P[D + 2];
         P[1] = (chw >> (4 * f)) & 15u;
 #pragma unroll
-        for (int j = 1; j <= D - 1; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(j - 1));
+        for (int j = 1; j <= D - 1; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(CB + j - 1));
         if (DECIDE) {
-            const uint32_t t = lut_ld(tab, P[D] * RS + ms[D] + IB_SO(D - 1));
+            const uint32_t t = lut_ld(tab, P[D] * RS + ms[D] + IB_SO(CB + D - 1));
             if (f < 4) dec_lo = put_byte(dec_lo, t, f & 3);
             else dec_hi = put_byte(dec_hi, t, f & 3);
         } else {
@@ -347,7 +349,7 @@ __device__ __forceinline__ void vn_word_n4(uint32_t chw, const uint32_t (&w)[D],
             for (int wo = 1; wo <= D; ++wo) {
                 uint32_t t = P[wo];
 #pragma unroll
-                for (int k = wo + 1; k <= D; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
+                for (int k = wo + 1; k <= D; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(CB + k - 2));
                 o[wo - 1] += t << (4 * f);
             }
         }
@@ -359,12 +361,12 @@ __device__ __forceinline__ void vn_word_n4(uint32_t chw, const uint32_t (&w)[D],
 // (G composed on the host with the matching row of degree D folded in).  One LDS.64 per frame
 // replaces 2(D-2) look-ups; column D-4, which produces every x_w, is stored as 4*x.
 // Shared-memory wavefronts per variable node and frame: D=8 35 -> 25, D=11 65 -> 49.
-template <int D>
+template <int D, int WT = 0, int CB = 0>
 __device__ __forceinline__ void vn_word_n4_pair(uint32_t chw, const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab,
                                                 const uint8_t* ptab, uint32_t lane4, uint32_t slot8)
 {
     static_assert(D >= 3, "tail-pair variant needs two update stages");
-    constexpr uint32_t W = n4_vn_words(D, false), RS = 128u * W, TRS = RS * kTS;
+    constexpr uint32_t W = WT ? WT : n4_vn_words(D, false), RS = 128u * W, TRS = RS * kTS;
     constexpr uint32_t PS = 8u * kPairSlots, TPS = PS * kTS;
 #pragma unroll
     for (int k = 0; k < D; ++k) o[k] = 0;
@@ -381,11 +383,11 @@ __device__ __forceinline__ void vn_word_n4_pair(uint32_t chw, const uint32_t (&w
 #pragma unroll
         for (int j = 1; j <= D - 2; ++j) {
             const bool in_x4 = (D >= 4) && (j == D - 2);
-            P[j + 1] = lut_ld(tab, P[j] * (in_x4 ? RS / 4u : RS) + ms[j] + IB_SO(j - 1));
+            P[j + 1] = lut_ld(tab, P[j] * (in_x4 ? RS / 4u : RS) + ms[j] + IB_SO(CB + j - 1));
         }
         // the two outputs that skip one of the tail messages
-        o[D - 2] += lut_ld(tab, P[D - 1] * RS + ms[D] + IB_SO(D - 2)) << (4 * f);       // w = D-1
-        o[D - 1] += lut_ld(tab, P[D - 1] * RS + ms[D - 1] + IB_SO(D - 2)) << (4 * f);   // w = D
+        o[D - 2] += lut_ld(tab, P[D - 1] * RS + ms[D] + IB_SO(CB + D - 2)) << (4 * f);       // w = D-1
+        o[D - 1] += lut_ld(tab, P[D - 1] * RS + ms[D - 1] + IB_SO(CB + D - 2)) << (4 * f);   // w = D
 #pragma unroll
         for (int wo = 1; wo <= D - 2; ++wo) {
             uint32_t e;   // 4 * x_w
@@ -396,7 +398,7 @@ __device__ __forceinline__ void vn_word_n4_pair(uint32_t chw, const uint32_t (&w
             } else {
                 uint32_t t = P[wo];
 #pragma unroll
-                for (int k = wo + 1; k <= D - 2; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(k - 2));
+                for (int k = wo + 1; k <= D - 2; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(CB + k - 2));
                 e = t;   // the last look-up read column D-4
             }
             o[wo - 1] += ((uint32_t)(g >> e) & 15u) << (4 * f);
@@ -591,15 +593,39 @@ __global__ void pack_n4_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
     if (any_bad) atomicOr(bad, 1);
 }
 
-// Range check of a uint8 cluster buffer for the kernel families that read it in place (uint8 family, generic path).
-static __global__ void range_check_u8_kernel(const uint8_t* __restrict__ src, int rows, long long B, long long pitch, int T,
-                                      int* __restrict__ bad)
+// Sanitised copy of a padded uint8 cluster buffer (n 16-byte vectors) for the kernel families that use the channel
+// values as table indices without repacking (uint8 family, generic path): values >= T are clamped to T-1 and
+// reported through *bad.
+static __global__ void clamp_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long n, int T,
+                                       int* __restrict__ bad)
 {
-    const long long n = (long long)rows * B;
     bool any_bad = false;
+    const uint32_t kadd = (uint32_t)(128 - (T > 128 ? 128 : T)) * 0x01010101u;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / B, c = i - r * B;
-        any_bad |= src[r * pitch + c] >= T;
+        uint4 v = reinterpret_cast<const uint4*>(src)[i];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        bool ok = true;
+        if (T <= 128) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ok &= ((w[q] | (w[q] + kadd)) & 0x80808080u) == 0u;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ok &= (int)((w[q] >> (8 * k)) & 0xffu) < T;
+        }
+        if (!ok) {
+            any_bad = true;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t r = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r |= (uint32_t)min((int)((w[q] >> (8 * k)) & 0xffu), T - 1) << (8 * k);
+                w[q] = r;
+            }
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        reinterpret_cast<uint4*>(dst)[i] = v;
     }
     if (any_bad) atomicOr(bad, 1);
 }

@@ -1,0 +1,281 @@
+// ib_phase.cu -- host side of the fused per-phase kernels (ib_phase_n4.cuh): pre-expanded shared-memory images of
+// every phase, built once at ibldpc_set_luts, and the launch sequence of one decode (one launch per phase).
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ibldpc_internal.h"
+#include "ib_phase_sets.h"
+
+namespace ibldpc {
+
+struct PhaseImages {
+    const PhaseSetOps* ops = nullptr;
+    int imax = 0;
+    uint8_t* d_images = nullptr;            // [imax CN blocks][imax VN update images][imax decision images]
+    size_t cn_bytes = 0, vn_bytes = 0, out_bytes = 0;
+    // node lists in the order of the degree set (heaviest first) and their inbox start offsets
+    const int* cn_nodes[kPhaseMaxClasses] = {};
+    const int* vn_nodes[kPhaseMaxClasses] = {};
+    int* cn_starts[kPhaseMaxClasses] = {};
+    int* vn_starts[kPhaseMaxClasses] = {};
+    int cn_count[kPhaseMaxClasses] = {}, vn_count[kPhaseMaxClasses] = {};
+    int occ_checked = 0;
+};
+
+namespace {
+
+bool same_degrees(const std::vector<int>& set, const std::vector<NodeClass>& classes)
+{
+    if (set.size() != classes.size()) return false;
+    for (int d : set) {
+        bool found = false;
+        for (auto& c : classes) found |= c.degree == d;
+        if (!found) return false;
+    }
+    return true;
+}
+
+int class_index(const std::vector<NodeClass>& classes, int degree)
+{
+    for (size_t i = 0; i < classes.size(); ++i)
+        if (classes[i].degree == degree) return (int)i;
+    return -1;
+}
+
+// One image: [pair regions][256 rows (m*16+t) x words x 32 lanes x 4 stage columns].
+//   stage(j)      -> T*T bytes of look-up stage j of this phase (reference order t*T+m)
+//   match_row(d)  -> T bytes of the matching row of degree d, or nullptr
+//   pair_rows(ci) -> T*T x 8 bytes of the composed tail-pair rows of class index ci (handle order), or nullptr
+template <typename StageFn, typename MatchFn, typename PairFn>
+void build_image(uint8_t* img, const PhaseLayoutRt& L, int mode, int T, const std::vector<NodeClass>& classes, StageFn stage,
+                 MatchFn match_row, PairFn pair_rows)
+{
+    memset(img, 0, (size_t)L.image_bytes);
+    uint32_t* tab = reinterpret_cast<uint32_t*>(img + (size_t)L.n_pair * kPairBytes);
+    const int W = L.words;
+    for (int i = 0; i < L.n; ++i) {
+        const PhaseClassLayout& c = L.cls[i];
+        const int D = c.degree;
+        // pair rows: kPairSlots lane slots of 8 bytes per row a*16+b
+        if (c.pair) {
+            const uint8_t* src = pair_rows(class_index(classes, D));
+            uint8_t* dst = img + (size_t)c.pair_index * kPairBytes;
+            for (int ra = 0; ra < T; ++ra)
+                for (int rb = 0; rb < T; ++rb)
+                    for (int s = 0; s < kPairSlots; ++s)
+                        memcpy(dst + ((size_t)(ra * kTS + rb) * kPairSlots + s) * 8, src + (size_t)(ra * T + rb) * 8, 8);
+        }
+        // the column stored as 4*x feeds the pair row: check nodes column D-5, variable nodes column D-4 (local index)
+        const int x4 = !c.pair ? -1 : (mode == kPhaseCn ? D - 5 : D - 4);
+        const uint8_t* mrow = mode == kPhaseOut ? nullptr : match_row(D);
+        const int ncols = mode == kPhaseOut ? D : c.cols;
+        for (int j = 0; j < ncols; ++j) {
+            const uint8_t* S = stage(j);
+            const int col = c.col_base + j;
+            const int wq = col >> 2, q = col & 3;
+            const bool fold = mrow != nullptr && j == ncols - 1;
+            for (int m = 0; m < T; ++m)
+                for (int t = 0; t < T; ++t) {
+                    uint32_t e = S[t * T + m];
+                    if (fold) e = mrow[e];
+                    if (j == x4) e *= 4u;
+                    uint32_t* row = tab + ((size_t)(m * kTS + t) * W + wq) * 32;
+                    const uint32_t mask = 0xffu << (8 * q);
+                    for (int l = 0; l < 32; ++l) row[l] = (row[l] & ~mask) | (e << (8 * q));
+                }
+        }
+    }
+}
+
+}  // namespace
+
+void phase_free(ibldpc_decoder* h)
+{
+    PhaseImages* p = h->phase;
+    if (!p) return;
+    if (p->d_images) cudaFree(p->d_images);
+    for (int i = 0; i < kPhaseMaxClasses; ++i) {
+        if (p->cn_starts[i]) cudaFree(p->cn_starts[i]);
+        if (p->vn_starts[i]) cudaFree(p->vn_starts[i]);
+    }
+    delete p;
+    h->phase = nullptr;
+}
+
+// Called at the end of ibldpc_set_luts (packed-nibble family, default tail-pair thresholds): picks the instantiated
+// degree set of this code, expands every phase image on the host and uploads them.  Leaves h->phase == nullptr
+// (per-class launches) when the code's degree sets are not instantiated.
+int phase_prepare(ibldpc_decoder* h)
+{
+    phase_free(h);
+    if (!h->nib || !h->use_pair || !h->use_phase) return IBLDPC_OK;
+    const PhaseSetOps* candidates[] = {phase_ops_wlan(), phase_ops_dvbs2(), phase_ops_reg36()};
+    const PhaseSetOps* ops = nullptr;
+    for (const PhaseSetOps* o : candidates)
+        if (same_degrees(o->cn_deg, h->cn_classes) && same_degrees(o->vn_deg, h->vn_classes)) ops = o;
+    if (!ops) return IBLDPC_OK;
+    PhaseImages* p = new PhaseImages();
+    h->phase = p;
+    p->ops = ops;
+    p->imax = h->lut_imax;
+    const int T = h->T, TT = T * T, DC = h->DC, DV = h->DV, imax = h->lut_imax;
+    p->cn_bytes = (size_t)ops->cn_layout.image_bytes;
+    p->vn_bytes = (size_t)ops->vn_layout.image_bytes;
+    p->out_bytes = (size_t)ops->out_layout.image_bytes;
+    const size_t total = (size_t)imax * (p->cn_bytes + p->vn_bytes + p->out_bytes);
+    std::vector<uint8_t> host(total);
+    const size_t ncc = h->cn_classes.size(), nvc = h->vn_classes.size();
+    for (int blk = 0; blk < imax; ++blk) {
+        // check-node phase of table block blk (0 = iteration-0 tables)
+        build_image(
+            host.data() + (size_t)blk * p->cn_bytes, ops->cn_layout, kPhaseCn, T, h->cn_classes,
+            [&](int j) { return h->h_cn8.data() + ((size_t)blk * (DC - 2) + j) * TT; },
+            [&](int d) -> const uint8_t* { return h->match ? h->h_mc8.data() + ((size_t)blk * DC + (d - 1)) * T : nullptr; },
+            [&](int ci) { return h->h_cn_pair.data() + ((size_t)blk * ncc + ci) * (size_t)TT * 8; });
+        // variable-node update of iteration blk
+        build_image(
+            host.data() + (size_t)imax * p->cn_bytes + (size_t)blk * p->vn_bytes, ops->vn_layout, kPhaseVn, T, h->vn_classes,
+            [&](int j) { return h->h_vn8.data() + ((size_t)blk * DV + j) * TT; },
+            [&](int d) -> const uint8_t* { return h->match ? h->h_mv8.data() + ((size_t)blk * DV + (d - 1)) * T : nullptr; },
+            [&](int ci) { return h->h_vn_pair.data() + ((size_t)blk * nvc + ci) * (size_t)TT * 8; });
+        // decision with the variable-node tables of iteration blk (no message alignment on the output)
+        build_image(
+            host.data() + (size_t)imax * (p->cn_bytes + p->vn_bytes) + (size_t)blk * p->out_bytes, ops->out_layout, kPhaseOut, T,
+            h->vn_classes, [&](int j) { return h->h_vn8.data() + ((size_t)blk * DV + j) * TT; },
+            [&](int) -> const uint8_t* { return nullptr; }, [&](int) -> const uint8_t* { return nullptr; });
+    }
+    IBLDPC_CK(cudaMalloc((void**)&p->d_images, total));
+    IBLDPC_CK(cudaMemcpy(p->d_images, host.data(), total, cudaMemcpyHostToDevice));
+    // node lists + start offsets in set order
+    auto starts_of = [&](const NodeClass& c, const std::vector<int>& all_starts, int** d_out) -> int {
+        std::vector<int> nodes((size_t)c.count), st((size_t)c.count);
+        IBLDPC_CK(cudaMemcpy(nodes.data(), c.d_nodes, sizeof(int) * (size_t)c.count, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < c.count; ++i) st[i] = all_starts[nodes[i]];
+        IBLDPC_CK(cudaMalloc((void**)d_out, sizeof(int) * (size_t)std::max(c.count, 1)));
+        IBLDPC_CK(cudaMemcpy(*d_out, st.data(), sizeof(int) * (size_t)c.count, cudaMemcpyHostToDevice));
+        return IBLDPC_OK;
+    };
+    for (size_t i = 0; i < ops->cn_deg.size(); ++i) {
+        const NodeClass& c = h->cn_classes[class_index(h->cn_classes, ops->cn_deg[i])];
+        p->cn_nodes[i] = c.d_nodes;
+        p->cn_count[i] = c.count;
+        if (int rc = starts_of(c, h->h_sc, &p->cn_starts[i])) return rc;
+    }
+    for (size_t i = 0; i < ops->vn_deg.size(); ++i) {
+        const NodeClass& c = h->vn_classes[class_index(h->vn_classes, ops->vn_deg[i])];
+        p->vn_nodes[i] = c.d_nodes;
+        p->vn_count[i] = c.count;
+        if (int rc = starts_of(c, h->h_sv, &p->vn_starts[i])) return rc;
+    }
+    return IBLDPC_OK;
+}
+
+bool phase_available(const ibldpc_decoder* h) { return h->phase != nullptr; }
+
+namespace {
+
+struct PhaseProf {
+    ibldpc_decoder* h;
+    cudaStream_t st;
+    int idx = -1;
+    int begin(int phase)
+    {
+        if (!h->profiling) return IBLDPC_OK;
+        PhaseEvent ev;
+        ev.phase = phase;
+        IBLDPC_CK(cudaEventCreate(&ev.a));
+        IBLDPC_CK(cudaEventCreate(&ev.b));
+        IBLDPC_CK(cudaEventRecord(ev.a, st));
+        h->events.push_back(ev);
+        idx = (int)h->events.size() - 1;
+        return IBLDPC_OK;
+    }
+    int end()
+    {
+        if (!h->profiling || idx < 0) return IBLDPC_OK;
+        IBLDPC_CK(cudaEventRecord(h->events[idx].b, st));
+        return IBLDPC_OK;
+    }
+};
+
+}  // namespace
+
+// One decode with the fused kernels.  `a` carries graph pointers, buffers (packed channel values in a.ch, message
+// array, output), pitches, flags and the iteration control of decode_ib_n4; the launches go to `st`.
+int decode_ib_phase(ibldpc_decoder* h, const IbArgs& a, int imax, int early, cudaStream_t st)
+{
+    PhaseImages* p = h->phase;
+    const PhaseSetOps* ops = p->ops;
+    if (!p->occ_checked) {
+        const struct { PhaseKernel k; size_t smem; } ks[] = {{ops->cn_kernel[0], p->cn_bytes}, {ops->cn_kernel[1], p->cn_bytes},
+                                                             {ops->vn_kernel, p->vn_bytes}, {ops->out_kernel, p->out_bytes}};
+        for (auto& e : ks) {
+            IBLDPC_CK(cudaFuncSetAttribute((const void*)e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem));
+            int occ = 0;
+            IBLDPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e.k, kPhaseThreads, e.smem));
+            if (occ < 1) return fail_msg(IBLDPC_E_CUDA, "fused per-phase kernel does not fit on an SM");
+        }
+        p->occ_checked = 1;
+    }
+    auto grid_for = [&](const PhaseLayoutRt& L, const int* counts) {
+        long long chunks = 0;   // groups of 32 items: below one group per CTA there is nothing to share
+        for (int i = 0; i < L.n; ++i) {
+            const long long tiles = ((long long)a.pitch + 128LL * L.cls[i].vec - 1) / (128LL * L.cls[i].vec);
+            chunks += ((long long)counts[i] * tiles + 31) / 32;
+        }
+        return (int)std::max<long long>(1, std::min<long long>(h->sm_count, chunks));
+    };
+    PhaseArgs base{};
+    base.a = a;
+    base.a.early = early;
+    base.a.imax = imax;
+    PhaseProf prof{h, st};
+    int rc;
+    auto launch_cn = [&](int it) -> int {
+        PhaseArgs q = base;
+        q.a.it = it;
+        q.a.iter0 = it < 0;
+        q.image = p->d_images + (size_t)(it + 1) * p->cn_bytes;
+        for (int i = 0; i < ops->cn_layout.n; ++i) {
+            q.nodes[i] = p->cn_nodes[i]; q.starts[i] = p->cn_starts[i]; q.n_nodes[i] = p->cn_count[i];
+        }
+        if ((rc = prof.begin(it < 0 ? 2 : 0))) return rc;
+        const int grid = grid_for(ops->cn_layout, p->cn_count);
+        ops->cn_kernel[early ? 1 : 0]<<<grid, kPhaseThreads, p->cn_bytes, st>>>(q);
+        h->last_launches++; h->last_grid = grid; h->last_smem = (int)p->cn_bytes;
+        return prof.end();
+    };
+    auto launch_vn = [&](int it, bool decide) -> int {
+        PhaseArgs q = base;
+        q.a.it = it;
+        q.a.iter0 = 0;
+        if (decide) {
+            q.image = p->d_images + (size_t)p->imax * (p->cn_bytes + p->vn_bytes);
+            q.image_stride = (long long)p->out_bytes;
+        } else {
+            q.image = p->d_images + (size_t)p->imax * p->cn_bytes + (size_t)it * p->vn_bytes;
+        }
+        for (int i = 0; i < ops->vn_layout.n; ++i) {
+            q.nodes[i] = p->vn_nodes[i]; q.starts[i] = p->vn_starts[i]; q.n_nodes[i] = p->vn_count[i];
+        }
+        if ((rc = prof.begin(decide ? 2 : 1))) return rc;
+        const PhaseLayoutRt& L = decide ? ops->out_layout : ops->vn_layout;
+        const int grid = grid_for(L, p->vn_count);
+        const size_t smem = decide ? p->out_bytes : p->vn_bytes;
+        (decide ? ops->out_kernel : ops->vn_kernel)<<<grid, kPhaseThreads, smem, st>>>(q);
+        h->last_launches++;
+        return prof.end();
+    };
+    if ((rc = launch_cn(-1))) return rc;
+    for (int it = 0; it < imax - 1; ++it) {
+        if ((rc = launch_vn(it, false))) return rc;
+        if ((rc = launch_cn(it))) return rc;
+    }
+    if ((rc = launch_vn(0, true))) return rc;
+    IBLDPC_CK(cudaGetLastError());
+    return IBLDPC_OK;
+}
+
+}  // namespace ibldpc

@@ -1,0 +1,323 @@
+// ib_phase_n4.cuh -- fused per-phase kernels of the packed-nibble family: ONE launch per check-node / variable-node
+// phase of the flooding schedule covering ALL degree classes of an irregular code.
+//
+// The per-class kernels of ib_kernels_n4.cuh pay a fixed cost per launch (launch latency, table staging through a
+// scratch copy + striping loop + two block barriers, one partial wave at the end); an 802.11n decode is 301 launches
+// of 60-160 us, and the small classes (d_c = 8: 108 checks, d_v = 4: 54 variables) cannot fill the tail of the big
+// ones.  Here
+//   * every CTA is identical: 1024 threads (32 warps at <= 64 registers), one CTA per SM, persistent;
+//   * the shared-memory image of the phase -- lane-striped stage columns of every class side by side plus the
+//     tail-pair rows -- is expanded ONCE on the host at ibldpc_set_luts (build_phase_images, ib_phase.cu) and
+//     brought in by one thread with cp.async.bulk (TMA bulk copy, mbarrier complete_tx) while the warps are already
+//     fetching the indices and messages of their first node;
+//   * work = (class, node, frame tile) items, heaviest class first; a CTA owns a contiguous 1/gridDim share of every
+//     class and its warps pull items from a shared-memory counter, so nothing waits for a slow class.
+// The phase bodies are the per-class device functions (cn_word_n4_pair, vn_word_n4, vn_word_n4_pair) with the class's
+// column base inside the shared image as a template parameter: same look-up order, bit-identical results
+// (kernels_template_irreg.cl:33-99, :103-179, :181-246, :249-325).
+//
+// Instantiated per degree SET (DegreeSet<...>, heaviest first): the column layout is a compile-time function of the
+// set, exactly like the multi-class cooperative kernel.  Other degree sets keep the per-class launches.
+#pragma once
+#include <utility>
+
+#include "ib_coop_n4.cuh"   // DegreeSet
+#include "ib_kernels_n4.cuh"
+
+namespace ibldpc {
+
+constexpr int kPhaseThreads = 1024;
+constexpr int kPhaseMaxClasses = 4;
+constexpr int kPhaseCnPairMin = 6;   // tail-pair rows from this degree on (same thresholds as the per-class kernels)
+constexpr int kPhaseVnPairMin = 5;
+
+enum PhaseMode { kPhaseCn = 0, kPhaseVn = 1, kPhaseOut = 2 };
+
+// ---- compile-time layout of a phase image -------------------------------------------------------------------
+__host__ __device__ constexpr int phase_cols(int mode, int d) { return mode == kPhaseCn ? d - 2 : mode == kPhaseVn ? d - 1 : d; }
+__host__ __device__ constexpr bool phase_pair(int mode, int d)
+{
+    return mode == kPhaseCn ? d >= kPhaseCnPairMin : mode == kPhaseVn ? d >= kPhaseVnPairMin : false;
+}
+// words (8 frames each) a lane moves per message row: the widest access the register budget of 64 allows
+__host__ __device__ constexpr int phase_vec(int mode, int d)
+{
+    return mode == kPhaseCn ? 2 : mode == kPhaseVn ? (d <= 4 ? 4 : d <= 7 ? 2 : 1) : 2;
+}
+
+template <int MODE, int... Ds>
+struct PhaseLayout {
+    static constexpr int n = sizeof...(Ds);
+    __host__ __device__ static constexpr int degree(int i)
+    {
+        constexpr int d[] = {Ds...};
+        return d[i];
+    }
+    // first stage column of class i (the decision phase shares its plain columns between the classes)
+    __host__ __device__ static constexpr int col_base(int i)
+    {
+        if (MODE == kPhaseOut) return 0;
+        int c = 0;
+        for (int j = 0; j < i; ++j) c += phase_cols(MODE, degree(j));
+        return c;
+    }
+    __host__ __device__ static constexpr int total_cols()
+    {
+        int c = 0;
+        for (int j = 0; j < n; ++j) c = MODE == kPhaseOut ? (degree(j) > c ? degree(j) : c) : c + phase_cols(MODE, degree(j));
+        return c;
+    }
+    static constexpr int words = total_cols() <= 4 ? 1 : (total_cols() + 3) / 4;
+    __host__ __device__ static constexpr int pair_index(int i)
+    {
+        int p = 0;
+        for (int j = 0; j < i; ++j) p += phase_pair(MODE, degree(j)) ? 1 : 0;
+        return p;
+    }
+    static constexpr int n_pair = pair_index(n);
+    static constexpr int image_bytes = n_pair * (int)kPairBytes + n4_table_bytes(words);
+};
+
+// run-time description of the same layout for the host-side image builder (ib_phase.cu)
+struct PhaseClassLayout { int degree, col_base, cols, pair_index, vec; bool pair; };
+struct PhaseLayoutRt { int n, words, n_pair, image_bytes; PhaseClassLayout cls[kPhaseMaxClasses]; };
+
+template <int MODE, int... Ds>
+PhaseLayoutRt phase_layout_rt(DegreeSet<Ds...>)
+{
+    using L = PhaseLayout<MODE, Ds...>;
+    PhaseLayoutRt r{};
+    r.n = L::n; r.words = L::words; r.n_pair = L::n_pair; r.image_bytes = L::image_bytes;
+    for (int i = 0; i < L::n; ++i) {
+        const int d = L::degree(i);
+        r.cls[i] = PhaseClassLayout{d, L::col_base(i), phase_cols(MODE, d), L::pair_index(i), phase_vec(MODE, d), phase_pair(MODE, d)};
+    }
+    return r;
+}
+
+struct PhaseArgs {
+    IbArgs a;                    // graph, buffers, iteration control (lut / match / pair fields unused)
+    const uint8_t* image;        // shared-memory image of this phase in global memory (16-byte aligned)
+    long long image_stride;      // decision phase: bytes between the images of consecutive iterations
+    const int* nodes[kPhaseMaxClasses];    // node ids of every class, in the order of the degree set
+    const int* starts[kPhaseMaxClasses];   // sc[node] resp. sv[node] of the same nodes (saves one dependent load)
+    int n_nodes[kPhaseMaxClasses];
+};
+
+// ---- TMA bulk copy of the image ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void phase_image_issue(void* smem_dst, const uint8_t* gsrc, uint32_t bytes, uint64_t* mbar)
+{
+    const uint32_t mb = smem_u32(mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    constexpr uint32_t kChunk = 32768;   // several bulk operations in flight
+    const uint32_t dst = smem_u32(smem_dst);
+    for (uint32_t off = 0; off < bytes; off += kChunk) {
+        const uint32_t n = bytes - off < kChunk ? bytes - off : kChunk;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                     "l"(gsrc + off), "r"(n), "r"(mb)
+                     : "memory");
+    }
+}
+
+__device__ __forceinline__ void phase_image_wait(uint64_t* mbar)
+{
+    const uint32_t mb = smem_u32(mbar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(mb)
+            : "memory");
+    }
+}
+
+// a warp-uniform int re-read through the read-only path WITHOUT common-subexpression elimination against an earlier
+// load of the same address: lets the high-degree classes drop their row indices during the look-up chains and fetch
+// them again (L1 hits) for the stores, instead of holding D registers or spilling
+__device__ __forceinline__ int ld_nc_again(const int* p)
+{
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// ---- one item = one (node, tile) of class I ------------------------------------------------------------------
+template <int MODE, bool EARLY, typename L, int I>
+struct PhaseItem {
+    static constexpr int D = L::degree(I);
+    static constexpr int VEC = phase_vec(MODE, D);
+    static constexpr int WT = L::words;
+    static constexpr int CB = L::col_base(I);
+    static constexpr bool PAIR = phase_pair(MODE, D);
+    static constexpr int PI = L::pair_index(I);
+
+    // returns the syndrome bits seen (check-node phase with EARLY), 0 otherwise
+    static __device__ __forceinline__ uint32_t run(const IbArgs& a, const uint8_t* s_img, int node, int start, uint32_t col,
+                                                   uint32_t lane4)
+    {
+        const uint8_t* tab = s_img + L::n_pair * kPairBytes;
+        const uint8_t* ptab = s_img + PI * kPairBytes;
+        if constexpr (MODE == kPhaseCn) {
+            return cn_node_n4<D, false, EARLY, VEC, PAIR, WT, CB>(a, tab, ptab, start, col, lane4, a.B - 2 * (int)col);
+        } else {
+            constexpr bool DECIDE = MODE == kPhaseOut;
+            constexpr bool kKeepRows = D <= 6;   // row indices stay in registers only where the budget allows
+            int rows[D];
+            VnIn4<D, VEC> in;
+            ld_words<VEC>(a.ch + (uint64_t)(uint32_t)node * a.pitch + col, in.c);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                rows[k] = a.tv[start + k];
+                ld_words<VEC>(a.msg + (uint64_t)(uint32_t)rows[k] * a.pitch + col, in.m[k]);
+            }
+            if (!DECIDE && D == 1) {   // degree-1 variable node forwards the raw channel value (:132-136)
+                st_words<VEC>(a.msg + (uint64_t)(uint32_t)rows[0] * a.pitch + col, in.c);
+                return 0;
+            }
+            uint32_t r[D][VEC];
+            uint32_t dec[2 * VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                uint32_t w[D], o[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) w[k] = in.m[k][j];
+                if constexpr (PAIR) vn_word_n4_pair<D, WT, CB>(in.c[j], w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
+                else vn_word_n4<D, DECIDE, WT, CB>(in.c[j], w, o, dec[2 * j], dec[2 * j + 1], tab, lane4);
+                if (!DECIDE) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) r[k][j] = o[k];
+                }
+            }
+            if constexpr (DECIDE) {
+                // decided cluster indices leave as uint8 (one byte per frame): 8*VEC bytes per lane
+                const uint32_t ocol = 2u * col;
+                uint8_t* dst = a.out + (uint64_t)(uint32_t)node * a.out_pitch + ocol;
+                if constexpr (VEC >= 2) {
+#pragma unroll
+                    for (int q = 0; q < VEC / 2; ++q)
+                        if (ocol + 16u * q < a.out_pitch)
+                            *reinterpret_cast<uint4*>(dst + 16 * q) = make_uint4(dec[4 * q], dec[4 * q + 1], dec[4 * q + 2], dec[4 * q + 3]);
+                } else {
+                    if (ocol < a.out_pitch) *reinterpret_cast<uint2*>(dst) = make_uint2(dec[0], dec[1]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const int row = kKeepRows ? rows[k] : ld_nc_again(a.tv + start + k);
+                    st_words<VEC>(a.msg + (uint64_t)(uint32_t)row * a.pitch + col, r[k]);
+                }
+            }
+            return 0;
+        }
+    }
+};
+
+template <typename F, int... Is>
+__device__ __forceinline__ void phase_unroll(F& f, std::integer_sequence<int, Is...>)
+{
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------------
+template <int MODE, bool EARLY, int... Ds>
+__global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_kernel(PhaseArgs p)
+{
+    using L = PhaseLayout<MODE, Ds...>;
+    static_assert(L::n <= kPhaseMaxClasses, "too many degree classes");
+    extern __shared__ __align__(128) uint8_t s_img[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ int s_next[kPhaseMaxClasses];
+    __shared__ int s_passes;
+    const IbArgs& a = p.a;
+    if (MODE != kPhaseOut && (EARLY || a.early) && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
+
+    const int lane = threadIdx.x & 31;
+    const uint32_t lane4 = lane * 4;
+    // this CTA's contiguous share [lo, hi) of every class (items = nodes x tiles)
+    int lo[L::n], hi[L::n], tiles[L::n];
+    {
+        constexpr int degs[] = {Ds...};
+#pragma unroll
+        for (int c = 0; c < L::n; ++c) {
+            const int vec = phase_vec(MODE, degs[c]);
+            tiles[c] = (int)((a.pitch + 128u * vec - 1) / (128u * vec));
+            const long long items = (long long)p.n_nodes[c] * tiles[c];
+            lo[c] = (int)(items * blockIdx.x / gridDim.x);
+            hi[c] = (int)(items * (blockIdx.x + 1) / gridDim.x);
+        }
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < L::n; ++c) s_next[c] = lo[c] + kPhaseThreads / 32;   // the first 32 items are taken statically
+        const uint8_t* img = p.image;
+        if (MODE == kPhaseOut) {
+            s_passes = executed_passes(a);
+            if (blockIdx.x == 0) *a.inum = s_passes + 1;
+            img += (long long)s_passes * p.image_stride;
+        }
+        phase_image_issue(s_img, img, (uint32_t)L::image_bytes, &s_mbar);
+    }
+    __syncthreads();   // mbarrier initialised, counters set; the image is still in flight
+
+    uint32_t syn = 0;
+    bool have_image = false;
+    constexpr int degs[] = {Ds...};
+    auto class_loop = [&](auto IC) {
+        constexpr int I = decltype(IC)::value;
+        using Item = PhaseItem<MODE, EARLY, L, I>;
+        constexpr int VEC = Item::VEC;
+        const int* __restrict__ nodes = p.nodes[I];
+        const int* __restrict__ starts = p.starts[I];
+        const uint32_t tl = (uint32_t)tiles[I];
+        int i = lo[I] + (threadIdx.x >> 5);
+        int node = 0, start = 0;
+        if (i < hi[I]) {
+            const uint32_t ni = (uint32_t)i / tl;
+            node = nodes[ni];
+            start = starts[ni];
+        }
+        while (i < hi[I]) {
+            // take the next item and fetch its node before working on this one
+            int i2 = 0;
+            if (lane == 0) i2 = atomicAdd(&s_next[I], 1);
+            i2 = __shfl_sync(0xffffffffu, i2, 0);
+            int node2 = 0, start2 = 0;
+            if (i2 < hi[I]) {
+                const uint32_t ni2 = (uint32_t)i2 / tl;
+                node2 = nodes[ni2];
+                start2 = starts[ni2];
+            }
+            const uint32_t tile = (uint32_t)i - ((uint32_t)i / tl) * tl;
+            const uint32_t col = (tile * 32u + lane) * (4u * VEC);
+            if (!have_image) {        // first item of this warp: its row indices are on their way, now wait for the tables
+                phase_image_wait(&s_mbar);
+                have_image = true;
+            }
+            if (col < a.pitch) syn |= Item::run(a, s_img, node, start, col, lane4);
+            i = i2;
+            node = node2;
+            start = start2;
+        }
+        (void)degs;
+    };
+    // classes in the order of the degree set (heaviest first)
+    phase_unroll(class_loop, std::make_integer_sequence<int, L::n>{});
+
+    if (MODE == kPhaseCn && EARLY && !a.iter0) {
+        const unsigned any = __ballot_sync(0xffffffffu, syn != 0);
+        if (any != 0 && lane == 0) atomicOr(&a.flags[a.it], 1);
+    }
+    // the bulk copy must have landed before the CTA may exit (its shared memory is the destination)
+    if (!have_image) phase_image_wait(&s_mbar);
+}
+
+using PhaseKernel = void (*)(PhaseArgs);
+
+}  // namespace ibldpc

@@ -205,7 +205,7 @@ std::vector<int64_t> host_chunk_schedule(int64_t B, int64_t n_var, int64_t host_
             take(q);
             take(c - q);
             while (left > c) take(c);
-            if (left > q) take(left - q);
+            if (left > q) take(std::max<int64_t>(512, (left - q) / 512 * 512));   // every chunk but the last: whole 512-frame tiles
             take(left);
         }
     }
@@ -268,10 +268,17 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
         if (rc) return rc;
     }
     CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)(std::max(imax, 1) + 1), st));
-    {   // these families read the caller's uint8 buffer in place: report cluster indices >= |T_channel|
-        const long long n = (long long)h->N * B;
+    {   // These families use the channel values as table indices as they are: work on a sanitised copy (values
+        // >= |T_channel| clamped and reported through flags[0]) so that no look-up can leave its table.
+        void* p = w.ch4;
+        rc = ensure(&p, &w.ch4_bytes, (size_t)h->N * (size_t)pitch);
+        w.ch4 = (uint8_t*)p;
+        if (rc) return rc;
+        const long long n = (long long)h->N * (pitch / 16);
         const int grid = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 16);
-        range_check_u8_kernel<<<grid, 256, 0, st>>>(ch, h->N, B, pitch, h->Tc, w.flags);
+        clamp_u8_kernel<<<grid, 256, 0, st>>>(ch, w.ch4, n, h->Tc, w.flags);
+        h->last_launches = 0;
+        ch = w.ch4;
     }
     IbArgs a{};
     a.sc = h->d_sc; a.deg_c = h->d_dc; a.sv = h->d_sv; a.deg_v = h->d_dv; a.tv = h->d_tv; a.vidx = h->d_vidx;
@@ -567,6 +574,8 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
             return IBLDPC_OK;
         }
     }
+    // ---- one launch per phase over all degree classes (ib_phase_n4.cuh) where the degree sets are instantiated
+    if (h->phase) return decode_ib_phase(h, a, imax, early, st);
     // launch geometry of one degree class (plan_geometry): tiles per CTA, tile groups, CTAs per tile group
     auto plan_launch = [&](IbArgs& b, const void* fn, int smem, int threads, int vec, int n_nodes, int* tile_groups, int* grid) -> int {
         int occ;
@@ -1006,6 +1015,8 @@ int ibldpc_create(const ibldpc_code_desc* code, int device, ibldpc_handle* out)
     h->dc_min = *std::min_element(dc.begin(), dc.end());
     h->dv_max = *std::max_element(dv.begin(), dv.end());
     h->dv_min = *std::min_element(dv.begin(), dv.end());
+    h->h_sc.assign(code->inbox_start_chk, code->inbox_start_chk + M);
+    h->h_sv.assign(code->inbox_start_var, code->inbox_start_var + N);
     // variable index of every CN-major row: row tv[sv[v]+k] belongs to variable v
     std::vector<int> vidx(E);
     for (int v = 0; v < N; ++v)
@@ -1080,6 +1091,7 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
         if ((rc = upload(&h->d_mc8, mc.data(), mc.size()))) return rc;
         if ((rc = upload(&h->d_mv8, mv.data(), mv.size()))) return rc;
     }
+    h->h_cn8 = cn; h->h_vn8 = vn; h->h_mc8 = mc; h->h_mv8 = mv;
     h->T = T; h->Tc = Tc; h->lut_imax = imax; h->DC = DC; h->DV = DV; h->match = match;
     h->tshift = -1;
     for (int s = 1; s <= 8; ++s)
@@ -1128,6 +1140,7 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
                         }
             }
         if ((rc = upload(&h->d_cn_pair, pair.data(), pair.size()))) return rc;
+        h->h_cn_pair.swap(pair);
     }
     if (h->d_vn_pair) { CK(cudaFree(h->d_vn_pair)); h->d_vn_pair = nullptr; }
     if (const char* e = getenv("IBLDPC_VN_PAIR_MIN_DEGREE")) h->vn_pair_min_degree = std::max(3, atoi(e));
@@ -1159,7 +1172,14 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
                         }
             }
         if ((rc = upload(&h->d_vn_pair, vpair.data(), vpair.size()))) return rc;
+        h->h_vn_pair.swap(vpair);
     }
+    // Fused per-phase kernels (ib_phase_n4.cuh): default whenever the code's degree sets are instantiated; every switch
+    // that selects a particular per-class kernel variant (A/B measurements, parity variants) keeps per-class launches.
+    h->use_phase = getenv("IBLDPC_NO_PHASE") == nullptr && getenv("IBLDPC_PAIR_MIN_DEGREE") == nullptr &&
+                   getenv("IBLDPC_VN_PAIR_MIN_DEGREE") == nullptr && h->vn_vec == 0 && h->cn_threads == 0 &&
+                   h->vn_threads == 0 && h->vn_pair_threads == 0 && getenv("IBLDPC_NO_PLAN") == nullptr;
+    if ((rc = phase_prepare(h))) return rc;
     h->occ_cache.clear();
     h->have_luts = true;
     return IBLDPC_OK;
@@ -1592,6 +1612,7 @@ int ibldpc_destroy(ibldpc_handle h)
     DeviceGuard guard_(h->device);
     cudaDeviceSynchronize();
     ibldpc_nccl_finalize(h);
+    phase_free(h);
     clear_events(h);
     for (int* p : {h->d_sc, h->d_dc, h->d_tc, h->d_sv, h->d_dv, h->d_tv, h->d_vidx})
         if (p) cudaFree(p);

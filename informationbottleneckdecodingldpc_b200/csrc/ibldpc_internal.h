@@ -83,6 +83,7 @@ struct Workspace {
 };
 
 struct PhaseImages;   // ib_phase.cu: pre-expanded shared-memory table images of the fused per-phase kernels
+struct IbArgs;
 
 }  // namespace ibldpc
 
@@ -135,6 +136,13 @@ struct ibldpc_decoder {
     // NCCL communicator of the counter all-reduce (nccl_abi.cu), opaque here
     void* nccl_comm = nullptr;
 };
+
+namespace ibldpc {
+// fused per-phase kernels (ib_phase.cu)
+int phase_prepare(ibldpc_decoder* h);   // end of ibldpc_set_luts: build + upload the phase images (or leave h->phase null)
+void phase_free(ibldpc_decoder* h);
+int decode_ib_phase(ibldpc_decoder* h, const IbArgs& a, int imax, int early, cudaStream_t st);
+}  // namespace ibldpc
 
 #define IBLDPC_CK(call)                                                                                       \
     do {                                                                                                      \

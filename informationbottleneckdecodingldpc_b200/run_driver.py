@@ -71,6 +71,13 @@ def install_stubs() -> None:
     sys.modules["matplotlib.pyplot"] = plt
 
 
+class Silent:
+    """Object whose every attribute is a no-op callable."""
+
+    def __getattr__(self, name):
+        return lambda *a, **k: None
+
+
 def apply_overrides(source: str, overrides: dict) -> str:
     """Replace the right-hand side of the first ``name = <literal>`` line for every override."""
     for name, value in overrides.items():
@@ -81,8 +88,10 @@ def apply_overrides(source: str, overrides: dict) -> str:
     return source
 
 
-def run(path: str, overrides: dict | None = None, chdir: bool = True) -> dict:
-    """Execute the driver at ``path``; returns its global namespace (BER_vector, EbN0_dB_vector, ...)."""
+def run(path: str, overrides: dict | None = None, chdir: bool = True, inject: dict | None = None) -> dict:
+    """Execute the driver at ``path``; returns its global namespace (BER_vector, EbN0_dB_vector, ...).
+    ``inject`` pre-defines globals the script uses without defining them (two of the shipped drivers end with
+    ``pb.push_note(...)`` on an undefined Pushbullet client; ``inject={"pb": run_driver.Silent()}`` lets them finish)."""
     install_shadow()
     install_stubs()
     path = os.path.abspath(path)
@@ -91,6 +100,7 @@ def run(path: str, overrides: dict | None = None, chdir: bool = True) -> dict:
     if overrides:
         source = apply_overrides(source, overrides)
     ns = {"__name__": "__main__", "__file__": path, "__builtins__": __builtins__}
+    ns.update(inject or {})
     old = os.getcwd()
     import numpy as np
     err = np.geterr()
@@ -118,7 +128,7 @@ def main(argv=None) -> int:
             ov[k.strip()] = ast.literal_eval(v)
         except Exception:
             ov[k.strip()] = v
-    run(a.driver, ov)
+    run(a.driver, ov, inject={"pb": Silent()})
     return 0
 
 

@@ -34,12 +34,14 @@ def _dev(a):
 #   n4_pair4 / n4_nopair  tail-pair check-node kernels from degree 4 on / no tail-pair kernels at all
 #   n4_vpair3 / n4_vpair3_256  tail-pair variable-node kernels from degree 3 on, 512- / 256-thread CTAs
 #   n4_small_ctas  512- / 256-thread CTAs instead of the default 1024-thread ones (per-phase launches)
-#   n4_nocoop  per-phase launches also for small batches of regular codes (default: one cooperative whole-decode kernel
-#              up to 4096 frames)
+#   n4_nocoop  per-phase launches also for small batches (default: one cooperative whole-decode kernel up to 4096 frames);
+#              for the instantiated degree sets these are the fused per-phase kernels of ib_phase_n4.cuh (one launch per
+#              phase over all degree classes, TMA-staged table image), n4_nophase = one launch per degree class instead
 IB_VARIANTS = {"n4": {}, "n4_vn4": {"IBLDPC_VN_VEC": "4"}, "n4_vn2": {"IBLDPC_VN_VEC": "2"}, "n4_pair4": {"IBLDPC_PAIR_MIN_DEGREE": "4"},
                "n4_vpair3": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3"},
                "n4_vpair3_256": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3", "IBLDPC_VN_PAIR_THREADS": "256"},
-               "n4_nocoop": {"IBLDPC_COOP_MAX_B": "0"},
+               "n4_nocoop": {"IBLDPC_COOP_MAX_B": "0"},          # small batches too through the fused per-phase kernels (where instantiated)
+               "n4_nophase": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_NO_PHASE": "1"},   # one launch per degree class (round-1 default)
                "n4_small_ctas": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_CN_THREADS": "512", "IBLDPC_VN_THREADS": "256"},
                "n4_nopair": {"IBLDPC_NO_PAIR": "1"}, "u8": {"IBLDPC_NO_NIBBLE": "1"}}
 
@@ -56,7 +58,7 @@ def ib_variant(request, monkeypatch):
 def test_ib_golden_device_buffers(gpu, case, force_generic, monkeypatch, ib_variant):
     g = load_golden(case)
     if force_generic:
-        if ib_variant != 2 or any(os.environ.get(k) for k in ("IBLDPC_VN_VEC", "IBLDPC_PAIR_MIN_DEGREE", "IBLDPC_NO_PAIR", "IBLDPC_VN_PAIR_MIN_DEGREE", "IBLDPC_COOP_MAX_B", "IBLDPC_CN_THREADS")):
+        if ib_variant != 2 or any(os.environ.get(k) for k in ("IBLDPC_VN_VEC", "IBLDPC_PAIR_MIN_DEGREE", "IBLDPC_NO_PAIR", "IBLDPC_VN_PAIR_MIN_DEGREE", "IBLDPC_COOP_MAX_B", "IBLDPC_CN_THREADS", "IBLDPC_NO_PHASE")):
             pytest.skip("the generic path has one variant")
         monkeypatch.setenv("IBLDPC_FORCE_GENERIC", "1")
     T, imax = int(g["T"]), int(g["imax"])

@@ -281,3 +281,54 @@ def test_timed_bench_geometry_is_bit_exact(gpu):
     cols = np.r_[0:8, 8191:8199, 32760:32776]
     ref, _ = _oracle_ib(t, ch.tensor[:, torch.from_numpy(cols).cuda()].cpu().numpy(), 16, 50, tb, False)
     assert np.array_equal(out.tensor[:, torch.from_numpy(cols).cuda()].cpu().numpy(), ref.astype(np.uint8))
+
+
+@pytest.mark.parametrize("code", ["wlan1296", "dvb6480", "reg36"])
+@pytest.mark.parametrize("B", [1, 77, 513, 1040, 4097, 20011])
+@pytest.mark.parametrize("match", [True, False])
+def test_fused_phase_kernels_vs_oracle(gpu, monkeypatch, code, B, match):
+    """ib_phase_n4.cuh: one launch per phase over all degree classes (TMA-staged table image, dynamic item
+    distribution) against the oracle for ragged batch sizes -- one tile, partial tiles, more items than warps."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    monkeypatch.setenv("IBLDPC_COOP_MAX_B", "0")
+    H = {"wlan1296": lambda: codes.wlan_80211n(54), "dvb6480": lambda: codes.dvbs2_like_half_rate(6480, q_groups=36),
+         "reg36": lambda: codes.regular_random(2000, 3, 6, seed=5)}[code]()
+    if code == "reg36" and match:
+        pytest.skip("regular decoder has no message alignment")
+    t = graph.edge_tables(H)
+    T, imax = 16, 5
+    tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=B, matching=match)
+    rng = np.random.Generator(np.random.PCG64(B + 1))
+    ch = rng.integers(0, T, size=(t.n_var, B)).astype(np.uint8)
+    if code == "reg36":
+        dec = pkg.Discrete_LDPC_Decoder_class(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a, B)
+    else:
+        dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                        tb.matching_vector_checknode, tb.matching_vector_varnode, B,
+                                                        match='true' if match else 'false')
+    dec.init_OpenCL_decoding(B)
+    out = dec.decode_OpenCL(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True).get()
+    assert dec.info()[0] == 2 and dec.info()[1] == 1 + 2 * imax, dec.info()      # pack + 1 + 2 (imax - 1) + 1 launches
+    sel = np.arange(B) if B <= 1100 else np.r_[0:24, B // 2:B // 2 + 16, B - 24:B]
+    ref, i_num = _oracle_ib(t, np.ascontiguousarray(ch[:, sel]), T, imax, tb, B <= 1100)
+    assert np.array_equal(out[:, sel], ref)
+    if B <= 1100:
+        assert dec.last_i_num == i_num
+
+
+def test_fused_phase_kernels_early_termination(gpu, monkeypatch):
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    monkeypatch.setenv("IBLDPC_COOP_MAX_B", "0")
+    H = codes.wlan_80211n(54)
+    t = graph.edge_tables(H)
+    tb = luts.minsum_like_tables(16, t.d_c_max, t.d_v_max, 12)
+    dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, 12, 16, 16, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                    tb.matching_vector_checknode, tb.matching_vector_varnode, 300)
+    dec.init_OpenCL_decoding(300)
+    rng = np.random.Generator(np.random.PCG64(3))
+    ch = np.where(rng.random((t.n_var, 300)) < 0.93, rng.integers(9, 16, size=(t.n_var, 300)), rng.integers(0, 8, size=(t.n_var, 300))).astype(np.uint8)
+    out = dec.decode_OpenCL(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True).get()
+    ref, i_num = _oracle_ib(t, ch, 16, 12, tb, True)
+    assert np.array_equal(out, ref) and dec.last_i_num == i_num and 2 < i_num < 12
