@@ -10,7 +10,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libibldpc.so")
+LIB_PATH = os.environ.get("IBLDPC_LIB") or os.path.join(HERE, "libibldpc.so")   # IBLDPC_LIB: A/B builds of the same sources
 UNITS = ["ibldpc.cu", "ib_fast_cn.cu", "ib_fast_vn.cu", "ib_n4_cn_v2.cu", "ib_n4_cn_pair.cu", "ib_n4_vn_pair.cu", "ib_n4_vn_v2.cu", "ib_n4_vn_v4.cu", "ib_n4_coop.cu",
          "llr_f32.cu", "llr_f64.cu", "encoder.cu", "nccl_abi.cu", "ib_phase.cu", "ib_phase_wlan.cu", "ib_phase_dvbs2.cu", "ib_phase_reg36.cu"]   # compiled in parallel
 SOURCES = [os.path.join(HERE, "csrc", f) for f in UNITS + ["ib_kernels.cuh", "ib_kernels_n4.cuh", "ib_coop_n4.cuh", "llr_kernels.cuh", "kernel_tables.h", "ibldpc_internal.h", "ib_phase_n4.cuh", "ib_phase_sets.h"]]
@@ -117,6 +117,28 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
     return LIB_PATH
+
+
+def build_variant(name: str, defines, verbose: bool = False) -> str:
+    """A/B build of the same sources with extra -D defines into libibldpc_<name>.so (select it with IBLDPC_LIB=<path>).
+    Used for measured kernel experiments; the product library is build_library()'s."""
+    from concurrent.futures import ThreadPoolExecutor
+    build_dir = os.path.join(HERE, "csrc", f"build_{name}")
+    os.makedirs(build_dir, exist_ok=True)
+    out = os.path.join(HERE, f"libibldpc_{name}.so")
+
+    def compile_unit(unit):
+        obj = os.path.join(build_dir, unit.replace(".cu", ".o"))
+        cmd = ["nvcc"] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-c", os.path.join(HERE, "csrc", unit), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
+        objs = list(pool.map(compile_unit, UNITS))
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-ldl"])
+    return out
 
 
 _lib = None

@@ -34,6 +34,18 @@ __host__ __device__ constexpr int n4_table_bytes(int W) { return kTS * kTS * W *
 template <int VEC>
 __device__ __forceinline__ void ld_words(const uint8_t* p, uint32_t (&w)[VEC])
 {
+#ifdef IBLDPC_LD_NOALLOC
+    // A/B experiment: message rows are read once per phase; keep them out of the L1 data array the look-up tables
+    // share their banks with
+    if constexpr (VEC == 4) {
+        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p));
+    } else if constexpr (VEC == 2) {
+        asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p));
+    } else {
+        asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(w[0]) : "l"(p));
+    }
+    return;
+#endif
     if constexpr (VEC == 4) {
         const uint4 v = *reinterpret_cast<const uint4*>(p);
         w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;

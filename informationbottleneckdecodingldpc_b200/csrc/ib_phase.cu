@@ -1,6 +1,7 @@
 // ib_phase.cu -- host side of the fused per-phase kernels (ib_phase_n4.cuh): pre-expanded shared-memory images of
 // every phase, built once at ibldpc_set_luts, and the launch sequence of one decode (one launch per phase).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -111,10 +112,17 @@ int phase_prepare(ibldpc_decoder* h)
 {
     phase_free(h);
     if (!h->nib || !h->use_pair || !h->use_phase) return IBLDPC_OK;
-    const PhaseSetOps* candidates[] = {phase_ops_wlan(), phase_ops_dvbs2(), phase_ops_reg36()};
+    // Measured on B200 (profiles/README.md, round 2): the fused kernels sit on the same look-up-pipe / issue ceiling as
+    // the per-class ones, so they win where a phase is several launches with short classes (802.11n: 3.01 -> 3.51
+    // Gbit/s) and lose a few per cent where one class dominates a phase (DVB-S2 rate 1/2: 4.15 -> 3.95, regular (3,6):
+    // 6.01 -> 5.82).  Default: on for the 802.11n degree sets; IBLDPC_PHASE=1 turns them on for every instantiated set.
+    struct Cand { const PhaseSetOps* ops; bool by_default; };
+    const Cand candidates[] = {{phase_ops_wlan(), true}, {phase_ops_dvbs2(), false}, {phase_ops_reg36(), false}};
+    const bool force = getenv("IBLDPC_PHASE") != nullptr && atoi(getenv("IBLDPC_PHASE")) != 0;
     const PhaseSetOps* ops = nullptr;
-    for (const PhaseSetOps* o : candidates)
-        if (same_degrees(o->cn_deg, h->cn_classes) && same_degrees(o->vn_deg, h->vn_classes)) ops = o;
+    for (const Cand& c : candidates)
+        if ((c.by_default || force) && same_degrees(c.ops->cn_deg, h->cn_classes) && same_degrees(c.ops->vn_deg, h->vn_classes))
+            ops = c.ops;
     if (!ops) return IBLDPC_OK;
     PhaseImages* p = new PhaseImages();
     h->phase = p;

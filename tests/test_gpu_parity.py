@@ -40,7 +40,7 @@ def _dev(a):
 IB_VARIANTS = {"n4": {}, "n4_vn4": {"IBLDPC_VN_VEC": "4"}, "n4_vn2": {"IBLDPC_VN_VEC": "2"}, "n4_pair4": {"IBLDPC_PAIR_MIN_DEGREE": "4"},
                "n4_vpair3": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3"},
                "n4_vpair3_256": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3", "IBLDPC_VN_PAIR_THREADS": "256"},
-               "n4_nocoop": {"IBLDPC_COOP_MAX_B": "0"},          # small batches too through the fused per-phase kernels (where instantiated)
+               "n4_nocoop": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_PHASE": "1"},   # small batches too through the fused per-phase kernels (every instantiated degree set)
                "n4_nophase": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_NO_PHASE": "1"},   # one launch per degree class (round-1 default)
                "n4_small_ctas": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_CN_THREADS": "512", "IBLDPC_VN_THREADS": "256"},
                "n4_nopair": {"IBLDPC_NO_PAIR": "1"}, "u8": {"IBLDPC_NO_NIBBLE": "1"}}
