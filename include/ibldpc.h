@@ -188,7 +188,8 @@ int ibldpc_allreduce_counters(ibldpc_handle h, int64_t *counters_dev, int n, voi
 int ibldpc_nccl_finalize(ibldpc_handle h);
 
 /* Introspection for tests / benchmarks: which[0] = kernel family of the loaded tables (0 = generic path: tables in
- * global memory; 1 = uint8 shared-memory fast path; 2 = packed-nibble fast path), which[1] = kernels launched by the
+ * global memory; 1 = uint8 shared-memory fast path; 2 = packed-nibble fast path; 3 = |T| <= 32 shared-memory family),
+ * which[1] = kernels launched by the
  * last decode call, which[2] = persistent grid size, which[3] = dynamic smem bytes. */
 int ibldpc_info(ibldpc_handle h, int32_t *which4);
 

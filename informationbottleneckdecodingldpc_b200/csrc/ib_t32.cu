@@ -1,0 +1,196 @@
+// ib_t32.cu -- host side of the |T| <= 32 shared-memory family (ib_kernels_t32.cuh): table images of every
+// (iteration, degree class), built once at ibldpc_set_luts, and the launch sequence of one decode.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ibldpc_internal.h"
+#include "ib_kernels_t32.cuh"
+
+namespace ibldpc {
+
+struct T32Images {
+    uint8_t* d_images = nullptr;
+    // byte offsets inside d_images: [class][iteration]
+    std::vector<std::vector<size_t>> cn_off, vn_off, out_off;
+    std::vector<int*> cn_starts, vn_starts;
+    bool attrs_set = false;
+};
+
+namespace {
+
+// image of one class: [striped stages (the last ones)][plain stages (the first ones)], see ib_kernels_t32.cuh
+void build_t32_image(uint8_t* img, int nst, int T, const uint8_t* stages /* [nst][T*T] */, size_t stage_stride,
+                     const uint8_t* match_row)
+{
+    memset(img, 0, (size_t)t32_image_bytes(nst));
+    for (int c = 0; c < nst; ++c) {
+        const uint8_t* S = stages + (size_t)c * stage_stride;
+        uint8_t* dst = img + t32_col_base(nst, c);
+        const bool fold = match_row != nullptr && c == nst - 1;
+        for (int t = 0; t < T; ++t)
+            for (int m = 0; m < T; ++m) {
+                uint8_t e = S[t * T + m];
+                if (fold) e = match_row[e];
+                if (t32_is_striped(nst, c)) {
+                    uint8_t* row = dst + (size_t)t * 1024 + (size_t)(m >> 2) * 128 + (m & 3);
+                    for (int l = 0; l < 32; ++l) row[l * 4] = e;
+                } else {
+                    dst[t * 32 + m] = e;
+                }
+            }
+    }
+}
+
+}  // namespace
+
+void t32_free(ibldpc_decoder* h)
+{
+    T32Images* p = h->t32_images;
+    if (!p) return;
+    if (p->d_images) cudaFree(p->d_images);
+    for (int* q : p->cn_starts) if (q) cudaFree(q);
+    for (int* q : p->vn_starts) if (q) cudaFree(q);
+    delete p;
+    h->t32_images = nullptr;
+}
+
+int t32_prepare(ibldpc_decoder* h)
+{
+    t32_free(h);
+    if (!h->t32) return IBLDPC_OK;
+    T32Images* p = new T32Images();
+    h->t32_images = p;
+    const int T = h->T, TT = T * T, DC = h->DC, DV = h->DV, imax = h->lut_imax;
+    std::vector<uint8_t> host;
+    auto add = [&](int nst, const uint8_t* stages, const uint8_t* mrow) -> size_t {
+        const size_t off = host.size();
+        host.resize(off + (size_t)t32_image_bytes(nst));
+        if (nst > 0) build_t32_image(host.data() + off, nst, T, stages, (size_t)TT, mrow);
+        return off;
+    };
+    for (auto& c : h->cn_classes) {
+        std::vector<size_t> offs;
+        for (int blk = 0; blk < imax; ++blk)
+            offs.push_back(add(c.degree - 2, h->h_cn8.data() + (size_t)blk * (DC - 2) * TT,
+                               h->match ? h->h_mc8.data() + ((size_t)blk * DC + (c.degree - 1)) * T : nullptr));
+        p->cn_off.push_back(offs);
+    }
+    for (auto& c : h->vn_classes) {
+        std::vector<size_t> up, dec;
+        for (int it = 0; it < imax; ++it) {
+            up.push_back(add(c.degree - 1, h->h_vn8.data() + (size_t)it * DV * TT,
+                             h->match ? h->h_mv8.data() + ((size_t)it * DV + (c.degree - 1)) * T : nullptr));
+        }
+        for (int it = 0; it < imax; ++it) dec.push_back(add(c.degree, h->h_vn8.data() + (size_t)it * DV * TT, nullptr));
+        p->vn_off.push_back(up);
+        p->out_off.push_back(dec);
+    }
+    IBLDPC_CK(cudaMalloc((void**)&p->d_images, std::max<size_t>(host.size(), 16)));
+    IBLDPC_CK(cudaMemcpy(p->d_images, host.data(), host.size(), cudaMemcpyHostToDevice));
+    auto starts_of = [&](const NodeClass& c, const std::vector<int>& all_starts, std::vector<int*>& out) -> int {
+        std::vector<int> nodes((size_t)c.count), st((size_t)c.count);
+        IBLDPC_CK(cudaMemcpy(nodes.data(), c.d_nodes, sizeof(int) * (size_t)c.count, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < c.count; ++i) st[i] = all_starts[nodes[i]];
+        int* d = nullptr;
+        IBLDPC_CK(cudaMalloc((void**)&d, sizeof(int) * (size_t)std::max(c.count, 1)));
+        IBLDPC_CK(cudaMemcpy(d, st.data(), sizeof(int) * (size_t)c.count, cudaMemcpyHostToDevice));
+        out.push_back(d);
+        return IBLDPC_OK;
+    };
+    for (auto& c : h->cn_classes)
+        if (int rc = starts_of(c, h->h_sc, p->cn_starts)) return rc;
+    for (auto& c : h->vn_classes)
+        if (int rc = starts_of(c, h->h_sv, p->vn_starts)) return rc;
+    return IBLDPC_OK;
+}
+
+// One decode; `a` = graph pointers, sanitised uint8 channel buffer, message array, output, pitch, flags.
+int decode_ib_t32(ibldpc_decoder* h, const IbArgs& a, int imax, int early, cudaStream_t st)
+{
+    T32Images* p = h->t32_images;
+    if (!p->attrs_set) {
+        for (auto& c : h->cn_classes)
+            for (int e = 0; e < 2; ++e)
+                IBLDPC_CK(cudaFuncSetAttribute((const void*)t32_cn_kernel(c.degree, e != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               t32_image_bytes(c.degree - 2)));
+        for (auto& c : h->vn_classes) {
+            IBLDPC_CK(cudaFuncSetAttribute((const void*)t32_vn_kernel(c.degree), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           t32_image_bytes(c.degree - 1)));
+            IBLDPC_CK(cudaFuncSetAttribute((const void*)t32_out_kernel(c.degree), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           t32_image_bytes(c.degree)));
+        }
+        p->attrs_set = true;
+    }
+    auto grid_for = [&](int mode, const NodeClass& c) {
+        const long long vec = t32_vec(mode, c.degree);
+        const long long tiles = ((long long)a.pitch + 128 * vec - 1) / (128 * vec);
+        return (int)std::max<long long>(1, std::min<long long>(h->sm_count, ((long long)c.count * tiles + 31) / 32));
+    };
+    auto prof_begin = [&](int phase) -> int {
+        if (!h->profiling) return IBLDPC_OK;
+        PhaseEvent ev;
+        ev.phase = phase;
+        IBLDPC_CK(cudaEventCreate(&ev.a));
+        IBLDPC_CK(cudaEventCreate(&ev.b));
+        IBLDPC_CK(cudaEventRecord(ev.a, st));
+        h->events.push_back(ev);
+        return IBLDPC_OK;
+    };
+    auto prof_end = [&]() -> int {
+        if (h->profiling) IBLDPC_CK(cudaEventRecord(h->events.back().b, st));
+        return IBLDPC_OK;
+    };
+    T32Args base{};
+    base.a = a;
+    base.a.early = early;
+    base.a.imax = imax;
+    int rc;
+    auto launch_cn = [&](int it) -> int {
+        if ((rc = prof_begin(it < 0 ? 2 : 0))) return rc;
+        for (size_t ci = 0; ci < h->cn_classes.size(); ++ci) {
+            const NodeClass& c = h->cn_classes[ci];
+            T32Args q = base;
+            q.a.it = it;
+            q.a.iter0 = it < 0;
+            q.image = p->d_images + p->cn_off[ci][it + 1];
+            q.nodes = c.d_nodes; q.starts = p->cn_starts[ci]; q.n_nodes = c.count;
+            const int grid = grid_for(kPhaseCn, c);
+            t32_cn_kernel(c.degree, early != 0)<<<grid, kT32Threads, t32_image_bytes(c.degree - 2), st>>>(q);
+            h->last_launches++; h->last_grid = grid; h->last_smem = t32_image_bytes(c.degree - 2);
+        }
+        return prof_end();
+    };
+    auto launch_vn = [&](int it, bool decide) -> int {
+        if ((rc = prof_begin(decide ? 2 : 1))) return rc;
+        for (size_t ci = 0; ci < h->vn_classes.size(); ++ci) {
+            const NodeClass& c = h->vn_classes[ci];
+            T32Args q = base;
+            q.a.it = it;
+            q.a.iter0 = 0;
+            q.nodes = c.d_nodes; q.starts = p->vn_starts[ci]; q.n_nodes = c.count;
+            if (decide) {
+                q.image = p->d_images + p->out_off[ci][0];
+                q.image_stride = h->lut_imax > 1 ? (long long)(p->out_off[ci][1] - p->out_off[ci][0]) : 0;
+                t32_out_kernel(c.degree)<<<grid_for(kPhaseOut, c), kT32Threads, t32_image_bytes(c.degree), st>>>(q);
+            } else {
+                q.image = p->d_images + p->vn_off[ci][it];
+                const int smem = c.degree > 1 ? t32_image_bytes(c.degree - 1) : 0;
+                t32_vn_kernel(c.degree)<<<grid_for(kPhaseVn, c), kT32Threads, smem, st>>>(q);
+            }
+            h->last_launches++;
+        }
+        return prof_end();
+    };
+    if ((rc = launch_cn(-1))) return rc;
+    for (int it = 0; it < imax - 1; ++it) {
+        if ((rc = launch_vn(it, false))) return rc;
+        if ((rc = launch_cn(it))) return rc;
+    }
+    if ((rc = launch_vn(0, true))) return rc;
+    IBLDPC_CK(cudaGetLastError());
+    return IBLDPC_OK;
+}
+
+}  // namespace ibldpc

@@ -267,7 +267,7 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
         w.msg = (uint8_t*)p;
         if (rc) return rc;
     }
-    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)(std::max(imax, 1) + 1), st));
+    CK(cudaMemsetAsync(w.flags + 1, 0, sizeof(int) * (size_t)std::max(imax, 1), st));   // flags[0] (input range) is sticky until read
     {   // These families use the channel values as table indices as they are: work on a sanitised copy (values
         // >= |T_channel| clamped and reported through flags[0]) so that no look-up can leave its table.
         void* p = w.ch4;
@@ -293,6 +293,7 @@ int decode_ib_padded(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long lo
     a.DC = h->DC; a.DV = h->DV; a.xp_col = -1;
     const int T = h->T, Tc = h->Tc, TT = T * T;
     h->last_launches = 0;
+    if (h->t32) return decode_ib_t32(h, a, imax, early, st);
     Prof prof{h, st};
 
     // Irregular codes: the degree classes of one phase are independent, so their kernels CAN run
@@ -473,7 +474,7 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
         w.ch4 = (uint8_t*)p;
         if (rc) return rc;
     }
-    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)(std::max(imax, 1) + 1), st));
+    CK(cudaMemsetAsync(w.flags + 1, 0, sizeof(int) * (size_t)std::max(imax, 1), st));   // flags[0] (input range) is sticky until read
     h->last_launches = 0;
     Prof prof{h, st};
     if (!ch_packed) {   // ch_packed: the caller already filled w.ch4 (packed host path)
@@ -700,6 +701,7 @@ int read_back_status(Workspace& w, cudaStream_t st, int32_t* i_num_host)
     CK(cudaMemcpyAsync(&host2[1], w.flags, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (i_num_host) *i_num_host = host2[0];
+    if (host2[1] != 0) CK(cudaMemsetAsync(w.flags, 0, sizeof(int), st));   // reported once
     if (host2[1] != 0)
         return fail(IBLDPC_E_INVALID, "channel cluster indices must lie in [0, cardinality_T_channel): the decode clamped out-of-range values");
     return IBLDPC_OK;
@@ -782,7 +784,7 @@ int decode_llr_padded(ibldpc_decoder* h, Workspace& w, const F* ch, long long pi
             return fail(IBLDPC_E_NOMEM, "cudaMalloc of LLR message arrays failed");
         w.llr_bytes = need;
     }
-    CK(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)(std::max(imax, 1) + 1), st));
+    CK(cudaMemsetAsync(w.flags + 1, 0, sizeof(int) * (size_t)std::max(imax, 1), st));   // flags[0] (input range) is sticky until read
     LlrArgs a{};
     a.sc = h->d_sc; a.deg_c = h->d_dc; a.tc = h->d_tc; a.sv = h->d_sv; a.deg_v = h->d_dv; a.tv = h->d_tv;
     a.n_var = h->N; a.n_chk = h->M;
@@ -1109,6 +1111,10 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
               (size_t)h->nrows_c * h->Wc * 128 <= smem_max && (size_t)h->nrows_v * h->Wv * 128 <= smem_max &&
               (size_t)h->nrows_o * h->Wo * 128 <= smem_max;
     if (getenv("IBLDPC_FORCE_GENERIC")) h->fast = false;
+    // 16 < |T| <= 32 (the reference's 802.11n design uses 32): byte messages, per-lane replicated 32 x 32 stage tables
+    // (ib_kernels_t32.cuh).  Degree-2 checks (explicit matching column) and T_c != T stay on the generic path.
+    h->t32 = !h->fast && T > 16 && T <= 32 && Tc == T && h->dc_min >= 3 && h->dc_max <= 10 && h->dv_max <= 12 &&
+             getenv("IBLDPC_FORCE_GENERIC") == nullptr && getenv("IBLDPC_NO_T32") == nullptr;
     // packed-nibble messages need an even |T| (address terms are shifts of the packed word)
     h->nib = h->fast && (T % 2 == 0) && getenv("IBLDPC_NO_NIBBLE") == nullptr;
     h->vn_vec = 0;
@@ -1180,6 +1186,7 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
                    getenv("IBLDPC_VN_PAIR_MIN_DEGREE") == nullptr && h->vn_vec == 0 && h->cn_threads == 0 &&
                    h->vn_threads == 0 && h->vn_pair_threads == 0 && getenv("IBLDPC_NO_PLAN") == nullptr;
     if ((rc = phase_prepare(h))) return rc;
+    if ((rc = t32_prepare(h))) return rc;
     h->occ_cache.clear();
     h->have_luts = true;
     return IBLDPC_OK;
@@ -1549,7 +1556,7 @@ int ibldpc_uniform(int device, uint64_t seed, uint64_t offset, int64_t n, double
 int ibldpc_info(ibldpc_handle h, int32_t* which4)
 {
     if (!h || !which4) return fail(IBLDPC_E_INVALID, "null argument");
-    which4[0] = h->fast ? (h->nib ? 2 : 1) : 0;   // 0 generic, 1 uint8 fast path, 2 packed-nibble fast path
+    which4[0] = h->fast ? (h->nib ? 2 : 1) : h->t32 ? 3 : 0;   // 0 generic, 1 uint8, 2 packed-nibble, 3 |T| <= 32 family
     which4[1] = h->last_launches;
     which4[2] = h->last_grid;
     which4[3] = h->last_smem;
@@ -1613,6 +1620,7 @@ int ibldpc_destroy(ibldpc_handle h)
     cudaDeviceSynchronize();
     ibldpc_nccl_finalize(h);
     phase_free(h);
+    t32_free(h);
     clear_events(h);
     for (int* p : {h->d_sc, h->d_dc, h->d_tc, h->d_sv, h->d_dv, h->d_tv, h->d_vidx})
         if (p) cudaFree(p);

@@ -83,6 +83,7 @@ struct Workspace {
 };
 
 struct PhaseImages;   // ib_phase.cu: pre-expanded shared-memory table images of the fused per-phase kernels
+struct T32Images;     // ib_t32.cu: table images of the |T| <= 32 family
 struct IbArgs;
 
 }  // namespace ibldpc
@@ -124,6 +125,7 @@ struct ibldpc_decoder {
     int host_chunk = 0;   // 0 = auto: about 256 MiB of channel values per chunk
     // fused per-phase kernels (ib_phase_n4.cuh): one launch per phase over all degree classes
     ibldpc::PhaseImages* phase = nullptr;
+    ibldpc::T32Images* t32_images = nullptr;
     int use_phase = 1;    // IBLDPC_NO_PHASE=1 keeps one launch per degree class
     // stream / workspace of the last decode (lazy i_num read-back)
     cudaStream_t last_stream = nullptr;
@@ -142,6 +144,10 @@ namespace ibldpc {
 int phase_prepare(ibldpc_decoder* h);   // end of ibldpc_set_luts: build + upload the phase images (or leave h->phase null)
 void phase_free(ibldpc_decoder* h);
 int decode_ib_phase(ibldpc_decoder* h, const IbArgs& a, int imax, int early, cudaStream_t st);
+// |T| <= 32 shared-memory family (ib_t32.cu)
+int t32_prepare(ibldpc_decoder* h);
+void t32_free(ibldpc_decoder* h);
+int decode_ib_t32(ibldpc_decoder* h, const IbArgs& a, int imax, int early, cudaStream_t st);
 }  // namespace ibldpc
 
 #define IBLDPC_CK(call)                                                                                       \

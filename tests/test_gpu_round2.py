@@ -337,3 +337,69 @@ def test_fused_phase_kernels_early_termination(gpu, monkeypatch):
     ref, i_num = _oracle_ib(t, ch, 16, 12, tb, True)
     assert dec.info()[1] == 1 + 2 * 12          # fused kernels (every launch is issued; converged passes return at once)
     assert np.array_equal(out, ref) and dec.last_i_num == i_num and 2 < i_num < 12, (dec.last_i_num, i_num)
+
+
+# ---------------------------------------------------------------------------------- |T| <= 32 family (ib_kernels_t32.cuh)
+@pytest.mark.parametrize("T", [32, 24, 18])
+@pytest.mark.parametrize("match", [True, False])
+def test_t32_family_all_degrees(gpu, T, match):
+    """Every instantiated degree (checks 3..10, variables 1..12) of the |T| <= 32 family against the oracle, ragged batch."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    deg_v = [1, 1] + [d for d in range(2, 13) for _ in range(6)]
+    E = sum(deg_v)
+    deg_c = [3] * 9 + [4] * 8 + [5] * 8 + [6] * 8 + [7] * 6 + [8] * 6 + [9] * 4 + [10] * 4
+    deg_c += [4] * ((E - sum(deg_c)) // 4)
+    rest = E - sum(deg_c)
+    assert 0 <= rest < 4
+    if rest:
+        deg_c[0:rest] = [d + 1 for d in deg_c[0:rest]]
+    H = codes.random_from_degrees(deg_v, deg_c, seed=8)
+    t = graph.edge_tables(H)
+    assert set(t.degree_chk) >= set(range(3, 11)) and set(t.degree_var) == set(range(1, 13))
+    imax, B = 5, 333
+    tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=T, matching=match)
+    ch = np.random.Generator(np.random.PCG64(T)).integers(0, T, size=(t.n_var, B)).astype(np.uint8)
+    dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                    tb.matching_vector_checknode, tb.matching_vector_varnode, B,
+                                                    match='true' if match else 'false')
+    dec.init_OpenCL_decoding(B)
+    out = dec.decode_OpenCL(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True).get()
+    assert dec.info()[0] == 3
+    ref, i_num = _oracle_ib(t, ch, T, imax, tb, True)
+    assert np.array_equal(out, ref) and dec.last_i_num == i_num
+
+
+@pytest.mark.parametrize("B", [1, 100, 2049, 20011])
+def test_t32_family_wlan_vs_oracle_and_generic(gpu, monkeypatch, B):
+    """802.11n with the reference's cardinality 32: oracle on a sample of frames, the generic path on all of them;
+    host-buffer contract (int numpy in / out) through the same kernels."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    H = codes.wlan_80211n(54)
+    t = graph.edge_tables(H)
+    T, imax = 32, 6
+    tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=B, matching=True)
+    ch = np.random.Generator(np.random.PCG64(B)).integers(0, T, size=(t.n_var, B)).astype(np.uint8)
+
+    def run():
+        dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                        tb.matching_vector_checknode, tb.matching_vector_varnode, B)
+        dec.init_OpenCL_decoding(B)
+        dec.early_termination = False
+        return dec, dec.decode_OpenCL(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True).get()
+
+    dec, out = run()
+    assert dec.info()[0] == 3
+    sel = np.arange(B) if B <= 100 else np.r_[0:12, B - 12:B]
+    ref, _ = _oracle_ib(t, np.ascontiguousarray(ch[:, sel]), T, imax, tb, False)
+    assert np.array_equal(out[:, sel], ref)
+    host = dec.decode_OpenCL(ch.astype(np.int32))
+    assert host.dtype == np.int32 and np.array_equal(host, out)
+    monkeypatch.setenv("IBLDPC_NO_T32", "1")
+    dec_g, out_g = run()
+    assert dec_g.info()[0] == 0 and np.array_equal(out_g, out)
+    bad = ch.copy()
+    bad[3, 0] = 40
+    with pytest.raises(ValueError):
+        dec.decode_OpenCL(bad)
