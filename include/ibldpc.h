@@ -96,6 +96,16 @@ int ibldpc_decode_ib(ibldpc_handle h, const uint8_t *ch_dev, int64_t B, int imax
 int ibldpc_decode_ib_host(ibldpc_handle h, const uint8_t *ch_host, int64_t B, int imax, int early_term,
                           uint8_t *out_host, int32_t *i_num_host);
 
+/* Opt-in, beyond the reference: PER-FRAME early termination with frame compaction.  The
+ * reference stops a batch only when ALL its frames have zero syndrome (discrete_LDPC_decoder.py:233,273); this call
+ * returns, for every frame, exactly what the reference returns when that frame is decoded on its own
+ * (msg_at_time = 1): decided cluster indices out_dev (n_var, B) and, if i_num_frames_dev != NULL, the frame's own
+ * i_num (int32 [B], device).  Converged frames are decided at once and dropped from the message arrays, so the cost
+ * follows the average -- not the maximum -- iteration count.  Asynchronous on `stream`; ibldpc_last_i_num gives the
+ * largest per-frame i_num.  Needs the packed-nibble family and an instantiated degree set (IBLDPC_E_STATE otherwise). */
+int ibldpc_decode_ib_perframe(ibldpc_handle h, const uint8_t *ch_dev, int64_t B, int imax, uint8_t *out_dev,
+                              int32_t *i_num_frames_dev, void *stream);
+
 /* i_num of the last decode issued on this handle, read back lazily: synchronises the stream of that decode.  Lets
  * BER loops call ibldpc_decode_ib with i_num_host == NULL (fully asynchronous) and still query the reference's
  * i_num afterwards.  Returns IBLDPC_E_INVALID if the channel buffer of that decode held a value >= card_channel

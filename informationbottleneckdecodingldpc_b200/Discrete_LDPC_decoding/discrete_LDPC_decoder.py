@@ -42,8 +42,11 @@ class Discrete_LDPC_Decoder_class(GraphDecoderBase):
 
     def _post_init(self):
         # The reference always stops as soon as the whole batch has zero syndrome
-        # (discrete_LDPC_decoder.py:233-276).  Set False for fixed-imax (throughput) runs.
+        # (discrete_LDPC_decoder.py:233-276).  Set False for fixed-imax (throughput) runs, or 'frame' for the opt-in
+        # per-frame stop with frame compaction: every frame gets exactly the result (and i_num, see
+        # last_i_num_per_frame) the reference gives when that frame is decoded on its own (msg_at_time = 1).
         self.early_termination = True
+        self.last_i_num_per_frame = None
         self.host_output_dtype = np.int32   # dtype decode_OpenCL(..., return_buffer=False) returns
         self.last_i_num = None
         self._luts_uploaded = False
@@ -108,10 +111,36 @@ class Discrete_LDPC_Decoder_class(GraphDecoderBase):
         early = self.early_termination if early_termination is None else early_termination
         L = _lib.lib()
         inum = C.c_int32(0)
+        per_frame = isinstance(early, str) and early.lower() == 'frame'
+        if per_frame and not buffer_in:
+            # host arrays: one upload, the device path below, one download (no chunking: the stop is per frame)
+            rb = np.asarray(received_blocks)
+            if rb.ndim == 1:
+                rb = rb[:, None]
+            if rb.dtype != np.uint8:
+                if rb.size and (rb.min() < 0 or rb.max() >= int(self.cardinality_T_channel)):
+                    raise ValueError("channel cluster indices must lie in [0, cardinality_T_channel)")
+                rb = rb.astype(np.uint8)
+            out = self.decode_OpenCL(DeviceArray(torch.from_numpy(np.ascontiguousarray(rb)).cuda()), buffer_in=True,
+                                     return_buffer=True, early_termination='frame')
+            if return_buffer:
+                return out
+            return out.get().astype(self.host_output_dtype, copy=False)
         if buffer_in:
             ch = self._device_input(received_blocks, torch.uint8)
             B = ch.shape[1]
             out = torch.empty_like(ch)
+            if per_frame:
+                inum_f = torch.empty(B, dtype=torch.int32, device=ch.device)
+                _lib.check(L.ibldpc_decode_ib_perframe(h, C.c_void_p(ch.data_ptr()), B, int(self.imax), C.c_void_p(out.data_ptr()),
+                                                       C.c_void_p(inum_f.data_ptr()), C.c_void_p(stream_ptr())))
+                self.last_i_num_per_frame = DeviceArray(inum_f)
+                self._inum_pending = True
+                if return_buffer:
+                    return DeviceArray(out)
+                res = out.cpu().numpy().astype(self.host_output_dtype, copy=False)
+                self.last_i_num
+                return res
             # asynchronous on the current stream: i_num stays on the device until someone reads self.last_i_num
             _lib.check(L.ibldpc_decode_ib(h, C.c_void_p(ch.data_ptr()), B, int(self.imax), int(bool(early)),
                                           C.c_void_p(out.data_ptr()), None, C.c_void_p(stream_ptr())))

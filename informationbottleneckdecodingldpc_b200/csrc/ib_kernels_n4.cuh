@@ -218,7 +218,7 @@ __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t
 
 template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR, int WT = 0, int CB = 0>
 __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* tab, const uint8_t* ptab, int s, uint32_t col,
-                                               uint32_t lane4, int valid_frames)
+                                               uint32_t lane4, int valid_frames, uint32_t* fsyn = nullptr)
 {
     uint32_t m[D][VEC];
     if (a.iter0) {
@@ -256,6 +256,8 @@ __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* t
             const int nv = valid_frames - 8 * j;   // ignore padding frames
             const uint32_t vmask = nv >= 8 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (4 * nv)) - 1u);
             syn |= par & vmask;
+            // per-frame early termination: bit 4f of fsyn[word] = frame f of that word failed a check in this pass
+            if (fsyn != nullptr && (par & vmask) != 0u) atomicOr(fsyn + j, par & vmask);
         }
         if constexpr (PAIR) cn_word_n4_pair<D, WT, CB>(w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
         else cn_word_n4<D, MATCH, WT, CB>(w, o, tab, lane4);

@@ -182,6 +182,54 @@ int phase_prepare(ibldpc_decoder* h)
 
 bool phase_available(const ibldpc_decoder* h) { return h->phase != nullptr; }
 
+const PhaseSetOps* phase_ops_of(const ibldpc_decoder* h) { return h->phase ? h->phase->ops : nullptr; }
+
+// image pointer, node lists and dynamic shared memory of one phase: mode kPhaseCn with table block `index`,
+// kPhaseVn with iteration `index`, kPhaseOut with the decision tables of iteration `index` (per-frame mode)
+void phase_fill_args(const ibldpc_decoder* h, int mode, int index, PhaseArgs& q, size_t* smem)
+{
+    const PhaseImages* p = h->phase;
+    const PhaseSetOps* ops = p->ops;
+    if (mode == kPhaseCn) {
+        q.image = p->d_images + (size_t)index * p->cn_bytes;
+        *smem = p->cn_bytes;
+        for (int i = 0; i < ops->cn_layout.n; ++i) {
+            q.nodes[i] = p->cn_nodes[i]; q.starts[i] = p->cn_starts[i]; q.n_nodes[i] = p->cn_count[i];
+        }
+        return;
+    }
+    if (mode == kPhaseVn) {
+        q.image = p->d_images + (size_t)p->imax * p->cn_bytes + (size_t)index * p->vn_bytes;
+        *smem = p->vn_bytes;
+    } else {
+        q.image = p->d_images + (size_t)p->imax * (p->cn_bytes + p->vn_bytes);
+        q.image_stride = (long long)p->out_bytes;       // the kernel adds a.it * stride
+        *smem = p->out_bytes;
+    }
+    for (int i = 0; i < ops->vn_layout.n; ++i) {
+        q.nodes[i] = p->vn_nodes[i]; q.starts[i] = p->vn_starts[i]; q.n_nodes[i] = p->vn_count[i];
+    }
+}
+
+int phase_set_attributes(ibldpc_decoder* h)
+{
+    PhaseImages* p = h->phase;
+    const PhaseSetOps* ops = p->ops;
+    if (p->occ_checked) return IBLDPC_OK;
+    const struct { PhaseKernel k; size_t smem; } ks[] = {{ops->cn_kernel[0], p->cn_bytes}, {ops->cn_kernel[1], p->cn_bytes},
+                                                         {ops->vn_kernel, p->vn_bytes}, {ops->out_kernel, p->out_bytes},
+                                                         {ops->cn_pf_kernel, p->cn_bytes}, {ops->vn_pf_kernel, p->vn_bytes},
+                                                         {ops->out_pf_kernel, p->out_bytes}};
+    for (auto& e : ks) {
+        IBLDPC_CK(cudaFuncSetAttribute((const void*)e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem));
+        int occ = 0;
+        IBLDPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e.k, kPhaseThreads, e.smem));
+        if (occ < 1) return fail_msg(IBLDPC_E_CUDA, "fused per-phase kernel does not fit on an SM");
+    }
+    p->occ_checked = 1;
+    return IBLDPC_OK;
+}
+
 namespace {
 
 struct PhaseProf {
@@ -216,17 +264,7 @@ int decode_ib_phase(ibldpc_decoder* h, const IbArgs& a, int imax, int early, cud
 {
     PhaseImages* p = h->phase;
     const PhaseSetOps* ops = p->ops;
-    if (!p->occ_checked) {
-        const struct { PhaseKernel k; size_t smem; } ks[] = {{ops->cn_kernel[0], p->cn_bytes}, {ops->cn_kernel[1], p->cn_bytes},
-                                                             {ops->vn_kernel, p->vn_bytes}, {ops->out_kernel, p->out_bytes}};
-        for (auto& e : ks) {
-            IBLDPC_CK(cudaFuncSetAttribute((const void*)e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem));
-            int occ = 0;
-            IBLDPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e.k, kPhaseThreads, e.smem));
-            if (occ < 1) return fail_msg(IBLDPC_E_CUDA, "fused per-phase kernel does not fit on an SM");
-        }
-        p->occ_checked = 1;
-    }
+    if (int rc0 = phase_set_attributes(h)) return rc0;
     auto grid_for = [&](const PhaseLayoutRt& L, const int* counts) {
         long long chunks = 0;   // groups of 32 items: below one group per CTA there is nothing to share
         for (int i = 0; i < L.n; ++i) {

@@ -102,6 +102,27 @@ struct PhaseArgs {
     const int* nodes[kPhaseMaxClasses];    // node ids of every class, in the order of the degree set
     const int* starts[kPhaseMaxClasses];   // sc[node] resp. sv[node] of the same nodes (saves one dependent load)
     int n_nodes[kPhaseMaxClasses];
+    // per-frame early termination with frame compaction (ib_perframe.cu); unused (null) otherwise
+    const struct PfState* pf;       // device-side state: active columns, current ping-pong buffer, done flag
+    uint8_t* pf_msg[2];             // message arrays (ping-pong across compactions)
+    const uint8_t* pf_ch[2];        // packed channel values (ping-pong)
+    const int* pf_idx[2];           // original frame index of every column (ping-pong)
+    uint32_t* pf_fsyn;              // [words] bit 4f: frame f of the word failed a check in this pass
+    const uint32_t* pf_conv;        // [words] nibble mask of the frames to decide in this launch
+};
+
+// Device-side state of a per-frame-early-termination decode: every kernel of the schedule is launched unconditionally
+// and reads what is left to do from here (no host synchronisation inside a decode).
+struct PfState {
+    int n_act;        // columns [0, n_act) of the current buffers are in use (alive or converged since the last compaction)
+    int act_pitch;    // ceil(n_act / 2) rounded up to 16 bytes
+    int cur;          // current ping-pong buffer
+    int n_alive;      // frames still iterating
+    int done;         // n_alive == 0: every later kernel returns at once
+    int do_compact;   // set by pf_scan_kernel when the next gather is worth it
+    int new_n;        // alive columns after that gather
+    int alive_acc;    // accumulator of pf_update_kernel
+    unsigned blocks_done;
 };
 
 // ---- TMA bulk copy of the image ------------------------------------------------------------------------------
@@ -149,7 +170,9 @@ __device__ __forceinline__ int ld_nc_again(const int* p)
 }
 
 // ---- one item = one (node, tile) of class I ------------------------------------------------------------------
-template <int MODE, bool EARLY, typename L, int I>
+struct PfCtx { uint32_t* fsyn; const uint32_t* conv; const int* idx; };
+
+template <int MODE, bool EARLY, typename L, int I, bool PF = false>
 struct PhaseItem {
     static constexpr int D = L::degree(I);
     static constexpr int VEC = phase_vec(MODE, D);
@@ -160,15 +183,26 @@ struct PhaseItem {
 
     // returns the syndrome bits seen (check-node phase with EARLY), 0 otherwise
     static __device__ __forceinline__ uint32_t run(const IbArgs& a, const uint8_t* s_img, int node, int start, uint32_t col,
-                                                   uint32_t lane4)
+                                                   uint32_t lane4, const PfCtx& pf)
     {
         const uint8_t* tab = s_img + L::n_pair * kPairBytes;
         const uint8_t* ptab = s_img + PI * kPairBytes;
         if constexpr (MODE == kPhaseCn) {
-            return cn_node_n4<D, false, EARLY, VEC, PAIR, WT, CB>(a, tab, ptab, start, col, lane4, a.B - 2 * (int)col);
+            return cn_node_n4<D, false, EARLY, VEC, PAIR, WT, CB>(a, tab, ptab, start, col, lane4, a.B - 2 * (int)col,
+                                                                  PF ? pf.fsyn + (col >> 2) : nullptr);
         } else {
             constexpr bool DECIDE = MODE == kPhaseOut;
             constexpr bool kKeepRows = D <= 6;   // row indices stay in registers only where the budget allows
+            uint32_t cm[VEC];                    // per-frame ET, decision: nibble mask of the frames to decide
+            if constexpr (PF && DECIDE) {
+                uint32_t any = 0;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    cm[j] = pf.conv[(col >> 2) + j];
+                    any |= cm[j];
+                }
+                if (any == 0) return 0;          // none of this lane's frames converged in this pass
+            }
             int rows[D];
             VnIn4<D, VEC> in;
             ld_words<VEC>(a.ch + (uint64_t)(uint32_t)node * a.pitch + col, in.c);
@@ -195,7 +229,19 @@ struct PhaseItem {
                     for (int k = 0; k < D; ++k) r[k][j] = o[k];
                 }
             }
-            if constexpr (DECIDE) {
+            if constexpr (DECIDE && PF) {
+                // only the frames that converged in this pass, scattered to their original column
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    if (cm[j] == 0) continue;
+                    const int* ix = pf.idx + (((col >> 2) + j) << 3);
+#pragma unroll
+                    for (int f = 0; f < 8; ++f)
+                        if ((cm[j] >> (4 * f)) & 1u)
+                            a.out[(uint64_t)(uint32_t)node * a.out_pitch + (uint32_t)ix[f]] =
+                                (uint8_t)(dec[2 * j + (f >> 2)] >> (8 * (f & 3)));
+                }
+            } else if constexpr (DECIDE) {
                 // decided cluster indices leave as uint8 (one byte per frame): 8*VEC bytes per lane
                 const uint32_t ocol = 2u * col;
                 uint8_t* dst = a.out + (uint64_t)(uint32_t)node * a.out_pitch + ocol;
@@ -226,8 +272,8 @@ __device__ __forceinline__ void phase_unroll(F& f, std::integer_sequence<int, Is
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------
-template <int MODE, bool EARLY, int... Ds>
-__global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_kernel(PhaseArgs p)
+template <int MODE, bool EARLY, bool PF, int... Ds>
+__device__ __forceinline__ void phase_kernel_body(const PhaseArgs& p, const IbArgs& a, uint32_t bound, const PfCtx& pfc)
 {
     using L = PhaseLayout<MODE, Ds...>;
     static_assert(L::n <= kPhaseMaxClasses, "too many degree classes");
@@ -235,8 +281,6 @@ __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_kernel(PhaseArgs p)
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ int s_next[kPhaseMaxClasses];
     __shared__ int s_passes;
-    const IbArgs& a = p.a;
-    if (MODE != kPhaseOut && (EARLY || a.early) && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
 
     const int lane = threadIdx.x & 31;
     const uint32_t lane4 = lane * 4;
@@ -247,7 +291,7 @@ __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_kernel(PhaseArgs p)
 #pragma unroll
         for (int c = 0; c < L::n; ++c) {
             const int vec = phase_vec(MODE, degs[c]);
-            tiles[c] = (int)((a.pitch + 128u * vec - 1) / (128u * vec));
+            tiles[c] = (int)((bound + 128u * vec - 1) / (128u * vec));
             const long long items = (long long)p.n_nodes[c] * tiles[c];
             lo[c] = (int)(items * blockIdx.x / gridDim.x);
             hi[c] = (int)(items * (blockIdx.x + 1) / gridDim.x);
@@ -257,7 +301,9 @@ __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_kernel(PhaseArgs p)
 #pragma unroll
         for (int c = 0; c < L::n; ++c) s_next[c] = lo[c] + kPhaseThreads / 32;   // the first 32 items are taken statically
         const uint8_t* img = p.image;
-        if (MODE == kPhaseOut) {
+        if (MODE == kPhaseOut && PF) {
+            img += (long long)a.it * p.image_stride;      // the host names the pass whose converged frames are decided
+        } else if (MODE == kPhaseOut) {
             s_passes = executed_passes(a);
             if (blockIdx.x == 0) *a.inum = s_passes + 1;
             img += (long long)s_passes * p.image_stride;
@@ -271,7 +317,7 @@ __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_kernel(PhaseArgs p)
     constexpr int degs[] = {Ds...};
     auto class_loop = [&](auto IC) {
         constexpr int I = decltype(IC)::value;
-        using Item = PhaseItem<MODE, EARLY, L, I>;
+        using Item = PhaseItem<MODE, EARLY, L, I, PF>;
         constexpr int VEC = Item::VEC;
         const int* __restrict__ nodes = p.nodes[I];
         const int* __restrict__ starts = p.starts[I];
@@ -300,7 +346,7 @@ __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_kernel(PhaseArgs p)
                 phase_image_wait(&s_mbar);
                 have_image = true;
             }
-            if (col < a.pitch) syn |= Item::run(a, s_img, node, start, col, lane4);
+            if (col < bound) syn |= Item::run(a, s_img, node, start, col, lane4, pfc);
             i = i2;
             node = node2;
             start = start2;
@@ -310,12 +356,34 @@ __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_kernel(PhaseArgs p)
     // classes in the order of the degree set (heaviest first)
     phase_unroll(class_loop, std::make_integer_sequence<int, L::n>{});
 
-    if (MODE == kPhaseCn && EARLY && !a.iter0) {
+    if (MODE == kPhaseCn && EARLY && !PF && !a.iter0) {
         const unsigned any = __ballot_sync(0xffffffffu, syn != 0);
         if (any != 0 && lane == 0) atomicOr(&a.flags[a.it], 1);
     }
     // the bulk copy must have landed before the CTA may exit (its shared memory is the destination)
     if (!have_image) phase_image_wait(&s_mbar);
+}
+
+template <int MODE, bool EARLY, int... Ds>
+__global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_kernel(PhaseArgs p)
+{
+    const IbArgs& a = p.a;
+    if (MODE != kPhaseOut && (EARLY || a.early) && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
+    phase_kernel_body<MODE, EARLY, false, Ds...>(p, a, a.pitch, PfCtx{nullptr, nullptr, nullptr});
+}
+
+// Per-frame early termination: same bodies over the ACTIVE columns of the current ping-pong buffers; the check-node
+// phase records which frames failed a check (pf_fsyn), the decision phase writes only the frames named by pf_conv.
+template <int MODE, int... Ds>
+__global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_pf_kernel(PhaseArgs p)
+{
+    const PfState st = *p.pf;
+    if (st.done || st.n_act == 0) return;
+    IbArgs a = p.a;
+    a.msg = p.pf_msg[st.cur];
+    a.ch = p.pf_ch[st.cur];
+    a.B = st.n_act;
+    phase_kernel_body<MODE, MODE == kPhaseCn, true, Ds...>(p, a, (uint32_t)st.act_pitch, PfCtx{p.pf_fsyn, p.pf_conv, p.pf_idx[st.cur]});
 }
 
 using PhaseKernel = void (*)(PhaseArgs);

@@ -494,6 +494,8 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
     a.flags = w.flags + 1; a.inum = w.inum; a.early = early; a.imax = imax;
     a.DC = h->DC; a.DV = h->DV; a.xp_col = -1;
     const int T = h->T, TT = T * T;
+    // ---- opt-in: per-frame early termination with frame compaction (ib_perframe.cu)
+    if (h->pf_request) return decode_ib_perframe(h, w, a, B, imax, h->pf_inum, st);
     // ---- small batches of regular codes: the whole decode in one cooperative launch (ib_coop_n4.cuh)
     // (worth it while a phase is short: measured break-even near 100 MB of packed messages -- DVB-S2 n=64800 wins at
     // B=512 (58 MB: 9.3 -> 6.9 ms) and loses at B=2048 (232 MB); C1 and 802.11n win up to the 4096-frame limit)
@@ -1218,6 +1220,37 @@ int ibldpc_decode_ib(ibldpc_handle h, const uint8_t* ch_dev, int64_t B, int imax
     return IBLDPC_OK;
 }
 
+int ibldpc_decode_ib_perframe(ibldpc_handle h, const uint8_t* ch_dev, int64_t B, int imax, uint8_t* out_dev,
+                              int32_t* i_num_frames_dev, void* stream)
+{
+    int rc = check_decode_args(h, B, imax);
+    if (rc) return rc;
+    if (!ch_dev || !out_dev) return fail(IBLDPC_E_INVALID, "null buffer");
+    if (!(h->fast && h->nib) || h->phase == nullptr)
+        return fail(IBLDPC_E_STATE, "per-frame early termination needs the packed-nibble family and the fused per-phase kernels "
+                                    "(even |T| <= 16, instantiated degree sets: 802.11n, DVB-S2 rate 1/2, regular (3,6))");
+    DeviceGuard guard_(h->device);
+    CK(guard_.err);
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace& w = h->ws[0];
+    if (h->profiling) clear_events(h);
+    const long long pitch = (B + 15) / 16 * 16;
+    const bool aligned = (B % 16 == 0) && ((uintptr_t)ch_dev % 16 == 0) && ((uintptr_t)out_dev % 16 == 0);
+    h->pf_request = true;
+    h->pf_inum = i_num_frames_dev;
+    if (aligned) {
+        rc = decode_ib_padded(h, w, ch_dev, pitch, B, imax, 1, out_dev, st);
+    } else {
+        rc = ensure_pad(w, (size_t)h->N * pitch);
+        if (!rc) rc = launch_pad<uint8_t>(ch_dev, w.padbuf_in, h->N, B, pitch, 0, st);
+        if (!rc) rc = decode_ib_padded(h, w, w.padbuf_in, pitch, B, imax, 1, w.padbuf_out, st);
+        if (!rc) rc = launch_unpad<uint8_t>(w.padbuf_out, out_dev, h->N, B, pitch, st);
+    }
+    h->pf_request = false;
+    h->pf_inum = nullptr;
+    return rc;
+}
+
 int ibldpc_last_i_num(ibldpc_handle h, int32_t* i_num_host)
 {
     if (!h || !i_num_host) return fail(IBLDPC_E_INVALID, "null argument");
@@ -1271,9 +1304,10 @@ int ibldpc_decode_ib_host(ibldpc_handle h, const uint8_t* ch_host, int64_t B, in
         off += wd;
         slot ^= (nslots - 1);
     }
+    int first_rc = IBLDPC_OK;   // read (and thereby clear) the status of every slot, report the first failure
     for (int s = nslots - 1; s >= 0; --s)
-        if ((rc = read_back_status(h->ws[s], h->ws[s].stream, s == 0 ? i_num_host : nullptr))) return rc;
-    return IBLDPC_OK;
+        if ((rc = read_back_status(h->ws[s], h->ws[s].stream, s == 0 ? i_num_host : nullptr)) && !first_rc) first_rc = rc;
+    return first_rc;
 }
 
 // ---- packed host buffers: nibble-packed channel values in, bit-packed hard decisions of the first `rows` rows out
@@ -1346,9 +1380,10 @@ int ibldpc_decode_ib_host_packed(ibldpc_handle h, const uint8_t* ch4_host, int64
         slot ^= (nslots - 1);
     }
     CK(cudaGetLastError());
+    int first_rc = IBLDPC_OK;   // read (and thereby clear) the status of every slot, report the first failure
     for (int s = nslots - 1; s >= 0; --s)
-        if ((rc = read_back_status(h->ws[s], h->ws[s].stream, s == 0 ? i_num_host : nullptr))) return rc;
-    return IBLDPC_OK;
+        if ((rc = read_back_status(h->ws[s], h->ws[s].stream, s == 0 ? i_num_host : nullptr)) && !first_rc) first_rc = rc;
+    return first_rc;
 }
 
 // ---- the reference's own host contract: int32 cluster indices in, int32 cluster indices out
@@ -1461,9 +1496,10 @@ int ibldpc_decode_ib_host_i32(ibldpc_handle h, const int32_t* ch_host, int64_t B
     // drain in issue order: `slot` now names the older of the two pending chunks
     if ((rc = drain(slot))) return rc;
     if (nslots > 1 && (rc = drain(slot ^ 1))) return rc;
+    int first_rc = IBLDPC_OK;   // read (and thereby clear) the status of every slot, report the first failure
     for (int s = nslots - 1; s >= 0; --s)
-        if ((rc = read_back_status(h->ws[s], h->ws[s].stream, s == 0 ? i_num_host : nullptr))) return rc;
-    return IBLDPC_OK;
+        if ((rc = read_back_status(h->ws[s], h->ws[s].stream, s == 0 ? i_num_host : nullptr)) && !first_rc) first_rc = rc;
+    return first_rc;
 }
 
 int ibldpc_decode_llr(ibldpc_handle h, int algo, int dtype, const void* ch_dev, int64_t B, int imax, int early_term,

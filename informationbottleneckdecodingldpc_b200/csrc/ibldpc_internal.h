@@ -127,6 +127,9 @@ struct ibldpc_decoder {
     ibldpc::PhaseImages* phase = nullptr;
     ibldpc::T32Images* t32_images = nullptr;
     int use_phase = 1;    // IBLDPC_NO_PHASE=1 keeps one launch per degree class
+    // request of ibldpc_decode_ib_perframe for the decode being issued
+    bool pf_request = false;
+    int32_t* pf_inum = nullptr;
     // stream / workspace of the last decode (lazy i_num read-back)
     cudaStream_t last_stream = nullptr;
     int last_ws = 0;
@@ -144,6 +147,9 @@ namespace ibldpc {
 int phase_prepare(ibldpc_decoder* h);   // end of ibldpc_set_luts: build + upload the phase images (or leave h->phase null)
 void phase_free(ibldpc_decoder* h);
 int decode_ib_phase(ibldpc_decoder* h, const IbArgs& a, int imax, int early, cudaStream_t st);
+// per-frame early termination with frame compaction (ib_perframe.cu)
+int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long long B, int imax, int32_t* i_num_frames_dev,
+                       cudaStream_t st);
 // |T| <= 32 shared-memory family (ib_t32.cu)
 int t32_prepare(ibldpc_decoder* h);
 void t32_free(ibldpc_decoder* h);

@@ -403,3 +403,73 @@ def test_t32_family_wlan_vs_oracle_and_generic(gpu, monkeypatch, B):
     bad[3, 0] = 40
     with pytest.raises(ValueError):
         dec.decode_OpenCL(bad)
+
+
+# ---------------------------------------------------------------------------------- per-frame early termination (ib_perframe.cu)
+def _per_frame_oracle(t, ch, T, imax, tb):
+    """The reference result of decoding every frame on its own (msg_at_time = 1)."""
+    outs, inums = [], []
+    for f in range(ch.shape[1]):
+        o, i = _oracle_ib(t, np.ascontiguousarray(ch[:, f:f + 1]), T, imax, tb, True)
+        outs.append(o[:, 0])
+        inums.append(i)
+    return np.stack(outs, axis=1), np.asarray(inums)
+
+
+@pytest.mark.parametrize("code,B,ebn0", [("wlan1296", 300, 2.2), ("wlan1296", 4099, 2.2), ("wlan1296", 1, 2.2), ("reg36", 333, 2.0),
+                                         ("dvb6480", 130, 1.6)])
+def test_per_frame_early_termination_equals_single_frame_reference(gpu, code, B, ebn0):
+    """early_termination='frame': outputs AND per-frame i_num equal to the oracle run with one frame per call, with
+    frames converging at different passes (designed tables, channel draws near the waterfall), frames that never
+    converge, and several compactions on the way."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_irregular_config, generate_regular_config
+    T, imax = 16, 25
+    if code == "reg36":
+        H = codes.regular_random(2000, 3, 6, seed=5)
+        tb, _ = generate_regular_config(1.2, 3, 6, T, imax)
+        dec = pkg.Discrete_LDPC_Decoder_class(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a, B)
+    else:
+        H = codes.wlan_80211n(54) if code == "wlan1296" else codes.dvbs2_like_half_rate(6480, q_groups=36)
+        tb, _ = generate_irregular_config(1.0, H, T, imax)
+        dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                        tb.matching_vector_checknode, tb.matching_vector_varnode, B)
+    t = graph.edge_tables(H)
+    dec.init_OpenCL_decoding(B)
+    q = pkg.AWGN_Channel_Quantizer(10 ** (-ebn0 / 10) / (2 * 0.5), 3, T, 2000)
+    u = np.random.Generator(np.random.PCG64(B)).random(size=(t.n_var, B))
+    ch = (((u[:, :, None] - q.cdf_t_given_x_equals_zero) > 0).sum(2) - 1).astype(np.uint8)
+    dec.early_termination = 'frame'
+    out = dec.decode_OpenCL(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True).get()
+    inum = dec.last_i_num_per_frame.get()
+    sel = np.arange(B) if B <= 400 else np.r_[0:100, B // 2:B // 2 + 100, B - 100:B]
+    ref, ref_inum = _per_frame_oracle(t, ch[:, sel], T, imax, tb)
+    assert np.array_equal(inum[sel], ref_inum), (inum[sel][:20], ref_inum[:20])
+    assert np.array_equal(out[:, sel], ref)
+    assert dec.last_i_num == int(inum.max())
+    if code == "wlan1296" and B >= 300:
+        assert len(set(ref_inum.tolist())) >= 6 and ref_inum.max() == imax     # a real spread, incl. frames that never converge
+    # host-array contract of the same mode
+    if B <= 400:
+        host = dec.decode_OpenCL(ch.astype(np.int32))
+        assert host.dtype == np.int32 and np.array_equal(host, out)
+    # and the batch-granular default is untouched
+    dec.early_termination = True
+    out_b = dec.decode_OpenCL(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True).get()
+    assert dec.last_i_num == int(ref_inum.max()) or B > 400
+    conv = ref_inum[: len(sel)] == dec.last_i_num
+    assert np.array_equal(out_b[:, sel][:, conv], ref[:, conv])
+
+
+def test_per_frame_early_termination_needs_an_instantiated_degree_set(gpu):
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    H = codes.random_from_degrees([2] * 40 + [3] * 40 + [4] * 16, [4] * 16 + [5] * 8 + [6] * 8 + [7] * 6 + [8] * 4 + [9] * 2 + [10] * 2, seed=4)
+    t = graph.edge_tables(H)
+    tb = luts.random_tables(16, t.d_c_max, t.d_v_max, 4, seed=1, matching=True)
+    dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, 4, 16, 16, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                    tb.matching_vector_checknode, tb.matching_vector_varnode, 8)
+    dec.early_termination = 'frame'
+    with pytest.raises(RuntimeError, match="degree set"):
+        dec.decode_OpenCL(pkg.DeviceArray(torch.zeros((t.n_var, 8), dtype=torch.uint8, device="cuda")), buffer_in=True, return_buffer=True)
