@@ -480,6 +480,40 @@ def leg_llr(pkg, algo, steps, rank, B=16384):
     return res
 
 
+def leg_early_termination(pkg, steps, rank, name="c1"):
+    """The BER drivers' operating mode: early termination on.  Same workload and inputs three ways -- fixed i_max (the
+    headline), the reference's batch-granular stop (discrete_LDPC_decoder.py:233,273) and the opt-in per-frame stop
+    with frame compaction (ibldpc_decode_ib_perframe) -- with the iteration statistics that explain the difference."""
+    import torch
+    wl = workload(name)
+    B = wl["B"]
+    t, tb, quanti, decodi = build_ib(pkg, wl, B, rank)
+    N, M = t.n_var, t.n_chk
+    ch = quanti.quantize_direct_OpenCL(N, B)
+    res = {"workload": wl["name"].replace("ET off", "ET on"), "frames_per_step": B, "EbN0_dB": wl["ebn0"], "steps": steps}
+    outs = {}
+    for mode, et in (("fixed_imax", False), ("batch_stop", True), ("per_frame_stop", "frame")):
+        decodi.early_termination = et
+        ms, out = time_steps(lambda: decodi.decode_OpenCL(ch, buffer_in=True, return_buffer=True), steps, 1)
+        outs[mode] = out.tensor.clone()
+        entry = {"value": (N - M) * B * steps / (ms * 1e-3) / 1e9, "unit": "Gbit/s", "ms_per_step": ms / steps,
+                 "i_num": int(decodi.last_i_num), "gpu_launches_per_step": decodi.info()[1]}
+        if et == "frame":
+            inum = decodi.last_i_num_per_frame.tensor.to(torch.float32)
+            entry.update({"mean_i_num": float(inum.mean()), "frames_at_imax": int((inum >= IMAX).sum()),
+                          "median_i_num": float(inum.median())})
+        res[mode] = entry
+    # a frame that stopped (in either mode) is a codeword; the per-frame result of a frame that ran to i_max equals the
+    # fixed-i_max result
+    inum = decodi.last_i_num_per_frame.tensor
+    full = inum >= IMAX
+    res["per_frame_equals_fixed_imax_on_unconverged_frames"] = bool(torch.equal(outs["per_frame_stop"][:, full], outs["fixed_imax"][:, full]))
+    res["bit_errors"] = {m: int((o[: N if not wl["irregular"] else int(decodi.data_len)] < T // 2).sum()) for m, o in outs.items()}
+    del decodi, ch, outs
+    torch.cuda.empty_cache()
+    return res
+
+
 def e2e_contracts(pkg, decodi, ch, N, K_info, B, T_, world, steps, rows_counted, dist):
     """The same metric through the class API with HOST buffers, copies inside the timed region, three contracts:
       packed        decode_packed: pinned nibble-packed cluster indices in, bit-packed hard decisions of the counted rows out
@@ -663,6 +697,7 @@ def main():
             for name in ("wlan", "wlan1944", "dvbs2"):
                 legs[name] = leg_ib(pkg, name, args.leg_steps, rank)
             legs["wlan_T32"] = leg_ib(pkg, "wlan", args.leg_steps, rank, T_=32, frames=32768)
+            legs["c1_early_termination"] = leg_early_termination(pkg, args.leg_steps, rank)
             legs["minsum_f64"] = leg_llr(pkg, "minsum", args.leg_steps, rank)
             legs["bp_f64"] = leg_llr(pkg, "bp", args.leg_steps, rank)
         if not args.no_cpu_baseline:

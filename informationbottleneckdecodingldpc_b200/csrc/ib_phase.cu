@@ -120,9 +120,12 @@ int phase_prepare(ibldpc_decoder* h)
     const Cand candidates[] = {{phase_ops_wlan(), true}, {phase_ops_dvbs2(), false}, {phase_ops_reg36(), false}};
     const bool force = getenv("IBLDPC_PHASE") != nullptr && atoi(getenv("IBLDPC_PHASE")) != 0;
     const PhaseSetOps* ops = nullptr;
+    h->phase_default = false;
     for (const Cand& c : candidates)
-        if ((c.by_default || force) && same_degrees(c.ops->cn_deg, h->cn_classes) && same_degrees(c.ops->vn_deg, h->vn_classes))
-            ops = c.ops;
+        if (same_degrees(c.ops->cn_deg, h->cn_classes) && same_degrees(c.ops->vn_deg, h->vn_classes)) {
+            ops = c.ops;                                   // images are built for every instantiated set (per-frame early
+            h->phase_default = c.by_default || force;      // termination runs on them); the plain decode uses them by default
+        }                                                  // only where they win
     if (!ops) return IBLDPC_OK;
     PhaseImages* p = new PhaseImages();
     h->phase = p;

@@ -578,7 +578,7 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
         }
     }
     // ---- one launch per phase over all degree classes (ib_phase_n4.cuh) where the degree sets are instantiated
-    if (h->phase) return decode_ib_phase(h, a, imax, early, st);
+    if (h->phase && h->phase_default) return decode_ib_phase(h, a, imax, early, st);
     // launch geometry of one degree class (plan_geometry): tiles per CTA, tile groups, CTAs per tile group
     auto plan_launch = [&](IbArgs& b, const void* fn, int smem, int threads, int vec, int n_nodes, int* tile_groups, int* grid) -> int {
         int occ;

@@ -127,6 +127,7 @@ struct ibldpc_decoder {
     ibldpc::PhaseImages* phase = nullptr;
     ibldpc::T32Images* t32_images = nullptr;
     int use_phase = 1;    // IBLDPC_NO_PHASE=1 keeps one launch per degree class
+    bool phase_default = false;   // plain decodes use the fused kernels (802.11n sets; IBLDPC_PHASE=1: every instantiated set)
     // request of ibldpc_decode_ib_perframe for the decode being issued
     bool pf_request = false;
     int32_t* pf_inum = nullptr;
