@@ -396,10 +396,16 @@ def phase_roofline(decodi, ch, N, E, B, workload_name):
     return roofline_from_phase_times(list(ms3), list(n3), N, E, B, IMAX, fam == 2, workload_name, family=fam)
 
 
-def time_steps(step, steps, warmup):
+def time_steps(step, steps, warmup, min_warm_s=0.4):
+    """`warmup` untimed steps -- and at least `min_warm_s` seconds of them: a leg starts after seconds of host-side table
+    design during which the idle GPU drops its clocks -- then `steps` timed ones (CUDA events on the current stream)."""
     import torch
-    for _ in range(max(warmup, 1)):
+    t0 = time.perf_counter()
+    n = 0
+    while n < max(warmup, 1) or time.perf_counter() - t0 < min_warm_s:
         step()
+        torch.cuda.synchronize()
+        n += 1
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
