@@ -192,6 +192,29 @@ __global__ void pf_flip_kernel(PfState* st)
     st->do_compact = 0;
 }
 
+// result nibbles (original frame order) -> the caller's uint8 output
+__global__ void pf_expand_kernel(const uint8_t* __restrict__ res, uint8_t* __restrict__ out, int n_var, int B, uint32_t pitch4,
+                                 uint32_t out_pitch)
+{
+    const uint32_t wpr = pitch4 >> 2;
+    const long long total = (long long)n_var * wpr;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / wpr), w = (int)(i - (long long)row * wpr);
+        const uint32_t v = reinterpret_cast<const uint32_t*>(res + (size_t)row * pitch4)[w];
+        uint8_t* dst = out + (size_t)row * out_pitch + 8 * (size_t)w;
+        if (8 * w + 8 <= (int)out_pitch && (out_pitch & 7u) == 0u) {
+            const uint32_t lo = (v & 0xfu) | ((v & 0xf0u) << 4) | ((v & 0xf00u) << 8) | ((v & 0xf000u) << 12);
+            const uint32_t hv = v >> 16;
+            const uint32_t hi = (hv & 0xfu) | ((hv & 0xf0u) << 4) | ((hv & 0xf00u) << 8) | ((hv & 0xf000u) << 12);
+            *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+        } else {
+            for (int f = 0; f < 8; ++f)
+                if (8 * w + f < (int)out_pitch) dst[f] = (uint8_t)((v >> (4 * f)) & 15u);
+        }
+    }
+    (void)B;
+}
+
 int ensure_buf(void** p, size_t* have, size_t need)
 {
     if (*have >= need && *p) return IBLDPC_OK;
@@ -224,8 +247,8 @@ int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long lo
         p = w.pf_ch2;
         if ((rc = ensure_buf(&p, &w.pf_ch2_bytes, (size_t)h->N * pitch4))) return rc;
         w.pf_ch2 = (uint8_t*)p;
-        // [idx0][idx1][order] ints of words*8, [alive][fsyn][conv] words, state
-        const size_t need = sizeof(int) * (size_t)words * 8 * 3 + sizeof(uint32_t) * (size_t)words * 3 + 256;
+        // [idx0][idx1][order] ints of words*8, [alive][fsyn][conv] words, state, [result nibbles n_var x pitch4]
+        const size_t need = sizeof(int) * (size_t)words * 8 * 3 + sizeof(uint32_t) * (size_t)words * 3 + 256 + (size_t)h->N * pitch4;
         p = w.pf_idx;
         if ((rc = ensure_buf(&p, &w.pf_idx_bytes, need))) return rc;
         w.pf_idx = (int*)p;
@@ -237,6 +260,8 @@ int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long lo
     uint32_t* fsyn = alive + words;
     uint32_t* conv = fsyn + words;
     PfState* state = reinterpret_cast<PfState*>(conv + words);
+    uint8_t* res = reinterpret_cast<uint8_t*>(conv + words) + 256;
+    IBLDPC_CK(cudaMemsetAsync(res, 0, (size_t)h->N * pitch4, st));
     const int small_grid = std::max(1, std::min(h->sm_count * 4, (words + 255) / 256));
     pf_init_kernel<<<small_grid, 256, 0, st>>>(state, (int)B, (int)pitch4, alive, fsyn, conv, idx0, words);
     h->last_launches++;
@@ -251,12 +276,21 @@ int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long lo
     base.pf_idx[0] = idx0; base.pf_idx[1] = idx1;
     base.pf_fsyn = fsyn;
     base.pf_conv = conv;
+    base.pf_res = res;
     auto launch = [&](int mode, int index, int it, PhaseKernel k) -> int {
         PhaseArgs q = base;
         q.a.it = it;
         q.a.iter0 = (mode == kPhaseCn && index == 0 && it < 0);
         size_t smem = 0;
         phase_fill_args(h, mode, index, q, &smem);
+        if (mode == kPhaseCn) {
+            // syndrome accumulator behind the image when the whole batch fits (227 KB per CTA minus image and statics)
+            const size_t room = (size_t)227 * 1024 - 1024 - smem;
+            if ((size_t)words * 4 <= room) {
+                q.pf_fsyn_smem_words = words;
+                smem += (size_t)words * 4;
+            }
+        }
         k<<<h->sm_count, kPhaseThreads, smem, st>>>(q);
         h->last_launches++;
         return IBLDPC_OK;
@@ -292,6 +326,12 @@ int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long lo
         // then every second / fourth pass
         const bool try_compact = it < imax - 2 && (it < 8 || (it < 24 && it % 2 == 1) || it % 4 == 3);
         if (try_compact && (rc = compact())) return rc;
+    }
+    {
+        const long long total = (long long)h->N * words;
+        const int g = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * 16, (total + 255) / 256));
+        pf_expand_kernel<<<g, 256, 0, st>>>(res, a.out, h->N, (int)B, pitch4, a.out_pitch);
+        h->last_launches++;
     }
     IBLDPC_CK(cudaGetLastError());
     return IBLDPC_OK;

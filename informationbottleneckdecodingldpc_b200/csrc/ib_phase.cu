@@ -224,7 +224,9 @@ int phase_set_attributes(ibldpc_decoder* h)
                                                          {ops->cn_pf_kernel, p->cn_bytes}, {ops->vn_pf_kernel, p->vn_bytes},
                                                          {ops->out_pf_kernel, p->out_bytes}};
     for (auto& e : ks) {
-        IBLDPC_CK(cudaFuncSetAttribute((const void*)e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem));
+        // the per-frame check-node kernel keeps its syndrome accumulator behind the image: allow the full 227 KB
+        const int limit = e.k == ops->cn_pf_kernel ? 227 * 1024 - 1024 : (int)e.smem;
+        IBLDPC_CK(cudaFuncSetAttribute((const void*)e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, limit));
         int occ = 0;
         IBLDPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e.k, kPhaseThreads, e.smem));
         if (occ < 1) return fail_msg(IBLDPC_E_CUDA, "fused per-phase kernel does not fit on an SM");

@@ -109,6 +109,9 @@ struct PhaseArgs {
     const int* pf_idx[2];           // original frame index of every column (ping-pong)
     uint32_t* pf_fsyn;              // [words] bit 4f: frame f of the word failed a check in this pass
     const uint32_t* pf_conv;        // [words] nibble mask of the frames to decide in this launch
+    uint8_t* pf_res;                // [n_var][pitch] decided cluster indices as nibbles in ORIGINAL frame order (zeroed)
+    int pf_fsyn_smem_words;         // check-node phase: words of shared memory behind the table image for the per-CTA
+                                    // syndrome accumulator (0 = accumulate in global memory)
 };
 
 // Device-side state of a per-frame-early-termination decode: every kernel of the schedule is launched unconditionally
@@ -230,16 +233,37 @@ struct PhaseItem {
                 }
             }
             if constexpr (DECIDE && PF) {
-                // only the frames that converged in this pass, scattered to their original column
+                // Only the frames that converged in this pass, as nibbles OR-ed into the (zeroed) result array at their
+                // ORIGINAL position: a.out = result nibbles, a.out_pitch = its pitch.  Compaction keeps the frame order,
+                // so the frames of one word land in few destination words (one, before the first compaction).
+                uint32_t* res = reinterpret_cast<uint32_t*>(a.out + (uint64_t)(uint32_t)node * a.out_pitch);
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
                     if (cm[j] == 0) continue;
-                    const int* ix = pf.idx + (((col >> 2) + j) << 3);
+                    const uint32_t lo = dec[2 * j] & 0x0f0f0f0fu, hi = dec[2 * j + 1] & 0x0f0f0f0fu;
+                    const uint32_t l2 = (lo | (lo >> 4)) & 0x00ff00ffu, h2 = (hi | (hi >> 4)) & 0x00ff00ffu;
+                    const uint32_t val = (((l2 | (l2 >> 8)) & 0xffffu) | (((h2 | (h2 >> 8)) & 0xffffu) << 16)) & cm[j];
+                    const int4* ix4 = reinterpret_cast<const int4*>(pf.idx + (((col >> 2) + j) << 3));
+                    const int4 ia = ix4[0], ib = ix4[1];
+                    const int ix[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+                    if ((ix[0] & 7) == 0 && ix[7] - ix[0] == 7) {
+                        atomicOr(res + (ix[0] >> 3), val);
+                    } else {
+                        uint32_t acc = 0;
+                        int cur = -1;
 #pragma unroll
-                    for (int f = 0; f < 8; ++f)
-                        if ((cm[j] >> (4 * f)) & 1u)
-                            a.out[(uint64_t)(uint32_t)node * a.out_pitch + (uint32_t)ix[f]] =
-                                (uint8_t)(dec[2 * j + (f >> 2)] >> (8 * (f & 3)));
+                        for (int f = 0; f < 8; ++f)
+                            if ((cm[j] >> (4 * f)) & 1u) {
+                                const int dw = ix[f] >> 3;
+                                if (dw != cur) {
+                                    if (acc) atomicOr(res + cur, acc);
+                                    acc = 0;
+                                    cur = dw;
+                                }
+                                acc |= ((val >> (4 * f)) & 15u) << (4 * (ix[f] & 7));
+                            }
+                        if (acc) atomicOr(res + cur, acc);
+                    }
                 }
             } else if constexpr (DECIDE) {
                 // decided cluster indices leave as uint8 (one byte per frame): 8*VEC bytes per lane
@@ -377,13 +401,34 @@ __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_kernel(PhaseArgs p)
 template <int MODE, int... Ds>
 __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_pf_kernel(PhaseArgs p)
 {
+    using L = PhaseLayout<MODE, Ds...>;
+    extern __shared__ __align__(128) uint8_t s_img[];
     const PfState st = *p.pf;
     if (st.done || st.n_act == 0) return;
     IbArgs a = p.a;
     a.msg = p.pf_msg[st.cur];
     a.ch = p.pf_ch[st.cur];
     a.B = st.n_act;
-    phase_kernel_body<MODE, MODE == kPhaseCn, true, Ds...>(p, a, (uint32_t)st.act_pitch, PfCtx{p.pf_fsyn, p.pf_conv, p.pf_idx[st.cur]});
+    if (MODE == kPhaseOut) {
+        a.out = p.pf_res;
+        a.out_pitch = a.pitch;
+    }
+    // check-node phase: per-CTA syndrome accumulator in shared memory behind the table image (one global atomicOr per
+    // word and CTA at the end instead of one per check and word)
+    const int act_words = st.act_pitch >> 2;
+    const bool smem_syn = MODE == kPhaseCn && p.pf_fsyn_smem_words >= act_words;
+    uint32_t* s_fs = reinterpret_cast<uint32_t*>(s_img + L::image_bytes);
+    if (smem_syn)
+        for (int w = threadIdx.x; w < act_words; w += kPhaseThreads) s_fs[w] = 0u;   // ordered by the body's first barrier
+    phase_kernel_body<MODE, MODE == kPhaseCn, true, Ds...>(p, a, (uint32_t)st.act_pitch,
+                                                           PfCtx{smem_syn ? s_fs : p.pf_fsyn, p.pf_conv, p.pf_idx[st.cur]});
+    if (smem_syn) {
+        __syncthreads();
+        for (int w = threadIdx.x; w < act_words; w += kPhaseThreads) {
+            const uint32_t v = s_fs[w];
+            if (v) atomicOr(p.pf_fsyn + w, v);
+        }
+    }
 }
 
 using PhaseKernel = void (*)(PhaseArgs);
