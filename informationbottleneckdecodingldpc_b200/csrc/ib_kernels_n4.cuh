@@ -257,7 +257,12 @@ __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* t
             const uint32_t vmask = nv >= 8 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (4 * nv)) - 1u);
             syn |= par & vmask;
             // per-frame early termination: bit 4f of fsyn[word] = frame f of that word failed a check in this pass
-            if (fsyn != nullptr && (par & vmask) != 0u) atomicOr(fsyn + j, par & vmask);
+            if (fsyn != nullptr && (par & vmask) != 0u) {
+                if (__isShared(fsyn))   // per-CTA accumulator: a native shared-memory reduction, not a generic atomic
+                    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(fsyn + j)), "r"(par & vmask) : "memory");
+                else
+                    atomicOr(fsyn + j, par & vmask);
+            }
         }
         if constexpr (PAIR) cn_word_n4_pair<D, WT, CB>(w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
         else cn_word_n4<D, MATCH, WT, CB>(w, o, tab, lane4);

@@ -34,9 +34,10 @@ int phase_set_attributes(ibldpc_decoder* h);
 namespace {
 
 __global__ void pf_init_kernel(PfState* st, int B, int pitch4, uint32_t* alive, uint32_t* fsyn, uint32_t* conv, int* idx0,
-                               int words)
+                               int* dstw, int words)
 {
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+        dstw[w] = w;
         const int nv = B - 8 * w;
         alive[w] = nv >= 8 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (4 * nv)) - 1u);
         fsyn[w] = 0u;
@@ -183,6 +184,18 @@ __global__ void pf_commit_kernel(PfState* st, uint32_t* alive, uint32_t* fsyn, u
     // grid-wide: the state flips after every block has read the old n_act -- done by a second, one-thread launch
 }
 
+// destination-word shortcut of the decision kernel for the compacted order (reads the NEW index list)
+__global__ void pf_dstw_kernel(const PfState* st, const int* idx0, const int* idx1, int* dstw)
+{
+    if (st->done || !st->do_compact) return;
+    const int* idx = st->cur ? idx0 : idx1;          // the buffer the scan wrote = the one that becomes current
+    const int nw = (st->new_n + 7) >> 3;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += gridDim.x * blockDim.x) {
+        const int i0 = idx[8 * w], i7 = idx[8 * w + 7];
+        dstw[w] = (8 * w + 8 <= st->new_n && (i0 & 7) == 0 && i7 - i0 == 7) ? (i0 >> 3) : -1;
+    }
+}
+
 __global__ void pf_flip_kernel(PfState* st)
 {
     if (st->done || !st->do_compact) return;
@@ -248,7 +261,7 @@ int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long lo
         if ((rc = ensure_buf(&p, &w.pf_ch2_bytes, (size_t)h->N * pitch4))) return rc;
         w.pf_ch2 = (uint8_t*)p;
         // [idx0][idx1][order] ints of words*8, [alive][fsyn][conv] words, state, [result nibbles n_var x pitch4]
-        const size_t need = sizeof(int) * (size_t)words * 8 * 3 + sizeof(uint32_t) * (size_t)words * 3 + 256 + (size_t)h->N * pitch4;
+        const size_t need = sizeof(int) * (size_t)words * 8 * 3 + sizeof(uint32_t) * (size_t)words * 4 + 256 + (size_t)h->N * pitch4;
         p = w.pf_idx;
         if ((rc = ensure_buf(&p, &w.pf_idx_bytes, need))) return rc;
         w.pf_idx = (int*)p;
@@ -259,11 +272,12 @@ int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long lo
     uint32_t* alive = reinterpret_cast<uint32_t*>(order + (size_t)words * 8);
     uint32_t* fsyn = alive + words;
     uint32_t* conv = fsyn + words;
-    PfState* state = reinterpret_cast<PfState*>(conv + words);
-    uint8_t* res = reinterpret_cast<uint8_t*>(conv + words) + 256;
+    int* dstw = reinterpret_cast<int*>(conv + words);
+    PfState* state = reinterpret_cast<PfState*>(dstw + words);
+    uint8_t* res = reinterpret_cast<uint8_t*>(dstw + words) + 256;
     IBLDPC_CK(cudaMemsetAsync(res, 0, (size_t)h->N * pitch4, st));
     const int small_grid = std::max(1, std::min(h->sm_count * 4, (words + 255) / 256));
-    pf_init_kernel<<<small_grid, 256, 0, st>>>(state, (int)B, (int)pitch4, alive, fsyn, conv, idx0, words);
+    pf_init_kernel<<<small_grid, 256, 0, st>>>(state, (int)B, (int)pitch4, alive, fsyn, conv, idx0, dstw, words);
     h->last_launches++;
 
     PhaseArgs base{};
@@ -277,6 +291,7 @@ int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long lo
     base.pf_fsyn = fsyn;
     base.pf_conv = conv;
     base.pf_res = res;
+    base.pf_dstw = dstw;
     auto launch = [&](int mode, int index, int it, PhaseKernel k) -> int {
         PhaseArgs q = base;
         q.a.it = it;
@@ -309,8 +324,9 @@ int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long lo
         const int g = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * 16, (total + 255) / 256));
         pf_gather_kernel<<<g, 256, 0, st>>>(state, a.msg, w.pf_msg2, const_cast<uint8_t*>(a.ch), w.pf_ch2, h->E, h->N, pitch4, order);
         pf_commit_kernel<<<small_grid, 256, 0, st>>>(state, alive, fsyn, conv, words);
+        pf_dstw_kernel<<<small_grid, 256, 0, st>>>(state, idx0, idx1, dstw);
         pf_flip_kernel<<<1, 1, 0, st>>>(state);
-        h->last_launches += 4;
+        h->last_launches += 5;
         return IBLDPC_OK;
     };
     // check-node phase of iteration 0 (table block 0, channel values through vidx)

@@ -107,6 +107,7 @@ struct PhaseArgs {
     uint8_t* pf_msg[2];             // message arrays (ping-pong across compactions)
     const uint8_t* pf_ch[2];        // packed channel values (ping-pong)
     const int* pf_idx[2];           // original frame index of every column (ping-pong)
+    const int* pf_dstw;             // [words] destination word of a word whose 8 frames are one aligned original word, else -1
     uint32_t* pf_fsyn;              // [words] bit 4f: frame f of the word failed a check in this pass
     const uint32_t* pf_conv;        // [words] nibble mask of the frames to decide in this launch
     uint8_t* pf_res;                // [n_var][pitch] decided cluster indices as nibbles in ORIGINAL frame order (zeroed)
@@ -173,7 +174,7 @@ __device__ __forceinline__ int ld_nc_again(const int* p)
 }
 
 // ---- one item = one (node, tile) of class I ------------------------------------------------------------------
-struct PfCtx { uint32_t* fsyn; const uint32_t* conv; const int* idx; };
+struct PfCtx { uint32_t* fsyn; const uint32_t* conv; const int* idx; const int* dstw; };
 
 template <int MODE, bool EARLY, typename L, int I, bool PF = false>
 struct PhaseItem {
@@ -243,12 +244,15 @@ struct PhaseItem {
                     const uint32_t lo = dec[2 * j] & 0x0f0f0f0fu, hi = dec[2 * j + 1] & 0x0f0f0f0fu;
                     const uint32_t l2 = (lo | (lo >> 4)) & 0x00ff00ffu, h2 = (hi | (hi >> 4)) & 0x00ff00ffu;
                     const uint32_t val = (((l2 | (l2 >> 8)) & 0xffffu) | (((h2 | (h2 >> 8)) & 0xffffu) << 16)) & cm[j];
-                    const int4* ix4 = reinterpret_cast<const int4*>(pf.idx + (((col >> 2) + j) << 3));
-                    const int4 ia = ix4[0], ib = ix4[1];
-                    const int ix[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
-                    if ((ix[0] & 7) == 0 && ix[7] - ix[0] == 7) {
-                        atomicOr(res + (ix[0] >> 3), val);
+                    const int dw0 = pf.dstw[(col >> 2) + j];
+                    if (dw0 >= 0) {
+                        // the eight frames of this word ARE destination word dw0 (frame order is kept), and no other
+                        // lane of this launch touches it: plain read-modify-write
+                        res[dw0] |= val;
                     } else {
+                        const int4* ix4 = reinterpret_cast<const int4*>(pf.idx + (((col >> 2) + j) << 3));
+                        const int4 ia = ix4[0], ib = ix4[1];
+                        const int ix[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
                         uint32_t acc = 0;
                         int cur = -1;
 #pragma unroll
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_kernel(PhaseArgs p)
 {
     const IbArgs& a = p.a;
     if (MODE != kPhaseOut && (EARLY || a.early) && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
-    phase_kernel_body<MODE, EARLY, false, Ds...>(p, a, a.pitch, PfCtx{nullptr, nullptr, nullptr});
+    phase_kernel_body<MODE, EARLY, false, Ds...>(p, a, a.pitch, PfCtx{nullptr, nullptr, nullptr, nullptr});
 }
 
 // Per-frame early termination: same bodies over the ACTIVE columns of the current ping-pong buffers; the check-node
@@ -421,7 +425,7 @@ __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_pf_kernel(PhaseArgs
     if (smem_syn)
         for (int w = threadIdx.x; w < act_words; w += kPhaseThreads) s_fs[w] = 0u;   // ordered by the body's first barrier
     phase_kernel_body<MODE, MODE == kPhaseCn, true, Ds...>(p, a, (uint32_t)st.act_pitch,
-                                                           PfCtx{smem_syn ? s_fs : p.pf_fsyn, p.pf_conv, p.pf_idx[st.cur]});
+                                                           PfCtx{smem_syn ? s_fs : p.pf_fsyn, p.pf_conv, p.pf_idx[st.cur], p.pf_dstw});
     if (smem_syn) {
         __syncthreads();
         for (int w = threadIdx.x; w < act_words; w += kPhaseThreads) {

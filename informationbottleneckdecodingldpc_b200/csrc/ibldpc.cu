@@ -825,7 +825,10 @@ int decode_llr_padded(ibldpc_decoder* h, Workspace& w, const F* ch, long long pi
             return IBLDPC_OK;
         }
         for (auto& c : h->cn_classes) {
-            LlrNodeKernel k = llr_cn_kernel_for(sizeof(F) == 8, ALGO, c.degree);
+            // float64 BP: forward/backward recursion (ALGO 2) unless the reference's operation order is asked for
+            const bool bp_sequential = getenv("IBLDPC_BP_SEQUENTIAL") != nullptr;
+            const int algo_k = (ALGO == 1 && sizeof(F) == 8 && !bp_sequential) ? 2 : ALGO;
+            LlrNodeKernel k = llr_cn_kernel_for(sizeof(F) == 8, algo_k, c.degree);
             int grid;
             int r = grid_for(h, (const void*)k, 0, (long long)c.count * b.tiles, &grid);
             if (r) return r;
