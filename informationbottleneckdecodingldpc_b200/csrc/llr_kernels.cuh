@@ -59,15 +59,10 @@ __device__ __forceinline__ double boxplus(double a, double b)
     const double bp = log((1.0 + exp(a + b)) / (exp(a) + exp(b)));
     return clip150(bp);
 }
-// float64 box-plus in the overflow-free form (algebraically identical to the reference expression); used by the
-// forward/backward recursion (ALGO 2)
-__device__ __forceinline__ double boxplus_stable(double a, double b)
-{
-    const double s = fmin(fabs(a), fabs(b));
-    const double sg = ((a < 0.0) != (b < 0.0)) ? -s : s;
-    const double bp = sg + log1p(exp(-fabs(a + b))) - log1p(exp(-fabs(a - b)));
-    return clip150((a == 0.0 || b == 0.0) ? 0.0 : bp);
-}
+// Box-plus of the forward/backward recursion (ALGO 2).  float64: the reference expression itself -- inputs are clipped
+// to +-150, so exp(a + b) <= e^300 cannot overflow; measured on B200 it is 1.46x faster than the log1p form
+// (0.169 vs 0.115 Gbit/s, (3,6) n=8000): two double-precision log1p cost more than one log, one exp and one division.
+__device__ __forceinline__ double boxplus_stable(double a, double b) { return boxplus(a, b); }
 __device__ __forceinline__ float boxplus_stable(float a, float b);
 __device__ __forceinline__ float boxplus(float a, float b)
 {
