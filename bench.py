@@ -608,6 +608,7 @@ def main():
 
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / warnings never land on stdout
     import torch
     import torch.distributed as dist
     import informationbottleneckdecodingldpc_b200 as pkg
@@ -633,7 +634,17 @@ def main():
     totals = torch.zeros(4, dtype=torch.int64, device="cuda")
     base = torch.tensor([0, 0, B, IMAX * B], dtype=torch.int64, device="cuda")
     rows_counted = N if not wl["irregular"] else int(decodi.data_len)
-    allreduce = counter_allreduce_fn(decodi) if world > 1 else None
+    # the one collective of the path goes through the library's own NCCL binding (C ABI: ibldpc_allreduce_counters);
+    # torch.distributed stays the fallback when libnccl cannot be bound at run time
+    allreduce = None
+    if world > 1:
+        os.environ.setdefault("IBLDPC_ABI_ALLREDUCE", "1")
+        try:
+            allreduce = counter_allreduce_fn(decodi)
+        except Exception as e:   # noqa: BLE001
+            print(f"[bench] C-ABI all-reduce unavailable ({e}); using torch.distributed", file=sys.stderr)
+            os.environ["IBLDPC_ABI_ALLREDUCE"] = "0"
+            allreduce = counter_allreduce_fn(decodi)
     abi_allreduce = bool(getattr(decodi, "_nccl_ready", False))
 
     def step():
