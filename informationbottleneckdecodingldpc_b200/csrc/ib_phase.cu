@@ -60,14 +60,14 @@ void build_image(uint8_t* img, const PhaseLayoutRt& L, int mode, int T, const st
         const PhaseClassLayout& c = L.cls[i];
         const int D = c.degree;
         // pair rows: kPairSlots lane slots of 8 bytes per row a*16+b
-        if (c.pair) {
-            const uint8_t* src = pair_rows(class_index(classes, D));
-            uint8_t* dst = img + (size_t)c.pair_index * kPairBytes;
+        auto expand_rows = [&](const uint8_t* src, int region) {
+            uint8_t* dst = img + (size_t)region * kPairBytes;
             for (int ra = 0; ra < T; ++ra)
                 for (int rb = 0; rb < T; ++rb)
                     for (int s = 0; s < kPairSlots; ++s)
                         memcpy(dst + ((size_t)(ra * kTS + rb) * kPairSlots + s) * 8, src + (size_t)(ra * T + rb) * 8, 8);
-        }
+        };
+        if (c.pair) expand_rows(pair_rows(class_index(classes, D)), c.pair_index);
         // the column stored as 4*x feeds the pair row: check nodes column D-5, variable nodes column D-4 (local index)
         const int x4 = !c.pair ? -1 : (mode == kPhaseCn ? D - 5 : D - 4);
         const uint8_t* mrow = mode == kPhaseOut ? nullptr : match_row(D);

@@ -34,11 +34,22 @@ constexpr int kPhaseVnPairMin = 5;
 enum PhaseMode { kPhaseCn = 0, kPhaseVn = 1, kPhaseOut = 2 };
 
 // ---- compile-time layout of a phase image -------------------------------------------------------------------
+// A class of a degree set is written as its degree d (default composition: tail pair from degree 6 / 5 on) or as
+// d + 100 * (pm + 1) with an explicit pair mode pm: 0 = plain chains, 1 = tail pair.  The composed table costs 32 KB of
+// the phase image, which a class of a handful of nodes (DVB-S2: one check of degree 6) is not worth.
+// (A second composed row in the MIDDLE of the chains, H(m_{D-4}, m_{D-3})[t], was implemented and measured in round 2: it
+// removes 17-24 % of the shared-memory wavefronts, is bit-exact, and is SLOWER -- (3,6) check-node phase 0.48 -> 0.56 ms,
+// DVB-S2 0.67 -> 0.72 ms, 802.11n 0.178 -> 0.189 ms: the 64-bit nibble selects cost more issue slots than the look-ups
+// they replace, and issue is the co-limiter.  profiles/README.md.)
+__host__ __device__ constexpr int spec_deg(int v) { return v % 100; }
 __host__ __device__ constexpr int phase_cols(int mode, int d) { return mode == kPhaseCn ? d - 2 : mode == kPhaseVn ? d - 1 : d; }
-__host__ __device__ constexpr bool phase_pair(int mode, int d)
+__host__ __device__ constexpr int phase_pm(int mode, int v)
 {
-    return mode == kPhaseCn ? d >= kPhaseCnPairMin : mode == kPhaseVn ? d >= kPhaseVnPairMin : false;
+    if (mode == kPhaseOut) return 0;
+    if (v >= 100) return v / 100 - 1;
+    return mode == kPhaseCn ? (v >= kPhaseCnPairMin ? 1 : 0) : (v >= kPhaseVnPairMin ? 1 : 0);
 }
+__host__ __device__ constexpr bool phase_pair(int mode, int v) { return phase_pm(mode, v) >= 1; }
 // words (8 frames each) a lane moves per message row: the widest access the register budget of 64 allows
 __host__ __device__ constexpr int phase_vec(int mode, int d)
 {
@@ -48,11 +59,13 @@ __host__ __device__ constexpr int phase_vec(int mode, int d)
 template <int MODE, int... Ds>
 struct PhaseLayout {
     static constexpr int n = sizeof...(Ds);
-    __host__ __device__ static constexpr int degree(int i)
+    __host__ __device__ static constexpr int spec(int i)
     {
         constexpr int d[] = {Ds...};
         return d[i];
     }
+    __host__ __device__ static constexpr int degree(int i) { return spec_deg(spec(i)); }
+    __host__ __device__ static constexpr int pm(int i) { return phase_pm(MODE, spec(i)); }
     // first stage column of class i (the decision phase shares its plain columns between the classes)
     __host__ __device__ static constexpr int col_base(int i)
     {
@@ -71,7 +84,7 @@ struct PhaseLayout {
     __host__ __device__ static constexpr int pair_index(int i)
     {
         int p = 0;
-        for (int j = 0; j < i; ++j) p += phase_pair(MODE, degree(j)) ? 1 : 0;
+        for (int j = 0; j < i; ++j) p += pm(j);
         return p;
     }
     static constexpr int n_pair = pair_index(n);
@@ -79,7 +92,7 @@ struct PhaseLayout {
 };
 
 // run-time description of the same layout for the host-side image builder (ib_phase.cu)
-struct PhaseClassLayout { int degree, col_base, cols, pair_index, vec; bool pair; };
+struct PhaseClassLayout { int degree, col_base, cols, pair_index, vec, pm; bool pair; };
 struct PhaseLayoutRt { int n, words, n_pair, image_bytes; PhaseClassLayout cls[kPhaseMaxClasses]; };
 
 template <int MODE, int... Ds>
@@ -90,7 +103,7 @@ PhaseLayoutRt phase_layout_rt(DegreeSet<Ds...>)
     r.n = L::n; r.words = L::words; r.n_pair = L::n_pair; r.image_bytes = L::image_bytes;
     for (int i = 0; i < L::n; ++i) {
         const int d = L::degree(i);
-        r.cls[i] = PhaseClassLayout{d, L::col_base(i), phase_cols(MODE, d), L::pair_index(i), phase_vec(MODE, d), phase_pair(MODE, d)};
+        r.cls[i] = PhaseClassLayout{d, L::col_base(i), phase_cols(MODE, d), L::pair_index(i), phase_vec(MODE, d), L::pm(i), L::pm(i) >= 1};
     }
     return r;
 }
@@ -182,7 +195,8 @@ struct PhaseItem {
     static constexpr int VEC = phase_vec(MODE, D);
     static constexpr int WT = L::words;
     static constexpr int CB = L::col_base(I);
-    static constexpr bool PAIR = phase_pair(MODE, D);
+    static constexpr int PM = L::pm(I);
+    static constexpr bool PAIR = PM >= 1;
     static constexpr int PI = L::pair_index(I);
 
     // returns the syndrome bits seen (check-node phase with EARLY), 0 otherwise
@@ -318,7 +332,7 @@ __device__ __forceinline__ void phase_kernel_body(const PhaseArgs& p, const IbAr
         constexpr int degs[] = {Ds...};
 #pragma unroll
         for (int c = 0; c < L::n; ++c) {
-            const int vec = phase_vec(MODE, degs[c]);
+            const int vec = phase_vec(MODE, spec_deg(degs[c]));
             tiles[c] = (int)((bound + 128u * vec - 1) / (128u * vec));
             const long long items = (long long)p.n_nodes[c] * tiles[c];
             lo[c] = (int)(items * blockIdx.x / gridDim.x);

@@ -21,8 +21,8 @@ PhaseSetOps make_phase_ops(const char* name, DegreeSet<Cs...> cs, DegreeSet<Vs..
 {
     PhaseSetOps o;
     o.name = name;
-    o.cn_deg = {Cs...};
-    o.vn_deg = {Vs...};
+    o.cn_deg = {spec_deg(Cs)...};
+    o.vn_deg = {spec_deg(Vs)...};
     o.cn_layout = phase_layout_rt<kPhaseCn>(cs);
     o.vn_layout = phase_layout_rt<kPhaseVn>(vs);
     o.out_layout = phase_layout_rt<kPhaseOut>(vs);
