@@ -48,6 +48,8 @@ def _prepare(tmp_path, rel, H, configs):
     code_file.parent.mkdir(parents=True, exist_ok=True)
     if str(code_file).endswith(".npy"):
         np.save(code_file, np.asarray(H.toarray(), dtype=np.int8))
+    elif str(code_file).endswith(".npz"):
+        codes.save_csr_npz(H, str(code_file))
     else:
         graph.write_alist(H, str(code_file))
     for name, (tables, extras) in configs.items():
@@ -149,3 +151,17 @@ def test_wlan_quant_bp_driver(tmp_path, wlan):
     ns = run_driver.run(path, {"min_errors": 2000, "EbN0_dB_max_value": 0.05})
     dl = int(ns["decodi"].data_len)
     _check(ns, H, dl, float(ns["transi"].R_c), frames=96, llr_algo="bp")
+
+
+def test_dvbs2_ib_driver(tmp_path):
+    """Irregular_LDPC_Decoding/DVB-S2/BER_simulation_OpenCL.py (msg_at_time = 2: the cooperative small-batch kernel of the
+    DVB-S2 degree sets) on a DVB-S2-like rate-1/2 code of length 6480 (the script reads the length from the code file)."""
+    rel = "Irregular_LDPC_Decoding/DVB-S2/BER_simulation_OpenCL.py"
+    H = codes.dvbs2_like_half_rate(6480, q_groups=36)
+    tb, ex = generate_irregular_config(0.6, H, T, 50)
+    path = _prepare(tmp_path, rel, H, {"decoder_config_EbN0_gen_0.6_16adapt71.pkl": (tb, ex)})
+    from informationbottleneckdecodingldpc_b200 import run_driver
+    ns = run_driver.run(path, {"min_errors": 3000, "EbN0_dB_max_value": 0.05}, inject={"pb": run_driver.Silent()})
+    dl = int(ns["decodi"].data_len)
+    assert ns["decodi"].info()[0] == 2 and ns["msg_at_time"] == 2
+    _check(ns, H, dl, float(ns["transi"].R_c), frames=64, ib=tb)
