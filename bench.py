@@ -321,13 +321,20 @@ def run_reference_arm(args):
     return 0
 
 
+# translation units and headers the per-class packed-nibble kernels (the dominant kernels of the headline workload) are
+# compiled from; profiles/traffic.json is tied to exactly these
+TRAFFIC_SOURCES = ("ib_kernels.cuh", "ib_kernels_n4.cuh", "ib_n4_cn_pair.cu", "ib_n4_cn_v2.cu", "ib_n4_vn_v2.cu", "ib_n4_vn_v4.cu",
+                   "ib_n4_vn_pair.cu", "kernel_tables.h")
+
+
 def source_hash():
-    """sha256 (16 hex digits) over the kernel sources: ties profiles/traffic.json to the kernels it was captured on."""
+    """sha256 (16 hex digits) over the sources of the per-class packed-nibble kernels: ties profiles/traffic.json to the
+    kernels it was captured on."""
     import hashlib
     from informationbottleneckdecodingldpc_b200 import _lib
     h = hashlib.sha256()
     for f in sorted(_lib.SOURCES):
-        if f.endswith((".cu", ".cuh", ".h")) and os.path.exists(f):
+        if os.path.basename(f) in TRAFFIC_SOURCES and os.path.exists(f):
             h.update(open(f, "rb").read())
     return h.hexdigest()[:16]
 
@@ -396,16 +403,26 @@ def phase_roofline(decodi, ch, N, E, B, workload_name):
     return roofline_from_phase_times(list(ms3), list(n3), N, E, B, IMAX, fam == 2, workload_name, family=fam)
 
 
-def time_steps(step, steps, warmup, min_warm_s=0.4):
-    """`warmup` untimed steps -- and at least `min_warm_s` seconds of them: a leg starts after seconds of host-side table
-    design during which the idle GPU drops its clocks -- then `steps` timed ones (CUDA events on the current stream)."""
+def time_steps(step, steps, warmup, min_warm_s=0.5, max_warm_s=6.0):
+    """`warmup` untimed steps -- at least `min_warm_s` seconds of them, and until two consecutive steps agree within 2 %
+    (at most `max_warm_s`): a leg starts after seconds of host-side table design during which the idle GPU drops its
+    clocks, and some boxes take more than a second under load to come back -- then `steps` timed ones (CUDA events on
+    the current stream)."""
     import torch
     t0 = time.perf_counter()
-    n = 0
-    while n < max(warmup, 1) or time.perf_counter() - t0 < min_warm_s:
+    n, prev, stable = 0, None, False
+    while n < max(warmup, 2) or time.perf_counter() - t0 < min_warm_s or not stable:
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
         step()
+        w1.record()
         torch.cuda.synchronize()
+        cur = w0.elapsed_time(w1)
+        stable = prev is not None and abs(cur - prev) <= 0.02 * max(cur, prev)
+        prev = cur
         n += 1
+        if time.perf_counter() - t0 > max_warm_s:
+            break
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

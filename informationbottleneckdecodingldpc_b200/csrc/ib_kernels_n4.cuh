@@ -216,9 +216,14 @@ __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t
     }
 }
 
-template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR, int WT = 0, int CB = 0>
+// FS: per-frame syndrome flags (per-frame early termination, ib_perframe.cu): 0 none, 1 OR-ed into a shared-memory
+// accumulator at the 32-bit shared address fsyn_s, 2 OR-ed into global memory at fsyn.  Both are issued UNCONDITIONALLY: a
+// branch around them in this fully unrolled body makes ptxas keep the shared-memory base of the tables in a register and
+// add it to every look-up address (one extra IMAD.IADD per LDS: +23 % instructions, measured in round 2).
+template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR, int WT = 0, int CB = 0, int FS = 0>
 __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* tab, const uint8_t* ptab, int s, uint32_t col,
-                                               uint32_t lane4, int valid_frames, uint32_t* fsyn = nullptr)
+                                               uint32_t lane4, int valid_frames, uint32_t* fsyn = nullptr,
+                                               const uint32_t* frz = nullptr, uint32_t fsyn_s = 0xffffffffu)
 {
     uint32_t m[D][VEC];
     if (a.iter0) {
@@ -257,15 +262,18 @@ __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* t
             const uint32_t vmask = nv >= 8 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (4 * nv)) - 1u);
             syn |= par & vmask;
             // per-frame early termination: bit 4f of fsyn[word] = frame f of that word failed a check in this pass
-            if (fsyn != nullptr && (par & vmask) != 0u) {
-                if (__isShared(fsyn))   // per-CTA accumulator: a native shared-memory reduction, not a generic atomic
-                    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(fsyn + j)), "r"(par & vmask) : "memory");
-                else
-                    atomicOr(fsyn + j, par & vmask);
-            }
+            if constexpr (FS == 1) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(fsyn_s + 4u * j), "r"(par & vmask));
+            if constexpr (FS == 2) asm volatile("red.global.or.b32 [%0], %1;" ::"l"(fsyn + j), "r"(par & vmask));
         }
         if constexpr (PAIR) cn_word_n4_pair<D, WT, CB>(w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
         else cn_word_n4<D, MATCH, WT, CB>(w, o, tab, lane4);
+        // per-frame early termination: frames that have converged keep the messages they converged with (nibble mask
+        // frz[j] = frames of word j that still iterate); they are decided later from exactly this state (ib_perframe.cu)
+        if (frz != nullptr && !a.iter0) {
+            const uint32_t am = frz[j];
+#pragma unroll
+            for (int k = 0; k < D; ++k) o[k] = (o[k] & am) | (w[k] & ~am);
+        }
 #pragma unroll
         for (int k = 0; k < D; ++k) r[k][j] = o[k];
     }

@@ -5,18 +5,27 @@
 // (msg_at_time = 1) stops each frame as soon as ITS syndrome is zero; that is the result this mode reproduces for a
 // whole batch in one call -- outputs and per-frame i_num equal to the reference run with one frame per call -- while
 // only the frames that still iterate cost anything:
-//   * every check-node phase records, per frame, whether a check failed (bit 4f of pf_fsyn[word], atomicOr);
-//   * pf_update_kernel turns "alive and no failed check in this pass" into the nibble mask pf_conv, stores the frame's
-//     i_num, and counts what is left;
-//   * the decision kernel of the SAME pass (table of iteration i_num - 1, like calc_varnode_output at
-//     discrete_LDPC_decoder.py:280-287) writes exactly those frames, to their original columns;
-//   * at scheduled passes the surviving columns are gathered to the front of the other ping-pong buffer (packed
-//     nibbles: one word-gather kernel) when at least a quarter of the active columns has finished, and every later
-//     kernel works on the shorter prefix.
+//   * every check-node phase records, per frame, whether a check failed (bit 4f of pf_fsyn[word]);
+//   * pf_update_kernel retires the alive frames without a failed check: it stores their i_num, clears them from the
+//     `alive` nibble mask and hands every one of them a dense RESULT SLOT (group g = pass g - 1 owns the slots
+//     [gstart[g], gstart[g + 1]));
+//   * from then on both phases leave the messages of such a frame untouched (cn_node_n4 / PhaseItem merge under the
+//     alive mask): the frame stays FROZEN in the state calc_varnode_output would read
+//     (discrete_LDPC_decoder.py:280-287);
+//   * ib_phase_pfdecide_kernel decides the frozen frames group by group with the tables of their own iteration
+//     (i_num - 1), gathering the eight frames of a result word from their columns: every frame is decided exactly once,
+//     densely, however the convergence passes interleave inside a word;
+//   * after the pending groups are decided, the batch is compacted IN PLACE when that pays: every dead column of the new
+//     front [0, n_alive) is filled with an alive column of the tail (only the holes move: one CTA per row stages the row
+//     in shared memory, patches the hole nibbles and writes the front back).  It pays when the passes' worth of work
+//     spent on dead columns since the last compaction has reached the cost of one, and the rest of the schedule is long
+//     enough to win it back (ski-rental rule, evaluated on the device);
+//   * one kernel at the end permutes the result nibbles from slot order back to the caller's frame order (uint8).
 // Nothing synchronises with the host: all launches of the schedule are issued up front and read what is left to do
 // from a device-side PfState.  Runs on the fused per-phase kernels (ib_phase_n4.cuh), i.e. for the degree sets those
 // are instantiated for.
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -33,45 +42,54 @@ int phase_set_attributes(ibldpc_decoder* h);
 
 namespace {
 
-__global__ void pf_init_kernel(PfState* st, int B, int pitch4, uint32_t* alive, uint32_t* fsyn, uint32_t* conv, int* idx0,
-                               int* dstw, int words)
+constexpr int kGatherThreads = 512;
+constexpr int kExpandThreads = 512;
+constexpr size_t kRowSmemMax = 200 * 1024;   // a row of active columns must fit in shared memory to be compacted in place
+
+__global__ void pf_init_kernel(PfState* st, int B, int pitch4, uint32_t* alive, uint32_t* fsyn, int* idx0, int* gstart, int words)
 {
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
-        dstw[w] = w;
         const int nv = B - 8 * w;
         alive[w] = nv >= 8 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (4 * nv)) - 1u);
         fsyn[w] = 0u;
-        conv[w] = 0u;
     }
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < words * 8; f += gridDim.x * blockDim.x) idx0[f] = f < B ? f : 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        st->n_act = B; st->act_pitch = pitch4; st->cur = 0; st->n_alive = B; st->done = 0; st->do_compact = 0;
-        st->new_n = B; st->alive_acc = 0; st->blocks_done = 0u;
+        st->n_act = B; st->act_pitch = pitch4; st->n_holes = 0; st->n_alive = B; st->done = 0; st->do_compact = 0;
+        st->new_n = B; st->alive_acc = 0; st->blocks_done = 0u; st->blocks_done2 = 0u; st->fin_count = 0; st->waste = 0.f;
+        gstart[0] = 0;
     }
 }
 
-// After the check-node phase of pass `it`: conv = alive frames without a failed check (all alive frames in the last
-// pass), i_num of those frames = it + 2 (passes executed + 1), alive -= conv, fsyn = 0, count the rest.
-__global__ void pf_update_kernel(PfState* st, uint32_t* alive, uint32_t* fsyn, uint32_t* conv, const int* idx0, const int* idx1,
-                                 int32_t* inum_frames, int* inum_batch, int it, int last)
+// After the check-node phase of pass `it`: the alive frames without a failed check (all alive frames in the last pass)
+// are retired -- i_num = it + 2 (passes executed + 1), a result slot of group it + 1 each, cleared from `alive` -- and the
+// rest is counted.  The last block closes the group (slot count rounded up to a result word) and raises `done`.
+__global__ void pf_update_kernel(PfState* st, uint32_t* alive, uint32_t* fsyn, const int* idx, int* fin, int* slot_of, int* gstart,
+                                 int32_t* inum_frames, int* inum_batch, int it, int last, int imax)
 {
     if (st->done) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) *inum_batch = it + 2;   // i_num of the last frame to finish = the batch's i_num
-    const int words = (st->n_act + 7) >> 3;
-    const int* idx = st->cur ? idx1 : idx0;
+    const int n_act = st->n_act;
+    const int words = (n_act + 7) >> 3;
     int cnt = 0;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
         const uint32_t al = alive[w];
         const uint32_t failed = (fsyn[w] & 0x11111111u) * 15u;
         const uint32_t cv = last ? al : (al & ~failed);
-        conv[w] = cv;
-        alive[w] = al & ~cv;
         fsyn[w] = 0u;
         cnt += __popc(al & ~cv) >> 2;
-        if (cv != 0u && inum_frames != nullptr) {
+        if (cv != 0u) {
+            alive[w] = al & ~cv;
+            int slot = atomicAdd(&st->fin_count, __popc(cv) >> 2);
 #pragma unroll
             for (int f = 0; f < 8; ++f)
-                if ((cv >> (4 * f)) & 1u) inum_frames[idx[8 * w + f]] = it + 2;
+                if ((cv >> (4 * f)) & 1u) {
+                    const int orig = idx[8 * w + f];
+                    fin[slot] = 8 * w + f;
+                    slot_of[orig] = slot;
+                    if (inum_frames != nullptr) inum_frames[orig] = it + 2;
+                    ++slot;
+                }
         }
     }
     // block reduction, last block publishes
@@ -90,142 +108,171 @@ __global__ void pf_update_kernel(PfState* st, uint32_t* alive, uint32_t* fsyn, u
             const int n = atomicExch(&st->alive_acc, 0);
             st->n_alive = n;
             st->blocks_done = 0u;
-            // st->done is raised by pf_finish_kernel AFTER the decision kernel of this pass has written its frames
+            int fc = atomicAdd(&st->fin_count, 0);
+            while (fc & 7) fin[fc++] = -1;            // padding slots of the group's last result word
+            st->fin_count = fc;
+            gstart[it + 2] = fc;                      // group it + 1 = [gstart[it + 1], gstart[it + 2])
+            st->waste += (float)(n_act - n) / (float)n_act;
+            if (n == 0) {                             // nothing left: the groups of the remaining passes are empty
+                for (int g = it + 3; g <= imax; ++g) gstart[g] = fc;
+                st->done = 1;
+            }
         }
     }
 }
 
-__global__ void pf_finish_kernel(PfState* st)
+// One CTA: decide whether a compaction pays now (see the header) and, if so, pair every dead column of the new front
+// [0, n_alive) -- a HOLE -- with an alive column of the tail [n_alive, n_act): hole_dst[i] receives column hole_src[i].
+// Only the holes move; every other alive column stays where it is.
+__global__ void __launch_bounds__(1024) pf_scan_kernel(PfState* st, const uint32_t* alive, int* hole_dst, int* hole_src,
+                                                       int remaining, float cost, int max_act_pitch)
 {
-    if (st->n_alive == 0) st->done = 1;
-}
-
-// One CTA: if at least a quarter of the active columns has finished, list the alive columns (stable order) and the
-// original frame index of each; otherwise leave do_compact = 0 and the gather is skipped.
-__global__ void __launch_bounds__(1024) pf_scan_kernel(PfState* st, const uint32_t* alive, const int* idx0, const int* idx1,
-                                                       int* order, int* idx0w, int* idx1w)
-{
-    __shared__ int s_sum[1024];
+    __shared__ int s_f[1024], s_t[1024];
     if (st->done) return;
     const int n_act = st->n_act, n_alive = st->n_alive;
-    if (n_alive == 0 || (long long)n_alive * 4 > (long long)n_act * 3) {
+    const float dead = (float)(n_act - n_alive) / (float)n_act;
+    const bool pays = n_alive > 0 && n_act > 1024 && st->act_pitch <= max_act_pitch && (st->waste >= cost || dead >= 0.25f) &&
+                      dead * (float)remaining >= cost;
+    if (!pays) {
         if (threadIdx.x == 0) st->do_compact = 0;
         return;
     }
     const int words = (n_act + 7) >> 3;
     const int per = (words + 1023) / 1024;
     const int w0 = threadIdx.x * per, w1 = min(words, w0 + per);
-    int cnt = 0;
-    for (int w = w0; w < w1; ++w) cnt += __popc(alive[w]) >> 2;
-    s_sum[threadIdx.x] = cnt;
-    __syncthreads();
-    // inclusive scan (Hillis-Steele, 1024 entries)
-    for (int off = 1; off < 1024; off <<= 1) {
-        const int v = threadIdx.x >= off ? s_sum[threadIdx.x - off] : 0;
-        __syncthreads();
-        s_sum[threadIdx.x] += v;
-        __syncthreads();
-    }
-    int pos = s_sum[threadIdx.x] - cnt;
-    const int* idx = st->cur ? idx1 : idx0;
-    int* idxw = st->cur ? idx0w : idx1w;          // the OTHER buffer receives the compacted index list
+    int cf = 0, ct = 0;
     for (int w = w0; w < w1; ++w) {
         const uint32_t al = alive[w];
-        for (int f = 0; f < 8; ++f)
-            if ((al >> (4 * f)) & 1u) {
-                order[pos] = 8 * w + f;
-                idxw[pos] = idx[8 * w + f];
-                ++pos;
-            }
+        for (int f = 0; f < 8; ++f) {
+            const int c = 8 * w + f;
+            const bool a1 = (al >> (4 * f)) & 1u;
+            cf += (c < n_alive && !a1) ? 1 : 0;
+            ct += (c >= n_alive && a1) ? 1 : 0;
+        }
+    }
+    s_f[threadIdx.x] = cf;
+    s_t[threadIdx.x] = ct;
+    __syncthreads();
+    // inclusive scans (Hillis-Steele, 1024 entries)
+    for (int off = 1; off < 1024; off <<= 1) {
+        const int vf = threadIdx.x >= off ? s_f[threadIdx.x - off] : 0;
+        const int vt = threadIdx.x >= off ? s_t[threadIdx.x - off] : 0;
+        __syncthreads();
+        s_f[threadIdx.x] += vf;
+        s_t[threadIdx.x] += vt;
+        __syncthreads();
+    }
+    int pf = s_f[threadIdx.x] - cf, pt = s_t[threadIdx.x] - ct;
+    for (int w = w0; w < w1; ++w) {
+        const uint32_t al = alive[w];
+        for (int f = 0; f < 8; ++f) {
+            const int c = 8 * w + f;
+            const bool a1 = (al >> (4 * f)) & 1u;
+            if (c < n_alive && !a1) hole_dst[pf++] = c;
+            if (c >= n_alive && a1) hole_src[pt++] = c;
+        }
     }
     if (threadIdx.x == 1023) {
-        st->new_n = s_sum[1023];
+        st->n_holes = s_f[1023];          // == s_t[1023]: dead columns in front = alive columns behind it
+        st->new_n = n_alive;
         st->do_compact = 1;
     }
 }
 
-// dst[row][word j] = nibbles of the alive columns order[8j .. 8j+7] of src[row]; rows = message rows, then channel rows
-__global__ void pf_gather_kernel(const PfState* st, uint8_t* msg0, uint8_t* msg1, uint8_t* ch0, uint8_t* ch1, int n_edge,
-                                 int n_var, uint32_t pitch, const int* __restrict__ order)
+// In-place compaction: row by row (message rows, then channel rows), the active prefix of a row is staged in shared
+// memory, the holes of the new front are patched with the nibbles of the tail columns, and the front is written back.
+__global__ void __launch_bounds__(kGatherThreads) pf_gather_kernel(const PfState* st, uint8_t* msg, uint8_t* ch, int n_edge, int n_var,
+                                                                  uint32_t pitch, const int* __restrict__ hole_dst,
+                                                                  const int* __restrict__ hole_src)
 {
+    extern __shared__ __align__(16) uint8_t s_row[];
     if (st->done || !st->do_compact) return;
-    const int new_n = st->new_n;
-    const int nw = (new_n + 7) >> 3;
-    const uint8_t* smsg = st->cur ? msg1 : msg0;
-    uint8_t* dmsg = st->cur ? msg0 : msg1;
-    const uint8_t* sch = st->cur ? ch1 : ch0;
-    uint8_t* dch = st->cur ? ch0 : ch1;
-    const long long total = (long long)(n_edge + n_var) * nw;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int row = (int)(i / nw), j = (int)(i - (long long)row * nw);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(row < n_edge ? smsg + (size_t)row * pitch : sch + (size_t)(row - n_edge) * pitch);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(row < n_edge ? dmsg + (size_t)row * pitch : dch + (size_t)(row - n_edge) * pitch);
-        uint32_t v = 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int c = 8 * j + q < new_n ? order[8 * j + q] : -1;
-            if (c >= 0) v |= ((src[c >> 3] >> (4 * (c & 7))) & 15u) << (4 * q);
+    const int new_n = st->new_n, n_holes = st->n_holes;
+    const int act16 = st->act_pitch >> 4;
+    const int new16 = (((new_n + 1) / 2 + 15) / 16);
+    uint32_t* s32 = reinterpret_cast<uint32_t*>(s_row);
+    for (int row = blockIdx.x; row < n_edge + n_var; row += gridDim.x) {
+        uint8_t* base = row < n_edge ? msg + (size_t)row * pitch : ch + (size_t)(row - n_edge) * pitch;
+        __syncthreads();   // the previous row has left the staging buffer
+        for (int i = threadIdx.x; i < act16; i += kGatherThreads) reinterpret_cast<uint4*>(s_row)[i] = reinterpret_cast<const uint4*>(base)[i];
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_holes; i += kGatherThreads) {
+            const int d = hole_dst[i], c = hole_src[i];
+            const uint32_t nib = (s32[c >> 3] >> (4 * (c & 7))) & 15u;            // tail columns are never patched
+            const uint32_t old = (s32[d >> 3] >> (4 * (d & 7))) & 15u;            // only this thread changes nibble d
+            atomicXor(&s32[d >> 3], (old ^ nib) << (4 * (d & 7)));
         }
-        dst[j] = v;
+        __syncthreads();
+        for (int i = threadIdx.x; i < new16; i += kGatherThreads) reinterpret_cast<uint4*>(base)[i] = reinterpret_cast<const uint4*>(s_row)[i];
     }
 }
 
-__global__ void pf_commit_kernel(PfState* st, uint32_t* alive, uint32_t* fsyn, uint32_t* conv, int old_words_max)
+// New column layout: all alive; the original frame index of every moved column follows it.  The last block flips the state.
+__global__ void pf_commit_kernel(PfState* st, uint32_t* alive, uint32_t* fsyn, int* idx, const int* hole_dst, const int* hole_src)
 {
     if (st->done || !st->do_compact) return;
-    const int new_n = st->new_n;
+    const int new_n = st->new_n, n_holes = st->n_holes;
     const int old_words = (st->n_act + 7) >> 3;
-    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < old_words && w < old_words_max; w += gridDim.x * blockDim.x) {
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < old_words; w += gridDim.x * blockDim.x) {
         const int nv = new_n - 8 * w;
         alive[w] = nv >= 8 ? 0xffffffffu : nv <= 0 ? 0u : ((1u << (4 * nv)) - 1u);
         fsyn[w] = 0u;
-        conv[w] = 0u;
     }
-    // grid-wide: the state flips after every block has read the old n_act -- done by a second, one-thread launch
-}
-
-// destination-word shortcut of the decision kernel for the compacted order (reads the NEW index list)
-__global__ void pf_dstw_kernel(const PfState* st, const int* idx0, const int* idx1, int* dstw)
-{
-    if (st->done || !st->do_compact) return;
-    const int* idx = st->cur ? idx0 : idx1;          // the buffer the scan wrote = the one that becomes current
-    const int nw = (st->new_n + 7) >> 3;
-    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += gridDim.x * blockDim.x) {
-        const int i0 = idx[8 * w], i7 = idx[8 * w + 7];
-        dstw[w] = (8 * w + 8 <= st->new_n && (i0 & 7) == 0 && i7 - i0 == 7) ? (i0 >> 3) : -1;
-    }
-}
-
-__global__ void pf_flip_kernel(PfState* st)
-{
-    if (st->done || !st->do_compact) return;
-    st->n_act = st->new_n;
-    st->act_pitch = (((st->new_n + 1) / 2 + 15) / 16) * 16;
-    st->cur ^= 1;
-    st->do_compact = 0;
-}
-
-// result nibbles (original frame order) -> the caller's uint8 output
-__global__ void pf_expand_kernel(const uint8_t* __restrict__ res, uint8_t* __restrict__ out, int n_var, int B, uint32_t pitch4,
-                                 uint32_t out_pitch)
-{
-    const uint32_t wpr = pitch4 >> 2;
-    const long long total = (long long)n_var * wpr;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int row = (int)(i / wpr), w = (int)(i - (long long)row * wpr);
-        const uint32_t v = reinterpret_cast<const uint32_t*>(res + (size_t)row * pitch4)[w];
-        uint8_t* dst = out + (size_t)row * out_pitch + 8 * (size_t)w;
-        if (8 * w + 8 <= (int)out_pitch && (out_pitch & 7u) == 0u) {
-            const uint32_t lo = (v & 0xfu) | ((v & 0xf0u) << 4) | ((v & 0xf00u) << 8) | ((v & 0xf000u) << 12);
-            const uint32_t hv = v >> 16;
-            const uint32_t hi = (hv & 0xfu) | ((hv & 0xf0u) << 4) | ((hv & 0xf00u) << 8) | ((hv & 0xf000u) << 12);
-            *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
-        } else {
-            for (int f = 0; f < 8; ++f)
-                if (8 * w + f < (int)out_pitch) dst[f] = (uint8_t)((v >> (4 * f)) & 15u);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_holes; i += gridDim.x * blockDim.x) idx[hole_dst[i]] = idx[hole_src[i]];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(&st->blocks_done2, 1u);
+        if (done == gridDim.x - 1) {          // every block has read the old n_act
+            st->n_act = new_n;
+            st->act_pitch = (((new_n + 1) / 2 + 15) / 16) * 16;
+            st->do_compact = 0;
+            st->waste = 0.f;
+            st->blocks_done2 = 0u;
         }
     }
-    (void)B;
+}
+
+// result nibbles in slot order -> the caller's uint8 output in frame order: out[row][f] = nibble slot_of[f] of res[row].
+// `rows_per_pass` result rows are staged in shared memory at a time (0: read them from global memory).
+__global__ void __launch_bounds__(kExpandThreads) pf_expand_kernel(const uint8_t* __restrict__ res, uint32_t res_pitch,
+                                                                  const int* __restrict__ slot_of, uint8_t* __restrict__ out, int n_var,
+                                                                  int B, uint32_t out_pitch, int rows_per_pass)
+{
+    extern __shared__ __align__(16) uint8_t s_res[];
+    const int words = (B + 7) >> 3;
+    const int rp = rows_per_pass > 0 ? rows_per_pass : 1;
+    for (int r0 = blockIdx.x * rp; r0 < n_var; r0 += gridDim.x * rp) {
+        const int nr = min(rp, n_var - r0);
+        if (rows_per_pass > 0) {
+            __syncthreads();
+            const int n16 = (int)(res_pitch >> 4) * nr;
+            const uint4* src = reinterpret_cast<const uint4*>(res + (size_t)r0 * res_pitch);
+            for (int i = threadIdx.x; i < n16; i += kExpandThreads) reinterpret_cast<uint4*>(s_res)[i] = src[i];
+            __syncthreads();
+        }
+        for (int w = threadIdx.x; w < words; w += kExpandThreads) {
+            int sl[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sl[q] = 8 * w + q < B ? slot_of[8 * w + q] : 0;
+            for (int r = 0; r < nr; ++r) {
+                const uint8_t* row = rows_per_pass > 0 ? s_res + (size_t)r * res_pitch : res + (size_t)(r0 + r) * res_pitch;
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    lo |= ((uint32_t)(row[sl[q] >> 1] >> (4 * (sl[q] & 1))) & 15u) << (8 * q);
+                    hi |= ((uint32_t)(row[sl[q + 4] >> 1] >> (4 * (sl[q + 4] & 1))) & 15u) << (8 * q);
+                }
+                uint8_t* dst = out + (size_t)(r0 + r) * out_pitch + 8 * (size_t)w;
+                if (8 * (uint32_t)w + 8 <= out_pitch && (out_pitch & 7u) == 0u) {
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+                } else {
+                    for (int f = 0; f < 8; ++f)
+                        if (8 * (uint32_t)w + f < out_pitch) dst[f] = (uint8_t)(((f < 4 ? lo : hi) >> (8 * (f & 3))) & 0xffu);
+                }
+            }
+        }
+    }
 }
 
 int ensure_buf(void** p, size_t* have, size_t need)
@@ -252,32 +299,36 @@ int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long lo
     const int words = (int)(pitch4 / 4);
     int rc;
     if ((rc = phase_set_attributes(h))) return rc;
-    // second message / channel arrays, index lists, masks, state
+    // result slots: one per frame + at most 7 padding slots per group (imax groups)
+    const size_t slots = (size_t)words * 8 + 8 * (size_t)(imax + 1);
+    const uint32_t res_pitch = (uint32_t)(((slots / 2 + 15) / 16) * 16);
     {
-        void* p = w.pf_msg2;
-        if ((rc = ensure_buf(&p, &w.pf_msg2_bytes, (size_t)h->E * pitch4))) return rc;
-        w.pf_msg2 = (uint8_t*)p;
-        p = w.pf_ch2;
-        if ((rc = ensure_buf(&p, &w.pf_ch2_bytes, (size_t)h->N * pitch4))) return rc;
-        w.pf_ch2 = (uint8_t*)p;
-        // [idx0][idx1][order] ints of words*8, [alive][fsyn][conv] words, state, [result nibbles n_var x pitch4]
-        const size_t need = sizeof(int) * (size_t)words * 8 * 3 + sizeof(uint32_t) * (size_t)words * 4 + 256 + (size_t)h->N * pitch4;
-        p = w.pf_idx;
+        // ints: [idx][hole_dst][hole_src][slot_of] of words*8, [fin] of slots, [gstart] of imax+2 (rounded to 4);
+        // words: [alive][fsyn]; state (256 B); [result nibbles n_var x res_pitch]
+        const size_t n_int = (size_t)words * 8 * 4 + slots + (size_t)((imax + 2 + 3) / 4 * 4);
+        const size_t need = sizeof(int) * n_int + sizeof(uint32_t) * (size_t)words * 2 + 256 + 16 + (size_t)h->N * res_pitch;
+        void* p = w.pf_idx;
         if ((rc = ensure_buf(&p, &w.pf_idx_bytes, need))) return rc;
         w.pf_idx = (int*)p;
     }
     int* idx0 = w.pf_idx;
-    int* idx1 = idx0 + (size_t)words * 8;
-    int* order = idx1 + (size_t)words * 8;
-    uint32_t* alive = reinterpret_cast<uint32_t*>(order + (size_t)words * 8);
+    int* hole_dst = idx0 + (size_t)words * 8;
+    int* hole_src = hole_dst + (size_t)words * 8;
+    int* slot_of = hole_src + (size_t)words * 8;
+    int* fin = slot_of + (size_t)words * 8;
+    int* gstart = fin + slots;
+    uint32_t* alive = reinterpret_cast<uint32_t*>(gstart + (size_t)((imax + 2 + 3) / 4 * 4));
     uint32_t* fsyn = alive + words;
-    uint32_t* conv = fsyn + words;
-    int* dstw = reinterpret_cast<int*>(conv + words);
-    PfState* state = reinterpret_cast<PfState*>(dstw + words);
-    uint8_t* res = reinterpret_cast<uint8_t*>(dstw + words) + 256;
-    IBLDPC_CK(cudaMemsetAsync(res, 0, (size_t)h->N * pitch4, st));
+    PfState* state = reinterpret_cast<PfState*>(fsyn + words);
+    uint8_t* res = reinterpret_cast<uint8_t*>(fsyn + words) + 256;
+    res += (16 - (reinterpret_cast<uintptr_t>(res) & 15)) & 15;
+    static_assert(sizeof(PfState) <= 256, "PfState outgrew its slot");
+    uint8_t* msg = w.msg;
+    uint8_t* ch4 = w.ch4;
+    if (a.msg != msg || a.ch != ch4) return fail_msg(IBLDPC_E_STATE, "per-frame early termination: unexpected workspace buffers");
+
     const int small_grid = std::max(1, std::min(h->sm_count * 4, (words + 255) / 256));
-    pf_init_kernel<<<small_grid, 256, 0, st>>>(state, (int)B, (int)pitch4, alive, fsyn, conv, idx0, dstw, words);
+    pf_init_kernel<<<small_grid, 256, 0, st>>>(state, (int)B, (int)pitch4, alive, fsyn, idx0, gstart, words);
     h->last_launches++;
 
     PhaseArgs base{};
@@ -285,68 +336,80 @@ int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long lo
     base.a.early = 1;
     base.a.imax = imax;
     base.pf = state;
-    base.pf_msg[0] = a.msg; base.pf_msg[1] = w.pf_msg2;
-    base.pf_ch[0] = a.ch; base.pf_ch[1] = w.pf_ch2;
-    base.pf_idx[0] = idx0; base.pf_idx[1] = idx1;
+    base.pf_alive = alive;
     base.pf_fsyn = fsyn;
-    base.pf_conv = conv;
+    base.pf_fin = fin;
+    base.pf_gstart = gstart;
     base.pf_res = res;
-    base.pf_dstw = dstw;
-    auto launch = [&](int mode, int index, int it, PhaseKernel k) -> int {
+    base.pf_res_pitch = res_pitch;
+    auto launch = [&](int mode, int index, int it) -> int {
         PhaseArgs q = base;
         q.a.it = it;
         q.a.iter0 = (mode == kPhaseCn && index == 0 && it < 0);
         size_t smem = 0;
         phase_fill_args(h, mode, index, q, &smem);
+        PhaseKernel k = ops->vn_pf_kernel;
         if (mode == kPhaseCn) {
             // syndrome accumulator behind the image when the whole batch fits (227 KB per CTA minus image and statics)
             const size_t room = (size_t)227 * 1024 - 1024 - smem;
-            if ((size_t)words * 4 <= room) {
-                q.pf_fsyn_smem_words = words;
-                smem += (size_t)words * 4;
-            }
+            const bool fits = (size_t)words * 4 <= room;
+            if (fits) smem += (size_t)words * 4;
+            k = ops->cn_pf_kernel[fits ? 0 : 1];
         }
         k<<<h->sm_count, kPhaseThreads, smem, st>>>(q);
         h->last_launches++;
         return IBLDPC_OK;
     };
-    auto retire = [&](int it, int last) -> int {
-        pf_update_kernel<<<small_grid, 256, 0, st>>>(state, alive, fsyn, conv, idx0, idx1, i_num_frames_dev, a.inum, it, last);
-        // decision with the variable-node tables of iteration it + 1 for the frames named by conv
-        if ((rc = launch(kPhaseOut, it + 1, it + 1, ops->out_pf_kernel))) return rc;
-        pf_finish_kernel<<<1, 1, 0, st>>>(state);
-        h->last_launches += 2;
-        return IBLDPC_OK;
+    auto retire = [&](int it, int last) {
+        pf_update_kernel<<<small_grid, 256, 0, st>>>(state, alive, fsyn, idx0, fin, slot_of, gstart, i_num_frames_dev, a.inum, it, last, imax);
+        h->last_launches++;
     };
-    auto compact = [&]() -> int {
-        pf_scan_kernel<<<1, 1024, 0, st>>>(state, alive, idx0, idx1, order, idx0, idx1);
-        const long long total = (long long)(h->E + h->N) * words;
-        const int g = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * 16, (total + 255) / 256));
-        pf_gather_kernel<<<g, 256, 0, st>>>(state, a.msg, w.pf_msg2, const_cast<uint8_t*>(a.ch), w.pf_ch2, h->E, h->N, pitch4, order);
-        pf_commit_kernel<<<small_grid, 256, 0, st>>>(state, alive, fsyn, conv, words);
-        pf_dstw_kernel<<<small_grid, 256, 0, st>>>(state, idx0, idx1, dstw);
-        pf_flip_kernel<<<1, 1, 0, st>>>(state);
-        h->last_launches += 5;
-        return IBLDPC_OK;
+    // decision of the groups [g_lo, g_hi] (group g = pass g - 1, tables of iteration g)
+    int g_next = 0;
+    auto decide_pending = [&](int g_hi) {
+        if (g_hi < g_next) return;
+        PhaseArgs q = base;
+        size_t smem = 0;
+        phase_fill_args(h, kPhaseOut, 0, q, &smem);
+        ops->pf_decide_kernel<<<h->sm_count, kPhaseThreads, smem, st>>>(q, g_next, g_hi);
+        h->last_launches++;
+        g_next = g_hi + 1;
+    };
+    // cost of one compaction in passes of the same width (measured on B200: gather + scan + commit against a
+    // variable-node + check-node pass of the (3,6) and 802.11n codes); IBLDPC_PF_COST overrides
+    static const float cost = getenv("IBLDPC_PF_COST") ? (float)atof(getenv("IBLDPC_PF_COST")) : 0.3f;
+    const size_t row_smem = std::min<size_t>(pitch4, kRowSmemMax);
+    if (!w.pf_attr_set) {
+        IBLDPC_CK(cudaFuncSetAttribute((const void*)pf_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmemMax));
+        IBLDPC_CK(cudaFuncSetAttribute((const void*)pf_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmemMax));
+        w.pf_attr_set = true;
+    }
+    const int gather_grid = h->sm_count * (int)std::max<size_t>(1, std::min<size_t>(4, kRowSmemMax / std::max<size_t>(row_smem, 1)));
+    auto compact = [&](int it) {
+        pf_scan_kernel<<<1, 1024, 0, st>>>(state, alive, hole_dst, hole_src, imax - 2 - it, cost, (int)kRowSmemMax);
+        decide_pending(it + 1);          // the frozen columns are read before the gather may overwrite them
+        pf_gather_kernel<<<gather_grid, kGatherThreads, row_smem, st>>>(state, msg, ch4, h->E, h->N, pitch4, hole_dst, hole_src);
+        pf_commit_kernel<<<small_grid, 256, 0, st>>>(state, alive, fsyn, idx0, hole_dst, hole_src);
+        h->last_launches += 3;
     };
     // check-node phase of iteration 0 (table block 0, channel values through vidx)
-    if ((rc = launch(kPhaseCn, 0, -1, ops->cn_pf_kernel))) return rc;
-    if (imax <= 1) {
-        if ((rc = retire(-1, 1))) return rc;          // no pass at all: decide everything with table 0, i_num = 1
-    }
+    if ((rc = launch(kPhaseCn, 0, -1))) return rc;
+    if (imax <= 1) retire(-1, 1);          // no pass at all: decide everything with table 0, i_num = 1
     for (int it = 0; it < imax - 1; ++it) {
-        if ((rc = launch(kPhaseVn, it, it, ops->vn_pf_kernel))) return rc;
-        if ((rc = launch(kPhaseCn, it + 1, it, ops->cn_pf_kernel))) return rc;
-        if ((rc = retire(it, it == imax - 2))) return rc;
-        // compaction attempts: every pass at first (the waterfall region retires most frames within a few passes),
-        // then every second / fourth pass
-        const bool try_compact = it < imax - 2 && (it < 8 || (it < 24 && it % 2 == 1) || it % 4 == 3);
-        if (try_compact && (rc = compact())) return rc;
+        if ((rc = launch(kPhaseVn, it, it))) return rc;
+        if ((rc = launch(kPhaseCn, it + 1, it))) return rc;
+        retire(it, it == imax - 2);
+        // compaction attempts: every pass in the first half of the schedule (the waterfall region retires most frames
+        // within a few passes), then every second / fourth pass; whether one happens is decided on the device
+        const bool attempt = it < imax - 2 && (it < 24 || (it < 36 && it % 2 == 1) || it % 4 == 3);
+        if (attempt) compact(it);
     }
+    decide_pending(std::max(imax - 1, 0));
     {
-        const long long total = (long long)h->N * words;
-        const int g = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * 16, (total + 255) / 256));
-        pf_expand_kernel<<<g, 256, 0, st>>>(res, a.out, h->N, (int)B, pitch4, a.out_pitch);
+        const int rows_per_pass = res_pitch <= kRowSmemMax ? (int)std::min<size_t>(4, kRowSmemMax / res_pitch) : 0;
+        const size_t smem = (size_t)rows_per_pass * res_pitch;
+        const int g = std::max(1, std::min(h->sm_count * (smem <= 100 * 1024 ? 2 : 1), (h->N + std::max(rows_per_pass, 1) - 1) / std::max(rows_per_pass, 1)));
+        pf_expand_kernel<<<g, kExpandThreads, smem, st>>>(res, res_pitch, slot_of, a.out, h->N, (int)B, a.out_pitch, rows_per_pass);
         h->last_launches++;
     }
     IBLDPC_CK(cudaGetLastError());

@@ -219,16 +219,17 @@ int phase_set_attributes(ibldpc_decoder* h)
     PhaseImages* p = h->phase;
     const PhaseSetOps* ops = p->ops;
     if (p->occ_checked) return IBLDPC_OK;
-    const struct { PhaseKernel k; size_t smem; } ks[] = {{ops->cn_kernel[0], p->cn_bytes}, {ops->cn_kernel[1], p->cn_bytes},
-                                                         {ops->vn_kernel, p->vn_bytes}, {ops->out_kernel, p->out_bytes},
-                                                         {ops->cn_pf_kernel, p->cn_bytes}, {ops->vn_pf_kernel, p->vn_bytes},
-                                                         {ops->out_pf_kernel, p->out_bytes}};
+    const struct { const void* k; size_t smem; } ks[] = {{(const void*)ops->cn_kernel[0], p->cn_bytes}, {(const void*)ops->cn_kernel[1], p->cn_bytes},
+                                                         {(const void*)ops->vn_kernel, p->vn_bytes}, {(const void*)ops->out_kernel, p->out_bytes},
+                                                         {(const void*)ops->cn_pf_kernel[0], p->cn_bytes}, {(const void*)ops->cn_pf_kernel[1], p->cn_bytes},
+                                                         {(const void*)ops->vn_pf_kernel, p->vn_bytes},
+                                                         {(const void*)ops->pf_decide_kernel, p->out_bytes}};
     for (auto& e : ks) {
         // the per-frame check-node kernel keeps its syndrome accumulator behind the image: allow the full 227 KB
-        const int limit = e.k == ops->cn_pf_kernel ? 227 * 1024 - 1024 : (int)e.smem;
-        IBLDPC_CK(cudaFuncSetAttribute((const void*)e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, limit));
+        const int limit = e.k == (const void*)ops->cn_pf_kernel[0] ? 227 * 1024 - 1024 : (int)e.smem;
+        IBLDPC_CK(cudaFuncSetAttribute(e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, limit));
         int occ = 0;
-        IBLDPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e.k, kPhaseThreads, e.smem));
+        IBLDPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, e.k, kPhaseThreads, e.smem));
         if (occ < 1) return fail_msg(IBLDPC_E_CUDA, "fused per-phase kernel does not fit on an SM");
     }
     p->occ_checked = 1;

@@ -116,30 +116,31 @@ struct PhaseArgs {
     const int* starts[kPhaseMaxClasses];   // sc[node] resp. sv[node] of the same nodes (saves one dependent load)
     int n_nodes[kPhaseMaxClasses];
     // per-frame early termination with frame compaction (ib_perframe.cu); unused (null) otherwise
-    const struct PfState* pf;       // device-side state: active columns, current ping-pong buffer, done flag
-    uint8_t* pf_msg[2];             // message arrays (ping-pong across compactions)
-    const uint8_t* pf_ch[2];        // packed channel values (ping-pong)
-    const int* pf_idx[2];           // original frame index of every column (ping-pong)
-    const int* pf_dstw;             // [words] destination word of a word whose 8 frames are one aligned original word, else -1
+    const struct PfState* pf;       // device-side state: active columns, done flag
+    const uint32_t* pf_alive;       // [words] nibble mask of the frames that still iterate (the others are frozen)
     uint32_t* pf_fsyn;              // [words] bit 4f: frame f of the word failed a check in this pass
-    const uint32_t* pf_conv;        // [words] nibble mask of the frames to decide in this launch
-    uint8_t* pf_res;                // [n_var][pitch] decided cluster indices as nibbles in ORIGINAL frame order (zeroed)
-    int pf_fsyn_smem_words;         // check-node phase: words of shared memory behind the table image for the per-CTA
-                                    // syndrome accumulator (0 = accumulate in global memory)
+    // deferred decision of the converged frames (ib_phase_pfdecide_kernel)
+    const int* pf_fin;              // [slots] column of the current buffers behind every dense result slot (-1 = padding)
+    const int* pf_gstart;           // [imax + 1] first slot of the frames that converged in pass g - 1 (group g)
+    uint8_t* pf_res;                // [n_var][pf_res_pitch] decided cluster indices as nibbles, one per result slot
+    uint32_t pf_res_pitch;
 };
 
 // Device-side state of a per-frame-early-termination decode: every kernel of the schedule is launched unconditionally
 // and reads what is left to do from here (no host synchronisation inside a decode).
 struct PfState {
-    int n_act;        // columns [0, n_act) of the current buffers are in use (alive or converged since the last compaction)
+    int n_act;        // columns [0, n_act) of the buffers are in use (alive, or converged since the last compaction)
     int act_pitch;    // ceil(n_act / 2) rounded up to 16 bytes
-    int cur;          // current ping-pong buffer
+    int n_holes;      // columns the next compaction moves (dead columns of the new front = alive columns behind it)
     int n_alive;      // frames still iterating
-    int done;         // n_alive == 0: every later kernel returns at once
+    int done;         // n_alive == 0: every later phase kernel returns at once
     int do_compact;   // set by pf_scan_kernel when the next gather is worth it
     int new_n;        // alive columns after that gather
     int alive_acc;    // accumulator of pf_update_kernel
     unsigned blocks_done;
+    unsigned blocks_done2;   // pf_commit_kernel
+    int fin_count;    // dense result slots handed out so far
+    float waste;      // passes' worth of work spent on converged columns since the last compaction
 };
 
 // ---- TMA bulk copy of the image ------------------------------------------------------------------------------
@@ -187,9 +188,9 @@ __device__ __forceinline__ int ld_nc_again(const int* p)
 }
 
 // ---- one item = one (node, tile) of class I ------------------------------------------------------------------
-struct PfCtx { uint32_t* fsyn; const uint32_t* conv; const int* idx; const int* dstw; };
+struct PfCtx { uint32_t* fsyn; const uint32_t* alive; uint32_t fsyn_s; };   // fsyn_s: shared address of the per-CTA accumulator
 
-template <int MODE, bool EARLY, typename L, int I, bool PF = false>
+template <int MODE, bool EARLY, typename L, int I, int PF = 0>   // PF: per-frame early termination, 1 = syndrome flags in shared memory, 2 = in global memory
 struct PhaseItem {
     static constexpr int D = L::degree(I);
     static constexpr int VEC = phase_vec(MODE, D);
@@ -206,21 +207,12 @@ struct PhaseItem {
         const uint8_t* tab = s_img + L::n_pair * kPairBytes;
         const uint8_t* ptab = s_img + PI * kPairBytes;
         if constexpr (MODE == kPhaseCn) {
-            return cn_node_n4<D, false, EARLY, VEC, PAIR, WT, CB>(a, tab, ptab, start, col, lane4, a.B - 2 * (int)col,
-                                                                  PF ? pf.fsyn + (col >> 2) : nullptr);
+            return cn_node_n4<D, false, EARLY, VEC, PAIR, WT, CB, PF>(a, tab, ptab, start, col, lane4, a.B - 2 * (int)col,
+                                                                      PF ? pf.fsyn + (col >> 2) : nullptr,
+                                                                      PF ? pf.alive + (col >> 2) : nullptr, PF ? pf.fsyn_s + col : 0u);
         } else {
             constexpr bool DECIDE = MODE == kPhaseOut;
             constexpr bool kKeepRows = D <= 6;   // row indices stay in registers only where the budget allows
-            uint32_t cm[VEC];                    // per-frame ET, decision: nibble mask of the frames to decide
-            if constexpr (PF && DECIDE) {
-                uint32_t any = 0;
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    cm[j] = pf.conv[(col >> 2) + j];
-                    any |= cm[j];
-                }
-                if (any == 0) return 0;          // none of this lane's frames converged in this pass
-            }
             int rows[D];
             VnIn4<D, VEC> in;
             ld_words<VEC>(a.ch + (uint64_t)(uint32_t)node * a.pitch + col, in.c);
@@ -243,47 +235,17 @@ struct PhaseItem {
                 if constexpr (PAIR) vn_word_n4_pair<D, WT, CB>(in.c[j], w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
                 else vn_word_n4<D, DECIDE, WT, CB>(in.c[j], w, o, dec[2 * j], dec[2 * j + 1], tab, lane4);
                 if (!DECIDE) {
+                    if constexpr (PF) {
+                        // converged frames keep the check-to-variable messages they converged with (decided later)
+                        const uint32_t am = pf.alive[(col >> 2) + j];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) o[k] = (o[k] & am) | (w[k] & ~am);
+                    }
 #pragma unroll
                     for (int k = 0; k < D; ++k) r[k][j] = o[k];
                 }
             }
-            if constexpr (DECIDE && PF) {
-                // Only the frames that converged in this pass, as nibbles OR-ed into the (zeroed) result array at their
-                // ORIGINAL position: a.out = result nibbles, a.out_pitch = its pitch.  Compaction keeps the frame order,
-                // so the frames of one word land in few destination words (one, before the first compaction).
-                uint32_t* res = reinterpret_cast<uint32_t*>(a.out + (uint64_t)(uint32_t)node * a.out_pitch);
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    if (cm[j] == 0) continue;
-                    const uint32_t lo = dec[2 * j] & 0x0f0f0f0fu, hi = dec[2 * j + 1] & 0x0f0f0f0fu;
-                    const uint32_t l2 = (lo | (lo >> 4)) & 0x00ff00ffu, h2 = (hi | (hi >> 4)) & 0x00ff00ffu;
-                    const uint32_t val = (((l2 | (l2 >> 8)) & 0xffffu) | (((h2 | (h2 >> 8)) & 0xffffu) << 16)) & cm[j];
-                    const int dw0 = pf.dstw[(col >> 2) + j];
-                    if (dw0 >= 0) {
-                        // the eight frames of this word ARE destination word dw0 (frame order is kept), and no other
-                        // lane of this launch touches it: plain read-modify-write
-                        res[dw0] |= val;
-                    } else {
-                        const int4* ix4 = reinterpret_cast<const int4*>(pf.idx + (((col >> 2) + j) << 3));
-                        const int4 ia = ix4[0], ib = ix4[1];
-                        const int ix[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
-                        uint32_t acc = 0;
-                        int cur = -1;
-#pragma unroll
-                        for (int f = 0; f < 8; ++f)
-                            if ((cm[j] >> (4 * f)) & 1u) {
-                                const int dw = ix[f] >> 3;
-                                if (dw != cur) {
-                                    if (acc) atomicOr(res + cur, acc);
-                                    acc = 0;
-                                    cur = dw;
-                                }
-                                acc |= ((val >> (4 * f)) & 15u) << (4 * (ix[f] & 7));
-                            }
-                        if (acc) atomicOr(res + cur, acc);
-                    }
-                }
-            } else if constexpr (DECIDE) {
+            if constexpr (DECIDE) {
                 // decided cluster indices leave as uint8 (one byte per frame): 8*VEC bytes per lane
                 const uint32_t ocol = 2u * col;
                 uint8_t* dst = a.out + (uint64_t)(uint32_t)node * a.out_pitch + ocol;
@@ -314,7 +276,7 @@ __device__ __forceinline__ void phase_unroll(F& f, std::integer_sequence<int, Is
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------
-template <int MODE, bool EARLY, bool PF, int... Ds>
+template <int MODE, bool EARLY, int PF, int... Ds>
 __device__ __forceinline__ void phase_kernel_body(const PhaseArgs& p, const IbArgs& a, uint32_t bound, const PfCtx& pfc)
 {
     using L = PhaseLayout<MODE, Ds...>;
@@ -343,9 +305,7 @@ __device__ __forceinline__ void phase_kernel_body(const PhaseArgs& p, const IbAr
 #pragma unroll
         for (int c = 0; c < L::n; ++c) s_next[c] = lo[c] + kPhaseThreads / 32;   // the first 32 items are taken statically
         const uint8_t* img = p.image;
-        if (MODE == kPhaseOut && PF) {
-            img += (long long)a.it * p.image_stride;      // the host names the pass whose converged frames are decided
-        } else if (MODE == kPhaseOut) {
+        if (MODE == kPhaseOut) {
             s_passes = executed_passes(a);
             if (blockIdx.x == 0) *a.inum = s_passes + 1;
             img += (long long)s_passes * p.image_stride;
@@ -411,36 +371,30 @@ __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_kernel(PhaseArgs p)
 {
     const IbArgs& a = p.a;
     if (MODE != kPhaseOut && (EARLY || a.early) && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
-    phase_kernel_body<MODE, EARLY, false, Ds...>(p, a, a.pitch, PfCtx{nullptr, nullptr, nullptr, nullptr});
+    phase_kernel_body<MODE, EARLY, 0, Ds...>(p, a, a.pitch, PfCtx{nullptr, nullptr, 0u});
 }
 
-// Per-frame early termination: same bodies over the ACTIVE columns of the current ping-pong buffers; the check-node
-// phase records which frames failed a check (pf_fsyn), the decision phase writes only the frames named by pf_conv.
-template <int MODE, int... Ds>
+// Per-frame early termination: same bodies over the ACTIVE columns; the check-node phase records which frames failed a
+// check (pf_fsyn), and both phases leave the messages of the frames that have converged untouched (pf_alive).
+// SYN (check-node phase): 1 = per-CTA syndrome accumulator in shared memory behind the table image (one global atomicOr
+// per word and CTA at the end instead of one per check and word; the host checks that the active words fit), 2 = global.
+template <int MODE, int SYN, int... Ds>
 __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_pf_kernel(PhaseArgs p)
 {
+    static_assert(MODE != kPhaseOut, "converged frames are decided by ib_phase_pfdecide_kernel");
     using L = PhaseLayout<MODE, Ds...>;
     extern __shared__ __align__(128) uint8_t s_img[];
-    const PfState st = *p.pf;
-    if (st.done || st.n_act == 0) return;
+    const int done = p.pf->done, n_act = p.pf->n_act, act_pitch = p.pf->act_pitch;
+    if (done || n_act == 0) return;
     IbArgs a = p.a;
-    a.msg = p.pf_msg[st.cur];
-    a.ch = p.pf_ch[st.cur];
-    a.B = st.n_act;
-    if (MODE == kPhaseOut) {
-        a.out = p.pf_res;
-        a.out_pitch = a.pitch;
-    }
-    // check-node phase: per-CTA syndrome accumulator in shared memory behind the table image (one global atomicOr per
-    // word and CTA at the end instead of one per check and word)
-    const int act_words = st.act_pitch >> 2;
-    const bool smem_syn = MODE == kPhaseCn && p.pf_fsyn_smem_words >= act_words;
+    a.B = n_act;
+    const int act_words = act_pitch >> 2;
     uint32_t* s_fs = reinterpret_cast<uint32_t*>(s_img + L::image_bytes);
-    if (smem_syn)
+    if (MODE == kPhaseCn && SYN == 1)
         for (int w = threadIdx.x; w < act_words; w += kPhaseThreads) s_fs[w] = 0u;   // ordered by the body's first barrier
-    phase_kernel_body<MODE, MODE == kPhaseCn, true, Ds...>(p, a, (uint32_t)st.act_pitch,
-                                                           PfCtx{smem_syn ? s_fs : p.pf_fsyn, p.pf_conv, p.pf_idx[st.cur], p.pf_dstw});
-    if (smem_syn) {
+    phase_kernel_body<MODE, MODE == kPhaseCn, SYN, Ds...>(p, a, (uint32_t)act_pitch,
+                                                         PfCtx{p.pf_fsyn, p.pf_alive, smem_u32(s_img) + (uint32_t)L::image_bytes});
+    if (MODE == kPhaseCn && SYN == 1) {
         __syncthreads();
         for (int w = threadIdx.x; w < act_words; w += kPhaseThreads) {
             const uint32_t v = s_fs[w];
@@ -449,6 +403,112 @@ __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_pf_kernel(PhaseArgs
     }
 }
 
+// ---- deferred decision of the frames that converged (per-frame early termination) ----------------------------
+// Group g = the frames whose syndrome became zero in pass g - 1 (group 0: no pass at all, i_max <= 1); it owns the dense
+// result slots [gstart[g], gstart[g + 1]) (a multiple of 8), and pf_fin names, for every slot, the column of the message
+// and channel arrays in which that frame sits FROZEN since it converged.  One launch decides all groups [g_lo, g_hi]: for
+// every group the decision image of iteration g (calc_varnode_output with the tables of i_num - 1,
+// discrete_LDPC_decoder.py:280-287) is brought in by TMA, and one lane gathers the eight frames of a result word from
+// their columns, runs the same decision chain as ib_phase_kernel<kPhaseOut> and stores the word: every frame is decided
+// exactly once, densely, whatever the order in which the frames of a batch converge.
+template <int D>
+__device__ __forceinline__ uint32_t pf_gather8(const uint8_t* row, const int (&cols)[8])
+{
+    const uint32_t* r32 = reinterpret_cast<const uint32_t*>(row);
+    uint32_t v = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v |= ((r32[cols[q] >> 3] >> (4 * (cols[q] & 7))) & 15u) << (4 * q);
+    return v;
+}
+
+template <typename L, int I>
+struct PfDecideItem {
+    static constexpr int D = L::degree(I);
+    static __device__ __forceinline__ uint32_t run(const IbArgs& a, const uint8_t* s_img, int node, int start, const int (&cols)[8],
+                                                   uint32_t lane4)
+    {
+        const uint8_t* tab = s_img + L::n_pair * kPairBytes;
+        const uint32_t chw = pf_gather8<D>(a.ch + (uint64_t)(uint32_t)node * a.pitch, cols);
+        uint32_t w[D], o[D], dlo, dhi;
+#pragma unroll
+        for (int k = 0; k < D; ++k) w[k] = pf_gather8<D>(a.msg + (uint64_t)(uint32_t)a.tv[start + k] * a.pitch, cols);
+        vn_word_n4<D, true, L::words, L::col_base(I)>(chw, w, o, dlo, dhi, tab, lane4);
+        const uint32_t lo = dlo & 0x0f0f0f0fu, hi = dhi & 0x0f0f0f0fu;
+        const uint32_t l2 = (lo | (lo >> 4)) & 0x00ff00ffu, h2 = (hi | (hi >> 4)) & 0x00ff00ffu;
+        return ((l2 | (l2 >> 8)) & 0xffffu) | (((h2 | (h2 >> 8)) & 0xffffu) << 16);
+    }
+};
+
+template <int... Ds>
+__global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_pfdecide_kernel(PhaseArgs p, int g_lo, int g_hi)
+{
+    using L = PhaseLayout<kPhaseOut, Ds...>;
+    extern __shared__ __align__(128) uint8_t s_img[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    const int* __restrict__ gstart = p.pf_gstart;
+    if (gstart[g_hi + 1] == gstart[g_lo]) return;   // nothing converged in these passes
+    const IbArgs& a = p.a;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lane4 = lane * 4;
+    const int gw = blockIdx.x * (kPhaseThreads / 32) + (threadIdx.x >> 5), n_gw = gridDim.x * (kPhaseThreads / 32);
+    const uint32_t mb = smem_u32(&s_mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t parity = 0;
+    for (int g = g_lo; g <= g_hi; ++g) {
+        const int s0 = gstart[g], s1 = gstart[g + 1];
+        if (s1 == s0) continue;
+        __syncthreads();   // mbarrier initialised / nobody reads the previous image any more
+        if (threadIdx.x == 0) {
+            const uint8_t* img = p.image + (long long)g * p.image_stride;
+            constexpr uint32_t bytes = (uint32_t)L::image_bytes, kChunk = 32768;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            const uint32_t dst = smem_u32(s_img);
+            for (uint32_t off = 0; off < bytes; off += kChunk) {
+                const uint32_t n = bytes - off < kChunk ? bytes - off : kChunk;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                             "l"(img + off), "r"(n), "r"(mb)
+                             : "memory");
+            }
+        }
+        const int words_g = (s1 - s0) >> 3, tiles = (words_g + 31) >> 5;
+        {   // wait for the image (phase parity alternates per group)
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(ok)
+                    : "r"(mb), "r"(parity)
+                    : "memory");
+            }
+            parity ^= 1u;
+        }
+        auto class_loop = [&](auto IC) {
+            constexpr int I = decltype(IC)::value;
+            const int* __restrict__ nodes = p.nodes[I];
+            const int* __restrict__ starts = p.starts[I];
+            const long long items = (long long)p.n_nodes[I] * tiles;
+            for (long long i = gw; i < items; i += n_gw) {
+                const int ni = (int)(i / tiles), wd = (int)(i - (long long)ni * tiles) * 32 + lane;
+                if (wd >= words_g) continue;
+                const int4* f4 = reinterpret_cast<const int4*>(p.pf_fin + s0 + 8 * wd);
+                const int4 fa = f4[0], fb = f4[1];
+                const int cols[8] = {max(fa.x, 0), max(fa.y, 0), max(fa.z, 0), max(fa.w, 0),
+                                     max(fb.x, 0), max(fb.y, 0), max(fb.z, 0), max(fb.w, 0)};   // padding slots read column 0
+                const int node = nodes[ni];
+                const uint32_t val = PfDecideItem<L, I>::run(a, s_img, node, starts[ni], cols, lane4);
+                reinterpret_cast<uint32_t*>(p.pf_res + (uint64_t)(uint32_t)node * p.pf_res_pitch)[(s0 >> 3) + wd] = val;
+            }
+        };
+        phase_unroll(class_loop, std::make_integer_sequence<int, L::n>{});
+    }
+}
+
 using PhaseKernel = void (*)(PhaseArgs);
+using PhaseDecideKernel = void (*)(PhaseArgs, int, int);
 
 }  // namespace ibldpc

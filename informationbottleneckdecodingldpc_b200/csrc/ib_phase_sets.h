@@ -13,7 +13,8 @@ struct PhaseSetOps {
     PhaseLayoutRt cn_layout, vn_layout, out_layout;
     PhaseKernel cn_kernel[2];                   // [early]
     PhaseKernel vn_kernel, out_kernel;
-    PhaseKernel cn_pf_kernel, vn_pf_kernel, out_pf_kernel;   // per-frame early termination (ib_perframe.cu)
+    PhaseKernel cn_pf_kernel[2], vn_pf_kernel;  // per-frame early termination (ib_perframe.cu); [0] syndrome flags in shared memory, [1] global
+    PhaseDecideKernel pf_decide_kernel;         // deferred decision of the converged frames
 };
 
 template <int... Cs, int... Vs>
@@ -30,9 +31,10 @@ PhaseSetOps make_phase_ops(const char* name, DegreeSet<Cs...> cs, DegreeSet<Vs..
     o.cn_kernel[1] = ib_phase_kernel<kPhaseCn, true, Cs...>;
     o.vn_kernel = ib_phase_kernel<kPhaseVn, false, Vs...>;
     o.out_kernel = ib_phase_kernel<kPhaseOut, false, Vs...>;
-    o.cn_pf_kernel = ib_phase_pf_kernel<kPhaseCn, Cs...>;
-    o.vn_pf_kernel = ib_phase_pf_kernel<kPhaseVn, Vs...>;
-    o.out_pf_kernel = ib_phase_pf_kernel<kPhaseOut, Vs...>;
+    o.cn_pf_kernel[0] = ib_phase_pf_kernel<kPhaseCn, 1, Cs...>;
+    o.cn_pf_kernel[1] = ib_phase_pf_kernel<kPhaseCn, 2, Cs...>;
+    o.vn_pf_kernel = ib_phase_pf_kernel<kPhaseVn, 1, Vs...>;
+    o.pf_decide_kernel = ib_phase_pfdecide_kernel<Vs...>;
     return o;
 }
 

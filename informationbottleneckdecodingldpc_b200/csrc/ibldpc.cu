@@ -1671,7 +1671,7 @@ int ibldpc_destroy(ibldpc_handle h)
         for (void* p : {(void*)w.msg, (void*)w.ch4, w.cin, w.vin, (void*)w.padbuf_in, (void*)w.padbuf_out, (void*)w.stage_in,
                         (void*)w.stage_out, (void*)w.flags, (void*)w.inum})
             if (p) cudaFree(p);
-        for (void* p : {(void*)w.stage_bits, (void*)w.pf_msg2, (void*)w.pf_ch2, (void*)w.pf_idx})
+        for (void* p : {(void*)w.stage_bits, (void*)w.pf_idx})
             if (p) cudaFree(p);
         if (w.pin_in) cudaFreeHost(w.pin_in);
         if (w.pin_out) cudaFreeHost(w.pin_out);

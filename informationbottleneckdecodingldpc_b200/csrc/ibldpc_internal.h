@@ -68,13 +68,10 @@ struct Workspace {
     // degree classes of one phase run concurrently on these (fork/join around every phase)
     cudaStream_t aux[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr, join_ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    // per-frame early termination (frame compaction): see ib_perframe.cuh
-    uint8_t* pf_msg2 = nullptr;     // second message array (compaction target)
-    size_t pf_msg2_bytes = 0;
-    uint8_t* pf_ch2 = nullptr;      // second channel array
-    size_t pf_ch2_bytes = 0;
-    int* pf_idx = nullptr;          // [2][B] original frame index of every active column (ping-pong) + scratch
+    // per-frame early termination (in-place frame compaction, deferred decisions): see ib_perframe.cu
+    int* pf_idx = nullptr;          // index lists, masks, device-side state and the dense result nibbles
     size_t pf_idx_bytes = 0;
+    bool pf_attr_set = false;
     // pinned host staging of the int32 host contract (two slots)
     uint8_t* pin_in = nullptr;
     uint8_t* pin_out = nullptr;
