@@ -138,6 +138,18 @@ int ibldpc_decode_ib_host_packed(ibldpc_handle h, const uint8_t *ch4_host, int64
 int ibldpc_decode_llr(ibldpc_handle h, int algo, int dtype, const void *ch_dev, int64_t B, int imax,
                       int early_term, void *out_dev, int32_t *i_num_host, void *stream);
 
+/* Opt-in LAYERED (row-message-passing) schedule of the same two decoders -- SURVEY.md 8(f) rank 4; the reference
+ * (min_sum_decoder_irreg.py:242-273, bp_decoder_irreg.py:242-272) only has the flooding schedule, so this entry point has
+ * no reference counterpart and its results differ from ibldpc_decode_llr by construction.  One a-posteriori LLR per
+ * variable node, updated check by check: X = L - R_old, R_new = checknode(clip150(X)) with the reference's node
+ * arithmetic (kernels_min_and_BP.cl:126-167 min-sum, :5-9 box-plus), L = X + R_new; layers = greedy colouring of the
+ * checks in index order (checks of a layer share no variable).  At most imax - 1 passes; early_term stops the batch when
+ * the syndrome of the hard decisions is zero; out_dev = a-posteriori LLRs; *i_num = passes + 1.  Same buffers as
+ * ibldpc_decode_llr.  ibldpc_layer_count returns the number of layers of the handle's code. */
+int ibldpc_decode_llr_layered(ibldpc_handle h, int algo, int dtype, const void *ch_dev, int64_t B, int imax,
+                              int early_term, void *out_dev, int32_t *i_num_host, void *stream);
+int ibldpc_layer_count(ibldpc_handle h, int32_t *n_layers);
+
 /* Replaces return_errors_all_zero (discrete_LDPC_decoder.py:297-300,
  * discrete_LDPC_decoder_irreg.py:343-349) and the host-side comparison of the _enc drivers
  * (Irregular_LDPC_Decoding/WLAN/BER_simulation_OpenCL_enc.py:134): over the first `rows`

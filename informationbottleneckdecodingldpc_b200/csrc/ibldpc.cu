@@ -886,6 +886,39 @@ int decode_llr_typed(ibldpc_decoder* h, int algo, const F* ch, int64_t B, int im
     return IBLDPC_OK;
 }
 
+// layered schedule (llr_layered.cu): same buffer handling as decode_llr_typed
+template <typename F>
+int decode_llr_layered_typed(ibldpc_decoder* h, int algo, const F* ch, int64_t B, int imax, int early, F* out,
+                             int32_t* i_num_host, cudaStream_t st)
+{
+    constexpr int V = VecOf<F>::N;
+    Workspace& w = h->ws[0];
+    int rc = ensure_ws_common(h, w);
+    if (rc) return rc;
+    if ((rc = layered_prepare(h))) return rc;
+    const long long pitch = (B + V - 1) / V * V;
+    const bool aligned = (B % V == 0) && ((uintptr_t)ch % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    const F* chp = ch;
+    F* outp = out;
+    if (!aligned) {
+        if ((rc = ensure_pad(w, (size_t)h->N * pitch * sizeof(F)))) return rc;
+        if ((rc = launch_pad<F>(ch, (F*)w.padbuf_in, h->N, B, pitch, F(0), st))) return rc;
+        chp = (const F*)w.padbuf_in;
+        outp = (F*)w.padbuf_out;
+    }
+    if constexpr (sizeof(F) == 4) rc = decode_llr_layered_f32(h, w, algo, chp, pitch, B, imax, early, outp, st);
+    else rc = decode_llr_layered_f64(h, w, algo, chp, pitch, B, imax, early, outp, st);
+    if (rc) return rc;
+    if (!aligned && (rc = launch_unpad<F>(outp, out, h->N, B, pitch, st))) return rc;
+    h->last_stream = st;
+    h->last_ws = 0;
+    if (i_num_host) {
+        CK(cudaMemcpyAsync(i_num_host, w.inum, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return IBLDPC_OK;
+}
+
 template <int SRC>
 int quantize_common(int device, const double* x_dev, int64_t n, const double* limits_host, int card,
                     const double* llr_host, int out_kind, uint64_t seed, uint64_t offset, void* out_dev, void* stream)
@@ -1024,6 +1057,8 @@ int ibldpc_create(const ibldpc_code_desc* code, int device, ibldpc_handle* out)
     h->dv_min = *std::min_element(dv.begin(), dv.end());
     h->h_sc.assign(code->inbox_start_chk, code->inbox_start_chk + M);
     h->h_sv.assign(code->inbox_start_var, code->inbox_start_var + N);
+    h->h_dc = dc;
+    h->h_dv = dv;
     // variable index of every CN-major row: row tv[sv[v]+k] belongs to variable v
     std::vector<int> vidx(E);
     for (int v = 0; v < N; ++v)
@@ -1036,6 +1071,7 @@ int ibldpc_create(const ibldpc_code_desc* code, int device, ibldpc_handle* out)
     rc |= upload(&h->d_dv, code->degree_var, N);
     rc |= upload(&h->d_tv, code->target_cells_var, E);
     rc |= upload(&h->d_vidx, vidx.data(), E);
+    h->h_vidx = vidx;
     if (!rc) rc = build_classes(dc, h->cn_classes);
     if (!rc) rc = build_classes(dv, h->vn_classes);
     if (rc) { ibldpc_destroy(h); return rc; }
@@ -1523,6 +1559,35 @@ int ibldpc_decode_llr(ibldpc_handle h, int algo, int dtype, const void* ch_dev, 
     return fail(IBLDPC_E_INVALID, "dtype must be IBLDPC_F32 or IBLDPC_F64");
 }
 
+int ibldpc_decode_llr_layered(ibldpc_handle h, int algo, int dtype, const void* ch_dev, int64_t B, int imax, int early_term,
+                              void* out_dev, int32_t* i_num_host, void* stream)
+{
+    if (!h) return fail(IBLDPC_E_INVALID, "null handle");
+    if (!ch_dev || !out_dev) return fail(IBLDPC_E_INVALID, "null buffer");
+    if (B <= 0 || B > 0x7fffffffLL - 1024) return fail(IBLDPC_E_INVALID, "bad B");
+    if (imax < 1 || imax >= kMaxIter) return fail(IBLDPC_E_INVALID, "imax out of range");
+    if (algo != IBLDPC_ALGO_MINSUM && algo != IBLDPC_ALGO_BP) return fail(IBLDPC_E_INVALID, "unknown algorithm");
+    DeviceGuard guard_(h->device);
+    CK(guard_.err);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == IBLDPC_F32)
+        return decode_llr_layered_typed<float>(h, algo, (const float*)ch_dev, B, imax, early_term, (float*)out_dev, i_num_host, st);
+    if (dtype == IBLDPC_F64)
+        return decode_llr_layered_typed<double>(h, algo, (const double*)ch_dev, B, imax, early_term, (double*)out_dev, i_num_host, st);
+    return fail(IBLDPC_E_INVALID, "dtype must be IBLDPC_F32 or IBLDPC_F64");
+}
+
+int ibldpc_layer_count(ibldpc_handle h, int32_t* n_layers)
+{
+    if (!h || !n_layers) return fail(IBLDPC_E_INVALID, "null argument");
+    DeviceGuard guard_(h->device);
+    CK(guard_.err);
+    int rc = layered_prepare(h);
+    if (rc) return rc;
+    *n_layers = layered_count(h);
+    return IBLDPC_OK;
+}
+
 int ibldpc_count_errors_u8(int device, const uint8_t* out_dev, int64_t rows, int64_t B, int threshold,
                            const uint8_t* ref_bits_dev, int64_t* counters_host, void* stream)
 {
@@ -1660,6 +1725,7 @@ int ibldpc_destroy(ibldpc_handle h)
     ibldpc_nccl_finalize(h);
     phase_free(h);
     t32_free(h);
+    layered_free(h);
     clear_events(h);
     for (int* p : {h->d_sc, h->d_dc, h->d_tc, h->d_sv, h->d_dv, h->d_tv, h->d_vidx})
         if (p) cudaFree(p);

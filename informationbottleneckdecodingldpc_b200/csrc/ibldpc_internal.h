@@ -81,6 +81,7 @@ struct Workspace {
 
 struct PhaseImages;   // ib_phase.cu: pre-expanded shared-memory table images of the fused per-phase kernels
 struct T32Images;     // ib_t32.cu: table images of the |T| <= 32 family
+struct LayerPlan;     // llr_layered.cu: check-node layers of the layered LLR schedule
 struct IbArgs;
 
 }  // namespace ibldpc
@@ -92,7 +93,7 @@ struct ibldpc_decoder {
     int dc_max = 0, dv_max = 0, dc_min = 0, dv_min = 0;
     int *d_sc = nullptr, *d_dc = nullptr, *d_tc = nullptr, *d_sv = nullptr, *d_dv = nullptr, *d_tv = nullptr,
         *d_vidx = nullptr;
-    std::vector<int> h_sc, h_dc, h_sv, h_dv, h_tv;   // host copies (work lists of the fused per-phase kernels)
+    std::vector<int> h_sc, h_dc, h_sv, h_dv, h_tv, h_vidx;   // host copies (work lists of the fused per-phase kernels, layer colouring)
     std::vector<ibldpc::NodeClass> cn_classes, vn_classes;
     // LUTs
     bool have_luts = false;
@@ -123,6 +124,7 @@ struct ibldpc_decoder {
     // fused per-phase kernels (ib_phase_n4.cuh): one launch per phase over all degree classes
     ibldpc::PhaseImages* phase = nullptr;
     ibldpc::T32Images* t32_images = nullptr;
+    ibldpc::LayerPlan* layers = nullptr;   // layered LLR schedule (llr_layered.cu), built at the first layered decode
     int use_phase = 1;    // IBLDPC_NO_PHASE=1 keeps one launch per degree class
     bool phase_default = false;   // plain decodes use the fused kernels (802.11n sets; IBLDPC_PHASE=1: every instantiated set)
     // request of ibldpc_decode_ib_perframe for the decode being issued
@@ -152,6 +154,14 @@ int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long lo
 int t32_prepare(ibldpc_decoder* h);
 void t32_free(ibldpc_decoder* h);
 int decode_ib_t32(ibldpc_decoder* h, const IbArgs& a, int imax, int early, cudaStream_t st);
+// layered LLR schedule (llr_layered.cu)
+void layered_free(ibldpc_decoder* h);
+int layered_prepare(ibldpc_decoder* h);          // colour the checks (once per handle)
+int layered_count(const ibldpc_decoder* h);
+int decode_llr_layered_f32(ibldpc_decoder* h, Workspace& w, int algo, const float* ch, long long pitch, long long B, int imax,
+                           int early, float* out, cudaStream_t st);
+int decode_llr_layered_f64(ibldpc_decoder* h, Workspace& w, int algo, const double* ch, long long pitch, long long B, int imax,
+                           int early, double* out, cudaStream_t st);
 }  // namespace ibldpc
 
 #define IBLDPC_CK(call)                                                                                       \

@@ -34,6 +34,7 @@ struct LlrArgs {
     int* flags;
     int* inum;
     int it, early, imax;
+    const int* __restrict__ vidx;   // variable index of every CN-major slot (layered schedule, llr_layered.cu)
 };
 
 template <typename F> struct VecOf;

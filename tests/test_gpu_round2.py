@@ -473,3 +473,161 @@ def test_per_frame_early_termination_needs_an_instantiated_degree_set(gpu):
     dec.early_termination = 'frame'
     with pytest.raises(RuntimeError, match="degree set"):
         dec.decode_OpenCL(pkg.DeviceArray(torch.zeros((t.n_var, 8), dtype=torch.uint8, device="cuda")), buffer_in=True, return_buffer=True)
+
+
+# ---------------------------------------------------------------------------------- layered LLR schedule (llr_layered.cu)
+def _greedy_layers(t):
+    """The colouring of csrc/llr_layered.cu: checks in index order take the lowest colour no neighbour check has."""
+    sc, dc, tc = np.asarray(t.inbox_start_chk), np.asarray(t.degree_chk), np.asarray(t.target_cells_chk)
+    sv, dv = np.asarray(t.inbox_start_var), np.asarray(t.degree_var)
+    var_of_vrow = np.repeat(np.arange(t.n_var), dv)            # variable of every VN-major row
+    vidx = var_of_vrow[tc]                                     # variable of every CN-major slot
+    chk_of_crow = np.repeat(np.arange(t.n_chk), dc)
+    checks_of_var = [[] for _ in range(t.n_var)]
+    for e in range(t.n_edge):
+        checks_of_var[vidx[e]].append(chk_of_crow[e])
+    colour = -np.ones(t.n_chk, dtype=int)
+    for c in range(t.n_chk):
+        used = {colour[o] for k in range(dc[c]) for o in checks_of_var[vidx[sc[c] + k]] if colour[o] >= 0}
+        col = 0
+        while col in used:
+            col += 1
+        colour[c] = col
+    return colour, vidx
+
+
+def _clip150(x):
+    return np.where(x > 150, 150.0, np.where(x < -150, -150.0, np.where(x == 0, 0.0, x)))
+
+
+def _boxplus(a, b):
+    with np.errstate(over="ignore"):
+        return _clip150(np.log((1.0 + np.exp(a + b)) / (np.exp(a) + np.exp(b))))
+
+
+def _layered_reference(t, ch, imax, algo, early):
+    """numpy restatement of the layered schedule (header of csrc/llr_layered.cu), float64."""
+    colour, vidx = _greedy_layers(t)
+    sc, dc = np.asarray(t.inbox_start_chk), np.asarray(t.degree_chk)
+    L = ch.astype(np.float64).copy()
+    R = np.zeros((t.n_edge, ch.shape[1]))
+    order = [c for l in range(colour.max() + 1) for c in np.nonzero(colour == l)[0]]
+    passes = 0
+    for it in range(imax - 1):
+        for c in order:
+            s, d = sc[c], dc[c]
+            v = vidx[s:s + d]
+            x = L[v] - R[s:s + d]
+            q = _clip150(x)
+            o = np.empty_like(q)
+            if algo == "minsum":
+                if d == 2:
+                    o[0], o[1] = q[1], q[0]
+                else:
+                    aq, neg = np.abs(q), q < 0
+                    for k in range(d):
+                        mag = np.delete(aq, k, axis=0).min(axis=0)
+                        sneg = np.logical_xor.reduce(np.delete(neg, k, axis=0), axis=0)
+                        o[k] = np.where(mag == 0, 0.0, np.where(sneg, -mag, mag))
+            else:
+                if d >= 4:   # forward/backward box-plus, the order of llr_cn_compute<ALGO 2>
+                    fw, bw = [q[0]], {d - 1: q[d - 1]}
+                    for k in range(1, d - 1):
+                        fw.append(_boxplus(q[k], fw[k - 1]))
+                    for k in range(d - 2, 0, -1):
+                        bw[k] = _boxplus(q[k], bw[k + 1])
+                    o[0], o[d - 1] = _clip150(bw[1]), _clip150(fw[d - 2])
+                    for k in range(1, d - 1):
+                        o[k] = _clip150(_boxplus(fw[k - 1], bw[k + 1]))
+                else:        # sequential chains in slot order
+                    for k in range(d):
+                        others = [j for j in range(d) if j != k]
+                        tt = q[others[0]]
+                        for j in others[1:]:
+                            tt = _boxplus(q[j], tt)
+                        o[k] = _clip150(tt)
+            R[s:s + d] = o
+            L[v] = x + o
+        passes = it + 1
+        if early:
+            hard = (L < 0).astype(np.int64)
+            bad = False
+            for c in range(t.n_chk):
+                if (hard[vidx[sc[c]:sc[c] + dc[c]]].sum(axis=0) & 1).any():
+                    bad = True
+                    break
+            if not bad:
+                break
+    return L, passes + 1
+
+
+@pytest.mark.parametrize("algo", ["minsum", "bp"])
+@pytest.mark.parametrize("code,B", [("wlan648", 37), ("reg36", 64), ("deg12", 5)])
+def test_layered_schedule_matches_its_numpy_restatement(gpu, algo, code, B):
+    """schedule='layered' (opt-in): a-posteriori LLRs and i_num against the numpy restatement of the
+    documented schedule -- min-sum bit for bit, box-plus within 1e-9 and with identical hard decisions -- with early
+    termination off and on, unaligned batch sizes, regular / quasi-cyclic / mixed-degree codes."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    if code == "wlan648":     # the 802.11n prototype (d_c {7,8}, d_v {2,3,4,11}) expanded with a small lifting size
+        proto = codes.wlan_prototype(54)
+        H = codes.qc_expand(np.where(proto >= 0, proto % 27, -1), 27)
+    elif code == "reg36":
+        H = codes.regular_random(240, 3, 6, seed=9)
+    else:
+        H = codes.random_from_degrees([1] * 2 + [2] * 30 + [3] * 40 + [5] * 12, [2] * 4 + [4] * 16 + [6] * 16 + [8] * 5 + [11] * 2 + [12] * 1, seed=2)
+    t = graph.edge_tables(H)
+    cls = pkg.Min_Sum_Decoder_class_irregular if algo == "minsum" else pkg.BeliefPropagationDecoderClassIrregular
+    imax = 7
+    dec = cls(H, imax, 16, B)
+    dec.init_OpenCL_decoding(B)
+    dec.schedule = 'layered'
+    colour, _ = _greedy_layers(t)
+    assert dec.layer_count() == colour.max() + 1 >= int(np.asarray(t.degree_var).max())
+    rng = np.random.Generator(np.random.PCG64(11))
+    sigma2 = 10 ** (-2.5 / 10)
+    ch = 2.0 / sigma2 * (1.0 + np.sqrt(sigma2) * rng.standard_normal((t.n_var, B)))
+    ch[3, 0] = 0.0                                                # a zero input (sign(0) = 0 rule)
+    for early in (False, True):
+        dec.early_termination = early
+        out = dec.decode(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True).get()
+        ref, ref_inum = _layered_reference(t, ch, imax, algo, early)
+        assert dec.last_i_num == ref_inum
+        if algo == "minsum":
+            assert np.array_equal(out, ref)
+        else:
+            assert np.allclose(out, ref, rtol=0, atol=1e-9) and np.array_equal(out < 0, ref < 0)
+    # host-array contract and the float32 kernels run the same schedule
+    host = dec.decode(ch)
+    assert np.array_equal(host, out) if algo == "minsum" else np.allclose(host, out, atol=1e-9)
+    dec.precision = 'f32'
+    out32 = dec.decode(ch)
+    assert ((out32 < 0) == (out < 0)).mean() > 0.98
+    dec.schedule = 'row'
+    with pytest.raises(ValueError):
+        dec.decode(ch)
+
+
+def test_layered_schedule_needs_fewer_passes_than_flooding(gpu):
+    """The point of the schedule: at the same Eb/N0 the layered decoder stops (syndrome zero for the whole batch) after
+    clearly fewer passes than the flooding decoder, and what it returns are codewords."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    H = codes.regular_random(2000, 3, 6, seed=5)
+    t = graph.edge_tables(H)
+    B, imax = 256, 60
+    rng = np.random.Generator(np.random.PCG64(3))
+    sigma2 = 10 ** (-3.0 / 10)
+    ch = torch.from_numpy(2.0 / sigma2 * (1.0 + np.sqrt(sigma2) * rng.standard_normal((t.n_var, B)))).cuda()
+    inum = {}
+    for sched in ("flooding", "layered"):
+        dec = pkg.Min_Sum_Decoder_class_irregular(H, imax, 16, B)
+        dec.init_OpenCL_decoding(B)
+        dec.schedule = sched
+        out = dec.decode(pkg.DeviceArray(ch), buffer_in=True, return_buffer=True).get()
+        inum[sched] = dec.last_i_num
+        assert inum[sched] < imax                               # the batch converged
+        hard = (out < 0).astype(np.int64)
+        Hd = H.toarray() if hasattr(H, "toarray") else np.asarray(H)
+        assert not ((Hd @ hard) & 1).any()
+    assert inum["layered"] <= 0.7 * inum["flooding"], inum
