@@ -783,7 +783,7 @@ def main():
             legs = {}
             for name in ("wlan", "wlan1944", "dvbs2"):
                 legs[name] = leg_ib(pkg, name, args.leg_steps, rank)
-            legs["wlan_T32"] = leg_ib(pkg, "wlan", args.leg_steps, rank, T_=32, frames=32768)
+            legs["wlan_T32"] = leg_ib(pkg, "wlan", args.leg_steps, rank, T_=32)
             legs["c1_early_termination"] = leg_early_termination(pkg, args.leg_steps, rank)
             legs["wlan_early_termination"] = leg_early_termination(pkg, args.leg_steps, rank, name="wlan")
             legs["minsum_f64"] = leg_llr(pkg, "minsum", args.leg_steps, rank)
