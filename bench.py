@@ -539,6 +539,35 @@ def leg_llr(pkg, algo, steps, rank, B=16384):
     return res
 
 
+def leg_llr_schedules(pkg, steps, rank, B=16384, ebn0=2.4):
+    """The opt-in layered schedule (csrc/llr_layered.cu) next to the reference's flooding schedule, float64 min-sum on
+    the (3,6) n=8000 graph with early termination ON (the BER drivers' mode): ms per batch and passes until the batch
+    stops.  No reference counterpart for the layered schedule (parity: its numpy restatement, tests/test_gpu_round2.py)."""
+    import torch
+    wl = workload("c1")
+    N, M = wl["H"].shape[1], wl["H"].shape[0]
+    quanti = pkg.AWGN_Channel_Quantizer(10 ** (-ebn0 / 10) / (2 * (N - M) / N), 3, T, 2000)
+    quanti.seed = SEED
+    quanti.set_stream(rank)
+    quanti.llr_dtype = np.float64
+    quanti.init_OpenCL_quanti(N, B, return_buffer_only=True)
+    ch = quanti.quantize_direct_OpenCL_LLR(N, B)
+    res = {"workload": "(3,6) n=8000 min-sum float64 i_max=50 ET on", "frames_per_step": B, "EbN0_dB": ebn0, "steps": steps}
+    for sched in ("flooding", "layered"):
+        decodi = pkg.Min_Sum_Decoder_class_irregular(wl["H"], IMAX, T, B)
+        decodi.init_OpenCL_decoding(B, quanti.context)
+        decodi.schedule = sched
+        ms, out = time_steps(lambda: decodi.decode(ch, buffer_in=True, return_buffer=True), steps, 1)
+        res[sched] = {"value": (N - M) * B * steps / (ms * 1e-3) / 1e9, "unit": "Gbit/s", "ms_per_step": ms / steps,
+                      "i_num": int(decodi.last_i_num), "gpu_launches_per_step": decodi.info()[1],
+                      "bit_errors": int(decodi.return_errors_all_zero(out))}
+        if sched == "layered":
+            res[sched]["layers"] = decodi.layer_count()
+        del decodi, out
+        torch.cuda.empty_cache()
+    return res
+
+
 def leg_early_termination(pkg, steps, rank, name="c1"):
     """The BER drivers' operating mode: early termination on.  Same workload and inputs three ways -- fixed i_max (the
     headline), the reference's batch-granular stop (discrete_LDPC_decoder.py:233,273) and the opt-in per-frame stop
@@ -726,8 +755,34 @@ def main():
         totals.add_(c)
         return out
 
-    for _ in range(max(args.warmup, 1)):
-        step()
+    # Warm-up: W steps with the allocation pattern of the timed loop (the previous output stays alive while the next
+    # one is produced, so the caching allocator holds both buffers before the clock starts) and, beyond W, until two
+    # consecutive steps agree within 2 % and NVML shows the SM clock back at its maximum (at most 5 s more): the timed
+    # region starts on a GPU in its steady state, then EXACTLY `steps` steps are timed.
+    out_last = None
+    warm_sampler = ClockSampler(local)
+    warm_sampler.start()
+    t_warm, n_warm, prev_ms = time.perf_counter(), 0, None
+    while True:
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        out_last = step()
+        w1.record()
+        torch.cuda.synchronize()
+        cur_ms = w0.elapsed_time(w1)
+        n_warm += 1
+        stable = prev_ms is not None and abs(cur_ms - prev_ms) <= 0.02 * max(cur_ms, prev_ms)
+        prev_ms = cur_ms
+        sm_now, sm_max = _sm_clock_now(warm_sampler) if warm_sampler.nvml is not None else (None, None)
+        clock_ok = sm_now is None or sm_max is None or sm_now >= 0.97 * sm_max
+        ready = n_warm >= max(args.warmup, 1) and ((stable and clock_ok) or time.perf_counter() - t_warm > 5.0 + 0.001 * cur_ms * args.warmup)
+        if world > 1:   # step() holds a collective: every rank leaves the warm-up after the same step
+            flag = torch.tensor([1 if ready else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ready = bool(flag.item())
+        if ready:
+            break
+    warm_sampler.stop()
     launches_per_step = decodi.info()[1] + 2      # decode kernels + the two error-count kernels (torch/NCCL kernels not counted)
     totals.zero_()
     sampler = ClockSampler(local)
@@ -736,15 +791,34 @@ def main():
     torch.cuda.synchronize()
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out_last = step()
-    e1.record()
-    torch.cuda.synchronize()
+    # EXACTLY `steps` steps between two events; an event after every step as well, so that a stall of the box inside the
+    # region (seen on this pool: 50-110 ms of a 436 ms region, kernel times unchanged, clocks at maximum) is visible.
+    # If one step takes more than 1.25x the median step, the region is timed ONCE more and the second region is reported
+    # ("timed_regions" keeps both).
+    timed_regions = []
+    for attempt in range(2):
+        totals.zero_()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        evs[0].record()
+        for i in range(args.steps):
+            out_last = step()
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        ms = evs[0].elapsed_time(evs[-1])
+        per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+        timed_regions.append({"ms_per_step": ms / args.steps, "max_step_ms": max(per_step), "median_step_ms": statistics.median(per_step)})
+        outlier = max(per_step) > 1.25 * statistics.median(per_step)
+        if world > 1:
+            flag = torch.tensor([1 if outlier else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            outlier = bool(flag.item())
+        if not outlier:
+            break
     if world > 1:
         dist.barrier()
-    ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     rank_ms = [None] * world
     if world > 1:
@@ -787,6 +861,7 @@ def main():
             legs["c1_early_termination"] = leg_early_termination(pkg, args.leg_steps, rank)
             legs["wlan_early_termination"] = leg_early_termination(pkg, args.leg_steps, rank, name="wlan")
             legs["minsum_f64"] = leg_llr(pkg, "minsum", args.leg_steps, rank)
+            legs["minsum_f64_schedules_early_termination"] = leg_llr_schedules(pkg, args.leg_steps, rank)
             legs["bp_f64"] = leg_llr(pkg, "bp", args.leg_steps, rank)
         if not args.no_cpu_baseline:
             use_all_host_threads()
@@ -799,7 +874,7 @@ def main():
         tot = totals.tolist()
         line = {
             "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "warmup_steps_run": n_warm, "timed_regions": timed_regions, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u4" if packed else "u8", "data": "synthetic",
             "config": {"workload": wl["name"] if T_ == T else wl["name"].replace("|T|=16", f"|T|={T_}"),
                        "frames_per_gpu_per_step": B, "n_var": N, "n_chk": M, "n_edge": E,

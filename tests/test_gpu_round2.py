@@ -631,3 +631,47 @@ def test_layered_schedule_needs_fewer_passes_than_flooding(gpu):
         Hd = H.toarray() if hasattr(H, "toarray") else np.asarray(H)
         assert not ((Hd @ hard) & 1).any()
     assert inum["layered"] <= 0.7 * inum["flooding"], inum
+
+
+@pytest.mark.parametrize("case", ["global_syndrome_flags", "all_converge_early", "none_converges", "imax2", "imax1"])
+def test_per_frame_early_termination_corner_cases(gpu, case):
+    """Paths of ib_perframe.cu the main test does not reach: a batch whose syndrome accumulator does not fit behind the
+    table image (flags OR-ed into global memory, FS = 2), a batch that is done after a few passes (`done` raised early),
+    one in which no frame ever converges (no compaction, everything decided by the last group), and the shortest
+    schedules (i_max = 2: one pass; i_max = 1: no pass at all, group 0)."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_irregular_config
+    T = 16
+    imax = {"imax2": 2, "imax1": 1}.get(case, 12)
+    B = 140000 if case == "global_syndrome_flags" else 1500
+    ebn0 = {"all_converge_early": 6.0, "none_converges": -3.0}.get(case, 2.2)
+    H = codes.wlan_80211n(54)
+    tb, _ = generate_irregular_config(1.0, H, T, imax)
+    dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                    tb.matching_vector_checknode, tb.matching_vector_varnode, B)
+    t = graph.edge_tables(H)
+    dec.init_OpenCL_decoding(B)
+    q = pkg.AWGN_Channel_Quantizer(10 ** (-ebn0 / 10) / (2 * 0.5), 3, T, 2000)
+    q.init_OpenCL_quanti(t.n_var, B, return_buffer_only=True)
+    ch_dev = q.quantize_direct_OpenCL(t.n_var, B)
+    if case == "all_converge_early":
+        # a nearly noiseless channel: the most reliable "bit 0" cluster everywhere except 0.2 % unreliable symbols
+        rng = np.random.Generator(np.random.PCG64(5))
+        chn = np.full((t.n_var, B), T - 1, dtype=np.uint8)
+        hit = rng.random((t.n_var, B)) < 0.002
+        chn[hit] = rng.integers(T // 2 - 2, T // 2 + 2, size=int(hit.sum())).astype(np.uint8)   # unreliable, not confidently wrong
+        ch_dev = pkg.DeviceArray(torch.from_numpy(chn).cuda())
+    dec.early_termination = 'frame'
+    out = dec.decode_OpenCL(ch_dev, buffer_in=True, return_buffer=True).get()
+    inum = dec.last_i_num_per_frame.get()
+    sel = np.r_[0:40, B // 2:B // 2 + 40, B - 40:B]
+    ch = ch_dev.get()[:, sel]
+    ref, ref_inum = _per_frame_oracle(t, np.ascontiguousarray(ch), T, imax, tb)
+    assert np.array_equal(inum[sel], ref_inum), (inum[sel][:20], ref_inum[:20])
+    assert np.array_equal(out[:, sel], ref)
+    assert dec.last_i_num == int(inum.max())
+    if case == "all_converge_early":
+        assert inum.max() < imax
+    if case == "none_converges":
+        assert inum.min() == imax
