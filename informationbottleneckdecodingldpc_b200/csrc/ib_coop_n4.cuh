@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(kCoopThreads, 2) ib_decode_coop_kernel(IbArgs 
         }
         stage_tables_n4<n4_cn_words(DC, false), NT>(s_cn, b, b.lut);
         __syncthreads();
-        const uint32_t syn = cn_loop_n4<DC, false, EARLY, VEC, PAIR, NT>(b, reinterpret_cast<const uint8_t*>(s_cn), ptab, c.cn_nodes, c.n_cn);
+        const uint32_t syn = a.B <= kLaneModeMaxFrames
+                                 ? cn_lanes_n4<DC, false, EARLY, PAIR, NT>(b, reinterpret_cast<const uint8_t*>(s_cn), ptab, c.cn_nodes, c.n_cn)
+                                 : cn_loop_n4<DC, false, EARLY, VEC, PAIR, NT>(b, reinterpret_cast<const uint8_t*>(s_cn), ptab, c.cn_nodes, c.n_cn);
         if (EARLY && it >= 0) {
             const unsigned any = __ballot_sync(0xffffffffu, syn != 0);
             if (any != 0 && (threadIdx.x & 31) == 0) atomicOr(&a.flags[it], 1);
@@ -85,7 +87,8 @@ __global__ void __launch_bounds__(kCoopThreads, 2) ib_decode_coop_kernel(IbArgs 
         b.xp_col = -1;
         stage_tables_n4<n4_vn_words(DV, false), NT>(s_all, b, b.lut);
         __syncthreads();
-        vn_loop_n4<DV, false, VEC, false, NT>(b, reinterpret_cast<const uint8_t*>(s_all), nullptr, c.vn_nodes, c.n_vn);
+        if (a.B <= kLaneModeMaxFrames) vn_lanes_n4<DV, false, NT>(b, reinterpret_cast<const uint8_t*>(s_all), c.vn_nodes, c.n_vn);
+        else vn_loop_n4<DV, false, VEC, false, NT>(b, reinterpret_cast<const uint8_t*>(s_all), nullptr, c.vn_nodes, c.n_vn);
     };
 
     cn_phase(-1);
@@ -109,7 +112,8 @@ __global__ void __launch_bounds__(kCoopThreads, 2) ib_decode_coop_kernel(IbArgs 
         b.match = nullptr; b.nst = DV; b.dmax_match = 0; b.xp_col = -1;
         stage_tables_n4<n4_vn_words(DV, true), NT>(s_all, b, b.lut);
         __syncthreads();
-        vn_loop_n4<DV, true, VEC, false, NT>(b, reinterpret_cast<const uint8_t*>(s_all), nullptr, c.vn_nodes, c.n_vn);
+        if (a.B <= kLaneModeMaxFrames) vn_lanes_n4<DV, true, NT>(b, reinterpret_cast<const uint8_t*>(s_all), c.vn_nodes, c.n_vn);
+        else vn_loop_n4<DV, true, VEC, false, NT>(b, reinterpret_cast<const uint8_t*>(s_all), nullptr, c.vn_nodes, c.n_vn);
     }
 }
 
@@ -187,8 +191,11 @@ __device__ __forceinline__ void coop_cn_class(const IbArgs& a, const CoopClasses
     }
     stage_tables_n4<n4_cn_words(D, false), NT>(s_cn, b, b.lut);
     __syncthreads();
-    const uint32_t syn = cn_loop_n4<D, false, EARLY, 2, PAIR, NT>(b, reinterpret_cast<const uint8_t*>(s_cn),
-                                                                  reinterpret_cast<const uint8_t*>(s_all), c.cn_nodes[ci], c.cn_cnt[ci]);
+    const uint32_t syn = a.B <= kLaneModeMaxFrames
+                             ? cn_lanes_n4<D, false, EARLY, PAIR, NT>(b, reinterpret_cast<const uint8_t*>(s_cn),
+                                                                      reinterpret_cast<const uint8_t*>(s_all), c.cn_nodes[ci], c.cn_cnt[ci])
+                             : cn_loop_n4<D, false, EARLY, 2, PAIR, NT>(b, reinterpret_cast<const uint8_t*>(s_cn),
+                                                                        reinterpret_cast<const uint8_t*>(s_all), c.cn_nodes[ci], c.cn_cnt[ci]);
     if (EARLY && it >= 0) {
         const unsigned any = __ballot_sync(0xffffffffu, syn != 0);
         if (any != 0 && (threadIdx.x & 31) == 0) atomicOr(&a.flags[it], 1);
@@ -211,7 +218,8 @@ __device__ __forceinline__ void coop_vn_class(const IbArgs& a, const CoopClasses
         stage_tables_n4<n4_vn_words(D, DECIDE), NT>(s_all, b, b.lut);
         __syncthreads();
     }
-    vn_loop_n4<D, DECIDE, 2, false, NT>(b, reinterpret_cast<const uint8_t*>(s_all), nullptr, c.vn_nodes[ci], c.vn_cnt[ci]);
+    if (a.B <= kLaneModeMaxFrames) vn_lanes_n4<D, DECIDE, NT>(b, reinterpret_cast<const uint8_t*>(s_all), c.vn_nodes[ci], c.vn_cnt[ci]);
+    else vn_loop_n4<D, DECIDE, 2, false, NT>(b, reinterpret_cast<const uint8_t*>(s_all), nullptr, c.vn_nodes[ci], c.vn_cnt[ci]);
     __syncthreads();
 }
 

@@ -108,7 +108,11 @@ __device__ __forceinline__ void stage_tables_n4(uint32_t* s_tab, const IbArgs& a
     const bool fold = a.match != nullptr && a.nst >= 1;
     for (int rw = warp; rw < total; rw += NT / 32) {
         const int r = rw / W, w = rw - r * W;
+#ifdef IBLDPC_DP4A
+        const int t = r / kTS, m = r - t * kTS;   // row = t*16 + m: the message index is the minor one (stride 128 W bytes)
+#else
         const int m = r / kTS, t = r - m * kTS;
+#endif
         uint32_t v = 0;
         if (t < T) {
 #pragma unroll
@@ -131,6 +135,36 @@ __device__ __forceinline__ void stage_tables_n4(uint32_t* s_tab, const IbArgs& a
     }
 }
 
+#ifdef IBLDPC_DP4A
+// ------------------------------------------------------------------------------------------
+// dp4a address arithmetic (table rows t*16 + m: addr = t*TRS + m*RS + lane*4 + column offset, TRS = 16 RS).
+// The eight nibbles of a message word are spread to two words of four BYTES once per word (even / odd frames); the
+// address term of frame f is then ONE IDP.4A on the fma pipe -- byte (f >> 1) times the row stride plus the lane offset
+// -- instead of a shift and a LOP3 on the alu pipe (the pipe ncu shows as the busiest: math-pipe throttle is the top
+// stall of the check-node kernel).  Values and look-up order are unchanged: results stay bit-identical.
+// ------------------------------------------------------------------------------------------
+struct NibBytes { uint32_t e, o; };   // frames 0,2,4,6 and 1,3,5,7 of a word, one byte each
+template <uint32_t W>
+__device__ __forceinline__ NibBytes nib_bytes(uint32_t w)
+{
+    NibBytes b{w & 0x0f0f0f0fu, (w >> 4) & 0x0f0f0f0fu};
+    if constexpr (W > 1) { b.e *= W; b.o *= W; }   // 15 W <= 255: no carry between the bytes
+    return b;
+}
+// (byte of frame f) * MUL + add
+template <uint32_t MUL>
+__device__ __forceinline__ uint32_t byte_mad(const NibBytes& b, int f, uint32_t add)
+{
+    static_assert(MUL <= 255u, "dp4a multiplier is one byte");
+    return __dp4a((f & 1) ? b.o : b.e, MUL << (8 * (f >> 1)), add);
+}
+// the (m_a << 4 | m_b) bytes of two message words: row index of the tail-pair table
+__device__ __forceinline__ NibBytes pair_bytes(uint32_t wa, uint32_t wb)
+{
+    return NibBytes{((wa << 4) & 0xf0f0f0f0u) | (wb & 0x0f0f0f0fu), (wa & 0xf0f0f0f0u) | ((wb >> 4) & 0x0f0f0f0fu)};
+}
+#endif
+
 // ------------------------------------------------------------------------------------------
 // check node, 8 frames (one 32-bit word per message)
 // ------------------------------------------------------------------------------------------
@@ -140,6 +174,32 @@ template <int D, bool MATCH, int WT = 0, int CB = 0>
 __device__ __forceinline__ void cn_word_n4(const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab, uint32_t lane4)
 {
     constexpr uint32_t W = WT ? WT : n4_cn_words(D, MATCH), RS = 128u * W, TRS = RS * kTS;
+#ifdef IBLDPC_DP4A
+    const uint32_t match_off = (uint32_t)(D - 1) * RS + IB_SO(CB + D - 2) + lane4;
+    NibBytes b[D], r0 = nib_bytes<1>(w[0]), r1 = nib_bytes<1>(w[1]);
+#pragma unroll
+    for (int k = 0; k < D; ++k) b[k] = nib_bytes<W>(w[k]);
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = 0;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        uint32_t ms[D];
+#pragma unroll
+        for (int k = 1; k < D; ++k) ms[k] = byte_mad<128u>(b[k], f, lane4);
+        uint32_t P[D > 1 ? D : 2];
+        P[1] = byte_mad<1u>(r0, f, 0u);
+#pragma unroll
+        for (int j = 1; j <= D - 2; ++j) P[j + 1] = lut_ld(tab, P[j] * TRS + ms[j] + IB_SO(CB + j - 1));
+#pragma unroll
+        for (int wo = 0; wo < D; ++wo) {
+            uint32_t t = (wo == 0) ? byte_mad<1u>(r1, f, 0u) : P[wo];
+#pragma unroll
+            for (int k = (wo == 0 ? 2 : wo + 1); k < D; ++k) t = lut_ld(tab, t * TRS + ms[k] + IB_SO(CB + k - 2));
+            if (MATCH) t = lut_ld(tab, t * TRS + match_off);
+            o[wo] += t << (4 * f);
+        }
+    }
+#else
     const uint32_t match_off = (uint32_t)(D - 1) * TRS + IB_SO(CB + D - 2) + lane4;
 #pragma unroll
     for (int k = 0; k < D; ++k) o[k] = 0;
@@ -161,6 +221,7 @@ __device__ __forceinline__ void cn_word_n4(const uint32_t (&w)[D], uint32_t (&o)
             o[wo] += t << (4 * f);
         }
     }
+#endif
 }
 
 // Tail-pair variant (D >= 4), see cn_word_pair in ib_kernels.cuh: all outputs w <= D-3 end with
@@ -178,6 +239,49 @@ __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t
     static_assert(D >= 4, "tail-pair variant needs at least two look-up stages");
     constexpr uint32_t W = WT ? WT : n4_cn_words(D, false), RS = 128u * W, TRS = RS * kTS;
     constexpr uint32_t PS = 8u * kPairSlots, TPS = PS * kTS;
+#ifdef IBLDPC_DP4A
+    static_assert(PS <= 255u, "pair row stride must fit the dp4a multiplier");
+    NibBytes b[D], r0 = nib_bytes<1>(w[0]), r1 = nib_bytes<1>(w[1]);
+#pragma unroll
+    for (int k = 1; k < D; ++k) b[k] = nib_bytes<W>(w[k]);
+    const NibBytes pb = pair_bytes(w[D - 2], w[D - 1]);
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = 0;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        uint32_t ms[D];
+#pragma unroll
+        for (int k = 1; k < D; ++k) ms[k] = byte_mad<128u>(b[k], f, lane4);
+        const uint2 g2 = *reinterpret_cast<const uint2*>(ptab + byte_mad<PS>(pb, f, slot8));
+        const unsigned long long g = ((unsigned long long)g2.y << 32) | g2.x;
+        // prefix chain; P[D-3] comes out of column D-5, i.e. in x4 form (D >= 5)
+        uint32_t P[D];
+        P[1] = byte_mad<1u>(r0, f, 0u);
+#pragma unroll
+        for (int j = 1; j <= D - 3; ++j) {
+            const bool in_x4 = (D >= 5) && (j == D - 3);
+            P[j + 1] = lut_ld(tab, P[j] * (in_x4 ? TRS / 4u : TRS) + ms[j] + IB_SO(CB + j - 1));
+        }
+        // the two outputs that skip one of the tail messages
+        o[D - 1] += lut_ld(tab, P[D - 2] * TRS + ms[D - 2] + IB_SO(CB + D - 3)) << (4 * f);
+        o[D - 2] += lut_ld(tab, P[D - 2] * TRS + ms[D - 1] + IB_SO(CB + D - 3)) << (4 * f);
+#pragma unroll
+        for (int wo = 0; wo <= D - 3; ++wo) {
+            uint32_t e;   // 4 * x_w
+            if (D >= 5 && wo == D - 3) {
+                e = P[D - 3];
+            } else if (D == 4) {
+                e = byte_mad<4u>(wo == 0 ? r1 : r0, f, 0u);
+            } else {
+                uint32_t t = (wo == 0) ? byte_mad<1u>(r1, f, 0u) : P[wo];
+#pragma unroll
+                for (int k = (wo == 0 ? 2 : wo + 1); k <= D - 3; ++k) t = lut_ld(tab, t * TRS + ms[k] + IB_SO(CB + k - 2));
+                e = t;   // the last look-up read column D-5
+            }
+            o[wo] += ((uint32_t)(g >> e) & 15u) << (4 * f);
+        }
+    }
+#else
 #pragma unroll
     for (int k = 0; k < D; ++k) o[k] = 0;
 #pragma unroll
@@ -214,6 +318,7 @@ __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t
             o[wo] += ((uint32_t)(g >> e) & 15u) << (4 * f);
         }
     }
+#endif
 }
 
 // FS: per-frame syndrome flags (per-frame early termination, ib_perframe.cu): 0 none, 1 OR-ed into a shared-memory
@@ -355,20 +460,35 @@ __device__ __forceinline__ void vn_word_n4(uint32_t chw, const uint32_t (&w)[D],
                                            uint32_t& dec_hi, const uint8_t* tab, uint32_t lane4)
 {
     constexpr uint32_t W = WT ? WT : n4_vn_words(D, DECIDE), RS = 128u * W, TRS = RS * kTS;
+#ifdef IBLDPC_DP4A
+    constexpr uint32_t TSTR = TRS;   // stride of the running value t (rows t*16 + m)
+    NibBytes b[D + 1];
+    const NibBytes rc = nib_bytes<1>(chw);
+#pragma unroll
+    for (int k = 1; k <= D; ++k) b[k] = nib_bytes<W>(w[k - 1]);
+#else
+    constexpr uint32_t TSTR = RS;
+#endif
 #pragma unroll
     for (int k = 0; k < D; ++k) o[k] = 0;
     dec_lo = dec_hi = 0;
 #pragma unroll
     for (int f = 0; f < 8; ++f) {
         uint32_t ms[D + 1];   // ms[k] for y_k, k = 1..D
+        uint32_t P[D + 2];
+#ifdef IBLDPC_DP4A
+#pragma unroll
+        for (int k = 1; k <= D; ++k) ms[k] = byte_mad<128u>(b[k], f, lane4);
+        P[1] = byte_mad<1u>(rc, f, 0u);
+#else
 #pragma unroll
         for (int k = 1; k <= D; ++k) ms[k] = nib_times<TRS>(w[k - 1], f) | lane4;
-        uint32_t P[D + 2];
         P[1] = (chw >> (4 * f)) & 15u;
+#endif
 #pragma unroll
-        for (int j = 1; j <= D - 1; ++j) P[j + 1] = lut_ld(tab, P[j] * RS + ms[j] + IB_SO(CB + j - 1));
+        for (int j = 1; j <= D - 1; ++j) P[j + 1] = lut_ld(tab, P[j] * TSTR + ms[j] + IB_SO(CB + j - 1));
         if (DECIDE) {
-            const uint32_t t = lut_ld(tab, P[D] * RS + ms[D] + IB_SO(CB + D - 1));
+            const uint32_t t = lut_ld(tab, P[D] * TSTR + ms[D] + IB_SO(CB + D - 1));
             if (f < 4) dec_lo = put_byte(dec_lo, t, f & 3);
             else dec_hi = put_byte(dec_hi, t, f & 3);
         } else {
@@ -376,7 +496,7 @@ __device__ __forceinline__ void vn_word_n4(uint32_t chw, const uint32_t (&w)[D],
             for (int wo = 1; wo <= D; ++wo) {
                 uint32_t t = P[wo];
 #pragma unroll
-                for (int k = wo + 1; k <= D; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(CB + k - 2));
+                for (int k = wo + 1; k <= D; ++k) t = lut_ld(tab, t * TSTR + ms[k] + IB_SO(CB + k - 2));
                 o[wo - 1] += t << (4 * f);
             }
         }
@@ -395,37 +515,58 @@ __device__ __forceinline__ void vn_word_n4_pair(uint32_t chw, const uint32_t (&w
     static_assert(D >= 3, "tail-pair variant needs two update stages");
     constexpr uint32_t W = WT ? WT : n4_vn_words(D, false), RS = 128u * W, TRS = RS * kTS;
     constexpr uint32_t PS = 8u * kPairSlots, TPS = PS * kTS;
+#ifdef IBLDPC_DP4A
+    constexpr uint32_t TSTR = TRS;
+    NibBytes b[D + 1];
+    const NibBytes rc = nib_bytes<1>(chw);
+#pragma unroll
+    for (int k = 1; k <= D; ++k) b[k] = nib_bytes<W>(w[k - 1]);
+    const NibBytes pb = pair_bytes(w[D - 2], w[D - 1]);
+#else
+    constexpr uint32_t TSTR = RS;
+#endif
 #pragma unroll
     for (int k = 0; k < D; ++k) o[k] = 0;
 #pragma unroll
     for (int f = 0; f < 8; ++f) {
         uint32_t ms[D + 1];   // ms[k] for y_k, k = 1..D
+        uint32_t P[D + 1];
+#ifdef IBLDPC_DP4A
+#pragma unroll
+        for (int k = 1; k <= D; ++k) ms[k] = byte_mad<128u>(b[k], f, lane4);
+        const uint2 g2 = *reinterpret_cast<const uint2*>(ptab + byte_mad<PS>(pb, f, slot8));
+        P[1] = byte_mad<1u>(rc, f, 0u);
+#else
 #pragma unroll
         for (int k = 1; k <= D; ++k) ms[k] = nib_times<TRS>(w[k - 1], f) | lane4;
         const uint2 g2 = *reinterpret_cast<const uint2*>(ptab + (nib_times<TPS>(w[D - 2], f) | nib_times<PS>(w[D - 1], f) | slot8));
+        P[1] = (chw >> (4 * f)) & 15u;
+#endif
         const unsigned long long g = ((unsigned long long)g2.y << 32) | g2.x;
         // prefix chain P[1..D-1]; P[D-2] comes out of column D-4, i.e. as 4*x (D >= 4)
-        uint32_t P[D + 1];
-        P[1] = (chw >> (4 * f)) & 15u;
 #pragma unroll
         for (int j = 1; j <= D - 2; ++j) {
             const bool in_x4 = (D >= 4) && (j == D - 2);
-            P[j + 1] = lut_ld(tab, P[j] * (in_x4 ? RS / 4u : RS) + ms[j] + IB_SO(CB + j - 1));
+            P[j + 1] = lut_ld(tab, P[j] * (in_x4 ? TSTR / 4u : TSTR) + ms[j] + IB_SO(CB + j - 1));
         }
         // the two outputs that skip one of the tail messages
-        o[D - 2] += lut_ld(tab, P[D - 1] * RS + ms[D] + IB_SO(CB + D - 2)) << (4 * f);       // w = D-1
-        o[D - 1] += lut_ld(tab, P[D - 1] * RS + ms[D - 1] + IB_SO(CB + D - 2)) << (4 * f);   // w = D
+        o[D - 2] += lut_ld(tab, P[D - 1] * TSTR + ms[D] + IB_SO(CB + D - 2)) << (4 * f);       // w = D-1
+        o[D - 1] += lut_ld(tab, P[D - 1] * TSTR + ms[D - 1] + IB_SO(CB + D - 2)) << (4 * f);   // w = D
 #pragma unroll
         for (int wo = 1; wo <= D - 2; ++wo) {
             uint32_t e;   // 4 * x_w
             if (D >= 4 && wo == D - 2) {
                 e = P[D - 2];
             } else if (D == 3) {
+#ifdef IBLDPC_DP4A
+                e = byte_mad<4u>(rc, f, 0u);
+#else
                 e = nib_times<4u>(chw, f);
+#endif
             } else {
                 uint32_t t = P[wo];
 #pragma unroll
-                for (int k = wo + 1; k <= D - 2; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(CB + k - 2));
+                for (int k = wo + 1; k <= D - 2; ++k) t = lut_ld(tab, t * TSTR + ms[k] + IB_SO(CB + k - 2));
                 e = t;   // the last look-up read column D-4
             }
             o[wo - 1] += ((uint32_t)(g >> e) & 15u) << (4 * f);
@@ -507,6 +648,100 @@ __device__ __forceinline__ void vn_loop_n4(const IbArgs& a, const uint8_t* tab, 
         vn_compute_store_n4<D, DECIDE, VEC, PAIR>(a, tab, ptab, cur, buf, col, lane4);
         cur = nxt;
         nxt = nn;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Small batches (B <= 256: the reference's DVB-S2 / WLAN drivers decode msg_at_time = 2 frames per call,
+// Irregular_LDPC_Decoding/DVB-S2/BER_simulation_OpenCL.py:71): with one warp per (node, tile) all but one or two lanes
+// of a warp have no frames and a warp walks through its nodes one after the other.  Here a LANE is a (node, word) pair:
+// wpn = ceil(B / 8) words per node, 32 / wpn nodes per warp step.  The table copies are per lane, so the look-up
+// functions (cn_word_n4 / cn_word_n4_pair / vn_word_n4) are used unchanged: same chains, bit-identical results.
+// ------------------------------------------------------------------------------------------
+constexpr int kLaneModeMaxFrames = 256;   // up to 32 words per node: never fewer active lanes than the (node, tile) mapping
+
+template <int D, bool MATCH, bool EARLY, bool PAIR, int NT>
+__device__ __forceinline__ uint32_t cn_lanes_n4(const IbArgs& a, const uint8_t* tab, const uint8_t* ptab,
+                                                const int* __restrict__ nodes, int n_nodes)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t lane4 = lane * 4;
+    const int wpn = (a.B + 7) >> 3, per_warp = 32 / wpn;
+    const int j = lane / wpn, wd = lane - j * wpn;
+    const long long gw = (long long)(blockIdx.x + blockIdx.y * gridDim.x) * (NT / 32) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * gridDim.y * (NT / 32);
+    uint32_t syn = 0;
+    for (long long base = gw * per_warp; base < n_nodes; base += nw * per_warp) {
+        const int i = (int)base + j;
+        if (j >= per_warp || i >= n_nodes) continue;
+        const int s = a.sc[nodes[i]];
+        uint32_t w[D], o[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const uint8_t* row = a.iter0 ? a.ch + (uint64_t)(uint32_t)a.vidx[s + k] * a.pitch : a.msg + (uint64_t)(uint32_t)(s + k) * a.pitch;
+            w[k] = *reinterpret_cast<const uint32_t*>(row + 4 * wd);
+        }
+        if (EARLY && !a.iter0) {   // calc_syndrome on the VN->CN messages just read, see cn_node_n4
+            uint32_t par = 0;
+            if (a.tshift >= 0) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) x ^= w[k];
+                par = ((x >> a.tshift) & 0x11111111u) ^ ((D & 1) ? 0x11111111u : 0u);
+            } else {
+#pragma unroll
+                for (int f = 0; f < 8; ++f) {
+                    uint32_t p1 = 0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) p1 ^= (((w[k] >> (4 * f)) & 15u) < (uint32_t)(a.T / 2)) ? 1u : 0u;
+                    par |= p1 << (4 * f);
+                }
+            }
+            const int nv = a.B - 8 * wd;
+            syn |= par & (nv >= 8 ? 0xffffffffu : ((1u << (4 * nv)) - 1u));
+        }
+        if constexpr (PAIR) cn_word_n4_pair<D>(w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
+        else cn_word_n4<D, MATCH>(w, o, tab, lane4);
+#pragma unroll
+        for (int k = 0; k < D; ++k) *reinterpret_cast<uint32_t*>(a.msg + (uint64_t)(uint32_t)(s + k) * a.pitch + 4 * wd) = o[k];
+    }
+    return syn;
+}
+
+template <int D, bool DECIDE, int NT>
+__device__ __forceinline__ void vn_lanes_n4(const IbArgs& a, const uint8_t* tab, const int* __restrict__ nodes, int n_nodes)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t lane4 = lane * 4;
+    const int wpn = (a.B + 7) >> 3, per_warp = 32 / wpn;
+    const int j = lane / wpn, wd = lane - j * wpn;
+    const long long gw = (long long)(blockIdx.x + blockIdx.y * gridDim.x) * (NT / 32) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * gridDim.y * (NT / 32);
+    for (long long base = gw * per_warp; base < n_nodes; base += nw * per_warp) {
+        const int i = (int)base + j;
+        if (j >= per_warp || i >= n_nodes) continue;
+        const int v = nodes[i];
+        const int s = a.sv[v];
+        const uint32_t chw = *reinterpret_cast<const uint32_t*>(a.ch + (uint64_t)(uint32_t)v * a.pitch + 4 * wd);
+        int rows[D];
+        uint32_t w[D], o[D], dlo = 0, dhi = 0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            rows[k] = a.tv[s + k];
+            w[k] = *reinterpret_cast<const uint32_t*>(a.msg + (uint64_t)(uint32_t)rows[k] * a.pitch + 4 * wd);
+        }
+        if (!DECIDE && D == 1) {   // degree-1 variable node forwards the raw channel value (:132-136)
+            *reinterpret_cast<uint32_t*>(a.msg + (uint64_t)(uint32_t)rows[0] * a.pitch + 4 * wd) = chw;
+            continue;
+        }
+        vn_word_n4<D, DECIDE>(chw, w, o, dlo, dhi, tab, lane4);
+        if (DECIDE) {
+            if (8u * (uint32_t)wd < a.out_pitch)
+                *reinterpret_cast<uint2*>(a.out + (uint64_t)(uint32_t)v * a.out_pitch + 8 * wd) = make_uint2(dlo, dhi);
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) *reinterpret_cast<uint32_t*>(a.msg + (uint64_t)(uint32_t)rows[k] * a.pitch + 4 * wd) = o[k];
+        }
     }
 }
 

@@ -82,7 +82,11 @@ void build_image(uint8_t* img, const PhaseLayoutRt& L, int mode, int T, const st
                     uint32_t e = S[t * T + m];
                     if (fold) e = mrow[e];
                     if (j == x4) e *= 4u;
+#ifdef IBLDPC_DP4A
+                    uint32_t* row = tab + ((size_t)(t * kTS + m) * W + wq) * 32;   // rows t*16 + m (dp4a address arithmetic)
+#else
                     uint32_t* row = tab + ((size_t)(m * kTS + t) * W + wq) * 32;
+#endif
                     const uint32_t mask = 0xffu << (8 * q);
                     for (int l = 0; l < 32; ++l) row[l] = (row[l] & ~mask) | (e << (8 * q));
                 }

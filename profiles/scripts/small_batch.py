@@ -1,6 +1,6 @@
 """Decode time vs batch size (launch-bound regime), C1 tables, ET off and on (scratch)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import informationbottleneckdecodingldpc_b200 as pkg
 from informationbottleneckdecodingldpc_b200 import codes
@@ -8,7 +8,7 @@ from informationbottleneckdecodingldpc_b200.decoder_config_generation import gen
 H = codes.regular_random(8000, 3, 6, seed=20181001)
 tb, _ = generate_regular_config(1.2, 3, 6, 16, 50)
 q = pkg.AWGN_Channel_Quantizer(10 ** (-1.6 / 10) / (2 * 0.5), 3, 16, 2000)
-for B in (16, 100, 400, 512, 1024, 2048, 3000, 4096):
+for B in (2, 16, 64, 100, 256, 512, 2048):
     q.init_OpenCL_quanti(8000, B, return_buffer_only=True)
     dec = pkg.Discrete_LDPC_Decoder_class(H, 50, 16, 16, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a, B)
     dec.init_OpenCL_decoding(B, q.context)

@@ -1,10 +1,10 @@
 """Decode time vs batch size for the irregular codes (scratch)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import informationbottleneckdecodingldpc_b200 as pkg
 from informationbottleneckdecodingldpc_b200 import codes, luts, graph
-for name, H, Bs in (("wlan1296", codes.wlan_80211n(54), (2, 100, 512, 2048, 4096)), ("dvbs2", codes.dvbs2_like_half_rate(), (2, 100, 512, 2048))):
+for name, H, Bs in (("wlan1296", codes.wlan_80211n(54), (2, 16, 64, 100, 256, 512, 2048)), ("dvbs2", codes.dvbs2_like_half_rate(), (2, 16, 64, 100, 256, 512))):
     t = graph.edge_tables(H)
     tb = luts.random_tables(16, t.d_c_max, t.d_v_max, 50, seed=1, matching=True)
     K = t.n_var - t.n_chk

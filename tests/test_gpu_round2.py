@@ -675,3 +675,36 @@ def test_per_frame_early_termination_corner_cases(gpu, case):
         assert inum.max() < imax
     if case == "none_converges":
         assert inum.min() == imax
+
+
+@pytest.mark.parametrize("code", ["reg36", "wlan1296", "dvb6480"])
+@pytest.mark.parametrize("B", [1, 2, 9, 33, 100, 256, 257, 520])
+def test_small_batch_cooperative_kernels_lane_mode(gpu, code, B):
+    """Batches of up to 256 frames run the whole-decode cooperative kernels with one LANE per (node, word) pair
+    (cn_lanes_n4 / vn_lanes_n4: the reference's DVB-S2 drivers decode msg_at_time = 2 frames per call); 257 and 520 take the
+    warp-per-(node, tile) bodies of the same kernels.  Outputs and i_num against the oracle, early termination off and on."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    T, imax = 16, 7
+    if code == "reg36":
+        H = codes.regular_random(2000, 3, 6, seed=5)
+    else:
+        H = codes.wlan_80211n(54) if code == "wlan1296" else codes.dvbs2_like_half_rate(6480, q_groups=36)
+    t = graph.edge_tables(H)
+    tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=B, matching=code != "reg36")
+    if code == "reg36":
+        dec = pkg.Discrete_LDPC_Decoder_class(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a, B)
+    else:
+        dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                        tb.matching_vector_checknode, tb.matching_vector_varnode, B)
+    dec.init_OpenCL_decoding(B)
+    rng = np.random.Generator(np.random.PCG64(100 + B))
+    ch = rng.integers(0, T, size=(t.n_var, B)).astype(np.uint8)
+    ch[:, 0] = T - 1                                  # one frame that converges at once: the batch stop must wait for the others
+    for early in (False, True):
+        dec.early_termination = early
+        out = dec.decode_OpenCL(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True).get()
+        assert dec.info()[1] <= 3, "expected the single cooperative launch (+ pack / pad kernels)"
+        ref, ref_inum = _oracle_ib(t, ch, T, imax, tb, early)
+        assert dec.last_i_num == ref_inum
+        assert np.array_equal(out, ref.astype(np.uint8))
