@@ -76,7 +76,7 @@ def roofline_from_phase_times(ms3, n3, N, E, B, imax, packed, workload, family=N
     VN 2E+N per frame; the packed-nibble kernels store two frames per byte, so the bytes they really move
     ("stored") are half of that -- both figures are reported, and `frac` (algorithmic / peak) may exceed 1 for that
     reason; `frac_stored` is the physical fraction of the HBM peak.  `bound` names the real limiter: with four-bit
-    storage the kernels are NOT HBM-bound but sit on the shared-memory look-up pipe and instruction issue (ncu,
+    storage the kernels are NOT HBM-bound but sit on the shared-memory look-up pipe (92 % busy; ncu,
     profiles/README.md); the HBM peak stays the denominator SURVEY 8(d) prescribes.  When the whole decode ran as one
     cooperative launch (small batches) there are no per-phase times: the dominant "kernel" is then the whole decode
     with SURVEY's bytes per frame."""
@@ -117,8 +117,8 @@ def roofline_from_phase_times(ms3, n3, N, E, B, imax, packed, workload, family=N
         except Exception as e:   # noqa: BLE001
             traffic_note = f"profiles/traffic.json unreadable: {e}"
     if family in (1, 2):
-        bound = ("shared-memory look-up pipe + instruction issue (l1tex data-pipe 83-92 %, issue 82 %, DRAM 37-54 % in ncu); "
-                 "HBM peak is the roofline denominator of SURVEY 8(d)") if packed else "hbm / shared-memory look-up pipe"
+        bound = ("shared-memory look-up pipe (ncu: l1tex data-pipe 92 % busy in both the check-node and the variable-node kernel, "
+                 "issue 84 % / 75 %, DRAM 41 % / 54 %); HBM peak is the roofline denominator of SURVEY 8(d)") if packed else "hbm / shared-memory look-up pipe"
     elif family == 3:
         bound = "shared-memory look-up pipe (unstriped 32x32 byte tables, bank conflicts)"
     else:

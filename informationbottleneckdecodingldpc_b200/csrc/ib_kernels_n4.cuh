@@ -19,6 +19,14 @@
 #pragma once
 #include "ib_kernels.cuh"
 
+// Address arithmetic of the look-ups: IDP.4A on the fma pipe (default, see "dp4a address arithmetic" below) or shifts and
+// LOP3 on the alu pipe (-DIBLDPC_NO_DP4A: the round-1 form, kept for A/B builds and for the one kernel family that is
+// faster with it, ib_n4_vn_pair.cu).  The two forms use different table-row orders, so the switch is per translation
+// unit: a kernel stages its own tables (stage_tables_n4) or reads images built in the same mode (ib_phase.cu).
+#if !defined(IBLDPC_NO_DP4A) && !defined(IBLDPC_DP4A)
+#define IBLDPC_DP4A 1
+#endif
+
 namespace ibldpc {
 
 constexpr int kTS = 16;   // row stride per message value of the n4 table layout
