@@ -331,8 +331,8 @@ def run_reference_arm(args):
 
 # translation units and headers the per-class packed-nibble kernels (the dominant kernels of the headline workload) are
 # compiled from; profiles/traffic.json is tied to exactly these
-TRAFFIC_SOURCES = ("ib_kernels.cuh", "ib_kernels_n4.cuh", "ib_n4_cn_pair.cu", "ib_n4_cn_v2.cu", "ib_n4_vn_v2.cu", "ib_n4_vn_v4.cu",
-                   "ib_n4_vn_pair.cu", "kernel_tables.h")
+TRAFFIC_SOURCES = ("ib_kernels.cuh", "ib_kernels_n4.cuh", "ib_triple_n4.cuh", "ib_n4_vn3.cu", "ib_n4_cn_pair.cu", "ib_n4_cn_v2.cu",
+                   "ib_n4_vn_v2.cu", "ib_n4_vn_v4.cu", "ib_n4_vn_pair.cu", "kernel_tables.h")
 
 
 def source_hash():

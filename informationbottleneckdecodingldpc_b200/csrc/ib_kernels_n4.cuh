@@ -246,7 +246,7 @@ __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t
 {
     static_assert(D >= 4, "tail-pair variant needs at least two look-up stages");
     constexpr uint32_t W = WT ? WT : n4_cn_words(D, false), RS = 128u * W, TRS = RS * kTS;
-    constexpr uint32_t PS = 8u * kPairSlots, TPS = PS * kTS;
+    [[maybe_unused]] constexpr uint32_t PS = 8u * kPairSlots, TPS = PS * kTS;
 #ifdef IBLDPC_DP4A
     static_assert(PS <= 255u, "pair row stride must fit the dp4a multiplier");
     NibBytes b[D], r0 = nib_bytes<1>(w[0]), r1 = nib_bytes<1>(w[1]);
@@ -333,7 +333,11 @@ __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t
 // accumulator at the 32-bit shared address fsyn_s, 2 OR-ed into global memory at fsyn.  Both are issued UNCONDITIONALLY: a
 // branch around them in this fully unrolled body makes ptxas keep the shared-memory base of the tables in a register and
 // add it to every look-up address (one extra IMAD.IADD per LDS: +23 % instructions, measured in round 2).
-template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR, int WT = 0, int CB = 0, int FS = 0>
+// degree-6 check nodes through the three-input table of the first two stages (ib_triple_n4.cuh; TRI = 1 below)
+__device__ __forceinline__ void cn6_word_n4_triple(const uint32_t (&w)[6], uint32_t (&o)[6], const uint8_t* tab, const uint8_t* ptab,
+                                                   const uint8_t* ttab, uint32_t lane4, uint32_t slot8);
+
+template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR, int WT = 0, int CB = 0, int FS = 0, int TRI = 0>
 __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* tab, const uint8_t* ptab, int s, uint32_t col,
                                                uint32_t lane4, int valid_frames, uint32_t* fsyn = nullptr,
                                                const uint32_t* frz = nullptr, uint32_t fsyn_s = 0xffffffffu)
@@ -378,7 +382,8 @@ __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* t
             if constexpr (FS == 1) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(fsyn_s + 4u * j), "r"(par & vmask));
             if constexpr (FS == 2) asm volatile("red.global.or.b32 [%0], %1;" ::"l"(fsyn + j), "r"(par & vmask));
         }
-        if constexpr (PAIR) cn_word_n4_pair<D, WT, CB>(w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
+        if constexpr (TRI != 0 && D == 6) cn6_word_n4_triple(w, o, tab, ptab, ptab + kPairBytes, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
+        else if constexpr (PAIR) cn_word_n4_pair<D, WT, CB>(w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
         else cn_word_n4<D, MATCH, WT, CB>(w, o, tab, lane4);
         // per-frame early termination: frames that have converged keep the messages they converged with (nibble mask
         // frz[j] = frames of word j that still iterate); they are decided later from exactly this state (ib_perframe.cu)
@@ -403,7 +408,7 @@ __host__ __device__ constexpr int cn_n4_min_blocks(int D, int VEC, bool PAIR)
 // Node loop of one check-node launch (or of one check-node phase of the cooperative kernel): CTA -> (tile group
 // blockIdx.y, node subset), no divisions, 32-bit offsets; the next node's slot index is fetched while this node is
 // being computed.  Returns the OR of the syndrome bits this thread saw.
-template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR, int NT>
+template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR, int NT, int TRI = 0>
 __device__ __forceinline__ uint32_t cn_loop_n4(const IbArgs& a, const uint8_t* tab, const uint8_t* ptab,
                                                const int* __restrict__ nodes, int n_nodes)
 {
@@ -421,7 +426,7 @@ __device__ __forceinline__ uint32_t cn_loop_n4(const IbArgs& a, const uint8_t* t
         while (i < n_nodes) {
             const int i2 = i + stride;
             const int s2 = i2 < n_nodes ? a.sc[nodes[i2]] : 0;
-            syn |= cn_node_n4<D, MATCH, EARLY, VEC, PAIR>(a, tab, ptab, s, col, lane4, valid);
+            syn |= cn_node_n4<D, MATCH, EARLY, VEC, PAIR, 0, 0, 0, TRI>(a, tab, ptab, s, col, lane4, valid);
             i = i2;
             s = s2;
         }
@@ -522,7 +527,7 @@ __device__ __forceinline__ void vn_word_n4_pair(uint32_t chw, const uint32_t (&w
 {
     static_assert(D >= 3, "tail-pair variant needs two update stages");
     constexpr uint32_t W = WT ? WT : n4_vn_words(D, false), RS = 128u * W, TRS = RS * kTS;
-    constexpr uint32_t PS = 8u * kPairSlots, TPS = PS * kTS;
+    [[maybe_unused]] constexpr uint32_t PS = 8u * kPairSlots, TPS = PS * kTS;
 #ifdef IBLDPC_DP4A
     constexpr uint32_t TSTR = TRS;
     NibBytes b[D + 1];

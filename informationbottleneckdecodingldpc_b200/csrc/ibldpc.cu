@@ -15,6 +15,7 @@
 #include "ib_kernels.cuh"
 #include "ib_kernels_n4.cuh"
 #include "ib_coop_n4.cuh"
+#include "ib_triple_n4.cuh"
 #include "llr_kernels.cuh"
 #include "kernel_tables.h"
 
@@ -624,6 +625,14 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
                 k = cn_n4_pair_kernel_1024(c.degree, early != 0);
                 threads = 1024;
             }
+            if (pair && c.degree == 6 && h->d_cn3 != nullptr && h->cn_threads == 0 && h->n4_pair_min_degree <= 6) {
+                // degree 6: the first two stages of every chain through the three-input table (7 + 1 look-ups per frame
+                // instead of 10 + 1; 192 KB of shared memory per CTA)
+                b.lut_all = h->d_cn3 + (size_t)blk * kTS * kTS * kTS;
+                k = cn6_n4_tri_kernel(early != 0);
+                threads = 1024;
+                smem = (int)kPairBytes + kTripleBytes + n4_table_bytes(1) + stage_scratch_bytes(b.nst, T, b.dmax_match);
+            }
             int grid;
             if ((r = plan_launch(b, (const void*)k, smem, threads, vec, c.count, &tile_groups, &grid))) return r;
             k<<<dim3(grid, tile_groups), threads, smem, st>>>(b, c.d_nodes, c.count);
@@ -656,7 +665,16 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
             int threads = kThreads;
             b.xp_col = -1;
             NodeKernel k;
-            if (pair) {
+            const bool triple = !decide && !pair && c.degree == 3 && h->d_vn3 != nullptr && h->vn_vec == 0 && h->vn_threads == 0;
+            IbArgs b3 = b;
+            if (triple) {
+                // degree 3: three look-ups per frame in the three-input table F (128 KB per CTA) instead of five
+                b3.lut = h->d_vn3 + (size_t)it * kTS * kTS * kTS;
+                smem = kTripleBytes;
+                threads = 1024;
+                vec_used = pitch4 > 256 ? 4 : 2;
+                k = vn3_n4_kernel(vec_used);
+            } else if (pair) {
                 const size_t ci = (size_t)(&c - &h->vn_classes[0]);
                 b.pair = h->d_vn_pair + ((size_t)it * h->vn_classes.size() + ci) * (size_t)TT * 8;
                 b.xp_col = c.degree - 4;    // column stored as 4*x (-1 for degree 3: the channel value feeds the row)
@@ -679,8 +697,9 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
             }
             if (!k) return fail(IBLDPC_E_INVALID, "no packed variable-node kernel for degree " + std::to_string(c.degree));
             int grid;
-            if ((r = plan_launch(b, (const void*)k, smem, threads, vec_used, c.count, &tile_groups, &grid))) return r;
-            k<<<dim3(grid, tile_groups), threads, smem, st>>>(b, c.d_nodes, c.count);
+            IbArgs& bl = triple ? b3 : b;
+            if ((r = plan_launch(bl, (const void*)k, smem, threads, vec_used, c.count, &tile_groups, &grid))) return r;
+            k<<<dim3(grid, tile_groups), threads, smem, st>>>(bl, c.d_nodes, c.count);
             h->last_launches++;
         }
         return prof.end();
@@ -1221,6 +1240,52 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
         if ((rc = upload(&h->d_vn_pair, vpair.data(), vpair.size()))) return rc;
         h->h_vn_pair.swap(vpair);
     }
+    // Three-input table of the degree-3 variable-node update (ib_triple_n4.cuh): F(a, b, c) = M_3( S_1( S_0(a, b), c ) ),
+    // index b*256 + c*16 + a (channel value minor), one byte per entry, for every iteration
+    if (h->d_vn3) { CK(cudaFree(h->d_vn3)); h->d_vn3 = nullptr; }
+    h->use_triple = getenv("IBLDPC_NO_TRIPLE") == nullptr;
+    {
+        bool has3 = false;
+        for (auto& c : h->vn_classes) has3 |= c.degree == 3;
+        if (h->nib && h->use_triple && has3 && DV >= 3) {
+            const int TT = T * T;
+            std::vector<uint8_t> f3((size_t)imax * kTS * kTS * kTS, 0);
+            for (int it = 0; it < imax; ++it) {
+                const uint8_t* S0 = vn.data() + ((size_t)it * DV + 0) * TT;
+                const uint8_t* S1 = vn.data() + ((size_t)it * DV + 1) * TT;
+                const uint8_t* mrow = match ? mv.data() + ((size_t)it * DV + 2) * T : nullptr;
+                uint8_t* dst = f3.data() + (size_t)it * kTS * kTS * kTS;
+                for (int a = 0; a < T; ++a)
+                    for (int b = 0; b < T; ++b)
+                        for (int c = 0; c < T; ++c) {
+                            int v = S1[S0[a * T + b] * T + c];
+                            if (mrow) v = mrow[v];
+                            dst[(b * kTS + c) * kTS + a] = (uint8_t)v;   // channel value minor (ib_triple_n4.cuh)
+                        }
+            }
+            if ((rc = upload(&h->d_vn3, f3.data(), f3.size()))) return rc;
+        }
+    }
+    // ... and of the first two check-node stages for the degree-6 class: F(x, y, z) = 4 * C_1( C_0(x, y), z ), index
+    // (y*16 + z)*16 + x, for every table block (block 0 = iteration-0 tables)
+    if (h->d_cn3) { CK(cudaFree(h->d_cn3)); h->d_cn3 = nullptr; }
+    {
+        bool has6 = false;
+        for (auto& c : h->cn_classes) has6 |= c.degree == 6;
+        if (h->nib && h->use_triple && h->use_pair && has6 && DC >= 6 && h->d_cn_pair != nullptr) {
+            const int TT = T * T;
+            std::vector<uint8_t> f3((size_t)imax * kTS * kTS * kTS, 0);
+            for (int blk = 0; blk < imax; ++blk) {
+                const uint8_t* C0 = cn.data() + ((size_t)blk * (DC - 2) + 0) * TT;
+                const uint8_t* C1 = cn.data() + ((size_t)blk * (DC - 2) + 1) * TT;
+                uint8_t* dst = f3.data() + (size_t)blk * kTS * kTS * kTS;
+                for (int x = 0; x < T; ++x)
+                    for (int y = 0; y < T; ++y)
+                        for (int z = 0; z < T; ++z) dst[(y * kTS + z) * kTS + x] = (uint8_t)(4 * C1[C0[x * T + y] * T + z]);
+            }
+            if ((rc = upload(&h->d_cn3, f3.data(), f3.size()))) return rc;
+        }
+    }
     // Fused per-phase kernels (ib_phase_n4.cuh): default whenever the code's degree sets are instantiated; every switch
     // that selects a particular per-class kernel variant (A/B measurements, parity variants) keeps per-class launches.
     h->use_phase = getenv("IBLDPC_NO_PHASE") == nullptr && getenv("IBLDPC_PAIR_MIN_DEGREE") == nullptr &&
@@ -1729,7 +1794,7 @@ int ibldpc_destroy(ibldpc_handle h)
     clear_events(h);
     for (int* p : {h->d_sc, h->d_dc, h->d_tc, h->d_sv, h->d_dv, h->d_tv, h->d_vidx})
         if (p) cudaFree(p);
-    for (uint8_t* p : {h->d_cn8, h->d_vn8, h->d_mc8, h->d_mv8, h->d_cn_pair, h->d_vn_pair})
+    for (uint8_t* p : {h->d_cn8, h->d_vn8, h->d_mc8, h->d_mv8, h->d_cn_pair, h->d_vn_pair, h->d_vn3, h->d_cn3})
         if (p) cudaFree(p);
     for (auto& c : h->cn_classes) if (c.d_nodes) cudaFree(c.d_nodes);
     for (auto& c : h->vn_classes) if (c.d_nodes) cudaFree(c.d_nodes);

@@ -103,6 +103,9 @@ struct ibldpc_decoder {
     std::vector<uint8_t> h_cn8, h_vn8, h_mc8, h_mv8;   // host copies of the uint8 tables (image builders)
     uint8_t* d_cn_pair = nullptr;   // [imax blocks][cn classes][T*T rows][8 bytes] composed tail-pair tables
     uint8_t* d_vn_pair = nullptr;   // [imax][vn classes][T*T rows][8 bytes] composed tail-pair tables of the VN update
+    uint8_t* d_vn3 = nullptr;       // [imax][16*16*16] three-input table of the degree-3 variable-node update (ib_triple_n4.cuh)
+    uint8_t* d_cn3 = nullptr;       // [imax blocks][16*16*16] three-input table of the first two check-node stages, values * 4
+    bool use_triple = true;         // IBLDPC_NO_TRIPLE=1: degree-3 variable nodes through the two-input stage tables
     std::vector<uint8_t> h_cn_pair, h_vn_pair;
     int vn_pair_min_degree = 5;     // packed-nibble family (IBLDPC_VN_PAIR_MIN_DEGREE)
     int vn_pair_threads = 0;        // 0 = per-degree default, 256 / 512 forced (IBLDPC_VN_PAIR_THREADS)

@@ -2,7 +2,7 @@
 """Refresh profiles/traffic.json (read by bench.py for `roofline.traffic`) from an `ncu --set full` capture.
 
     # on the GPU box (after the same command has exited 0 without ncu):
-    ncu --set full --clock-control none --import-source on -k regex:"ib_(cn|vn)_n4_kernel" -s 12 -c 2 -f -o gpurun_out/prof_c1 \
+    ncu --set full --clock-control none --import-source on -k regex:"ib_(cn|vn)[0-9]*_n4" -s 12 -c 2 -f -o gpurun_out/prof_c1 \
         python bench.py --steps 1 --warmup 1 --no-legs --no-cpu-baseline --no-e2e
     # here:
     ncu -i gpurun_out/prof_c1.ncu-rep --page raw --csv > /tmp/raw_c1.csv

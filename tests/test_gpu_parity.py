@@ -37,12 +37,14 @@ def _dev(a):
 #   n4_nocoop  per-phase launches also for small batches (default: one cooperative whole-decode kernel up to 4096 frames);
 #              for the instantiated degree sets these are the fused per-phase kernels of ib_phase_n4.cuh (one launch per
 #              phase over all degree classes, TMA-staged table image), n4_nophase = one launch per degree class instead
+#              (degree-3 variable nodes through the three-input table of ib_triple_n4.cuh; n4_notriple = without it)
 IB_VARIANTS = {"n4": {}, "n4_vn4": {"IBLDPC_VN_VEC": "4"}, "n4_vn2": {"IBLDPC_VN_VEC": "2"}, "n4_pair4": {"IBLDPC_PAIR_MIN_DEGREE": "4"},
                "n4_vpair3": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3"},
                "n4_vpair3_256": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3", "IBLDPC_VN_PAIR_THREADS": "256"},
                "n4_nocoop": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_PHASE": "1"},   # small batches too through the fused per-phase kernels (every instantiated degree set)
                "n4_nophase": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_NO_PHASE": "1"},   # one launch per degree class (round-1 default)
                "n4_small_ctas": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_CN_THREADS": "512", "IBLDPC_VN_THREADS": "256"},
+               "n4_notriple": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_NO_PHASE": "1", "IBLDPC_NO_TRIPLE": "1"},   # degree-3 variable nodes through the two-input stage tables
                "n4_nopair": {"IBLDPC_NO_PAIR": "1"}, "u8": {"IBLDPC_NO_NIBBLE": "1"}}
 
 
