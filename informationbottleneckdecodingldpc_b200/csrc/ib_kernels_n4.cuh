@@ -173,6 +173,24 @@ __device__ __forceinline__ NibBytes pair_bytes(uint32_t wa, uint32_t wb)
 }
 #endif
 
+// Output nibble of frame f selected from a composed 64-bit row: o collects frame f in nibble f.
+// Default: push from the top -- o = (o >> 4) | (x << 28) is ONE funnel shift that also drops the bits of x above the
+// nibble, and after the eight frames of a word (f = 0..7 in order) frame f sits in nibble f.  Two instructions per
+// output and frame (SHF.R.U64 + SHF.R.W) instead of three (SHF, LOP3, IMAD/LEA); the kernels are issue-bound.
+// Measured on B200: (3,6) check-node phase 0.423 -> 0.414 ms, DVB-S2 d_c = 7 0.584 -> 0.572 ms.  The translation units
+// built with the shift / LOP3 address arithmetic (IBLDPC_NO_DP4A: the tail-pair variable-node kernels, alu-pipe bound)
+// keep the mask-shift-add form -- there the extra SHF made the DVB-S2 variable-node phase slower (0.641 -> 0.667 ms).
+// -DIBLDPC_NO_NIBPUSH: the mask-shift-add form everywhere (A/B builds).
+__device__ __forceinline__ void nib_push(uint32_t& o, unsigned long long g, uint32_t e, int f)
+{
+#if defined(IBLDPC_NO_NIBPUSH) || !defined(IBLDPC_DP4A)
+    o += ((uint32_t)(g >> e) & 15u) << (4 * f);
+#else
+    (void)f;
+    o = __funnelshift_r(o, (uint32_t)(g >> e), 4);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
 // check node, 8 frames (one 32-bit word per message)
 // ------------------------------------------------------------------------------------------
@@ -286,7 +304,7 @@ __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t
                 for (int k = (wo == 0 ? 2 : wo + 1); k <= D - 3; ++k) t = lut_ld(tab, t * TRS + ms[k] + IB_SO(CB + k - 2));
                 e = t;   // the last look-up read column D-5
             }
-            o[wo] += ((uint32_t)(g >> e) & 15u) << (4 * f);
+            nib_push(o[wo], g, e, f);
         }
     }
 #else
@@ -323,7 +341,7 @@ __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t
                 for (int k = (wo == 0 ? 2 : wo + 1); k <= D - 3; ++k) t = lut_ld(tab, t * RS + ms[k] + IB_SO(CB + k - 2));
                 e = t;   // the last look-up read column D-5
             }
-            o[wo] += ((uint32_t)(g >> e) & 15u) << (4 * f);
+            nib_push(o[wo], g, e, f);
         }
     }
 #endif
@@ -336,6 +354,9 @@ __device__ __forceinline__ void cn_word_n4_pair(const uint32_t (&w)[D], uint32_t
 // degree-6 check nodes through the three-input table of the first two stages (ib_triple_n4.cuh; TRI = 1 below)
 __device__ __forceinline__ void cn6_word_n4_triple(const uint32_t (&w)[6], uint32_t (&o)[6], const uint8_t* tab, const uint8_t* ptab,
                                                    const uint8_t* ttab, uint32_t lane4, uint32_t slot8);
+template <int D>   // degrees 7 and 8 (local stage columns: stage column c + 2 is column c of the staged table word)
+__device__ __forceinline__ void cn_word_n4_triple(const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab, const uint8_t* ptab,
+                                                  const uint8_t* ttab, uint32_t lane4, uint32_t slot8);
 
 template <int D, bool MATCH, bool EARLY, int VEC, bool PAIR, int WT = 0, int CB = 0, int FS = 0, int TRI = 0>
 __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* tab, const uint8_t* ptab, int s, uint32_t col,
@@ -383,6 +404,7 @@ __device__ __forceinline__ uint32_t cn_node_n4(const IbArgs& a, const uint8_t* t
             if constexpr (FS == 2) asm volatile("red.global.or.b32 [%0], %1;" ::"l"(fsyn + j), "r"(par & vmask));
         }
         if constexpr (TRI != 0 && D == 6) cn6_word_n4_triple(w, o, tab, ptab, ptab + kPairBytes, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
+        else if constexpr (TRI != 0) cn_word_n4_triple<D>(w, o, tab, ptab, ptab + kPairBytes, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
         else if constexpr (PAIR) cn_word_n4_pair<D, WT, CB>(w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
         else cn_word_n4<D, MATCH, WT, CB>(w, o, tab, lane4);
         // per-frame early termination: frames that have converged keep the messages they converged with (nibble mask
@@ -582,7 +604,7 @@ __device__ __forceinline__ void vn_word_n4_pair(uint32_t chw, const uint32_t (&w
                 for (int k = wo + 1; k <= D - 2; ++k) t = lut_ld(tab, t * TSTR + ms[k] + IB_SO(CB + k - 2));
                 e = t;   // the last look-up read column D-4
             }
-            o[wo - 1] += ((uint32_t)(g >> e) & 15u) << (4 * f);
+            nib_push(o[wo - 1], g, e, f);
         }
     }
 }

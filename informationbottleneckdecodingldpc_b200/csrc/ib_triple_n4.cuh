@@ -79,17 +79,86 @@ __device__ __forceinline__ void cn6_word_n4_triple(const uint32_t (&w)[6], uint3
         const uint32_t P4 = lut_ld(tab, e3 * (TRS / 4u) + byte_mad<128u>(b3, f, lane4) + IB_SO(2));
         o[5] += lut_ld(tab, P4 * TRS + byte_mad<128u>(b4, f, lane4) + IB_SO(3)) << (4 * f);
         o[4] += lut_ld(tab, P4 * TRS + byte_mad<128u>(b5, f, lane4) + IB_SO(3)) << (4 * f);
-        o[0] += ((uint32_t)(g >> e0) & 15u) << (4 * f);
-        o[1] += ((uint32_t)(g >> e1) & 15u) << (4 * f);
-        o[2] += ((uint32_t)(g >> e2) & 15u) << (4 * f);
-        o[3] += ((uint32_t)(g >> e3) & 15u) << (4 * f);
+        nib_push(o[0], g, e0, f);
+        nib_push(o[1], g, e1, f);
+        nib_push(o[2], g, e2, f);
+        nib_push(o[3], g, e3, f);
     }
 }
 
-// checknode_update (+ iteration 0, + syndrome) of the degree-6 class; a.lut_all = F of this table block (4096 bytes),
-// a.pair = tail-pair rows, a.lut / a.match = stage tables as for ib_cn_n4_kernel (only the columns 2 and 3 are read)
-template <bool EARLY, int NT>
-__global__ void __launch_bounds__(NT, 1) ib_cn6_n4_tri_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
+// ---- check nodes of degree 7 and 8 ---------------------------------------------------------------------------
+// Same F (it only depends on the stage tables 0 and 1, which every degree class shares): the four chains that start with
+// three of (m0..m3) take their first two stages from F and continue with the stage columns 2.. (D = 7: 12 + 1 look-ups
+// per frame instead of 15 + 1, D = 8: 18 + 1 instead of 21 + 1).  The kernel stages the columns 2..D-3 only -- LOCAL column
+// c is stage column c + 2 -- so the table set stays one word (32 KB) next to F and the tail-pair rows.
+// F values are 4 * v: as a table index they are scaled by TRS / 4, exactly like the values of the "x4" column D - 5.
+template <int D>
+__device__ __forceinline__ void cn_word_n4_triple(const uint32_t (&w)[D], uint32_t (&o)[D], const uint8_t* tab, const uint8_t* ptab,
+                                                  const uint8_t* ttab, uint32_t lane4, uint32_t slot8)
+{
+    static_assert(D == 7 || D == 8, "generic three-input-table variant: degrees 7 and 8 (degree 6: cn6_word_n4_triple)");
+    constexpr uint32_t RS = 128u, TRS = RS * kTS, PS = 8u * kPairSlots;
+    constexpr int XP = D - 5;                        // stage column in x4 form (feeds the tail-pair row)
+    const NibBytes p23 = pair_bytes(w[2], w[3]), p13 = pair_bytes(w[1], w[3]), p12 = pair_bytes(w[1], w[2]);
+    const SplitBytes x0 = split_bytes(w[0]), x1 = split_bytes(w[1]);
+    NibBytes b[D];
+#pragma unroll
+    for (int k = 3; k < D; ++k) b[k] = nib_bytes<1>(w[k]);
+    const NibBytes pb = pair_bytes(w[D - 2], w[D - 1]);
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = 0;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        const uint32_t u0 = byte_mad<128u>(x0.hi, f, byte_mad<1u>(x0.lo, f, lane4));
+        const uint32_t u1 = byte_mad<128u>(x1.hi, f, byte_mad<1u>(x1.lo, f, lane4));
+        const uint32_t t23 = byte_mad<128u>(p23, f, 0u) * 4u, t13 = byte_mad<128u>(p13, f, 0u) * 4u, t12 = byte_mad<128u>(p12, f, 0u) * 4u;
+        uint32_t ms[D];
+#pragma unroll
+        for (int k = 3; k < D; ++k) ms[k] = byte_mad<128u>(b[k], f, lane4);
+        const uint2 g2 = *reinterpret_cast<const uint2*>(ptab + byte_mad<PS>(pb, f, slot8));
+        const unsigned long long g = ((unsigned long long)g2.y << 32) | g2.x;
+        // c[wo]: state of the chain of output wo after its first three inputs, 4 * v; c[3] is also the prefix P[3]
+        uint32_t c[4];
+        c[0] = ttab[t23 + u1];   // m1, m2, m3
+        c[1] = ttab[t23 + u0];   // m0, m2, m3
+        c[2] = ttab[t13 + u0];   // m0, m1, m3
+        c[3] = ttab[t12 + u0];   // m0, m1, m2
+        // prefix chain P[j + 1] = S_{j-1}(P[j], m_j), j = 3 .. D-3 (stage column j - 1 = local column j - 3)
+        uint32_t P[D];
+        P[3] = c[3];
+#pragma unroll
+        for (int j = 3; j <= D - 3; ++j) {
+            const bool in_x4 = (j == 3) || (j - 2 == XP);          // P[j] came out of F or out of the x4 column
+            P[j + 1] = lut_ld(tab, P[j] * (in_x4 ? TRS / 4u : TRS) + ms[j] + IB_SO(j - 3));
+        }
+        // the two outputs that skip one of the tail messages (P[D-2] came out of column D-4: plain)
+        o[D - 1] += lut_ld(tab, P[D - 2] * TRS + ms[D - 2] + IB_SO(D - 5)) << (4 * f);
+        o[D - 2] += lut_ld(tab, P[D - 2] * TRS + ms[D - 1] + IB_SO(D - 5)) << (4 * f);
+#pragma unroll
+        for (int wo = 0; wo <= D - 3; ++wo) {
+            uint32_t e;   // 4 * x_w
+            if (wo == D - 3) {
+                e = P[D - 3];
+            } else {
+                uint32_t t = wo <= 3 ? c[wo] : P[wo];
+                bool x4 = wo <= 3 || (wo - 2 == XP);                 // wo >= 4: P[wo] came out of column wo - 2
+#pragma unroll
+                for (int k = (wo <= 3 ? 4 : wo + 1); k <= D - 3; ++k) {
+                    t = lut_ld(tab, t * (x4 ? TRS / 4u : TRS) + ms[k] + IB_SO(k - 4));
+                    x4 = (k - 2 == XP);
+                }
+                e = t;   // the last look-up read column D-5
+            }
+            nib_push(o[wo], g, e, f);
+        }
+    }
+}
+
+// checknode_update (+ iteration 0, + syndrome) of one degree class through the three-input table; a.lut_all = F of this
+// table block (4096 bytes), a.pair = tail-pair rows of the class, a.lut / a.nst / a.xp_col = the stage columns the class
+// still reads: degree 6 all four (only the columns 2 and 3 are read), degrees 7 and 8 the columns 2..D-3 as local 0..
+template <int D, bool EARLY, int NT>
+__global__ void __launch_bounds__(NT, 1) ib_cn_n4_tri_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 {
     extern __shared__ __align__(16) uint32_t s_all[];
     if (EARLY && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
@@ -107,7 +176,7 @@ __global__ void __launch_bounds__(NT, 1) ib_cn6_n4_tri_kernel(IbArgs a, const in
     }
     stage_tables_n4<1, NT>(s_tab, a, a.lut);
     __syncthreads();
-    const uint32_t syn = cn_loop_n4<6, false, EARLY, 2, true, NT, 1>(a, reinterpret_cast<const uint8_t*>(s_tab),
+    const uint32_t syn = cn_loop_n4<D, false, EARLY, 2, true, NT, 1>(a, reinterpret_cast<const uint8_t*>(s_tab),
                                                                      reinterpret_cast<const uint8_t*>(s_all), nodes, n_nodes);
     if (EARLY && !a.iter0) {
         const unsigned any = __ballot_sync(0xffffffffu, syn != 0);

@@ -625,17 +625,25 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
                 k = cn_n4_pair_kernel_1024(c.degree, early != 0);
                 threads = 1024;
             }
-            if (pair && c.degree == 6 && h->d_cn3 != nullptr && h->cn_threads == 0 && h->n4_pair_min_degree <= 6) {
-                // degree 6: the first two stages of every chain through the three-input table (7 + 1 look-ups per frame
-                // instead of 10 + 1; 192 KB of shared memory per CTA)
-                b.lut_all = h->d_cn3 + (size_t)blk * kTS * kTS * kTS;
-                k = cn6_n4_tri_kernel(early != 0);
+            IbArgs bt = b;
+            if (pair && c.degree >= 6 && c.degree <= h->cn_tri_max_degree && h->d_cn3 != nullptr && h->cn_threads == 0 &&
+                h->n4_pair_min_degree <= 6) {
+                // the first two stages of every chain through the three-input table (degree 6: 7 + 1 look-ups per frame
+                // instead of 10 + 1, degree 7: 12 + 1 instead of 15 + 1, degree 8: 18 + 1 instead of 21 + 1; 192 KB of
+                // shared memory per CTA).  Degrees 7 and 8 stage the columns 2..D-3 only, as local columns 0..
+                bt.lut_all = h->d_cn3 + (size_t)blk * kTS * kTS * kTS;
+                if (c.degree >= 7) {
+                    bt.lut = b.lut + (size_t)2 * TT;
+                    bt.nst = c.degree - 4;
+                    bt.xp_col = c.degree - 7;
+                }
+                k = cn_n4_tri_kernel(c.degree, early != 0);
                 threads = 1024;
-                smem = (int)kPairBytes + kTripleBytes + n4_table_bytes(1) + stage_scratch_bytes(b.nst, T, b.dmax_match);
+                smem = (int)kPairBytes + kTripleBytes + n4_table_bytes(1) + stage_scratch_bytes(bt.nst, T, bt.dmax_match);
             }
             int grid;
-            if ((r = plan_launch(b, (const void*)k, smem, threads, vec, c.count, &tile_groups, &grid))) return r;
-            k<<<dim3(grid, tile_groups), threads, smem, st>>>(b, c.d_nodes, c.count);
+            if ((r = plan_launch(bt, (const void*)k, smem, threads, vec, c.count, &tile_groups, &grid))) return r;
+            k<<<dim3(grid, tile_groups), threads, smem, st>>>(bt, c.d_nodes, c.count);
             h->last_launches++; h->last_grid = grid * tile_groups; h->last_smem = smem;
         }
         return prof.end();
@@ -1270,8 +1278,9 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
     // (y*16 + z)*16 + x, for every table block (block 0 = iteration-0 tables)
     if (h->d_cn3) { CK(cudaFree(h->d_cn3)); h->d_cn3 = nullptr; }
     {
-        bool has6 = false;
-        for (auto& c : h->cn_classes) has6 |= c.degree == 6;
+        bool has6 = false;   // a class the three-input-table kernels cover
+        h->cn_tri_max_degree = getenv("IBLDPC_CN_TRI_MAX_DEGREE") ? atoi(getenv("IBLDPC_CN_TRI_MAX_DEGREE")) : 8;
+        for (auto& c : h->cn_classes) has6 |= c.degree >= 6 && c.degree <= h->cn_tri_max_degree;
         if (h->nib && h->use_triple && h->use_pair && has6 && DC >= 6 && h->d_cn_pair != nullptr) {
             const int TT = T * T;
             std::vector<uint8_t> f3((size_t)imax * kTS * kTS * kTS, 0);

@@ -105,6 +105,7 @@ struct ibldpc_decoder {
     uint8_t* d_vn_pair = nullptr;   // [imax][vn classes][T*T rows][8 bytes] composed tail-pair tables of the VN update
     uint8_t* d_vn3 = nullptr;       // [imax][16*16*16] three-input table of the degree-3 variable-node update (ib_triple_n4.cuh)
     uint8_t* d_cn3 = nullptr;       // [imax blocks][16*16*16] three-input table of the first two check-node stages, values * 4
+    int cn_tri_max_degree = 8;      // check-node classes of degree 6..this run the three-input-table kernel (IBLDPC_CN_TRI_MAX_DEGREE)
     bool use_triple = true;         // IBLDPC_NO_TRIPLE=1: degree-3 variable nodes through the two-input stage tables
     std::vector<uint8_t> h_cn_pair, h_vn_pair;
     int vn_pair_min_degree = 5;     // packed-nibble family (IBLDPC_VN_PAIR_MIN_DEGREE)

@@ -22,7 +22,7 @@ NodeKernel cn_n4_pair_kernel_1024(int d, bool early);   // d <= 8 (default); cn_
 NodeKernel vn_n4_pair_kernel(int d, int threads);   // tail-pair variable-node update, d >= 3, threads = 256 / 512
 NodeKernel vn_n4_kernel_v2(int d, bool decide);
 NodeKernel vn_n4_kernel_v4(int d, bool decide);
-NodeKernel cn6_n4_tri_kernel(bool early);  // degree-6 check nodes: three-input table of the first two stages + tail-pair rows
+NodeKernel cn_n4_tri_kernel(int d, bool early);  // check nodes of degree 6..8: three-input table of the first two stages + tail-pair rows
 NodeKernel vn3_n4_kernel(int vec);         // degree-3 update through the three-input table (ib_triple_n4.cuh), 1024-thread CTAs
 NodeKernel vn_n4_kernel_v4_1024(int d);   // update kernels of degree 2..4 in 1024-thread CTAs (default)
 LlrNodeKernel llr_cn_kernel_for(bool f64, int algo, int d);

@@ -37,7 +37,8 @@ def _dev(a):
 #   n4_nocoop  per-phase launches also for small batches (default: one cooperative whole-decode kernel up to 4096 frames);
 #              for the instantiated degree sets these are the fused per-phase kernels of ib_phase_n4.cuh (one launch per
 #              phase over all degree classes, TMA-staged table image), n4_nophase = one launch per degree class instead
-#              (degree-3 variable nodes through the three-input table of ib_triple_n4.cuh; n4_notriple = without it)
+#              (degree-3 variable nodes and check nodes of degree 6..8 through the three-input tables of ib_triple_n4.cuh;
+#              n4_notriple = without them, n4_cn_tri6 = check nodes up to degree 6 only)
 IB_VARIANTS = {"n4": {}, "n4_vn4": {"IBLDPC_VN_VEC": "4"}, "n4_vn2": {"IBLDPC_VN_VEC": "2"}, "n4_pair4": {"IBLDPC_PAIR_MIN_DEGREE": "4"},
                "n4_vpair3": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3"},
                "n4_vpair3_256": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3", "IBLDPC_VN_PAIR_THREADS": "256"},
@@ -45,6 +46,7 @@ IB_VARIANTS = {"n4": {}, "n4_vn4": {"IBLDPC_VN_VEC": "4"}, "n4_vn2": {"IBLDPC_VN
                "n4_nophase": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_NO_PHASE": "1"},   # one launch per degree class (round-1 default)
                "n4_small_ctas": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_CN_THREADS": "512", "IBLDPC_VN_THREADS": "256"},
                "n4_notriple": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_NO_PHASE": "1", "IBLDPC_NO_TRIPLE": "1"},   # degree-3 variable nodes through the two-input stage tables
+               "n4_cn_tri6": {"IBLDPC_COOP_MAX_B": "0", "IBLDPC_NO_PHASE": "1", "IBLDPC_CN_TRI_MAX_DEGREE": "6"},   # check nodes of degree 7, 8 through the plain tail-pair kernels (default: three-input table up to degree 8)
                "n4_nopair": {"IBLDPC_NO_PAIR": "1"}, "u8": {"IBLDPC_NO_NIBBLE": "1"}}
 
 
@@ -147,13 +149,17 @@ def test_ib_irregular_vs_oracle(gpu, name, H, T, match, ib_variant):
     assert np.array_equal(got, ref) and dec.last_i_num == i_num
 
 
-@pytest.mark.parametrize("family", ["n4", "u8"])
+@pytest.mark.parametrize("family", ["n4", "n4_notriple", "u8"])
 def test_ib_tail_pair_variant_all_degrees(gpu, monkeypatch, family):
     """The composed tail-pair check-node kernels (cn_word_pair / cn_word_n4_pair) for every degree 4..10,
-    forced on with IBLDPC_PAIR_MIN_DEGREE=4, with and without message alignment, against the oracle."""
+    forced on with IBLDPC_PAIR_MIN_DEGREE=4, with and without message alignment, against the oracle.  In the packed
+    family the degrees 6..8 run the three-input-table kernels (ib_cn_n4_tri_kernel); n4_notriple keeps them on the
+    plain tail-pair kernels."""
     monkeypatch.setenv("IBLDPC_PAIR_MIN_DEGREE", "4")
     if family == "u8":
         monkeypatch.setenv("IBLDPC_NO_NIBBLE", "1")
+    if family == "n4_notriple":
+        monkeypatch.setenv("IBLDPC_NO_TRIPLE", "1")
     H = codes.random_from_degrees([2] * 40 + [3] * 40 + [4] * 16, [4] * 16 + [5] * 8 + [6] * 8 + [7] * 6 + [8] * 4 + [9] * 2 + [10] * 2, seed=4)
     t = graph.edge_tables(H)
     assert sorted(set(t.degree_chk)) == [4, 5, 6, 7, 8, 9, 10]
