@@ -854,7 +854,10 @@ int decode_llr_padded(ibldpc_decoder* h, Workspace& w, const F* ch, long long pi
         for (auto& c : h->cn_classes) {
             // float64 BP: forward/backward recursion (ALGO 2) unless the reference's operation order is asked for
             const bool bp_sequential = getenv("IBLDPC_BP_SEQUENTIAL") != nullptr;
-            const int algo_k = (ALGO == 1 && sizeof(F) == 8 && !bp_sequential) ? 2 : ALGO;
+            // float64 BP: forward/backward recursion in the likelihood-ratio domain (3); IBLDPC_BP_LOGDOMAIN=1: the same
+            // recursion with the reference box-plus expression per operation (2); IBLDPC_BP_SEQUENTIAL=1: reference order (1)
+            const bool bp_logdomain = getenv("IBLDPC_BP_LOGDOMAIN") != nullptr;
+            const int algo_k = (ALGO == 1 && sizeof(F) == 8 && !bp_sequential) ? (bp_logdomain ? 2 : 3) : ALGO;
             LlrNodeKernel k = llr_cn_kernel_for(sizeof(F) == 8, algo_k, c.degree);
             int grid;
             int r = grid_for(h, (const void*)k, 0, (long long)c.count * b.tiles, &grid);

@@ -38,7 +38,7 @@ LlrNodeKernel vn_sel(int d)
     }
 }
 }  // namespace
-LlrNodeKernel llr_cn_kernel_f64(int algo, int d) { return algo == 0 ? cn_sel<0>(d) : algo == 2 ? cn_sel<2>(d) : cn_sel<1>(d); }
+LlrNodeKernel llr_cn_kernel_f64(int algo, int d) { return algo == 0 ? cn_sel<0>(d) : algo == 3 ? cn_sel<3>(d) : algo == 2 ? cn_sel<2>(d) : cn_sel<1>(d); }
 LlrNodeKernel llr_vn_kernel_f64(int mode, int d) { return mode == 0 ? vn_sel<0>(d) : mode == 1 ? vn_sel<1>(d) : vn_sel<2>(d); }
 LlrSynKernel llr_syndrome_kernel_f64() { return llr_syndrome_kernel<double>; }
 LlrShflKernel llr_cn_minsum_shfl_kernel_f64() { return llr_cn_minsum_shfl_kernel<double>; }

@@ -113,7 +113,34 @@ __device__ __forceinline__ void llr_cn_compute(const Vec<F>* m, Vec<F>* o, int d
                 o[k].v[e] = r;
             }
         }
-    } else if ((sizeof(F) == 4 || ALGO == 2) && dd >= 4) {
+    } else if (ALGO == 3 && sizeof(F) == 8 && dd >= 4) {
+        // float64 default: the forward/backward recursion in the LIKELIHOOD-RATIO domain.  With A = e^a, B = e^b the
+        // reference box-plus is log(R), R = (1 + A B) / (A + B) (kernels_min_and_BP.cl:7), and the next box-plus needs e^{log R}
+        // = R again: carrying R instead of log R through the chains leaves d exp (one per input), d log (one per output)
+        // and 3(d-2) divisions per check instead of 9(d-2) exp, 3(d-2) log and 3(d-2) divisions -- the kernel is bound by
+        // the double-precision pipe.  The per-operation clip to +-150 (:8) is the clamp of R to [e^-150, e^150]; inputs
+        // beyond |709| overflow exactly where the reference's exp(a + b) does.  Differences to the reference order are
+        // rounding only (1e-13 on the golden vectors); the hard decisions stay identical (tests/test_gpu_parity.py:
+        // >= 99.99 % of 20000 frames).  IBLDPC_BP_LOGDOMAIN=1 selects ALGO 2, IBLDPC_BP_SEQUENTIAL=1 the reference order.
+        const double kRmax = 1.3937095806663797e65, kRmin = 7.1750959731644115e-66;   // e^150, e^-150
+        auto rbox = [&](double A, double B) { return fmin(fmax((1.0 + A * B) / (A + B), kRmin), kRmax); };
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            double M[D > 0 ? D : kMaxGenericDeg], fw[D > 0 ? D : kMaxGenericDeg], bw[D > 0 ? D : kMaxGenericDeg];
+#pragma unroll
+            for (int k = 0; k < dd; ++k) M[k] = exp((double)m[k].v[e]);
+            fw[0] = M[0];
+#pragma unroll
+            for (int k = 1; k <= dd - 2; ++k) fw[k] = rbox(M[k], fw[k - 1]);
+            bw[dd - 1] = M[dd - 1];
+#pragma unroll
+            for (int k = dd - 2; k >= 1; --k) bw[k] = rbox(M[k], bw[k + 1]);
+            o[0].v[e] = (F)clip150(log(bw[1]));
+            o[dd - 1].v[e] = (F)clip150(log(fw[dd - 2]));
+#pragma unroll
+            for (int k = 1; k <= dd - 2; ++k) o[k].v[e] = (F)clip150(log(rbox(fw[k - 1], bw[k + 1])));
+        }
+    } else if ((sizeof(F) == 4 || ALGO == 2 || ALGO == 3) && dd >= 4) {
         // forward/backward box-plus, 3(d-2) operations instead of 2(d-2) + (d-1)(d-2)/2.  Box-plus is associative in
         // exact arithmetic; the result differs from the reference's sequential order only by rounding: fp32 (covered
         // by the fp32 tolerance) and -- ALGO 2, the float64 default -- float64, where the hard decisions stay identical
@@ -123,14 +150,14 @@ __device__ __forceinline__ void llr_cn_compute(const Vec<F>* m, Vec<F>* o, int d
             F fw[D > 0 ? D : kMaxGenericDeg], bw[D > 0 ? D : kMaxGenericDeg];
             fw[0] = m[0].v[e];
 #pragma unroll
-            for (int k = 1; k <= dd - 2; ++k) fw[k] = (ALGO == 2 ? boxplus_stable(m[k].v[e], fw[k - 1]) : boxplus(m[k].v[e], fw[k - 1]));
+            for (int k = 1; k <= dd - 2; ++k) fw[k] = (ALGO >= 2 ? boxplus_stable(m[k].v[e], fw[k - 1]) : boxplus(m[k].v[e], fw[k - 1]));
             bw[dd - 1] = m[dd - 1].v[e];
 #pragma unroll
-            for (int k = dd - 2; k >= 1; --k) bw[k] = (ALGO == 2 ? boxplus_stable(m[k].v[e], bw[k + 1]) : boxplus(m[k].v[e], bw[k + 1]));
+            for (int k = dd - 2; k >= 1; --k) bw[k] = (ALGO >= 2 ? boxplus_stable(m[k].v[e], bw[k + 1]) : boxplus(m[k].v[e], bw[k + 1]));
             o[0].v[e] = clip150(bw[1]);
             o[dd - 1].v[e] = clip150(fw[dd - 2]);
 #pragma unroll
-            for (int k = 1; k <= dd - 2; ++k) o[k].v[e] = clip150(ALGO == 2 ? boxplus_stable(fw[k - 1], bw[k + 1]) : boxplus(fw[k - 1], bw[k + 1]));
+            for (int k = 1; k <= dd - 2; ++k) o[k].v[e] = clip150(ALGO >= 2 ? boxplus_stable(fw[k - 1], bw[k + 1]) : boxplus(fw[k - 1], bw[k + 1]));
         }
     } else {
 #pragma unroll

@@ -366,16 +366,19 @@ def test_early_termination_is_batch_granular(gpu):
 
 
 # ---------------------------------------------------------------------------------- min-sum / BP
-@pytest.mark.parametrize("bp_order", ["sequential", "forward_backward"])
+@pytest.mark.parametrize("bp_order", ["sequential", "forward_backward", "forward_backward_log"])
 @pytest.mark.parametrize("case", LLR_CASES)
 def test_llr_golden_float64_exact(gpu, case, bp_order, monkeypatch):
     """float64 messages: min-sum bit-identical to the reference; BP in the reference's operation order
-    (IBLDPC_BP_SEQUENTIAL=1) to 1e-9 (exp/log rounding), in the default forward/backward order to 1e-6 with identical
-    hard decisions and stop iteration."""
+    (IBLDPC_BP_SEQUENTIAL=1) to 1e-9 (exp/log rounding), in the default forward/backward order (likelihood-ratio domain;
+    IBLDPC_BP_LOGDOMAIN=1: the reference box-plus expression per operation) to 1e-6 with identical hard decisions and
+    stop iteration."""
     import torch
     import informationbottleneckdecodingldpc_b200 as pkg
     if bp_order == "sequential":
         monkeypatch.setenv("IBLDPC_BP_SEQUENTIAL", "1")
+    if bp_order == "forward_backward_log":
+        monkeypatch.setenv("IBLDPC_BP_LOGDOMAIN", "1")
     g = load_golden(case)
     imax = int(g["imax"])
     for cls, algo, meth in ((pkg.Min_Sum_Decoder_class_irregular, "minsum", "decode_OpenCL_min_sum"),
@@ -436,8 +439,8 @@ def test_llr_float64_frame_agreement_large_batch(gpu, monkeypatch, bp_order):
     import torch
     import informationbottleneckdecodingldpc_b200 as pkg
     from oracle import oracle
-    # float64 BP runs the forward/backward box-plus recursion by default (what bench.py times); IBLDPC_BP_SEQUENTIAL=1
-    # evaluates the reference's operation order.  Both must meet the bar.
+    # float64 BP runs the forward/backward box-plus recursion in the likelihood-ratio domain by default (what bench.py
+    # times); IBLDPC_BP_SEQUENTIAL=1 evaluates the reference's operation order.  Both must meet the bar.
     if bp_order == "sequential":
         monkeypatch.setenv("IBLDPC_BP_SEQUENTIAL", "1")
     B, imax = 20000, 20
