@@ -76,7 +76,7 @@ def roofline_from_phase_times(ms3, n3, N, E, B, imax, packed, workload, family=N
     VN 2E+N per frame; the packed-nibble kernels store two frames per byte, so the bytes they really move
     ("stored") are half of that -- both figures are reported, and `frac` (algorithmic / peak) may exceed 1 for that
     reason; `frac_stored` is the physical fraction of the HBM peak.  `bound` names the real limiter: with four-bit
-    storage the kernels are NOT HBM-bound but sit on the shared-memory look-up pipe (92 % busy; ncu,
+    storage the kernels are NOT HBM-bound but sit on the issue slots / the shared-memory look-up pipe (ncu,
     profiles/README.md); the HBM peak stays the denominator SURVEY 8(d) prescribes.  When the whole decode ran as one
     cooperative launch (small batches) there are no per-phase times: the dominant "kernel" is then the whole decode
     with SURVEY's bytes per frame."""
@@ -117,8 +117,15 @@ def roofline_from_phase_times(ms3, n3, N, E, B, imax, packed, workload, family=N
         except Exception as e:   # noqa: BLE001
             traffic_note = f"profiles/traffic.json unreadable: {e}"
     if family in (1, 2):
-        bound = ("shared-memory look-up pipe (ncu: l1tex data-pipe 92 % busy in both the check-node and the variable-node kernel, "
-                 "issue 84 % / 75 %, DRAM 41 % / 54 %); HBM peak is the roofline denominator of SURVEY 8(d)") if packed else "hbm / shared-memory look-up pipe"
+        if not packed:
+            bound = "hbm / shared-memory look-up pipe"
+        elif workload == "c1":
+            bound = ("issue slots + shared-memory look-up pipe (ncu, profiles/r02_ncu_full_c1_final_summary.csv: check-node kernel issue 82 %, "
+                     "l1tex data-pipe 82 %, DRAM 43 %; variable-node kernel issue 79 %, data-pipe 75 %, DRAM 63 % = 0.80 of the measured copy "
+                     "bandwidth on the bytes really moved); HBM peak is the roofline denominator of SURVEY 8(d)")
+        else:
+            bound = ("shared-memory look-up pipe (ncu, profiles/r02_ncu_full_phase_{wlan,dvbs2}_summary.csv: l1tex data-pipe 82-89 %, issue 76-87 %, "
+                     "DRAM 28-37 %); HBM peak is the roofline denominator of SURVEY 8(d)")
     elif family == 3:
         bound = "shared-memory look-up pipe (unstriped 32x32 byte tables, bank conflicts)"
     else:

@@ -579,7 +579,11 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
         }
     }
     // ---- one launch per phase over all degree classes (ib_phase_n4.cuh) where the degree sets are instantiated
-    if (h->phase && h->phase_default) return decode_ib_phase(h, a, imax, early, st);
+    // (by default for the 802.11n sets at every batch size; for the other instantiated sets in the launch-bound middle range
+    // above the cooperative kernel's lane mode, where one launch per phase beats one per class -- measured on B200,
+    // profiles/r02_small_and_mid_batches.txt: (3,6) B=2048 2.15 -> 1.90 ms, DVB-S2 B=1024 11.6 -> 8.6 ms, break-even at 4096)
+    if (h->phase && (h->phase_default || (!h->phase_off_midrange && B <= h->phase_mid_max_frames)))
+        return decode_ib_phase(h, a, imax, early, st);
     // launch geometry of one degree class (plan_geometry): tiles per CTA, tile groups, CTAs per tile group
     auto plan_launch = [&](IbArgs& b, const void* fn, int smem, int threads, int vec, int n_nodes, int* tile_groups, int* grid) -> int {
         int occ;
@@ -1223,7 +1227,6 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
     if (const char* e = getenv("IBLDPC_VN_PAIR_MIN_DEGREE")) h->vn_pair_min_degree = std::max(3, atoi(e));
     h->cn_threads = getenv("IBLDPC_CN_THREADS") ? atoi(getenv("IBLDPC_CN_THREADS")) : 0;
     h->vn_threads = getenv("IBLDPC_VN_THREADS") ? atoi(getenv("IBLDPC_VN_THREADS")) : 0;
-    if (const char* e = getenv("IBLDPC_COOP_MAX_B")) h->coop_max_frames = std::max(0LL, atoll(e));
     if (const char* e = getenv("IBLDPC_VN_PAIR_THREADS")) h->vn_pair_threads = atoi(e) == 512 ? 512 : atoi(e) == 256 ? 256 : 0;
     if (h->nib && h->use_pair) {
         // Composed tail-pair tables of the variable-node update (vn_word_n4_pair): for every iteration and every
@@ -1304,6 +1307,16 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
                    getenv("IBLDPC_VN_PAIR_MIN_DEGREE") == nullptr && h->vn_vec == 0 && h->cn_threads == 0 &&
                    h->vn_threads == 0 && h->vn_pair_threads == 0 && getenv("IBLDPC_NO_PLAN") == nullptr;
     if ((rc = phase_prepare(h))) return rc;
+    // Batch-size policy between the whole-decode cooperative kernel, the fused per-phase kernels and one launch per degree
+    // class (measured on B200, profiles/r02_small_and_mid_batches.txt).  Codes without fused kernels: cooperative kernel up
+    // to 4096 frames.  802.11n sets: the fused kernels at every batch size (B <= 2048: 1.24-1.34 ms per decode against
+    // 2.3-2.9 ms in the multi-class cooperative kernel, which restages its tables six times per iteration).  (3,6) and
+    // DVB-S2 sets: cooperative kernel while its lane = (node, word) mapping applies (B <= 256), fused kernels up to 4096
+    // frames, per-class launches above.  IBLDPC_COOP_MAX_B / IBLDPC_PHASE_MID_MAX_B override.
+    if (const char* e = getenv("IBLDPC_COOP_MAX_B")) h->coop_max_frames = std::max(0LL, atoll(e));
+    else h->coop_max_frames = h->phase == nullptr ? 4096 : h->phase_default ? 0 : kLaneModeMaxFrames;
+    h->phase_mid_max_frames = getenv("IBLDPC_PHASE_MID_MAX_B") ? std::max(0LL, atoll(getenv("IBLDPC_PHASE_MID_MAX_B"))) : 4096;
+    h->phase_off_midrange = getenv("IBLDPC_NO_PHASE") != nullptr;
     if ((rc = t32_prepare(h))) return rc;
     h->occ_cache.clear();
     h->have_luts = true;

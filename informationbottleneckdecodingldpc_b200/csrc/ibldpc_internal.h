@@ -112,7 +112,9 @@ struct ibldpc_decoder {
     int vn_pair_threads = 0;        // 0 = per-degree default, 256 / 512 forced (IBLDPC_VN_PAIR_THREADS)
     int cn_threads = 0, vn_threads = 0;   // 0 = default CTA sizes (1024 where instantiated); IBLDPC_CN_THREADS=512 /
                                           // IBLDPC_VN_THREADS=256 select the smaller CTAs (parity variants, A/B)
-    long long coop_max_frames = 4096;   // regular codes: whole-decode cooperative kernel up to this batch size
+    long long coop_max_frames = 4096;   // whole-decode cooperative kernel up to this batch size (policy: end of ibldpc_set_luts)
+    long long phase_mid_max_frames = 4096;   // instantiated sets without phase_default: fused per-phase kernels up to this batch size
+    bool phase_off_midrange = false;    // IBLDPC_NO_PHASE
                                         // (IBLDPC_COOP_MAX_B, 0 disables)
     int coop_supported = -1;        // device attribute cudaDevAttrCooperativeLaunch, queried once
     bool use_pair = true;

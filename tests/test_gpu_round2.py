@@ -679,12 +679,15 @@ def test_per_frame_early_termination_corner_cases(gpu, case):
 
 @pytest.mark.parametrize("code", ["reg36", "wlan1296", "dvb6480"])
 @pytest.mark.parametrize("B", [1, 2, 9, 33, 100, 256, 257, 520])
-def test_small_batch_cooperative_kernels_lane_mode(gpu, code, B):
+def test_small_batch_cooperative_kernels_lane_mode(gpu, code, B, monkeypatch):
     """Batches of up to 256 frames run the whole-decode cooperative kernels with one LANE per (node, word) pair
     (cn_lanes_n4 / vn_lanes_n4: the reference's DVB-S2 drivers decode msg_at_time = 2 frames per call); 257 and 520 take the
-    warp-per-(node, tile) bodies of the same kernels.  Outputs and i_num against the oracle, early termination off and on."""
+    warp-per-(node, tile) bodies of the same kernels.  Outputs and i_num against the oracle, early termination off and on.
+    (IBLDPC_COOP_MAX_B pins the cooperative kernels: by default the 802.11n sets and the batches above 256 frames of the
+    other instantiated sets run the fused per-phase kernels -- test_batch_size_policy.)"""
     import torch
     import informationbottleneckdecodingldpc_b200 as pkg
+    monkeypatch.setenv("IBLDPC_COOP_MAX_B", "4096")
     T, imax = 16, 7
     if code == "reg36":
         H = codes.regular_random(2000, 3, 6, seed=5)
@@ -705,6 +708,37 @@ def test_small_batch_cooperative_kernels_lane_mode(gpu, code, B):
         dec.early_termination = early
         out = dec.decode_OpenCL(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True).get()
         assert dec.info()[1] <= 3, "expected the single cooperative launch (+ pack / pad kernels)"
+        ref, ref_inum = _oracle_ib(t, ch, T, imax, tb, early)
+        assert dec.last_i_num == ref_inum
+        assert np.array_equal(out, ref.astype(np.uint8))
+
+
+@pytest.mark.parametrize("code,B,launches", [("reg36", 100, 3), ("reg36", 1000, 2 * 7 + 1), ("reg36", 5000, 2 * 7 + 1),
+                                             ("wlan1296", 2, 2 * 7 + 1), ("wlan1296", 2000, 2 * 7 + 1), ("dvb6480", 2, 3), ("dvb6480", 600, 2 * 7 + 1)])
+def test_batch_size_policy(gpu, code, B, launches):
+    """Default dispatch by batch size (end of ibldpc_set_luts): 802.11n sets -> fused per-phase kernels always; (3,6) and
+    DVB-S2 sets -> cooperative whole-decode kernel up to 256 frames, fused per-phase kernels up to 4096, one launch per
+    degree class above ((3,6): one class per phase, so the launch count is the same).  Results against the oracle."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    T, imax = 16, 7
+    H = codes.regular_random(2000, 3, 6, seed=5) if code == "reg36" else codes.wlan_80211n(54) if code == "wlan1296" \
+        else codes.dvbs2_like_half_rate(6480, q_groups=36)
+    t = graph.edge_tables(H)
+    tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=B, matching=code != "reg36")
+    if code == "reg36":
+        dec = pkg.Discrete_LDPC_Decoder_class(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a, B)
+    else:
+        dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                        tb.matching_vector_checknode, tb.matching_vector_varnode, B)
+    dec.init_OpenCL_decoding(B)
+    ch = np.random.Generator(np.random.PCG64(7 + B)).integers(0, T, size=(t.n_var, B)).astype(np.uint8)
+    for early in (False, True):
+        dec.early_termination = early
+        out = dec.decode_OpenCL(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True).get()
+        assert dec.info()[1] <= launches + 1, (dec.info(), launches)      # + pack / pad kernel
+        if launches > 3:
+            assert dec.info()[1] >= launches
         ref, ref_inum = _oracle_ib(t, ch, T, imax, tb, early)
         assert dec.last_i_num == ref_inum
         assert np.array_equal(out, ref.astype(np.uint8))
