@@ -695,7 +695,7 @@ __device__ __forceinline__ void vn_loop_n4(const IbArgs& a, const uint8_t* tab, 
 // ------------------------------------------------------------------------------------------
 constexpr int kLaneModeMaxFrames = 256;   // up to 32 words per node: never fewer active lanes than the (node, tile) mapping
 
-template <int D, bool MATCH, bool EARLY, bool PAIR, int NT>
+template <int D, bool MATCH, bool EARLY, bool PAIR, int NT, int WT = 0, int CB = 0>
 __device__ __forceinline__ uint32_t cn_lanes_n4(const IbArgs& a, const uint8_t* tab, const uint8_t* ptab,
                                                 const int* __restrict__ nodes, int n_nodes)
 {
@@ -735,16 +735,17 @@ __device__ __forceinline__ uint32_t cn_lanes_n4(const IbArgs& a, const uint8_t* 
             const int nv = a.B - 8 * wd;
             syn |= par & (nv >= 8 ? 0xffffffffu : ((1u << (4 * nv)) - 1u));
         }
-        if constexpr (PAIR) cn_word_n4_pair<D>(w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
-        else cn_word_n4<D, MATCH>(w, o, tab, lane4);
+        if constexpr (PAIR) cn_word_n4_pair<D, WT, CB>(w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
+        else cn_word_n4<D, MATCH, WT, CB>(w, o, tab, lane4);
 #pragma unroll
         for (int k = 0; k < D; ++k) *reinterpret_cast<uint32_t*>(a.msg + (uint64_t)(uint32_t)(s + k) * a.pitch + 4 * wd) = o[k];
     }
     return syn;
 }
 
-template <int D, bool DECIDE, int NT>
-__device__ __forceinline__ void vn_lanes_n4(const IbArgs& a, const uint8_t* tab, const int* __restrict__ nodes, int n_nodes)
+template <int D, bool DECIDE, int NT, int WT = 0, int CB = 0, bool PAIR = false>
+__device__ __forceinline__ void vn_lanes_n4(const IbArgs& a, const uint8_t* tab, const int* __restrict__ nodes, int n_nodes,
+                                            const uint8_t* ptab = nullptr)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t lane4 = lane * 4;
@@ -769,7 +770,8 @@ __device__ __forceinline__ void vn_lanes_n4(const IbArgs& a, const uint8_t* tab,
             *reinterpret_cast<uint32_t*>(a.msg + (uint64_t)(uint32_t)rows[0] * a.pitch + 4 * wd) = chw;
             continue;
         }
-        vn_word_n4<D, DECIDE>(chw, w, o, dlo, dhi, tab, lane4);
+        if constexpr (PAIR && !DECIDE) vn_word_n4_pair<D, WT, CB>(chw, w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
+        else vn_word_n4<D, DECIDE, WT, CB>(chw, w, o, dlo, dhi, tab, lane4);
         if (DECIDE) {
             if (8u * (uint32_t)wd < a.out_pitch)
                 *reinterpret_cast<uint2*>(a.out + (uint64_t)(uint32_t)v * a.out_pitch + 8 * wd) = make_uint2(dlo, dhi);

@@ -23,6 +23,7 @@ struct PhaseImages {
     int* vn_starts[kPhaseMaxClasses] = {};
     int cn_count[kPhaseMaxClasses] = {}, vn_count[kPhaseMaxClasses] = {};
     int occ_checked = 0;
+    int coop_checked = 0;
 };
 
 namespace {
@@ -331,6 +332,51 @@ int decode_ib_phase(ibldpc_decoder* h, const IbArgs& a, int imax, int early, cud
     }
     if ((rc = launch_vn(0, true))) return rc;
     IBLDPC_CK(cudaGetLastError());
+    return IBLDPC_OK;
+}
+
+// One decode of a small batch (B <= kLaneModeMaxFrames) in ONE cooperative launch (ib_coop_phase_kernel): lane = (node, word),
+// the image of every phase brought in by TMA while the grid barrier before the phase completes.
+int decode_ib_coop_phase(ibldpc_decoder* h, const IbArgs& a, long long B, int imax, int early, cudaStream_t st)
+{
+    PhaseImages* p = h->phase;
+    const PhaseSetOps* ops = p->ops;
+    const size_t smem = std::max(p->cn_bytes, std::max(p->vn_bytes, p->out_bytes));
+    const int NT = ops->coop_threads;
+    CoopPhaseKernel k = ops->coop_kernel[early ? 1 : 0];
+    if (!p->coop_checked) {
+        for (CoopPhaseKernel kk : {ops->coop_kernel[0], ops->coop_kernel[1]}) {
+            IBLDPC_CK(cudaFuncSetAttribute((const void*)kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 0;
+            IBLDPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kk, NT, smem));
+            if (occ < 1) return fail_msg(IBLDPC_E_CUDA, "cooperative per-phase kernel does not fit on an SM");
+        }
+        p->coop_checked = 1;
+    }
+    CoopPhaseArgs q{};
+    q.a = a;
+    q.a.early = early;
+    q.a.imax = imax;
+    q.cn_images = p->d_images;
+    q.vn_images = p->d_images + (size_t)p->imax * p->cn_bytes;
+    q.out_images = p->d_images + (size_t)p->imax * (p->cn_bytes + p->vn_bytes);
+    const long long wpn = (B + 7) / 8, per_warp = 32 / wpn;   // nodes per warp step
+    long long warps = 1;
+    for (int i = 0; i < ops->cn_layout.n; ++i) {
+        q.cn_nodes[i] = p->cn_nodes[i]; q.cn_count[i] = p->cn_count[i];
+        warps = std::max(warps, (p->cn_count[i] + per_warp - 1) / per_warp);
+    }
+    for (int i = 0; i < ops->vn_layout.n; ++i) {
+        q.vn_nodes[i] = p->vn_nodes[i]; q.vn_count[i] = p->vn_count[i];
+        warps = std::max(warps, (p->vn_count[i] + per_warp - 1) / per_warp);
+    }
+    const int grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, (warps + NT / 32 - 1) / (NT / 32)));
+    PhaseProf prof{h, st};
+    if (int rc = prof.begin(2)) return rc;
+    void* params[] = {&q};
+    IBLDPC_CK(cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(NT), params, smem, st));
+    h->last_launches++; h->last_grid = grid; h->last_smem = (int)smem;
+    if (int rc = prof.end()) return rc;
     return IBLDPC_OK;
 }
 

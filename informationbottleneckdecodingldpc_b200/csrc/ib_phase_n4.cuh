@@ -19,6 +19,8 @@
 // Instantiated per degree SET (DegreeSet<...>, heaviest first): the column layout is a compile-time function of the
 // set, exactly like the multi-class cooperative kernel.  Other degree sets keep the per-class launches.
 #pragma once
+#include <cooperative_groups.h>
+
 #include <utility>
 
 #include "ib_coop_n4.cuh"   // DegreeSet
@@ -507,6 +509,146 @@ __global__ void __launch_bounds__(kPhaseThreads, 1) ib_phase_pfdecide_kernel(Pha
         phase_unroll(class_loop, std::make_integer_sequence<int, L::n>{});
     }
 }
+
+
+// ---- small batches: the whole decode in ONE cooperative launch over the phase images ---------------------------
+// B <= kLaneModeMaxFrames (256): a lane is a (node, word) pair (cn_lanes_n4 / vn_lanes_n4), the whole flooding schedule
+// runs in one cooperative launch with a grid-wide barrier between the phases (ib_coop_n4.cuh) -- but where those kernels
+// restage the tables of every degree class of every phase with a striping loop and two block barriers (six times per
+// iteration for the DVB-S2 set: 39 us per iteration at B = 2, the reference's msg_at_time), this one brings in the
+// pre-expanded image of the WHOLE phase with one TMA bulk copy issued BEFORE the grid barrier, so the copy overlaps the
+// barrier and all classes of the phase run back to back without a block barrier in between.
+// Same look-up functions with the class's column base inside the image: bit-identical results, same stop rule, same i_num.
+struct CoopPhaseArgs {
+    IbArgs a;
+    const uint8_t* cn_images;   // [imax] check-node images (block 0 = iteration-0 tables)
+    const uint8_t* vn_images;   // [imax] variable-node update images
+    const uint8_t* out_images;  // [imax] decision images
+    const int* cn_nodes[kPhaseMaxClasses];
+    const int* vn_nodes[kPhaseMaxClasses];
+    int cn_count[kPhaseMaxClasses], vn_count[kPhaseMaxClasses];
+};
+
+template <int NT, bool EARLY, int... Cs, int... Vs>
+__device__ __forceinline__ void coop_phase_body(const CoopPhaseArgs& p, DegreeSet<Cs...>, DegreeSet<Vs...>)
+{
+    namespace cg = cooperative_groups;
+    using LC = PhaseLayout<kPhaseCn, Cs...>;
+    using LV = PhaseLayout<kPhaseVn, Vs...>;
+    using LO = PhaseLayout<kPhaseOut, Vs...>;
+    extern __shared__ __align__(128) uint8_t s_img[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    cg::grid_group grid = cg::this_grid();
+    const IbArgs& a = p.a;
+    const uint32_t mb = smem_u32(&s_mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t parity = 0;
+    // every thread of the CTA has left the previous image (and seen its mbarrier phase) before the next copy is issued
+    auto issue = [&](const uint8_t* img, uint32_t bytes) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of the old image before the async-proxy writes
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            constexpr uint32_t kChunk = 32768;
+            const uint32_t dst = smem_u32(s_img);
+            for (uint32_t off = 0; off < bytes; off += kChunk) {
+                const uint32_t n = bytes - off < kChunk ? bytes - off : kChunk;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                             "l"(img + off), "r"(n), "r"(mb)
+                             : "memory");
+            }
+        }
+    };
+    auto wait = [&]() {
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(mb), "r"(parity)
+                : "memory");
+        }
+        parity ^= 1u;
+    };
+    auto cn_phase = [&](int it) {
+        IbArgs b = a;
+        b.it = it; b.iter0 = (it < 0);
+        uint32_t syn = 0;
+        auto one = [&](auto IC) {
+            constexpr int I = decltype(IC)::value;
+            constexpr int D = LC::degree(I);
+            constexpr bool PAIR = LC::pm(I) >= 1;
+            syn |= cn_lanes_n4<D, false, EARLY, PAIR, NT, LC::words, LC::col_base(I)>(
+                b, s_img + LC::n_pair * kPairBytes, s_img + LC::pair_index(I) * kPairBytes, p.cn_nodes[I], p.cn_count[I]);
+        };
+        phase_unroll(one, std::make_integer_sequence<int, LC::n>{});
+        if (EARLY && it >= 0) {
+            const unsigned any = __ballot_sync(0xffffffffu, syn != 0);
+            if (any != 0 && (threadIdx.x & 31) == 0) atomicOr(&a.flags[it], 1);
+        }
+    };
+    auto vn_phase = [&](int it) {
+        IbArgs b = a;
+        b.it = it; b.iter0 = 0;
+        auto one = [&](auto IC) {
+            constexpr int I = decltype(IC)::value;
+            constexpr int D = LV::degree(I);
+            constexpr bool PAIR = LV::pm(I) >= 1;
+            vn_lanes_n4<D, false, NT, LV::words, LV::col_base(I), PAIR>(b, s_img + LV::n_pair * kPairBytes, p.vn_nodes[I], p.vn_count[I],
+                                                                        s_img + LV::pair_index(I) * kPairBytes);
+        };
+        phase_unroll(one, std::make_integer_sequence<int, LV::n>{});
+    };
+    auto out_phase = [&](int it) {
+        IbArgs b = a;
+        b.it = it; b.iter0 = 0;
+        auto one = [&](auto IC) {
+            constexpr int I = decltype(IC)::value;
+            vn_lanes_n4<LO::degree(I), true, NT, LO::words, LO::col_base(I), false>(b, s_img + LO::n_pair * kPairBytes, p.vn_nodes[I],
+                                                                                   p.vn_count[I]);
+        };
+        phase_unroll(one, std::make_integer_sequence<int, LO::n>{});
+    };
+
+    issue(p.cn_images, (uint32_t)LC::image_bytes);
+    wait();
+    cn_phase(-1);
+    int passes = 0;
+    bool converged = false;
+    for (int it = 0; it < a.imax - 1; ++it) {
+        issue(p.vn_images + (size_t)it * LV::image_bytes, (uint32_t)LV::image_bytes);   // overlaps the grid barrier
+        grid.sync();
+        wait();
+        // reference stop rule (discrete_LDPC_decoder.py:233-276): pass `it` runs iff it == 0 or pass it-1 left a non-zero
+        // syndrome somewhere in the batch; flags[] were written before the grid barrier
+        if (EARLY && it >= 1 && *reinterpret_cast<volatile int*>(&a.flags[it - 1]) == 0) { converged = true; break; }
+        vn_phase(it);
+        issue(p.cn_images + (size_t)(it + 1) * LC::image_bytes, (uint32_t)LC::image_bytes);
+        grid.sync();
+        wait();
+        cn_phase(it);
+        passes = it + 1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.inum = passes + 1;
+    // calc_varnode_output with the tables of iteration i_num - 1; after a converged stop the grid is already in step
+    issue(p.out_images + (size_t)passes * LO::image_bytes, (uint32_t)LO::image_bytes);
+    if (!converged) grid.sync();
+    wait();
+    out_phase(passes);
+}
+
+template <int NT, bool EARLY, typename CnSet, typename VnSet>
+__global__ void __launch_bounds__(NT, 1) ib_coop_phase_kernel(CoopPhaseArgs p)
+{
+    coop_phase_body<NT, EARLY>(p, CnSet{}, VnSet{});
+}
+
+using CoopPhaseKernel = void (*)(CoopPhaseArgs);
 
 using PhaseKernel = void (*)(PhaseArgs);
 using PhaseDecideKernel = void (*)(PhaseArgs, int, int);

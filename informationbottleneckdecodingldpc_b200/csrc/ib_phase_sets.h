@@ -15,7 +15,11 @@ struct PhaseSetOps {
     PhaseKernel vn_kernel, out_kernel;
     PhaseKernel cn_pf_kernel[2], vn_pf_kernel;  // per-frame early termination (ib_perframe.cu); [0] syndrome flags in shared memory, [1] global
     PhaseDecideKernel pf_decide_kernel;         // deferred decision of the converged frames
+    CoopPhaseKernel coop_kernel[2];             // [early] whole decode in one cooperative launch, B <= kLaneModeMaxFrames
+    int coop_threads;
 };
+
+constexpr int kCoopPhaseThreads = 512;          // 128 registers per thread: the degree-11 lane bodies keep their rows and words in registers
 
 template <int... Cs, int... Vs>
 PhaseSetOps make_phase_ops(const char* name, DegreeSet<Cs...> cs, DegreeSet<Vs...> vs)
@@ -35,6 +39,9 @@ PhaseSetOps make_phase_ops(const char* name, DegreeSet<Cs...> cs, DegreeSet<Vs..
     o.cn_pf_kernel[1] = ib_phase_pf_kernel<kPhaseCn, 2, Cs...>;
     o.vn_pf_kernel = ib_phase_pf_kernel<kPhaseVn, 1, Vs...>;
     o.pf_decide_kernel = ib_phase_pfdecide_kernel<Vs...>;
+    o.coop_kernel[0] = ib_coop_phase_kernel<kCoopPhaseThreads, false, DegreeSet<Cs...>, DegreeSet<Vs...>>;
+    o.coop_kernel[1] = ib_coop_phase_kernel<kCoopPhaseThreads, true, DegreeSet<Cs...>, DegreeSet<Vs...>>;
+    o.coop_threads = kCoopPhaseThreads;
     return o;
 }
 

@@ -497,6 +497,15 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
     const int T = h->T, TT = T * T;
     // ---- opt-in: per-frame early termination with frame compaction (ib_perframe.cu)
     if (h->pf_request) return decode_ib_perframe(h, w, a, B, imax, h->pf_inum, st);
+    // ---- small batches of the instantiated degree sets: one cooperative launch over the TMA-staged phase images
+    if (h->phase && !h->no_coop_phase && B <= kLaneModeMaxFrames && B <= h->coop_max_frames) {
+        if (h->coop_supported < 0) {
+            int v = 0;
+            CK(cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, h->device));
+            h->coop_supported = v;
+        }
+        if (h->coop_supported) return decode_ib_coop_phase(h, a, B, imax, early, st);
+    }
     // ---- small batches of regular codes: the whole decode in one cooperative launch (ib_coop_n4.cuh)
     // (worth it while a phase is short: measured break-even near 100 MB of packed messages -- DVB-S2 n=64800 wins at
     // B=512 (58 MB: 9.3 -> 6.9 ms) and loses at B=2048 (232 MB); C1 and 802.11n win up to the 4096-frame limit)
@@ -1309,12 +1318,14 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
     if ((rc = phase_prepare(h))) return rc;
     // Batch-size policy between the whole-decode cooperative kernel, the fused per-phase kernels and one launch per degree
     // class (measured on B200, profiles/r02_small_and_mid_batches.txt).  Codes without fused kernels: cooperative kernel up
-    // to 4096 frames.  802.11n sets: the fused kernels at every batch size (B <= 2048: 1.24-1.34 ms per decode against
-    // 2.3-2.9 ms in the multi-class cooperative kernel, which restages its tables six times per iteration).  (3,6) and
-    // DVB-S2 sets: cooperative kernel while its lane = (node, word) mapping applies (B <= 256), fused kernels up to 4096
-    // frames, per-class launches above.  IBLDPC_COOP_MAX_B / IBLDPC_PHASE_MID_MAX_B override.
+    // to 4096 frames.  Instantiated sets: up to 256 frames (lane = (node, word) mapping) one cooperative launch over the
+    // phase images (ib_coop_phase_kernel); above, the 802.11n sets run the fused per-phase kernels at every batch size
+    // (B <= 2048: 1.24-1.34 ms per decode against 2.3-2.9 ms in the table-restaging multi-class cooperative kernel), the
+    // (3,6) and DVB-S2 sets the fused kernels up to 4096 frames and per-class launches above.
+    // IBLDPC_COOP_MAX_B / IBLDPC_PHASE_MID_MAX_B / IBLDPC_NO_COOP_PHASE override.
     if (const char* e = getenv("IBLDPC_COOP_MAX_B")) h->coop_max_frames = std::max(0LL, atoll(e));
-    else h->coop_max_frames = h->phase == nullptr ? 4096 : h->phase_default ? 0 : kLaneModeMaxFrames;
+    else h->coop_max_frames = h->phase == nullptr ? 4096 : kLaneModeMaxFrames;
+    h->no_coop_phase = getenv("IBLDPC_NO_COOP_PHASE") != nullptr;
     h->phase_mid_max_frames = getenv("IBLDPC_PHASE_MID_MAX_B") ? std::max(0LL, atoll(getenv("IBLDPC_PHASE_MID_MAX_B"))) : 4096;
     h->phase_off_midrange = getenv("IBLDPC_NO_PHASE") != nullptr;
     if ((rc = t32_prepare(h))) return rc;

@@ -115,6 +115,7 @@ struct ibldpc_decoder {
     long long coop_max_frames = 4096;   // whole-decode cooperative kernel up to this batch size (policy: end of ibldpc_set_luts)
     long long phase_mid_max_frames = 4096;   // instantiated sets without phase_default: fused per-phase kernels up to this batch size
     bool phase_off_midrange = false;    // IBLDPC_NO_PHASE
+    bool no_coop_phase = false;         // IBLDPC_NO_COOP_PHASE=1: small batches through the table-restaging cooperative kernels (ib_coop_n4.cuh)
                                         // (IBLDPC_COOP_MAX_B, 0 disables)
     int coop_supported = -1;        // device attribute cudaDevAttrCooperativeLaunch, queried once
     bool use_pair = true;
@@ -153,6 +154,8 @@ namespace ibldpc {
 int phase_prepare(ibldpc_decoder* h);   // end of ibldpc_set_luts: build + upload the phase images (or leave h->phase null)
 void phase_free(ibldpc_decoder* h);
 int decode_ib_phase(ibldpc_decoder* h, const IbArgs& a, int imax, int early, cudaStream_t st);
+// B <= kLaneModeMaxFrames: the whole decode in one cooperative launch over the same phase images (ib_coop_phase_kernel)
+int decode_ib_coop_phase(ibldpc_decoder* h, const IbArgs& a, long long B, int imax, int early, cudaStream_t st);
 // per-frame early termination with frame compaction (ib_perframe.cu)
 int decode_ib_perframe(ibldpc_decoder* h, Workspace& w, const IbArgs& a, long long B, int imax, int32_t* i_num_frames_dev,
                        cudaStream_t st);

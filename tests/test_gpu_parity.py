@@ -39,7 +39,7 @@ def _dev(a):
 #              phase over all degree classes, TMA-staged table image), n4_nophase = one launch per degree class instead
 #              (degree-3 variable nodes and check nodes of degree 6..8 through the three-input tables of ib_triple_n4.cuh;
 #              n4_notriple = without them, n4_cn_tri6 = check nodes up to degree 6 only)
-IB_VARIANTS = {"n4": {}, "n4_coop": {"IBLDPC_COOP_MAX_B": "4096"},   # whole-decode cooperative kernel up to 4096 frames (default: see the batch-size policy at the end of ibldpc_set_luts)
+IB_VARIANTS = {"n4": {}, "n4_coop": {"IBLDPC_COOP_MAX_B": "4096", "IBLDPC_NO_COOP_PHASE": "1"},   # table-restaging cooperative kernels of ib_coop_n4.cuh up to 4096 frames (default: see the batch-size policy at the end of ibldpc_set_luts)
                "n4_vn4": {"IBLDPC_VN_VEC": "4"}, "n4_vn2": {"IBLDPC_VN_VEC": "2"}, "n4_pair4": {"IBLDPC_PAIR_MIN_DEGREE": "4"},
                "n4_vpair3": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3"},
                "n4_vpair3_256": {"IBLDPC_VN_PAIR_MIN_DEGREE": "3", "IBLDPC_VN_PAIR_THREADS": "256"},

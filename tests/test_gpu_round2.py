@@ -677,17 +677,22 @@ def test_per_frame_early_termination_corner_cases(gpu, case):
         assert inum.min() == imax
 
 
+@pytest.mark.parametrize("kernel", ["phase_images", "restaging"])
 @pytest.mark.parametrize("code", ["reg36", "wlan1296", "dvb6480"])
 @pytest.mark.parametrize("B", [1, 2, 9, 33, 100, 256, 257, 520])
-def test_small_batch_cooperative_kernels_lane_mode(gpu, code, B, monkeypatch):
+def test_small_batch_cooperative_kernels_lane_mode(gpu, code, B, kernel, monkeypatch):
     """Batches of up to 256 frames run the whole-decode cooperative kernels with one LANE per (node, word) pair
     (cn_lanes_n4 / vn_lanes_n4: the reference's DVB-S2 drivers decode msg_at_time = 2 frames per call); 257 and 520 take the
     warp-per-(node, tile) bodies of the same kernels.  Outputs and i_num against the oracle, early termination off and on.
-    (IBLDPC_COOP_MAX_B pins the cooperative kernels: by default the 802.11n sets and the batches above 256 frames of the
-    other instantiated sets run the fused per-phase kernels -- test_batch_size_policy.)"""
+    kernel = phase_images: ib_coop_phase_kernel (TMA-staged images of whole phases, the default up to 256 frames);
+    restaging: the kernels of ib_coop_n4.cuh (IBLDPC_NO_COOP_PHASE=1).  IBLDPC_COOP_MAX_B pins the cooperative kernels for
+    257 and 520 frames too: by default batches above 256 frames of the instantiated sets run the fused per-phase kernels
+    (test_batch_size_policy)."""
     import torch
     import informationbottleneckdecodingldpc_b200 as pkg
     monkeypatch.setenv("IBLDPC_COOP_MAX_B", "4096")
+    if kernel == "restaging":
+        monkeypatch.setenv("IBLDPC_NO_COOP_PHASE", "1")
     T, imax = 16, 7
     if code == "reg36":
         H = codes.regular_random(2000, 3, 6, seed=5)
@@ -714,11 +719,12 @@ def test_small_batch_cooperative_kernels_lane_mode(gpu, code, B, monkeypatch):
 
 
 @pytest.mark.parametrize("code,B,launches", [("reg36", 100, 3), ("reg36", 1000, 2 * 7 + 1), ("reg36", 5000, 2 * 7 + 1),
-                                             ("wlan1296", 2, 2 * 7 + 1), ("wlan1296", 2000, 2 * 7 + 1), ("dvb6480", 2, 3), ("dvb6480", 600, 2 * 7 + 1)])
+                                             ("wlan1296", 2, 3), ("wlan1296", 256, 3), ("wlan1296", 2000, 2 * 7 + 1), ("dvb6480", 2, 3), ("dvb6480", 600, 2 * 7 + 1)])
 def test_batch_size_policy(gpu, code, B, launches):
-    """Default dispatch by batch size (end of ibldpc_set_luts): 802.11n sets -> fused per-phase kernels always; (3,6) and
-    DVB-S2 sets -> cooperative whole-decode kernel up to 256 frames, fused per-phase kernels up to 4096, one launch per
-    degree class above ((3,6): one class per phase, so the launch count is the same).  Results against the oracle."""
+    """Default dispatch by batch size (end of ibldpc_set_luts) for the instantiated degree sets: one cooperative launch over
+    the phase images up to 256 frames; above, 802.11n sets -> fused per-phase kernels always, (3,6) and DVB-S2 sets -> fused
+    per-phase kernels up to 4096 frames, one launch per degree class above ((3,6): one class per phase, so the launch count
+    is the same).  Results against the oracle."""
     import torch
     import informationbottleneckdecodingldpc_b200 as pkg
     T, imax = 16, 7
