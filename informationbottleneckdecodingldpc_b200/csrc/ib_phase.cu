@@ -360,15 +360,22 @@ int decode_ib_coop_phase(ibldpc_decoder* h, const IbArgs& a, long long B, int im
     q.cn_images = p->d_images;
     q.vn_images = p->d_images + (size_t)p->imax * p->cn_bytes;
     q.out_images = p->d_images + (size_t)p->imax * (p->cn_bytes + p->vn_bytes);
-    const long long wpn = (B + 7) / 8, per_warp = 32 / wpn;   // nodes per warp step
+    // warps the busiest class can use: lane mode (B <= kLaneModeMaxFrames) 32 / ceil(B/8) nodes per warp step, above one
+    // (node, tile) item per warp step
+    const bool lanes = B <= kLaneModeMaxFrames;
+    const long long wpn = (B + 7) / 8, per_warp = lanes ? 32 / wpn : 1;
+    auto warps_of = [&](int count, int vec) -> long long {
+        if (lanes) return (count + per_warp - 1) / per_warp;
+        return (long long)count * (((long long)a.pitch + 128LL * vec - 1) / (128LL * vec));
+    };
     long long warps = 1;
     for (int i = 0; i < ops->cn_layout.n; ++i) {
-        q.cn_nodes[i] = p->cn_nodes[i]; q.cn_count[i] = p->cn_count[i];
-        warps = std::max(warps, (p->cn_count[i] + per_warp - 1) / per_warp);
+        q.cn_nodes[i] = p->cn_nodes[i]; q.cn_starts[i] = p->cn_starts[i]; q.cn_count[i] = p->cn_count[i];
+        warps = std::max(warps, warps_of(p->cn_count[i], ops->cn_layout.cls[i].vec));
     }
     for (int i = 0; i < ops->vn_layout.n; ++i) {
-        q.vn_nodes[i] = p->vn_nodes[i]; q.vn_count[i] = p->vn_count[i];
-        warps = std::max(warps, (p->vn_count[i] + per_warp - 1) / per_warp);
+        q.vn_nodes[i] = p->vn_nodes[i]; q.vn_starts[i] = p->vn_starts[i]; q.vn_count[i] = p->vn_count[i];
+        warps = std::max(warps, warps_of(p->vn_count[i], ops->vn_layout.cls[i].vec));
     }
     const int grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, (warps + NT / 32 - 1) / (NT / 32)));
     PhaseProf prof{h, st};

@@ -526,8 +526,30 @@ struct CoopPhaseArgs {
     const uint8_t* out_images;  // [imax] decision images
     const int* cn_nodes[kPhaseMaxClasses];
     const int* vn_nodes[kPhaseMaxClasses];
+    const int* cn_starts[kPhaseMaxClasses];   // sc[node] / sv[node] of the same nodes (warp-per-(node, tile) bodies)
+    const int* vn_starts[kPhaseMaxClasses];
     int cn_count[kPhaseMaxClasses], vn_count[kPhaseMaxClasses];
 };
+
+// one class of one phase with a warp per (node, tile) item, items dealt round-robin to the warps of the grid
+// (batches above the lane mode: kLaneModeMaxFrames < B <= coop_max_frames)
+template <int NT, typename Item>
+__device__ __forceinline__ uint32_t coop_phase_tiles(const IbArgs& b, const uint8_t* s_img, const int* __restrict__ nodes,
+                                                     const int* __restrict__ starts, int n_nodes)
+{
+    constexpr int VEC = Item::VEC;
+    const int lane = threadIdx.x & 31;
+    const uint32_t tiles = (uint32_t)((b.pitch + 128u * VEC - 1) / (128u * VEC));
+    const long long items = (long long)n_nodes * tiles;
+    const long long gw = (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5), nw = (long long)gridDim.x * (NT / 32);
+    uint32_t syn = 0;
+    for (long long i = gw; i < items; i += nw) {
+        const uint32_t ni = (uint32_t)(i / tiles), tile = (uint32_t)(i - (long long)ni * tiles);
+        const uint32_t col = (tile * 32u + lane) * (4u * VEC);
+        if (col < b.pitch) syn |= Item::run(b, s_img, nodes[ni], starts[ni], col, lane * 4u, PfCtx{nullptr, nullptr, 0u});
+    }
+    return syn;
+}
 
 template <int NT, bool EARLY, int... Cs, int... Vs>
 __device__ __forceinline__ void coop_phase_body(const CoopPhaseArgs& p, DegreeSet<Cs...>, DegreeSet<Vs...>)
@@ -546,6 +568,7 @@ __device__ __forceinline__ void coop_phase_body(const CoopPhaseArgs& p, DegreeSe
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     uint32_t parity = 0;
+    const bool lanes = a.B <= kLaneModeMaxFrames;   // lane = (node, word); above: warp = (node, tile)
     // every thread of the CTA has left the previous image (and seen its mbarrier phase) before the next copy is issued
     auto issue = [&](const uint8_t* img, uint32_t bytes) {
         __syncthreads();
@@ -583,8 +606,11 @@ __device__ __forceinline__ void coop_phase_body(const CoopPhaseArgs& p, DegreeSe
             constexpr int I = decltype(IC)::value;
             constexpr int D = LC::degree(I);
             constexpr bool PAIR = LC::pm(I) >= 1;
-            syn |= cn_lanes_n4<D, false, EARLY, PAIR, NT, LC::words, LC::col_base(I)>(
-                b, s_img + LC::n_pair * kPairBytes, s_img + LC::pair_index(I) * kPairBytes, p.cn_nodes[I], p.cn_count[I]);
+            if (lanes)
+                syn |= cn_lanes_n4<D, false, EARLY, PAIR, NT, LC::words, LC::col_base(I)>(
+                    b, s_img + LC::n_pair * kPairBytes, s_img + LC::pair_index(I) * kPairBytes, p.cn_nodes[I], p.cn_count[I]);
+            else
+                syn |= coop_phase_tiles<NT, PhaseItem<kPhaseCn, EARLY, LC, I, 0>>(b, s_img, p.cn_nodes[I], p.cn_starts[I], p.cn_count[I]);
         };
         phase_unroll(one, std::make_integer_sequence<int, LC::n>{});
         if (EARLY && it >= 0) {
@@ -599,8 +625,11 @@ __device__ __forceinline__ void coop_phase_body(const CoopPhaseArgs& p, DegreeSe
             constexpr int I = decltype(IC)::value;
             constexpr int D = LV::degree(I);
             constexpr bool PAIR = LV::pm(I) >= 1;
-            vn_lanes_n4<D, false, NT, LV::words, LV::col_base(I), PAIR>(b, s_img + LV::n_pair * kPairBytes, p.vn_nodes[I], p.vn_count[I],
-                                                                        s_img + LV::pair_index(I) * kPairBytes);
+            if (lanes)
+                vn_lanes_n4<D, false, NT, LV::words, LV::col_base(I), PAIR>(b, s_img + LV::n_pair * kPairBytes, p.vn_nodes[I], p.vn_count[I],
+                                                                            s_img + LV::pair_index(I) * kPairBytes);
+            else
+                coop_phase_tiles<NT, PhaseItem<kPhaseVn, false, LV, I, 0>>(b, s_img, p.vn_nodes[I], p.vn_starts[I], p.vn_count[I]);
         };
         phase_unroll(one, std::make_integer_sequence<int, LV::n>{});
     };
@@ -609,8 +638,11 @@ __device__ __forceinline__ void coop_phase_body(const CoopPhaseArgs& p, DegreeSe
         b.it = it; b.iter0 = 0;
         auto one = [&](auto IC) {
             constexpr int I = decltype(IC)::value;
-            vn_lanes_n4<LO::degree(I), true, NT, LO::words, LO::col_base(I), false>(b, s_img + LO::n_pair * kPairBytes, p.vn_nodes[I],
-                                                                                   p.vn_count[I]);
+            if (lanes)
+                vn_lanes_n4<LO::degree(I), true, NT, LO::words, LO::col_base(I), false>(b, s_img + LO::n_pair * kPairBytes, p.vn_nodes[I],
+                                                                                       p.vn_count[I]);
+            else
+                coop_phase_tiles<NT, PhaseItem<kPhaseOut, false, LO, I, 0>>(b, s_img, p.vn_nodes[I], p.vn_starts[I], p.vn_count[I]);
         };
         phase_unroll(one, std::make_integer_sequence<int, LO::n>{});
     };

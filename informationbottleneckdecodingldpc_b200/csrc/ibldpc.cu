@@ -498,7 +498,8 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
     // ---- opt-in: per-frame early termination with frame compaction (ib_perframe.cu)
     if (h->pf_request) return decode_ib_perframe(h, w, a, B, imax, h->pf_inum, st);
     // ---- small batches of the instantiated degree sets: one cooperative launch over the TMA-staged phase images
-    if (h->phase && !h->no_coop_phase && B <= kLaneModeMaxFrames && B <= h->coop_max_frames) {
+    if (h->phase && !h->no_coop_phase && B <= h->coop_max_frames &&
+        (B <= kLaneModeMaxFrames || h->coop_max_from_env || (long long)h->E * pitch4 <= (32LL << 20))) {
         if (h->coop_supported < 0) {
             int v = 0;
             CK(cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, h->device));
@@ -1318,13 +1319,15 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
     if ((rc = phase_prepare(h))) return rc;
     // Batch-size policy between the whole-decode cooperative kernel, the fused per-phase kernels and one launch per degree
     // class (measured on B200, profiles/r02_small_and_mid_batches.txt).  Codes without fused kernels: cooperative kernel up
-    // to 4096 frames.  Instantiated sets: up to 256 frames (lane = (node, word) mapping) one cooperative launch over the
-    // phase images (ib_coop_phase_kernel); above, the 802.11n sets run the fused per-phase kernels at every batch size
-    // (B <= 2048: 1.24-1.34 ms per decode against 2.3-2.9 ms in the table-restaging multi-class cooperative kernel), the
-    // (3,6) and DVB-S2 sets the fused kernels up to 4096 frames and per-class launches above.
+    // to 4096 frames.  Instantiated sets: one cooperative launch over the phase images (ib_coop_phase_kernel) up to 256
+    // frames (lane = (node, word) mapping) and up to 2048 frames while the packed messages stay below 32 MB ((3,6) B=2048
+    // 1.90 -> 1.71 ms, 802.11n 1.34 -> 1.15 ms; DVB-S2 n=64800 loses from 512 frames on: 5.25 -> 5.59 ms); above, the
+    // 802.11n sets run the fused per-phase kernels at every batch size, the (3,6) and DVB-S2 sets the fused kernels up to
+    // 4096 frames and per-class launches above.
     // IBLDPC_COOP_MAX_B / IBLDPC_PHASE_MID_MAX_B / IBLDPC_NO_COOP_PHASE override.
     if (const char* e = getenv("IBLDPC_COOP_MAX_B")) h->coop_max_frames = std::max(0LL, atoll(e));
-    else h->coop_max_frames = h->phase == nullptr ? 4096 : kLaneModeMaxFrames;
+    else h->coop_max_frames = h->phase == nullptr ? 4096 : 2048;
+    h->coop_max_from_env = getenv("IBLDPC_COOP_MAX_B") != nullptr;
     h->no_coop_phase = getenv("IBLDPC_NO_COOP_PHASE") != nullptr;
     h->phase_mid_max_frames = getenv("IBLDPC_PHASE_MID_MAX_B") ? std::max(0LL, atoll(getenv("IBLDPC_PHASE_MID_MAX_B"))) : 4096;
     h->phase_off_midrange = getenv("IBLDPC_NO_PHASE") != nullptr;

@@ -115,6 +115,7 @@ struct ibldpc_decoder {
     long long coop_max_frames = 4096;   // whole-decode cooperative kernel up to this batch size (policy: end of ibldpc_set_luts)
     long long phase_mid_max_frames = 4096;   // instantiated sets without phase_default: fused per-phase kernels up to this batch size
     bool phase_off_midrange = false;    // IBLDPC_NO_PHASE
+    bool coop_max_from_env = false;     // IBLDPC_COOP_MAX_B given: no message-size limit on the cooperative phase-image kernel
     bool no_coop_phase = false;         // IBLDPC_NO_COOP_PHASE=1: small batches through the table-restaging cooperative kernels (ib_coop_n4.cuh)
                                         // (IBLDPC_COOP_MAX_B, 0 disables)
     int coop_supported = -1;        // device attribute cudaDevAttrCooperativeLaunch, queried once

@@ -5,9 +5,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import numpy as np, torch
 import informationbottleneckdecodingldpc_b200 as pkg
 from informationbottleneckdecodingldpc_b200 import codes, luts, graph
-for name, H, irregular, Bs in (("c1", codes.regular_random(8000, 3, 6, seed=20181001), False, (512, 1024, 2048, 4096, 8192, 16384, 32768)),
+for name, H, irregular, Bs in (("c1", codes.regular_random(8000, 3, 6, seed=20181001), False, (512, 1024, 2048, 4096, 8192)),
                                ("dvbs2", codes.dvbs2_like_half_rate(), True, (256, 512, 1024, 2048, 4096)),
-                               ("wlan1296", codes.wlan_80211n(54), True, (2048, 8192, 32768))):
+                               ("wlan1296", codes.wlan_80211n(54), True, (512, 1024, 2048, 4096, 8192))):
     t = graph.edge_tables(H)
     tb = luts.random_tables(16, t.d_c_max, t.d_v_max, 50, seed=1, matching=irregular)
     K = t.n_var - t.n_chk

@@ -718,13 +718,14 @@ def test_small_batch_cooperative_kernels_lane_mode(gpu, code, B, kernel, monkeyp
         assert np.array_equal(out, ref.astype(np.uint8))
 
 
-@pytest.mark.parametrize("code,B,launches", [("reg36", 100, 3), ("reg36", 1000, 2 * 7 + 1), ("reg36", 5000, 2 * 7 + 1),
-                                             ("wlan1296", 2, 3), ("wlan1296", 256, 3), ("wlan1296", 2000, 2 * 7 + 1), ("dvb6480", 2, 3), ("dvb6480", 600, 2 * 7 + 1)])
+@pytest.mark.parametrize("code,B,launches", [("reg36", 100, 3), ("reg36", 1000, 3), ("reg36", 3000, 2 * 7 + 1), ("reg36", 5000, 2 * 7 + 1),
+                                             ("wlan1296", 2, 3), ("wlan1296", 256, 3), ("wlan1296", 2000, 3), ("wlan1296", 3000, 2 * 7 + 1),
+                                             ("dvb6480", 2, 3), ("dvb6480", 600, 3), ("dvb6480", 3000, 2 * 7 + 1)])
 def test_batch_size_policy(gpu, code, B, launches):
     """Default dispatch by batch size (end of ibldpc_set_luts) for the instantiated degree sets: one cooperative launch over
-    the phase images up to 256 frames; above, 802.11n sets -> fused per-phase kernels always, (3,6) and DVB-S2 sets -> fused
-    per-phase kernels up to 4096 frames, one launch per degree class above ((3,6): one class per phase, so the launch count
-    is the same).  Results against the oracle."""
+    the phase images up to 2048 frames (above 256 only while the packed messages stay below 32 MB); above, 802.11n sets ->
+    fused per-phase kernels always, (3,6) and DVB-S2 sets -> fused per-phase kernels up to 4096 frames, one launch per
+    degree class above ((3,6): one class per phase, so the launch count is the same).  Results against the oracle."""
     import torch
     import informationbottleneckdecodingldpc_b200 as pkg
     T, imax = 16, 7
