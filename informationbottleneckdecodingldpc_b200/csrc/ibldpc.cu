@@ -510,7 +510,10 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
     // ---- small batches of regular codes: the whole decode in one cooperative launch (ib_coop_n4.cuh)
     // (worth it while a phase is short: measured break-even near 100 MB of packed messages -- DVB-S2 n=64800 wins at
     // B=512 (58 MB: 9.3 -> 6.9 ms) and loses at B=2048 (232 MB); C1 and 802.11n win up to the 4096-frame limit)
-    const bool coop_fits = B <= h->coop_max_frames && pitch4 <= 8 * 256 && (long long)h->E * pitch4 <= (96LL << 20);
+    // (codes without phase images, or IBLDPC_NO_COOP_PHASE=1: the instantiated sets took the branch above or go on to
+    // the fused per-phase kernels)
+    const bool coop_fits = (h->phase == nullptr || h->no_coop_phase) && B <= h->coop_max_frames && pitch4 <= 8 * 256 &&
+                           (long long)h->E * pitch4 <= (96LL << 20);
     if (h->cn_classes.size() == 1 && h->vn_classes.size() == 1 && coop_fits &&
         (h->cn_classes[0].degree < 6 || (h->use_pair && h->d_cn_pair != nullptr))) {
         if (h->coop_supported < 0) {

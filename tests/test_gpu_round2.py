@@ -720,7 +720,8 @@ def test_small_batch_cooperative_kernels_lane_mode(gpu, code, B, kernel, monkeyp
 
 @pytest.mark.parametrize("code,B,launches", [("reg36", 100, 3), ("reg36", 1000, 3), ("reg36", 3000, 2 * 7 + 1), ("reg36", 5000, 2 * 7 + 1),
                                              ("wlan1296", 2, 3), ("wlan1296", 256, 3), ("wlan1296", 2000, 3), ("wlan1296", 3000, 2 * 7 + 1),
-                                             ("dvb6480", 2, 3), ("dvb6480", 600, 3), ("dvb6480", 3000, 2 * 7 + 1)])
+                                             ("dvb6480", 2, 3), ("dvb6480", 600, 3), ("dvb6480", 3000, 2 * 7 + 1),
+                                             ("dvb16200", 256, 3), ("dvb16200", 2048, 2 * 7 + 1)])   # 56699 edges x 1 KB > 32 MB
 def test_batch_size_policy(gpu, code, B, launches):
     """Default dispatch by batch size (end of ibldpc_set_luts) for the instantiated degree sets: one cooperative launch over
     the phase images up to 2048 frames (above 256 only while the packed messages stay below 32 MB); above, 802.11n sets ->
@@ -730,7 +731,7 @@ def test_batch_size_policy(gpu, code, B, launches):
     import informationbottleneckdecodingldpc_b200 as pkg
     T, imax = 16, 7
     H = codes.regular_random(2000, 3, 6, seed=5) if code == "reg36" else codes.wlan_80211n(54) if code == "wlan1296" \
-        else codes.dvbs2_like_half_rate(6480, q_groups=36)
+        else codes.dvbs2_like_half_rate(6480, q_groups=36) if code == "dvb6480" else codes.dvbs2_like_half_rate(16200, q_groups=90)
     t = graph.edge_tables(H)
     tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=B, matching=code != "reg36")
     if code == "reg36":
