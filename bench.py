@@ -501,6 +501,25 @@ def leg_ib(pkg, name, steps, rank, T_=T, frames=0):
     return res
 
 
+def leg_reference_batches(pkg, rank, decodes=20):
+    """The reference drivers' own batch sizes (msg_at_time = 100 / 2000 / 2: Regular_LDPC_Decoding/BPSK/BER_simulation_OpenCL.py:51,
+    Irregular_LDPC_Decoding/WLAN/BER_simulation_OpenCL.py:77, .../DVB-S2/BER_simulation_OpenCL.py:71): time per decode call with
+    device buffers, fixed i_max, and the WHOLE batch (at most 32 frames of it) against the oracle."""
+    import torch
+    res = {}
+    for name, B, T_ in (("c1", 100, T), ("wlan", 2000, T), ("dvbs2", 2, T), ("wlan", 2000, 32)):   # 32: the reference's WLAN cardinality
+        wl = workload(name)
+        t, tb, quanti, decodi = build_ib(pkg, wl, B, rank, T_)
+        ch = quanti.quantize_direct_OpenCL(t.n_var, B)
+        ms, out = time_steps(lambda: decodi.decode_OpenCL(ch, buffer_in=True, return_buffer=True), decodes, 3, min_warm_s=0.2)
+        res[f"{name}_B{B}" + ("" if T_ == T else f"_T{T_}")] = {"workload": wl["name"] if T_ == T else wl["name"].replace("|T|=16", f"|T|={T_}"), "frames_per_decode": B, "ms_per_decode": ms / decodes,
+                               "value": (t.n_var - t.n_chk) * B * decodes / (ms * 1e-3) / 1e9, "unit": "Gbit/s",
+                               "gpu_launches_per_decode": decodi.info()[1], "parity_sample": parity_sample_ib(decodi, ch, out, t, tb, wl, T_)}
+        del decodi, ch, out
+        torch.cuda.empty_cache()
+    return res
+
+
 def leg_llr(pkg, algo, steps, rank, B=16384):
     """min-sum / BP benchmark decoders on the (3,6) n=8000 graph in float64 (the reference's arithmetic; the only
     precision that meets the >= 99.99 % identical-frames bar, tests/test_gpu_parity.py)."""
@@ -870,6 +889,7 @@ def main():
             legs["minsum_f64"] = leg_llr(pkg, "minsum", args.leg_steps, rank)
             legs["minsum_f64_schedules_early_termination"] = leg_llr_schedules(pkg, args.leg_steps, rank)
             legs["bp_f64"] = leg_llr(pkg, "bp", args.leg_steps, rank)
+            legs["reference_batch_sizes"] = leg_reference_batches(pkg, rank)
         if not args.no_cpu_baseline:
             use_all_host_threads()
             frames = size_cpu_sample(wl, 12.0, T_)
