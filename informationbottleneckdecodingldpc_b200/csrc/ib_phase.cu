@@ -50,12 +50,19 @@ int class_index(const std::vector<NodeClass>& classes, int degree)
 //   stage(j)      -> T*T bytes of look-up stage j of this phase (reference order t*T+m)
 //   match_row(d)  -> T bytes of the matching row of degree d, or nullptr
 //   pair_rows(ci) -> T*T x 8 bytes of the composed tail-pair rows of class index ci (handle order), or nullptr
+//   tri_table     -> 16^3 bytes of the three-input table of this phase (ib_triple_n4.cuh), classes written d + 300 only
 template <typename StageFn, typename MatchFn, typename PairFn>
 void build_image(uint8_t* img, const PhaseLayoutRt& L, int mode, int T, const std::vector<NodeClass>& classes, StageFn stage,
-                 MatchFn match_row, PairFn pair_rows)
+                 MatchFn match_row, PairFn pair_rows, const uint8_t* tri_table = nullptr)
 {
     memset(img, 0, (size_t)L.image_bytes);
-    uint32_t* tab = reinterpret_cast<uint32_t*>(img + (size_t)L.n_pair * kPairBytes);
+    uint32_t* tab = reinterpret_cast<uint32_t*>(img + (size_t)L.tab_offset);
+    if (L.tab_offset != L.tri_offset && tri_table != nullptr) {
+        // per-lane replicated: word q of the shared-memory table = word q >> 5 of the compact one
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tri_table);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(img + (size_t)L.tri_offset);
+        for (int q = 0; q < kTripleBytes / 4; ++q) dst[q] = src[q >> 5];
+    }
     const int W = L.words;
     for (int i = 0; i < L.n; ++i) {
         const PhaseClassLayout& c = L.cls[i];
@@ -97,9 +104,8 @@ void build_image(uint8_t* img, const PhaseLayoutRt& L, int mode, int T, const st
 
 }  // namespace
 
-void phase_free(ibldpc_decoder* h)
+static void free_images(PhaseImages*& p)
 {
-    PhaseImages* p = h->phase;
     if (!p) return;
     if (p->d_images) cudaFree(p->d_images);
     for (int i = 0; i < kPhaseMaxClasses; ++i) {
@@ -107,33 +113,23 @@ void phase_free(ibldpc_decoder* h)
         if (p->vn_starts[i]) cudaFree(p->vn_starts[i]);
     }
     delete p;
-    h->phase = nullptr;
+    p = nullptr;
 }
 
-// Called at the end of ibldpc_set_luts (packed-nibble family, default tail-pair thresholds): picks the instantiated
-// degree set of this code, expands every phase image on the host and uploads them.  Leaves h->phase == nullptr
-// (per-class launches) when the code's degree sets are not instantiated.
-int phase_prepare(ibldpc_decoder* h)
+void phase_free(ibldpc_decoder* h)
 {
-    phase_free(h);
-    if (!h->nib || !h->use_pair || !h->use_phase) return IBLDPC_OK;
-    // Measured on B200 (profiles/README.md, round 2): the fused kernels sit on the same look-up-pipe / issue ceiling as
-    // the per-class ones, so they win where a phase is several launches with short classes (802.11n: 3.01 -> 3.51
-    // Gbit/s) and lose a few per cent where one class dominates a phase (DVB-S2 rate 1/2: 4.15 -> 3.95, regular (3,6):
-    // 6.01 -> 5.82).  Default: on for the 802.11n degree sets; IBLDPC_PHASE=1 turns them on for every instantiated set.
-    struct Cand { const PhaseSetOps* ops; bool by_default; };
-    const Cand candidates[] = {{phase_ops_wlan(), true}, {phase_ops_dvbs2(), false}, {phase_ops_reg36(), false}};
-    const bool force = getenv("IBLDPC_PHASE") != nullptr && atoi(getenv("IBLDPC_PHASE")) != 0;
-    const PhaseSetOps* ops = nullptr;
-    h->phase_default = false;
-    for (const Cand& c : candidates)
-        if (same_degrees(c.ops->cn_deg, h->cn_classes) && same_degrees(c.ops->vn_deg, h->vn_classes)) {
-            ops = c.ops;                                   // images are built for every instantiated set (per-frame early
-            h->phase_default = c.by_default || force;      // termination runs on them); the plain decode uses them by default
-        }                                                  // only where they win
-    if (!ops) return IBLDPC_OK;
+    free_images(h->phase);
+    free_images(h->phase_tri);
+}
+
+// images the per-frame-early-termination kernels run on
+static PhaseImages* pf_images(const ibldpc_decoder* h) { return h->phase_tri ? h->phase_tri : h->phase; }
+
+// expands every phase image of the degree set `ops` on the host and uploads them
+static int build_phase_images(ibldpc_decoder* h, const PhaseSetOps* ops, PhaseImages** out)
+{
     PhaseImages* p = new PhaseImages();
-    h->phase = p;
+    *out = p;
     p->ops = ops;
     p->imax = h->lut_imax;
     const int T = h->T, TT = T * T, DC = h->DC, DV = h->DV, imax = h->lut_imax;
@@ -149,13 +145,15 @@ int phase_prepare(ibldpc_decoder* h)
             host.data() + (size_t)blk * p->cn_bytes, ops->cn_layout, kPhaseCn, T, h->cn_classes,
             [&](int j) { return h->h_cn8.data() + ((size_t)blk * (DC - 2) + j) * TT; },
             [&](int d) -> const uint8_t* { return h->match ? h->h_mc8.data() + ((size_t)blk * DC + (d - 1)) * T : nullptr; },
-            [&](int ci) { return h->h_cn_pair.data() + ((size_t)blk * ncc + ci) * (size_t)TT * 8; });
+            [&](int ci) { return h->h_cn_pair.data() + ((size_t)blk * ncc + ci) * (size_t)TT * 8; },
+            h->h_cn3.empty() ? nullptr : h->h_cn3.data() + (size_t)blk * kTripleEntries);
         // variable-node update of iteration blk
         build_image(
             host.data() + (size_t)imax * p->cn_bytes + (size_t)blk * p->vn_bytes, ops->vn_layout, kPhaseVn, T, h->vn_classes,
             [&](int j) { return h->h_vn8.data() + ((size_t)blk * DV + j) * TT; },
             [&](int d) -> const uint8_t* { return h->match ? h->h_mv8.data() + ((size_t)blk * DV + (d - 1)) * T : nullptr; },
-            [&](int ci) { return h->h_vn_pair.data() + ((size_t)blk * nvc + ci) * (size_t)TT * 8; });
+            [&](int ci) { return h->h_vn_pair.data() + ((size_t)blk * nvc + ci) * (size_t)TT * 8; },
+            h->h_vn3.empty() ? nullptr : h->h_vn3.data() + (size_t)blk * kTripleEntries);
         // decision with the variable-node tables of iteration blk (no message alignment on the output)
         build_image(
             host.data() + (size_t)imax * (p->cn_bytes + p->vn_bytes) + (size_t)blk * p->out_bytes, ops->out_layout, kPhaseOut, T,
@@ -188,15 +186,46 @@ int phase_prepare(ibldpc_decoder* h)
     return IBLDPC_OK;
 }
 
+// Called at the end of ibldpc_set_luts (packed-nibble family, default tail-pair thresholds): picks the instantiated
+// degree set of this code, expands every phase image on the host and uploads them.  Leaves h->phase == nullptr
+// (per-class launches) when the code's degree sets are not instantiated.
+int phase_prepare(ibldpc_decoder* h)
+{
+    phase_free(h);
+    if (!h->nib || !h->use_pair || !h->use_phase) return IBLDPC_OK;
+    // Measured on B200 (profiles/README.md, round 2): the fused kernels sit on the same look-up-pipe / issue ceiling as
+    // the per-class ones, so they win where a phase is several launches with short classes (802.11n: 3.01 -> 3.51
+    // Gbit/s) and lose a few per cent where one class dominates a phase (DVB-S2 rate 1/2: 4.15 -> 3.95, regular (3,6):
+    // 6.01 -> 5.82).  Default: on for the 802.11n degree sets; IBLDPC_PHASE=1 turns them on for every instantiated set.
+    struct Cand { const PhaseSetOps* ops; bool by_default; };
+    const Cand candidates[] = {{phase_ops_wlan(), true}, {phase_ops_dvbs2(), false}, {phase_ops_reg36(), false}};
+    const bool force = getenv("IBLDPC_PHASE") != nullptr && atoi(getenv("IBLDPC_PHASE")) != 0;
+    const PhaseSetOps* ops = nullptr;
+    h->phase_default = false;
+    for (const Cand& c : candidates)
+        if (same_degrees(c.ops->cn_deg, h->cn_classes) && same_degrees(c.ops->vn_deg, h->vn_classes)) {
+            ops = c.ops;                                   // images are built for every instantiated set (per-frame early
+            h->phase_default = c.by_default || force;      // termination runs on them); the plain decode uses them by default
+        }                                                  // only where they win
+    if (!ops) return IBLDPC_OK;
+    if (int rc = build_phase_images(h, ops, &h->phase)) return rc;
+    // the (3,6) set a second time through the three-input tables: per-frame early termination runs on these images
+    // (check-node pass 547 -> 430 us, variable-node pass 450 -> 350 us at 65536 frames); the plain images stay the ones of
+    // the small-batch and mid-range paths, where a 192 KB image per launch would cost more than the look-ups it saves
+    if (ops == phase_ops_reg36() && !h->h_cn3.empty() && !h->h_vn3.empty() && getenv("IBLDPC_NO_PF_TRIPLE") == nullptr)
+        if (int rc = build_phase_images(h, phase_ops_reg36_tri(), &h->phase_tri)) return rc;
+    return IBLDPC_OK;
+}
+
 bool phase_available(const ibldpc_decoder* h) { return h->phase != nullptr; }
 
-const PhaseSetOps* phase_ops_of(const ibldpc_decoder* h) { return h->phase ? h->phase->ops : nullptr; }
+const PhaseSetOps* phase_ops_of(const ibldpc_decoder* h) { return pf_images(h) ? pf_images(h)->ops : nullptr; }
 
 // image pointer, node lists and dynamic shared memory of one phase: mode kPhaseCn with table block `index`,
 // kPhaseVn with iteration `index`, kPhaseOut with the decision tables of iteration `index` (per-frame mode)
 void phase_fill_args(const ibldpc_decoder* h, int mode, int index, PhaseArgs& q, size_t* smem)
 {
-    const PhaseImages* p = h->phase;
+    const PhaseImages* p = pf_images(h);
     const PhaseSetOps* ops = p->ops;
     if (mode == kPhaseCn) {
         q.image = p->d_images + (size_t)index * p->cn_bytes;
@@ -219,9 +248,8 @@ void phase_fill_args(const ibldpc_decoder* h, int mode, int index, PhaseArgs& q,
     }
 }
 
-int phase_set_attributes(ibldpc_decoder* h)
+static int set_attributes(PhaseImages* p)
 {
-    PhaseImages* p = h->phase;
     const PhaseSetOps* ops = p->ops;
     if (p->occ_checked) return IBLDPC_OK;
     const struct { const void* k; size_t smem; } ks[] = {{(const void*)ops->cn_kernel[0], p->cn_bytes}, {(const void*)ops->cn_kernel[1], p->cn_bytes},
@@ -239,6 +267,12 @@ int phase_set_attributes(ibldpc_decoder* h)
     }
     p->occ_checked = 1;
     return IBLDPC_OK;
+}
+
+int phase_set_attributes(ibldpc_decoder* h)
+{
+    if (int rc = set_attributes(h->phase)) return rc;
+    return h->phase_tri ? set_attributes(h->phase_tri) : IBLDPC_OK;
 }
 
 namespace {

@@ -25,6 +25,7 @@
 
 #include "ib_coop_n4.cuh"   // DegreeSet
 #include "ib_kernels_n4.cuh"
+#include "ib_triple_n4.cuh"
 
 namespace ibldpc {
 
@@ -51,7 +52,10 @@ __host__ __device__ constexpr int phase_pm(int mode, int v)
     if (v >= 100) return v / 100 - 1;
     return mode == kPhaseCn ? (v >= kPhaseCnPairMin ? 1 : 0) : (v >= kPhaseVnPairMin ? 1 : 0);
 }
-__host__ __device__ constexpr bool phase_pair(int mode, int v) { return phase_pm(mode, v) >= 1; }
+// pm = 2 (written d + 300): the three-input table of ib_triple_n4.cuh -- check nodes of degree 6 (next to the tail-pair rows),
+// variable nodes of degree 3 (instead of any stage column); single-class sets only (the table is 128 KB).
+__host__ __device__ constexpr bool phase_pair(int mode, int v) { return mode == kPhaseCn ? phase_pm(mode, v) >= 1 : phase_pm(mode, v) == 1; }
+__host__ __device__ constexpr bool phase_tri(int mode, int v) { return phase_pm(mode, v) == 2; }
 // words (8 frames each) a lane moves per message row: the widest access the register budget of 64 allows
 __host__ __device__ constexpr int phase_vec(int mode, int d)
 {
@@ -83,19 +87,32 @@ struct PhaseLayout {
         return c;
     }
     static constexpr int words = total_cols() <= 4 ? 1 : (total_cols() + 3) / 4;
+    __host__ __device__ static constexpr bool pair(int i) { return phase_pair(MODE, spec(i)); }
+    __host__ __device__ static constexpr bool tri(int i) { return phase_tri(MODE, spec(i)); }
     __host__ __device__ static constexpr int pair_index(int i)
     {
         int p = 0;
-        for (int j = 0; j < i; ++j) p += pm(j);
+        for (int j = 0; j < i; ++j) p += pair(j) ? 1 : 0;
+        return p;
+    }
+    __host__ __device__ static constexpr int tri_count()
+    {
+        int p = 0;
+        for (int j = 0; j < n; ++j) p += tri(j) ? 1 : 0;
         return p;
     }
     static constexpr int n_pair = pair_index(n);
-    static constexpr int image_bytes = n_pair * (int)kPairBytes + n4_table_bytes(words);
+    static constexpr int n_tri = tri_count();
+    static_assert(n_tri == 0 || n == 1, "three-input table: single-class degree sets only");
+    // image: [tail-pair rows of the classes][three-input table][stage columns]
+    static constexpr int tri_offset = n_pair * (int)kPairBytes;
+    static constexpr int tab_offset = tri_offset + n_tri * kTripleBytes;
+    static constexpr int image_bytes = tab_offset + n4_table_bytes(words);
 };
 
 // run-time description of the same layout for the host-side image builder (ib_phase.cu)
-struct PhaseClassLayout { int degree, col_base, cols, pair_index, vec, pm; bool pair; };
-struct PhaseLayoutRt { int n, words, n_pair, image_bytes; PhaseClassLayout cls[kPhaseMaxClasses]; };
+struct PhaseClassLayout { int degree, col_base, cols, pair_index, vec, pm; bool pair, tri; };
+struct PhaseLayoutRt { int n, words, n_pair, image_bytes, tri_offset, tab_offset; PhaseClassLayout cls[kPhaseMaxClasses]; };
 
 template <int MODE, int... Ds>
 PhaseLayoutRt phase_layout_rt(DegreeSet<Ds...>)
@@ -103,9 +120,10 @@ PhaseLayoutRt phase_layout_rt(DegreeSet<Ds...>)
     using L = PhaseLayout<MODE, Ds...>;
     PhaseLayoutRt r{};
     r.n = L::n; r.words = L::words; r.n_pair = L::n_pair; r.image_bytes = L::image_bytes;
+    r.tri_offset = L::tri_offset; r.tab_offset = L::tab_offset;
     for (int i = 0; i < L::n; ++i) {
         const int d = L::degree(i);
-        r.cls[i] = PhaseClassLayout{d, L::col_base(i), phase_cols(MODE, d), L::pair_index(i), phase_vec(MODE, d), L::pm(i), L::pm(i) >= 1};
+        r.cls[i] = PhaseClassLayout{d, L::col_base(i), phase_cols(MODE, d), L::pair_index(i), phase_vec(MODE, d), L::pm(i), L::pair(i), L::tri(i)};
     }
     return r;
 }
@@ -199,17 +217,20 @@ struct PhaseItem {
     static constexpr int WT = L::words;
     static constexpr int CB = L::col_base(I);
     static constexpr int PM = L::pm(I);
-    static constexpr bool PAIR = PM >= 1;
+    static constexpr bool PAIR = L::pair(I);
+    static constexpr bool TRI = L::tri(I);
+    static_assert(!TRI || (MODE == kPhaseCn && D == 6 && L::words == 1 && L::col_base(I) == 0) || (MODE == kPhaseVn && D == 3),
+                  "three-input table: check nodes of degree 6 / variable nodes of degree 3");
     static constexpr int PI = L::pair_index(I);
 
     // returns the syndrome bits seen (check-node phase with EARLY), 0 otherwise
     static __device__ __forceinline__ uint32_t run(const IbArgs& a, const uint8_t* s_img, int node, int start, uint32_t col,
                                                    uint32_t lane4, const PfCtx& pf)
     {
-        const uint8_t* tab = s_img + L::n_pair * kPairBytes;
-        const uint8_t* ptab = s_img + PI * kPairBytes;
+        const uint8_t* tab = s_img + L::tab_offset;
+        const uint8_t* ptab = s_img + PI * kPairBytes;   // the three-input table of a check-node class follows its pair rows
         if constexpr (MODE == kPhaseCn) {
-            return cn_node_n4<D, false, EARLY, VEC, PAIR, WT, CB, PF>(a, tab, ptab, start, col, lane4, a.B - 2 * (int)col,
+            return cn_node_n4<D, false, EARLY, VEC, PAIR, WT, CB, PF, TRI ? 1 : 0>(a, tab, ptab, start, col, lane4, a.B - 2 * (int)col,
                                                                       PF ? pf.fsyn + (col >> 2) : nullptr,
                                                                       PF ? pf.alive + (col >> 2) : nullptr, PF ? pf.fsyn_s + col : 0u);
         } else {
@@ -234,7 +255,8 @@ struct PhaseItem {
                 uint32_t w[D], o[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) w[k] = in.m[k][j];
-                if constexpr (PAIR) vn_word_n4_pair<D, WT, CB>(in.c[j], w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
+                if constexpr (TRI && D == 3) vn3_word_n4(in.c[j], w, o, s_img + L::tri_offset, lane4);
+                else if constexpr (PAIR) vn_word_n4_pair<D, WT, CB>(in.c[j], w, o, tab, ptab, lane4, (lane4 & (4u * (kPairSlots - 1))) * 2u);
                 else vn_word_n4<D, DECIDE, WT, CB>(in.c[j], w, o, dec[2 * j], dec[2 * j + 1], tab, lane4);
                 if (!DECIDE) {
                     if constexpr (PF) {
@@ -429,7 +451,7 @@ struct PfDecideItem {
     static __device__ __forceinline__ uint32_t run(const IbArgs& a, const uint8_t* s_img, int node, int start, const int (&cols)[8],
                                                    uint32_t lane4)
     {
-        const uint8_t* tab = s_img + L::n_pair * kPairBytes;
+        const uint8_t* tab = s_img + L::tab_offset;
         const uint32_t chw = pf_gather8<D>(a.ch + (uint64_t)(uint32_t)node * a.pitch, cols);
         uint32_t w[D], o[D], dlo, dhi;
 #pragma unroll
@@ -605,10 +627,10 @@ __device__ __forceinline__ void coop_phase_body(const CoopPhaseArgs& p, DegreeSe
         auto one = [&](auto IC) {
             constexpr int I = decltype(IC)::value;
             constexpr int D = LC::degree(I);
-            constexpr bool PAIR = LC::pm(I) >= 1;
+            constexpr bool PAIR = LC::pair(I);
             if (lanes)
                 syn |= cn_lanes_n4<D, false, EARLY, PAIR, NT, LC::words, LC::col_base(I)>(
-                    b, s_img + LC::n_pair * kPairBytes, s_img + LC::pair_index(I) * kPairBytes, p.cn_nodes[I], p.cn_count[I]);
+                    b, s_img + LC::tab_offset, s_img + LC::pair_index(I) * kPairBytes, p.cn_nodes[I], p.cn_count[I]);
             else
                 syn |= coop_phase_tiles<NT, PhaseItem<kPhaseCn, EARLY, LC, I, 0>>(b, s_img, p.cn_nodes[I], p.cn_starts[I], p.cn_count[I]);
         };
@@ -624,9 +646,9 @@ __device__ __forceinline__ void coop_phase_body(const CoopPhaseArgs& p, DegreeSe
         auto one = [&](auto IC) {
             constexpr int I = decltype(IC)::value;
             constexpr int D = LV::degree(I);
-            constexpr bool PAIR = LV::pm(I) >= 1;
+            constexpr bool PAIR = LV::pair(I);
             if (lanes)
-                vn_lanes_n4<D, false, NT, LV::words, LV::col_base(I), PAIR>(b, s_img + LV::n_pair * kPairBytes, p.vn_nodes[I], p.vn_count[I],
+                vn_lanes_n4<D, false, NT, LV::words, LV::col_base(I), PAIR>(b, s_img + LV::tab_offset, p.vn_nodes[I], p.vn_count[I],
                                                                             s_img + LV::pair_index(I) * kPairBytes);
             else
                 coop_phase_tiles<NT, PhaseItem<kPhaseVn, false, LV, I, 0>>(b, s_img, p.vn_nodes[I], p.vn_starts[I], p.vn_count[I]);
@@ -639,7 +661,7 @@ __device__ __forceinline__ void coop_phase_body(const CoopPhaseArgs& p, DegreeSe
         auto one = [&](auto IC) {
             constexpr int I = decltype(IC)::value;
             if (lanes)
-                vn_lanes_n4<LO::degree(I), true, NT, LO::words, LO::col_base(I), false>(b, s_img + LO::n_pair * kPairBytes, p.vn_nodes[I],
+                vn_lanes_n4<LO::degree(I), true, NT, LO::words, LO::col_base(I), false>(b, s_img + LO::tab_offset, p.vn_nodes[I],
                                                                                        p.vn_count[I]);
             else
                 coop_phase_tiles<NT, PhaseItem<kPhaseOut, false, LO, I, 0>>(b, s_img, p.vn_nodes[I], p.vn_starts[I], p.vn_count[I]);

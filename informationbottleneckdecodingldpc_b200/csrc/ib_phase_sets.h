@@ -47,6 +47,7 @@ PhaseSetOps make_phase_ops(const char* name, DegreeSet<Cs...> cs, DegreeSet<Vs..
 
 const PhaseSetOps* phase_ops_wlan();     // IEEE 802.11n rate 1/2: d_c {8,7}, d_v {11,4,3,2}   (generate_802.11_matrix.py)
 const PhaseSetOps* phase_ops_dvbs2();    // DVB-S2 rate 1/2: d_c {7,6}, d_v {8,3,2,1}           (DVB-S2/decoder_config_generation.py:32-34)
+const PhaseSetOps* phase_ops_reg36_tri();  // the same code through the three-input tables (d + 300): per-frame early termination
 const PhaseSetOps* phase_ops_reg36();    // regular (3,6): d_c {6}, d_v {3}                       (Regular_LDPC_Decoding/BPSK)
 
 }  // namespace ibldpc

@@ -1270,6 +1270,7 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
     // Three-input table of the degree-3 variable-node update (ib_triple_n4.cuh): F(a, b, c) = M_3( S_1( S_0(a, b), c ) ),
     // index b*256 + c*16 + a (channel value minor), one byte per entry, for every iteration
     if (h->d_vn3) { CK(cudaFree(h->d_vn3)); h->d_vn3 = nullptr; }
+    h->h_vn3.clear(); h->h_cn3.clear();
     h->use_triple = getenv("IBLDPC_NO_TRIPLE") == nullptr;
     {
         bool has3 = false;
@@ -1291,6 +1292,7 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
                         }
             }
             if ((rc = upload(&h->d_vn3, f3.data(), f3.size()))) return rc;
+            h->h_vn3.swap(f3);
         }
     }
     // ... and of the first two check-node stages for the degree-6 class: F(x, y, z) = 4 * C_1( C_0(x, y), z ), index
@@ -1312,6 +1314,7 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
                         for (int z = 0; z < T; ++z) dst[(y * kTS + z) * kTS + x] = (uint8_t)(4 * C1[C0[x * T + y] * T + z]);
             }
             if ((rc = upload(&h->d_cn3, f3.data(), f3.size()))) return rc;
+            h->h_cn3.swap(f3);
         }
     }
     // Fused per-phase kernels (ib_phase_n4.cuh): default whenever the code's degree sets are instantiated; every switch

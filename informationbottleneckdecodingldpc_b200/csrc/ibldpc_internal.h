@@ -103,6 +103,7 @@ struct ibldpc_decoder {
     std::vector<uint8_t> h_cn8, h_vn8, h_mc8, h_mv8;   // host copies of the uint8 tables (image builders)
     uint8_t* d_cn_pair = nullptr;   // [imax blocks][cn classes][T*T rows][8 bytes] composed tail-pair tables
     uint8_t* d_vn_pair = nullptr;   // [imax][vn classes][T*T rows][8 bytes] composed tail-pair tables of the VN update
+    std::vector<uint8_t> h_cn3, h_vn3;   // host copies of d_cn3 / d_vn3 (phase images of the three-input-table set)
     uint8_t* d_vn3 = nullptr;       // [imax][16*16*16] three-input table of the degree-3 variable-node update (ib_triple_n4.cuh)
     uint8_t* d_cn3 = nullptr;       // [imax blocks][16*16*16] three-input table of the first two check-node stages, values * 4
     int cn_tri_max_degree = 8;      // check-node classes of degree 6..this run the three-input-table kernel (IBLDPC_CN_TRI_MAX_DEGREE)
@@ -131,6 +132,7 @@ struct ibldpc_decoder {
     int host_chunk = 0;   // 0 = auto: about 256 MiB of channel values per chunk
     // fused per-phase kernels (ib_phase_n4.cuh): one launch per phase over all degree classes
     ibldpc::PhaseImages* phase = nullptr;
+    ibldpc::PhaseImages* phase_tri = nullptr;   // (3,6) set through the three-input tables: per-frame early termination runs on it
     ibldpc::T32Images* t32_images = nullptr;
     ibldpc::LayerPlan* layers = nullptr;   // layered LLR schedule (llr_layered.cu), built at the first layered decode
     int use_phase = 1;    // IBLDPC_NO_PHASE=1 keeps one launch per degree class

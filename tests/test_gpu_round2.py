@@ -417,15 +417,19 @@ def _per_frame_oracle(t, ch, T, imax, tb):
 
 
 @pytest.mark.parametrize("code,B,ebn0", [("wlan1296", 300, 2.2), ("wlan1296", 4099, 2.2), ("wlan1296", 1, 2.2), ("reg36", 333, 2.0),
-                                         ("dvb6480", 130, 1.6)])
-def test_per_frame_early_termination_equals_single_frame_reference(gpu, code, B, ebn0):
+                                         ("reg36", 2500, 1.8), ("reg36_notriple", 333, 2.0), ("dvb6480", 130, 1.6)])
+def test_per_frame_early_termination_equals_single_frame_reference(gpu, code, B, ebn0, monkeypatch):
     """early_termination='frame': outputs AND per-frame i_num equal to the oracle run with one frame per call, with
     frames converging at different passes (designed tables, channel draws near the waterfall), frames that never
-    converge, and several compactions on the way."""
+    converge, and several compactions on the way.  The (3,6) set runs on the phase images with the three-input tables
+    (ib_phase_reg36_tri.cu); reg36_notriple = IBLDPC_NO_PF_TRIPLE=1, the plain tail-pair images."""
     import torch
     import informationbottleneckdecodingldpc_b200 as pkg
     from informationbottleneckdecodingldpc_b200.decoder_config_generation import generate_irregular_config, generate_regular_config
     T, imax = 16, 25
+    if code == "reg36_notriple":
+        monkeypatch.setenv("IBLDPC_NO_PF_TRIPLE", "1")
+        code = "reg36"
     if code == "reg36":
         H = codes.regular_random(2000, 3, 6, seed=5)
         tb, _ = generate_regular_config(1.2, 3, 6, T, imax)
