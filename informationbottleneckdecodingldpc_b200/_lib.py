@@ -12,7 +12,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IBLDPC_LIB") or os.path.join(HERE, "libibldpc.so")   # IBLDPC_LIB: A/B builds of the same sources
 UNITS = ["ibldpc.cu", "ib_fast_cn.cu", "ib_fast_vn.cu", "ib_n4_cn_v2.cu", "ib_n4_cn_pair.cu", "ib_n4_vn_pair.cu", "ib_n4_vn_v2.cu", "ib_n4_vn_v4.cu", "ib_n4_vn3.cu", "ib_n4_coop.cu",
-         "llr_f32.cu", "llr_f64.cu", "encoder.cu", "nccl_abi.cu", "ib_phase.cu", "ib_phase_wlan.cu", "ib_phase_dvbs2.cu", "ib_phase_reg36.cu", "ib_phase_reg36_tri.cu", "ib_perframe.cu", "llr_layered.cu", "ib_t32.cu", "ib_t32_cn.cu", "ib_t32_vn.cu", "ib_t32_out.cu"]   # compiled in parallel
+         "llr_f32.cu", "llr_f64.cu", "encoder.cu", "nccl_abi.cu", "ib_phase.cu", "ib_phase_wlan.cu", "ib_phase_dvbs2.cu", "ib_phase_reg36.cu", "ib_phase_reg36_tri.cu", "ib_perframe.cu", "llr_layered.cu", "ib_t32.cu", "ib_t32_cn.cu", "ib_t32_vn.cu", "ib_t32_out.cu", "ib_t32_phase.cu"]   # compiled in parallel
 SOURCES = [os.path.join(HERE, "csrc", f) for f in UNITS + ["ib_kernels.cuh", "ib_kernels_n4.cuh", "ib_coop_n4.cuh", "llr_kernels.cuh", "kernel_tables.h", "ibldpc_internal.h", "ib_phase_n4.cuh", "ib_phase_sets.h", "ib_kernels_t32.cuh", "ib_triple_n4.cuh"]]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "ibldpc.h")
 

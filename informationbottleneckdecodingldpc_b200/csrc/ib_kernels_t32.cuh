@@ -298,6 +298,157 @@ __global__ void __launch_bounds__(kT32Threads, 1) ib_t32_kernel(T32Args p)
     if (!have_image) phase_image_wait(&s_mbar);
 }
 
+// ---- fused per-phase kernel: ONE launch per phase, the degree classes one after the other inside every CTA ---------
+// The per-class launches above pay launch latency + a 32-200 KB image per class and leave a partial wave behind every
+// class (802.11n: 6 launches per iteration, the four small ones 11-26 us each at B = 32768; 300 launches per decode).
+// Here a CTA owns a contiguous share of the items of EVERY class and walks through the classes: block barrier, one thread
+// issues the TMA copy of the next class's image into the same shared-memory buffer, block barrier, dynamic item loop of
+// that class (t32_item<MODE, EARLY, D>, selected by a switch over the class degree).  CTAs do not wait for each other, so
+// nothing but a CTA's own last item sits between two classes.  Any degree set of up to kT32MaxClasses classes.
+constexpr int kT32MaxClasses = 4;
+struct T32PhaseArgs {
+    IbArgs a;
+    int n_cls;
+    int deg[kT32MaxClasses];                    // heaviest class first
+    const uint8_t* image[kT32MaxClasses];       // table image of every class for this launch
+    long long image_stride[kT32MaxClasses];     // decision phase: bytes between the images of consecutive iterations
+    const int* nodes[kT32MaxClasses];
+    const int* starts[kT32MaxClasses];
+    int n_nodes[kT32MaxClasses];
+};
+
+__device__ __forceinline__ void t32_wait_parity(uint64_t* mbar, uint32_t parity)
+{
+    const uint32_t mb = smem_u32(mbar);
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(mb), "r"(parity)
+            : "memory");
+    }
+}
+
+// item loop of one class inside the fused kernel: items [., hi) of this CTA, first 32 taken statically, the rest from s_next
+template <int MODE, bool EARLY, int D>
+__device__ __forceinline__ uint32_t t32_class_items(const IbArgs& a, const uint8_t* s_img, const int* __restrict__ nodes,
+                                                    const int* __restrict__ starts, int lo, int hi, int* s_next, uint64_t* mbar,
+                                                    uint32_t parity, bool tables)
+{
+    constexpr int VEC = t32_vec(MODE, D);
+    const int lane = threadIdx.x & 31;
+    const uint32_t lane4 = lane * 4;
+    const uint32_t tl = (a.pitch + 128u * VEC - 1) / (128u * VEC);
+    uint32_t syn = 0;
+    bool have_image = !tables;
+    int i = lo + (threadIdx.x >> 5);
+    int node = 0, start = 0;
+    if (i < hi) {
+        const uint32_t ni = (uint32_t)i / tl;
+        node = nodes[ni];
+        start = starts[ni];
+    }
+    while (i < hi) {
+        int i2 = 0;
+        if (lane == 0) i2 = atomicAdd(s_next, 1);
+        i2 = __shfl_sync(0xffffffffu, i2, 0);
+        int node2 = 0, start2 = 0;
+        if (i2 < hi) {
+            const uint32_t ni2 = (uint32_t)i2 / tl;
+            node2 = nodes[ni2];
+            start2 = starts[ni2];
+        }
+        const uint32_t tile = (uint32_t)i - ((uint32_t)i / tl) * tl;
+        const uint32_t col = (tile * 32u + lane) * (4u * VEC);
+        if (!have_image) {
+            t32_wait_parity(mbar, parity);
+            have_image = true;
+        }
+        if (col < a.pitch) syn |= t32_item<MODE, EARLY, D>(a, s_img, node, start, col, lane4);
+        i = i2;
+        node = node2;
+        start = start2;
+    }
+    if (!have_image) t32_wait_parity(mbar, parity);   // every warp observes every copy: the barrier is re-armed for the next class
+    return syn;
+}
+
+template <int MODE, bool EARLY>
+__global__ void __launch_bounds__(kT32Threads, 1) ib_t32_phase_kernel(T32PhaseArgs p)
+{
+    extern __shared__ __align__(128) uint8_t s_img[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ int s_next;
+    const IbArgs& a = p.a;
+    if (MODE != kPhaseOut && (EARLY || a.early) && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
+    const uint32_t mb = smem_u32(&s_mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (MODE == kPhaseOut && blockIdx.x == 0) *a.inum = executed_passes(a) + 1;
+    }
+    uint32_t parity = 0, syn = 0;
+    for (int c = 0; c < p.n_cls; ++c) {
+        const int d = p.deg[c];
+        const int nst = t32_cols(MODE, d);
+        const uint32_t vec = (uint32_t)t32_vec(MODE, d);
+        const uint32_t tl = (a.pitch + 128u * vec - 1) / (128u * vec);
+        const long long items = (long long)p.n_nodes[c] * tl;
+        const int lo = (int)(items * blockIdx.x / gridDim.x), hi = (int)(items * (blockIdx.x + 1) / gridDim.x);
+        if (hi <= lo) continue;              // uniform per CTA: nothing of this class here, no image needed
+        const bool tables = nst > 0;
+        __syncthreads();                     // every warp has left the previous image and counter (first class: mbarrier initialised)
+        if (threadIdx.x == 0) {
+            s_next = lo + kT32Threads / 32;
+            if (tables) {
+                const uint8_t* img = p.image[c];
+                if (MODE == kPhaseOut) img += (long long)executed_passes(a) * p.image_stride[c];
+                const uint32_t bytes = (uint32_t)t32_image_bytes(nst);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the old image before the async writes
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+                constexpr uint32_t kChunk = 32768;
+                const uint32_t dst = smem_u32(s_img);
+                for (uint32_t off = 0; off < bytes; off += kChunk) {
+                    const uint32_t n = bytes - off < kChunk ? bytes - off : kChunk;
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                                 "l"(img + off), "r"(n), "r"(mb)
+                                 : "memory");
+                }
+            }
+        }
+        __syncthreads();
+#define IBLDPC_T32_CASE(DD) \
+    case DD: syn |= t32_class_items<MODE, EARLY, DD>(a, s_img, p.nodes[c], p.starts[c], lo, hi, &s_next, &s_mbar, parity, tables); break;
+        if constexpr (MODE == kPhaseCn) {
+            switch (d) {
+                IBLDPC_T32_CASE(3) IBLDPC_T32_CASE(4) IBLDPC_T32_CASE(5) IBLDPC_T32_CASE(6)
+                IBLDPC_T32_CASE(7) IBLDPC_T32_CASE(8) IBLDPC_T32_CASE(9) IBLDPC_T32_CASE(10)
+            default: break;
+            }
+        } else {
+            switch (d) {
+                IBLDPC_T32_CASE(1) IBLDPC_T32_CASE(2) IBLDPC_T32_CASE(3) IBLDPC_T32_CASE(4) IBLDPC_T32_CASE(5) IBLDPC_T32_CASE(6)
+                IBLDPC_T32_CASE(7) IBLDPC_T32_CASE(8) IBLDPC_T32_CASE(9) IBLDPC_T32_CASE(10) IBLDPC_T32_CASE(11) IBLDPC_T32_CASE(12)
+            default: break;
+            }
+        }
+#undef IBLDPC_T32_CASE
+        if (tables) parity ^= 1u;
+    }
+    if (MODE == kPhaseCn && EARLY && !a.iter0) {
+        const unsigned any = __ballot_sync(0xffffffffu, syn != 0);
+        if (any != 0 && (threadIdx.x & 31) == 0) atomicOr(&a.flags[a.it], 1);
+    }
+}
+
+using T32PhaseKernel = void (*)(T32PhaseArgs);
+T32PhaseKernel t32_phase_cn_kernel(bool early);   // ib_t32_phase.cu
+T32PhaseKernel t32_phase_vn_kernel();
+T32PhaseKernel t32_phase_out_kernel();
+
 using T32Kernel = void (*)(T32Args);
 T32Kernel t32_cn_kernel(int d, bool early);   // ib_t32_cn.cu, d in [3, 10]
 T32Kernel t32_vn_kernel(int d);               // ib_t32_vn.cu, d in [1, 12]

@@ -1,6 +1,7 @@
 // ib_t32.cu -- host side of the |T| <= 32 shared-memory family (ib_kernels_t32.cuh): table images of every
 // (iteration, degree class), built once at ibldpc_set_luts, and the launch sequence of one decode.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -16,6 +17,7 @@ struct T32Images {
     std::vector<std::vector<size_t>> cn_off, vn_off, out_off;
     std::vector<int*> cn_starts, vn_starts;
     bool attrs_set = false;
+    bool phase_attrs_set = false;
 };
 
 namespace {
@@ -142,6 +144,88 @@ int decode_ib_t32(ibldpc_decoder* h, const IbArgs& a, int imax, int early, cudaS
         if (h->profiling) IBLDPC_CK(cudaEventRecord(h->events.back().b, st));
         return IBLDPC_OK;
     };
+    // ---- one launch per phase over all degree classes (ib_t32_phase_kernel) for degree sets of up to four classes
+    const bool no_fused = getenv("IBLDPC_T32_NO_PHASE") != nullptr;   // one launch per degree class (A/B, parity tests)
+    if (!no_fused && h->cn_classes.size() <= (size_t)kT32MaxClasses && h->vn_classes.size() <= (size_t)kT32MaxClasses) {
+        int cn_smem = 16, vn_smem = 16, out_smem = 16;
+        for (auto& c : h->cn_classes) cn_smem = std::max(cn_smem, t32_image_bytes(c.degree - 2));
+        for (auto& c : h->vn_classes) {
+            vn_smem = std::max(vn_smem, c.degree > 1 ? t32_image_bytes(c.degree - 1) : 16);
+            out_smem = std::max(out_smem, t32_image_bytes(c.degree));
+        }
+        if (!p->phase_attrs_set) {
+            for (int e = 0; e < 2; ++e)
+                IBLDPC_CK(cudaFuncSetAttribute((const void*)t32_phase_cn_kernel(e != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, cn_smem));
+            IBLDPC_CK(cudaFuncSetAttribute((const void*)t32_phase_vn_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, vn_smem));
+            IBLDPC_CK(cudaFuncSetAttribute((const void*)t32_phase_out_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, out_smem));
+            p->phase_attrs_set = true;
+        }
+        // classes heaviest first
+        auto order_of = [](const std::vector<NodeClass>& cls) {
+            std::vector<int> o(cls.size());
+            for (size_t i = 0; i < cls.size(); ++i) o[i] = (int)i;
+            std::sort(o.begin(), o.end(), [&](int x, int y) { return cls[x].degree > cls[y].degree; });
+            return o;
+        };
+        const std::vector<int> cn_order = order_of(h->cn_classes), vn_order = order_of(h->vn_classes);
+        auto fill = [&](T32PhaseArgs& q, int mode, const std::vector<NodeClass>& cls, const std::vector<int>& order,
+                        const std::vector<int*>& starts) -> int {
+            long long chunks = 0;
+            q.n_cls = (int)order.size();
+            for (size_t k = 0; k < order.size(); ++k) {
+                const NodeClass& c = cls[order[k]];
+                q.deg[k] = c.degree; q.nodes[k] = c.d_nodes; q.starts[k] = starts[order[k]]; q.n_nodes[k] = c.count;
+                const long long vec = t32_vec(mode, c.degree);
+                const long long tiles = ((long long)a.pitch + 128 * vec - 1) / (128 * vec);
+                chunks += ((long long)c.count * tiles + 31) / 32;
+            }
+            return (int)std::max<long long>(1, std::min<long long>(h->sm_count, chunks));
+        };
+        T32PhaseArgs pb{};
+        pb.a = a;
+        pb.a.early = early;
+        pb.a.imax = imax;
+        int rc;
+        auto phase_cn = [&](int it) -> int {
+            if ((rc = prof_begin(it < 0 ? 2 : 0))) return rc;
+            T32PhaseArgs q = pb;
+            q.a.it = it;
+            q.a.iter0 = it < 0;
+            const int grid = fill(q, kPhaseCn, h->cn_classes, cn_order, p->cn_starts);
+            for (size_t k = 0; k < cn_order.size(); ++k) q.image[k] = p->d_images + p->cn_off[cn_order[k]][it + 1];
+            t32_phase_cn_kernel(early != 0)<<<grid, kT32Threads, cn_smem, st>>>(q);
+            h->last_launches++; h->last_grid = grid; h->last_smem = cn_smem;
+            return prof_end();
+        };
+        auto phase_vn = [&](int it, bool decide) -> int {
+            if ((rc = prof_begin(decide ? 2 : 1))) return rc;
+            T32PhaseArgs q = pb;
+            q.a.it = it;
+            q.a.iter0 = 0;
+            const int grid = fill(q, decide ? kPhaseOut : kPhaseVn, h->vn_classes, vn_order, p->vn_starts);
+            for (size_t k = 0; k < vn_order.size(); ++k) {
+                const int ci = vn_order[k];
+                if (decide) {
+                    q.image[k] = p->d_images + p->out_off[ci][0];
+                    q.image_stride[k] = h->lut_imax > 1 ? (long long)(p->out_off[ci][1] - p->out_off[ci][0]) : 0;
+                } else {
+                    q.image[k] = p->d_images + p->vn_off[ci][it];
+                }
+            }
+            if (decide) t32_phase_out_kernel()<<<grid, kT32Threads, out_smem, st>>>(q);
+            else t32_phase_vn_kernel()<<<grid, kT32Threads, vn_smem, st>>>(q);
+            h->last_launches++;
+            return prof_end();
+        };
+        if ((rc = phase_cn(-1))) return rc;
+        for (int it = 0; it < imax - 1; ++it) {
+            if ((rc = phase_vn(it, false))) return rc;
+            if ((rc = phase_cn(it))) return rc;
+        }
+        if ((rc = phase_vn(0, true))) return rc;
+        IBLDPC_CK(cudaGetLastError());
+        return IBLDPC_OK;
+    }
     T32Args base{};
     base.a = a;
     base.a.early = early;

@@ -370,6 +370,60 @@ def test_t32_family_all_degrees(gpu, T, match):
     assert np.array_equal(out, ref) and dec.last_i_num == i_num
 
 
+@pytest.mark.parametrize("group", [0, 1, 2])
+@pytest.mark.parametrize("T", [32, 24])
+def test_t32_fused_phase_kernels_all_degrees(gpu, monkeypatch, group, T):
+    """ib_t32_phase_kernel (one launch per phase, the degree classes one after the other inside every CTA, image reloaded by
+    TMA between the classes) for degree sets of four classes covering every degree -- checks 3..10, variables 1..12 -- against
+    the oracle (outputs, i_num with the batch-granular stop) and against one launch per class (IBLDPC_T32_NO_PHASE=1)."""
+    import torch
+    import informationbottleneckdecodingldpc_b200 as pkg
+    vset = ([1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12])[group]
+    cset = ([3, 4, 5, 6], [7, 8, 9, 10], [4, 6, 8, 10])[group]
+    deg_v = [d for d in vset for _ in range(24)]
+    E = sum(deg_v)
+    deg_c = [d for d in cset for _ in range(6)]
+    while sum(deg_c) + cset[0] <= E:
+        deg_c.append(cset[len(deg_c) % 4] if sum(deg_c) + cset[len(deg_c) % 4] <= E else cset[0])
+    rest = E - sum(deg_c)
+    # spread what is left over checks that stay inside the set's degrees: bump checks to the next degree of the set
+    i = 0
+    while rest > 0 and i < len(deg_c):
+        nxt = [d for d in cset if d > deg_c[i]]
+        if nxt and nxt[0] - deg_c[i] <= rest:
+            rest -= nxt[0] - deg_c[i]
+            deg_c[i] = nxt[0]
+        i += 1
+    if rest:
+        pytest.skip("degree bookkeeping left a remainder")
+    H = codes.random_from_degrees(deg_v, deg_c, seed=80 + group)
+    t = graph.edge_tables(H)
+    assert len(set(t.degree_chk)) <= 4 and set(t.degree_var) == set(vset)
+    imax = 6
+    tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=T + group, matching=True)
+    for B in (77, 1500):
+        ch = np.random.Generator(np.random.PCG64(T + B)).integers(0, T, size=(t.n_var, B)).astype(np.uint8)
+
+        def run():
+            dec = pkg.Discrete_LDPC_Decoder_class_irregular(H, imax, T, T, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                                                            tb.matching_vector_checknode, tb.matching_vector_varnode, B)
+            dec.init_OpenCL_decoding(B)
+            out = dec.decode_OpenCL(pkg.DeviceArray(torch.from_numpy(ch).cuda()), buffer_in=True, return_buffer=True).get()
+            return dec, out
+
+        dec, out = run()
+        assert dec.info()[0] == 3 and dec.info()[1] <= 2 * imax + 2, dec.info()      # one launch per phase (+ clamp / pad kernels)
+        sel = np.arange(B) if B <= 100 else np.r_[0:16, B - 16:B]
+        ref, i_num = _oracle_ib(t, np.ascontiguousarray(ch[:, sel]), T, imax, tb, B <= 100)
+        assert np.array_equal(out[:, sel], ref)
+        if B <= 100:
+            assert dec.last_i_num == i_num
+        monkeypatch.setenv("IBLDPC_T32_NO_PHASE", "1")
+        dec2, out2 = run()
+        monkeypatch.delenv("IBLDPC_T32_NO_PHASE")
+        assert dec2.info()[1] > dec.info()[1] and np.array_equal(out2, out) and dec2.last_i_num == dec.last_i_num
+
+
 @pytest.mark.parametrize("B", [1, 100, 2049, 20011])
 def test_t32_family_wlan_vs_oracle_and_generic(gpu, monkeypatch, B):
     """802.11n with the reference's cardinality 32: oracle on a sample of frames, the generic path on all of them;
