@@ -805,7 +805,7 @@ ib_vn_n4_kernel(IbArgs a, const int* __restrict__ nodes, int n_nodes)
 // [tail-pair rows (kPairBytes)][stage tables][staging scratch]; NT threads per CTA, 2 words per lane.
 __host__ __device__ constexpr int vn_n4_pair_min_blocks(int D, int NT)
 {
-    return NT == 512 ? (D <= 9 ? 2 : 1) : (D <= 5 ? 3 : (D <= 9 ? 2 : 1));
+    return NT >= 640 ? 1 : NT == 512 ? (D <= 9 ? 2 : 1) : (D <= 5 ? 3 : (D <= 9 ? 2 : 1));
 }
 template <int D, int NT>
 __global__ void __launch_bounds__(NT, vn_n4_pair_min_blocks(D, NT))

@@ -9,6 +9,13 @@
 namespace ibldpc {
 NodeKernel vn_n4_pair_kernel(int d, int threads)
 {
+    if (threads == 768) {   // one CTA per SM, 24 warps at <= 85 registers (degrees 8-9 need 116-124 unconstrained, spill at 64)
+        switch (d) {
+        case 8: return ib_vn_n4_pair_kernel<8, 768>;
+        case 9: return ib_vn_n4_pair_kernel<9, 768>;
+        default: return nullptr;
+        }
+    }
     if (threads == 512) {
         switch (d) {
         case 3: return ib_vn_n4_pair_kernel<3, 512>;

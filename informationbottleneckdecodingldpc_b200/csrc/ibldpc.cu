@@ -707,7 +707,9 @@ int decode_ib_n4(ibldpc_decoder* h, Workspace& w, const uint8_t* ch, long long p
                 // measured on B200: degrees 8-9 spill at the 64 registers a 2 x 512-thread residency allows (DVB-S2 d_v=8:
                 // 0.387 ms with 256 threads vs 0.420 ms), degree >= 10 has one table set per SM either way (WLAN d_v=11:
                 // 0.195 ms with 512 threads vs 0.229 ms)
-                threads = h->vn_pair_threads ? h->vn_pair_threads : (c.degree == 8 || c.degree == 9) ? 256 : 512;
+                // (second half of round 2: 768-thread CTAs for degrees 8-9 -- one CTA per SM, 24 warps at 80 registers, no spills)
+                threads = h->vn_pair_threads ? h->vn_pair_threads : (c.degree == 8 || c.degree == 9) ? 768 : 512;
+                if (threads == 768 && !vn_n4_pair_kernel(c.degree, 768)) threads = 512;
                 k = vn_n4_pair_kernel(c.degree, threads);
             } else {
                 k = vec == 4 ? vn_n4_kernel_v4(c.degree, decide) : vn_n4_kernel_v2(c.degree, decide);
@@ -1240,7 +1242,7 @@ int ibldpc_set_luts(ibldpc_handle h, const ibldpc_lut_desc* L)
     if (const char* e = getenv("IBLDPC_VN_PAIR_MIN_DEGREE")) h->vn_pair_min_degree = std::max(3, atoi(e));
     h->cn_threads = getenv("IBLDPC_CN_THREADS") ? atoi(getenv("IBLDPC_CN_THREADS")) : 0;
     h->vn_threads = getenv("IBLDPC_VN_THREADS") ? atoi(getenv("IBLDPC_VN_THREADS")) : 0;
-    if (const char* e = getenv("IBLDPC_VN_PAIR_THREADS")) h->vn_pair_threads = atoi(e) == 512 ? 512 : atoi(e) == 256 ? 256 : 0;
+    if (const char* e = getenv("IBLDPC_VN_PAIR_THREADS")) h->vn_pair_threads = atoi(e) == 768 ? 768 : atoi(e) == 512 ? 512 : atoi(e) == 256 ? 256 : 0;
     if (h->nib && h->use_pair) {
         // Composed tail-pair tables of the variable-node update (vn_word_n4_pair): for every iteration and every
         // variable-node degree d >= 3, G(a,b)[x] = M_d( S_{d-2}( S_{d-3}(x, a), b ) ), 16 nibbles per (a,b) row

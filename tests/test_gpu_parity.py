@@ -176,7 +176,7 @@ def test_ib_tail_pair_variant_all_degrees(gpu, monkeypatch, family):
             assert np.array_equal(got, ref) and dec.last_i_num == i_num
 
 
-@pytest.mark.parametrize("threads", ["256", "512"])
+@pytest.mark.parametrize("threads", ["256", "512", "768"])
 def test_ib_vn_tail_pair_variant_all_degrees(gpu, monkeypatch, threads):
     """The composed tail-pair variable-node kernels (vn_word_n4_pair) for every degree 3..12, forced on with
     IBLDPC_VN_PAIR_MIN_DEGREE=3, both CTA sizes, with and without message alignment, against the oracle."""
