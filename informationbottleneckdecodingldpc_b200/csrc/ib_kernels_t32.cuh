@@ -376,21 +376,15 @@ __device__ __forceinline__ uint32_t t32_class_items(const IbArgs& a, const uint8
     return syn;
 }
 
+// the classes of one phase, one after the other (shared by the per-phase and the cooperative whole-decode kernel);
+// the image of class c is p.image[c] + index * p.image_stride[c] (per-phase kernels: index = 0 except for the decision phase,
+// where it is the number of executed passes).  Returns the syndrome bits seen (check-node phase with EARLY).
 template <int MODE, bool EARLY>
-__global__ void __launch_bounds__(kT32Threads, 1) ib_t32_phase_kernel(T32PhaseArgs p)
+__device__ __forceinline__ uint32_t t32_phase_classes(const IbArgs& a, const T32PhaseArgs& p, int index, uint8_t* s_img, int* s_next,
+                                                      uint64_t* s_mbar, uint32_t& parity)
 {
-    extern __shared__ __align__(128) uint8_t s_img[];
-    __shared__ __align__(8) uint64_t s_mbar;
-    __shared__ int s_next;
-    const IbArgs& a = p.a;
-    if (MODE != kPhaseOut && (EARLY || a.early) && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
-    const uint32_t mb = smem_u32(&s_mbar);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (MODE == kPhaseOut && blockIdx.x == 0) *a.inum = executed_passes(a) + 1;
-    }
-    uint32_t parity = 0, syn = 0;
+    const uint32_t mb = smem_u32(s_mbar);
+    uint32_t syn = 0;
     for (int c = 0; c < p.n_cls; ++c) {
         const int d = p.deg[c];
         const int nst = t32_cols(MODE, d);
@@ -402,10 +396,9 @@ __global__ void __launch_bounds__(kT32Threads, 1) ib_t32_phase_kernel(T32PhaseAr
         const bool tables = nst > 0;
         __syncthreads();                     // every warp has left the previous image and counter (first class: mbarrier initialised)
         if (threadIdx.x == 0) {
-            s_next = lo + kT32Threads / 32;
+            *s_next = lo + kT32Threads / 32;
             if (tables) {
-                const uint8_t* img = p.image[c];
-                if (MODE == kPhaseOut) img += (long long)executed_passes(a) * p.image_stride[c];
+                const uint8_t* img = p.image[c] + (long long)index * p.image_stride[c];
                 const uint32_t bytes = (uint32_t)t32_image_bytes(nst);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the old image before the async writes
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
@@ -421,7 +414,7 @@ __global__ void __launch_bounds__(kT32Threads, 1) ib_t32_phase_kernel(T32PhaseAr
         }
         __syncthreads();
 #define IBLDPC_T32_CASE(DD) \
-    case DD: syn |= t32_class_items<MODE, EARLY, DD>(a, s_img, p.nodes[c], p.starts[c], lo, hi, &s_next, &s_mbar, parity, tables); break;
+    case DD: syn |= t32_class_items<MODE, EARLY, DD>(a, s_img, p.nodes[c], p.starts[c], lo, hi, s_next, s_mbar, parity, tables); break;
         if constexpr (MODE == kPhaseCn) {
             switch (d) {
                 IBLDPC_T32_CASE(3) IBLDPC_T32_CASE(4) IBLDPC_T32_CASE(5) IBLDPC_T32_CASE(6)
@@ -438,9 +431,89 @@ __global__ void __launch_bounds__(kT32Threads, 1) ib_t32_phase_kernel(T32PhaseAr
 #undef IBLDPC_T32_CASE
         if (tables) parity ^= 1u;
     }
+    return syn;
+}
+
+template <int MODE, bool EARLY>
+__global__ void __launch_bounds__(kT32Threads, 1) ib_t32_phase_kernel(T32PhaseArgs p)
+{
+    extern __shared__ __align__(128) uint8_t s_img[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ int s_next;
+    const IbArgs& a = p.a;
+    if (MODE != kPhaseOut && (EARLY || a.early) && a.it >= 1 && a.flags[a.it - 1] == 0) return;   // batch already converged
+    int passes = 0;
+    if (threadIdx.x == 0) {
+        const uint32_t mb = smem_u32(&s_mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (MODE == kPhaseOut && blockIdx.x == 0) *a.inum = executed_passes(a) + 1;
+    }
+    if (MODE == kPhaseOut) passes = executed_passes(a);
+    uint32_t parity = 0;
+    const uint32_t syn = t32_phase_classes<MODE, EARLY>(a, p, passes, s_img, &s_next, &s_mbar, parity);
     if (MODE == kPhaseCn && EARLY && !a.iter0) {
         const unsigned any = __ballot_sync(0xffffffffu, syn != 0);
         if (any != 0 && (threadIdx.x & 31) == 0) atomicOr(&a.flags[a.it], 1);
+    }
+}
+
+// ---- small batches: the whole decode in ONE cooperative launch (the |T| <= 32 counterpart of ib_coop_phase_kernel) ----
+// Same class walk per phase, a grid-wide barrier between the phases instead of a kernel boundary: at the reference's
+// 802.11n msg_at_time = 2000 a decode is 100 phases of ~10 us, most of it launch latency.
+struct T32CoopArgs {
+    IbArgs a;
+    T32PhaseArgs cn;    // image[k] = image of table block 0 of class k, image_stride[k] = bytes between consecutive blocks
+    T32PhaseArgs vn;    // update images of iteration 0 / stride
+    T32PhaseArgs out;   // decision images of iteration 0 / stride (same classes as vn)
+};
+
+template <bool EARLY>
+__global__ void __launch_bounds__(kT32Threads, 1) ib_t32_coop_kernel(T32CoopArgs p)
+{
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(128) uint8_t s_img[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ int s_next;
+    cg::grid_group grid = cg::this_grid();
+    const IbArgs& a = p.a;
+    if (threadIdx.x == 0) {
+        const uint32_t mb = smem_u32(&s_mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t parity = 0;
+    auto cn_phase = [&](int it) {
+        IbArgs b = a;
+        b.it = it; b.iter0 = (it < 0);
+        const uint32_t syn = t32_phase_classes<kPhaseCn, EARLY>(b, p.cn, it + 1, s_img, &s_next, &s_mbar, parity);
+        if (EARLY && it >= 0) {
+            const unsigned any = __ballot_sync(0xffffffffu, syn != 0);
+            if (any != 0 && (threadIdx.x & 31) == 0) atomicOr(&a.flags[it], 1);
+        }
+    };
+    auto vn_phase = [&](int it) {
+        IbArgs b = a;
+        b.it = it; b.iter0 = 0;
+        t32_phase_classes<kPhaseVn, false>(b, p.vn, it, s_img, &s_next, &s_mbar, parity);
+    };
+    cn_phase(-1);
+    int passes = 0;
+    for (int it = 0; it < a.imax - 1; ++it) {
+        grid.sync();
+        // reference stop rule (discrete_LDPC_decoder.py:233-276); flags[] were written before the grid barrier
+        if (EARLY && it >= 1 && *reinterpret_cast<volatile int*>(&a.flags[it - 1]) == 0) break;
+        vn_phase(it);
+        grid.sync();
+        cn_phase(it);
+        passes = it + 1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.inum = passes + 1;
+    grid.sync();
+    {
+        IbArgs b = a;
+        b.it = passes; b.iter0 = 0;
+        t32_phase_classes<kPhaseOut, false>(b, p.out, passes, s_img, &s_next, &s_mbar, parity);
     }
 }
 
@@ -448,6 +521,8 @@ using T32PhaseKernel = void (*)(T32PhaseArgs);
 T32PhaseKernel t32_phase_cn_kernel(bool early);   // ib_t32_phase.cu
 T32PhaseKernel t32_phase_vn_kernel();
 T32PhaseKernel t32_phase_out_kernel();
+using T32CoopKernel = void (*)(T32CoopArgs);
+T32CoopKernel t32_coop_kernel(bool early);
 
 using T32Kernel = void (*)(T32Args);
 T32Kernel t32_cn_kernel(int d, bool early);   // ib_t32_cn.cu, d in [3, 10]

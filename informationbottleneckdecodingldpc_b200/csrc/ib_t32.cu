@@ -18,6 +18,7 @@ struct T32Images {
     std::vector<int*> cn_starts, vn_starts;
     bool attrs_set = false;
     bool phase_attrs_set = false;
+    bool coop_attrs_set = false;
 };
 
 namespace {
@@ -186,6 +187,51 @@ int decode_ib_t32(ibldpc_decoder* h, const IbArgs& a, int imax, int early, cudaS
         pb.a.early = early;
         pb.a.imax = imax;
         int rc;
+        // ---- small batches: the whole decode in one cooperative launch (ib_t32_coop_kernel).  Measured on B200, 802.11n
+        // |T| = 32: B = 2000 1.55 -> see profiles/README.md; the per-phase launches win once a phase is long enough
+        // (threshold IBLDPC_T32_COOP_MAX_B, default 2048 frames and at most 32 MB of messages)
+        const long long coop_max = getenv("IBLDPC_T32_COOP_MAX_B") ? atoll(getenv("IBLDPC_T32_COOP_MAX_B")) : 2048;
+        if ((long long)a.B <= coop_max && (long long)h->E * a.pitch <= (32LL << 20)) {
+            if (h->coop_supported < 0) {
+                int v = 0;
+                IBLDPC_CK(cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, h->device));
+                h->coop_supported = v;
+            }
+            if (h->coop_supported) {
+                const int smem = std::max(cn_smem, std::max(vn_smem, out_smem));
+                T32CoopKernel k = t32_coop_kernel(early != 0);
+                if (!p->coop_attrs_set) {
+                    for (int e = 0; e < 2; ++e)
+                        IBLDPC_CK(cudaFuncSetAttribute((const void*)t32_coop_kernel(e != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                    p->coop_attrs_set = true;
+                }
+                T32CoopArgs q{};
+                q.a = pb.a;
+                const int g_cn = fill(q.cn, kPhaseCn, h->cn_classes, cn_order, p->cn_starts);
+                const int g_vn = fill(q.vn, kPhaseVn, h->vn_classes, vn_order, p->vn_starts);
+                const int g_out = fill(q.out, kPhaseOut, h->vn_classes, vn_order, p->vn_starts);
+                const long long one = h->lut_imax > 1 ? 1 : 0;
+                for (size_t kk = 0; kk < cn_order.size(); ++kk) {
+                    const int ci = cn_order[kk];
+                    q.cn.image[kk] = p->d_images + p->cn_off[ci][0];
+                    q.cn.image_stride[kk] = one ? (long long)(p->cn_off[ci][1] - p->cn_off[ci][0]) : 0;
+                }
+                for (size_t kk = 0; kk < vn_order.size(); ++kk) {
+                    const int ci = vn_order[kk];
+                    q.vn.image[kk] = p->d_images + p->vn_off[ci][0];
+                    q.vn.image_stride[kk] = one ? (long long)(p->vn_off[ci][1] - p->vn_off[ci][0]) : 0;
+                    q.out.image[kk] = p->d_images + p->out_off[ci][0];
+                    q.out.image_stride[kk] = one ? (long long)(p->out_off[ci][1] - p->out_off[ci][0]) : 0;
+                }
+                const int grid = std::max(g_cn, std::max(g_vn, g_out));
+                if ((rc = prof_begin(2))) return rc;
+                void* params[] = {&q};
+                IBLDPC_CK(cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(kT32Threads), params, (size_t)smem, st));
+                h->last_launches++; h->last_grid = grid; h->last_smem = smem;
+                if ((rc = prof_end())) return rc;
+                return IBLDPC_OK;
+            }
+        }
         auto phase_cn = [&](int it) -> int {
             if ((rc = prof_begin(it < 0 ? 2 : 0))) return rc;
             T32PhaseArgs q = pb;

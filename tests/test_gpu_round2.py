@@ -373,9 +373,10 @@ def test_t32_family_all_degrees(gpu, T, match):
 @pytest.mark.parametrize("group", [0, 1, 2])
 @pytest.mark.parametrize("T", [32, 24])
 def test_t32_fused_phase_kernels_all_degrees(gpu, monkeypatch, group, T):
-    """ib_t32_phase_kernel (one launch per phase, the degree classes one after the other inside every CTA, image reloaded by
-    TMA between the classes) for degree sets of four classes covering every degree -- checks 3..10, variables 1..12 -- against
-    the oracle (outputs, i_num with the batch-granular stop) and against one launch per class (IBLDPC_T32_NO_PHASE=1)."""
+    """ib_t32_coop_kernel (whole decode in one cooperative launch, small batches) and ib_t32_phase_kernel (one launch per
+    phase; the degree classes one after the other inside every CTA, image reloaded by TMA between the classes) for degree sets
+    of four classes covering every degree -- checks 3..10, variables 1..12 -- against the oracle (outputs, i_num with the
+    batch-granular stop) and against one launch per class (IBLDPC_T32_NO_PHASE=1)."""
     import torch
     import informationbottleneckdecodingldpc_b200 as pkg
     vset = ([1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12])[group]
@@ -418,10 +419,15 @@ def test_t32_fused_phase_kernels_all_degrees(gpu, monkeypatch, group, T):
         assert np.array_equal(out[:, sel], ref)
         if B <= 100:
             assert dec.last_i_num == i_num
-        monkeypatch.setenv("IBLDPC_T32_NO_PHASE", "1")
+        assert dec.info()[1] <= 3, dec.info()                 # small batch: the whole decode in one cooperative launch
+        monkeypatch.setenv("IBLDPC_T32_COOP_MAX_B", "0")      # one launch per phase
+        dec1, out1 = run()
+        monkeypatch.delenv("IBLDPC_T32_COOP_MAX_B")
+        assert 2 * imax <= dec1.info()[1] <= 2 * imax + 2 and np.array_equal(out1, out) and dec1.last_i_num == dec.last_i_num
+        monkeypatch.setenv("IBLDPC_T32_NO_PHASE", "1")         # one launch per phase and degree class
         dec2, out2 = run()
         monkeypatch.delenv("IBLDPC_T32_NO_PHASE")
-        assert dec2.info()[1] > dec.info()[1] and np.array_equal(out2, out) and dec2.last_i_num == dec.last_i_num
+        assert dec2.info()[1] > dec1.info()[1] and np.array_equal(out2, out) and dec2.last_i_num == dec.last_i_num
 
 
 @pytest.mark.parametrize("B", [1, 100, 2049, 20011])
