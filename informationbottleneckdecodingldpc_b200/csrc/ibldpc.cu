@@ -162,6 +162,7 @@ void plan_geometry(long long slots, int warps, int tiles, int n_nodes, bool wide
     int best_tpc = -1;
     for (int tpc = 5; tpc >= 0; --tpc) {      // up to all 32 warps of a 1024-thread CTA on consecutive tiles of one node
         if ((warps >> tpc) < 1) continue;
+        if (warps & ((1 << tpc) - 1)) continue;      // 24-warp CTAs (768 threads): the warps must split into whole groups of 2^tpc tiles
         if (tpc > 0 && (1 << (tpc - 1)) >= tiles) continue;      // wider than the row: only wasted warps
         if (widest_only && best_tpc >= 0) break;
         const long long tg = (tiles + (1 << tpc) - 1) >> tpc;

@@ -187,15 +187,18 @@ def test_ib_vn_tail_pair_variant_all_degrees(gpu, monkeypatch, threads):
     assert sorted(set(t.degree_var)) == list(range(3, 13))
     for T in (16, 8):
         for match in (True, False):
-            imax, B = 5, 70
+            imax = 5
             tb = luts.random_tables(T, t.d_c_max, t.d_v_max, imax, seed=41, matching=match)
-            ch = np.random.Generator(np.random.PCG64(42)).integers(0, T, size=(t.n_var, B)).astype(np.uint8)
-            dec = _mk_ib(H, T, imax, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
-                         tb.matching_vector_checknode, tb.matching_vector_varnode)
-            got = dec.decode_OpenCL(_dev(ch), buffer_in=True, return_buffer=True).get()
-            ref, i_num = _oracle_ib(t, ch, T, imax, tb, True)
-            assert dec.info()[0] == 2
-            assert np.array_equal(got, ref) and dec.last_i_num == i_num
+            # 5000 frames = 10 tiles per row with four nodes per class: the launch planner must not put a 24-warp CTA
+            # (768 threads) on 16 tiles of one node (warps 16..23 would visit the next node's tiles a second time)
+            for B in (70, 5000):
+                ch = np.random.Generator(np.random.PCG64(42)).integers(0, T, size=(t.n_var, B)).astype(np.uint8)
+                dec = _mk_ib(H, T, imax, tb.Trellis_checknodevector_a, tb.Trellis_varnodevector_a,
+                             tb.matching_vector_checknode, tb.matching_vector_varnode)
+                got = dec.decode_OpenCL(_dev(ch), buffer_in=True, return_buffer=True).get()
+                ref, i_num = _oracle_ib(t, ch, T, imax, tb, True)
+                assert dec.info()[0] == 2
+                assert np.array_equal(got, ref) and dec.last_i_num == i_num
 
 
 @pytest.mark.parametrize("B,chunk", [(9001, 0), (8200, 0), (5000, 1008), (777, 0)])

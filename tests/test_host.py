@@ -165,11 +165,12 @@ def test_launch_planner_geometry_invariants():
     rng = np.random.default_rng(5)
     for _ in range(2000):
         slots = int(rng.integers(1, 8)) * 148
-        warps = int(rng.choice([8, 16, 32]))
+        warps = int(rng.choice([8, 16, 24, 32]))      # 24: the 768-thread tail-pair variable-node kernels
         tiles = int(rng.integers(1, 400))
         nodes = int(rng.integers(1, 70000))
         tpc, tg, gx = plan(slots, warps, tiles, nodes)
         assert 0 <= tpc <= 5 and (warps >> tpc) >= 1
+        assert warps % (1 << tpc) == 0                              # whole groups of 2^tpc warps: no (node, tile) is visited twice
         assert tg == -(-tiles // (1 << tpc))                     # all tiles covered, no empty tile group
         assert tpc == 0 or (1 << (tpc - 1)) < tiles              # footprint not wider than the row needs
         nsteps = -(-nodes // (warps >> tpc))
@@ -181,6 +182,7 @@ def test_launch_planner_geometry_invariants():
     # (8 tiles per CTA would leave 4 SMs idle: 16 tile groups x 9 CTAs)
     assert plan(148, 32, 128, 4000) == (5, 4, 37) and plan(148, 32, 64, 8000) == (5, 2, 74)
     assert plan(296, 16, 128, 4000) == (4, 8, 37)
+    assert plan(148, 24, 10, 6)[0] <= 3                             # few nodes, 10 tiles: a tie must not go to 16 tiles per 24-warp CTA
     assert L.ibldpc_plan_geometry(0, 16, 1, 1, out) != 0 and L.ibldpc_plan_geometry(148, 12, 1, 1, out) != 0
 
 
